@@ -1,0 +1,321 @@
+"""Generate the committed golden fixtures by running the REAL reference (baldhat/yolov10-3D, imported
+read-only from /root/reference through oracle/ref_import.py) on seeded synthetic inputs.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Each fixture ``tests/golden/<case>.npz`` stores the recipe of its inputs (``tests/synth.py`` arguments, as a
+JSON string) plus a CRC of the regenerated inputs, and the reference's outputs.  The reference is run with
+``torch.topk`` replaced by a stable descending sort (lowest index wins ties, the tie-break BASELINE.json
+mandates) -- the fixture also records whether the unpatched reference agreed.
+"""
+import json
+import os
+import sys
+import types
+from functools import partial
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+from tests import synth  # noqa: E402
+
+ref_import.import_reference()
+import torch  # noqa: E402
+from ultralytics.nn.modules.block import DFL  # noqa: E402
+from ultralytics.nn.modules.head import Detect, v10Detect3d  # noqa: E402
+from ultralytics.utils import loss as ref_loss  # noqa: E402
+from ultralytics.utils import ops as ref_ops  # noqa: E402
+from ultralytics.utils import tal as ref_tal  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(8)
+_orig_topk = torch.topk
+
+
+def stable_topk(x, k, dim=-1, largest=True, sorted=True):
+    assert largest
+    v, i = torch.sort(x, dim=dim, descending=True, stable=True)
+    return v.narrow(dim, 0, k), i.narrow(dim, 0, k)
+
+
+class patched_topk:
+    def __enter__(self):
+        torch.topk = stable_topk
+
+    def __exit__(self, *a):
+        torch.topk = _orig_topk
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def save(name, recipe, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, recipe=json.dumps(recipe), **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+# ---------------------------------------------------------------------------------------------- 2D decode
+def head_ns(nc, strides):
+    ns = types.SimpleNamespace(nc=nc, reg_max=16, no=nc + 64, dynamic=False, shape=None, export=False, format=None,
+                               stride=torch.tensor(strides), dfl=DFL(16), anchors=torch.empty(0),
+                               strides=torch.empty(0))
+    ns.decode_bboxes = partial(Detect.decode_bboxes, ns)
+    return ns
+
+
+def case_decode_post(name, B, nc, img_hw, D, seed, quantise=None):
+    lv = synth.levels(*img_hw)
+    x = synth.head2d(B, nc, lv, seed=seed)
+    if quantise:  # coarse logits -> many exactly tied scores
+        x[:, 64:] = np.round(x[:, 64:] * quantise) / quantise
+    feats = [t(f) for f in synth.split_levels(x, lv)]
+    ns = head_ns(nc, synth.STRIDES)
+    with torch.no_grad():
+        y, _ = Detect.inference(ns, feats)
+        ns.export = True  # xyxy variant (head.py:107-108)
+        ns.shape = None
+        y_xyxy = Detect.inference(ns, feats)
+        with patched_topk():
+            boxes, scores, labels = ref_ops.v10postprocess(y.permute(0, 2, 1), D, nc)
+        b2, s2, l2 = ref_ops.v10postprocess(y.permute(0, 2, 1), D, nc)
+        agree = bool(torch.equal(labels, l2) and torch.equal(scores, s2) and torch.equal(boxes, b2))
+    recipe = dict(kind="decode_post", B=B, nc=nc, img_hw=img_hw, D=D, seed=seed, quantise=quantise)
+    save(name, recipe, in_crc=np.int64(synth.checksum(x)), y=y.numpy(), y_xyxy_box=y_xyxy[:, :4].numpy(),
+         boxes=boxes.numpy(), scores=scores.numpy(), labels=labels.numpy(), unpatched_agrees=np.bool_(agree))
+
+
+# ---------------------------------------------------------------------------------------------- 2D assigner
+def sparse_targets(ts):
+    """target_scores [B,A,nc] is one-hot * norm: store nonzeros only."""
+    idx = np.nonzero(ts)
+    return np.stack(idx, 1).astype(np.int32), ts[idx]
+
+
+def make_assign_inputs(kind, B, nc, img_hw, M, seed, crowd=False):
+    lv = synth.levels(*img_hw)
+    gt = synth.gt2d(B, M, nc, img_hw, seed=seed + 1, crowd=crowd)
+    if kind == "random":
+        x = synth.head2d(B, nc, lv, seed=seed)
+    else:
+        x = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 2, frac=0.05)
+    pd_scores, pd_bboxes, anc = synth.assigner_inputs_from_head(x, lv, nc)
+    if kind == "ties":
+        # adversarial: duplicated GT boxes, quantised scores / boxes, a GT over the top-left corner,
+        # one image whose scores are all zero, one GT far outside every prediction (CIoU <= 0)
+        gt[:, 1] = gt[:, 0]
+        gt[0, 2, 1:5] = (0.0, 0.0, 70.0, 50.0)
+        gt[1, 3, 1:5] = (1.0, 1.0, 30.0, 20.0)
+        pd_scores = np.round(pd_scores * 8) / 8
+        pd_bboxes = np.round(pd_bboxes / 4) * 4
+        pd_scores[B - 1] = 0.0
+        pd_scores = pd_scores.astype(np.float32)
+        pd_bboxes = pd_bboxes.astype(np.float32)
+    return gt, pd_scores, pd_bboxes, anc
+
+
+def case_assign(name, kind, B, nc, img_hw, M, topk, seed, crowd=False, alpha=0.5, beta=6.0):
+    gt, pd_scores, pd_bboxes, anc = make_assign_inputs(kind, B, nc, img_hw, M, seed, crowd)
+    gl, gb = t(gt[..., :1]), t(gt[..., 1:5])
+    mg = gb.sum(2, keepdim=True).gt_(0)
+    asg = ref_tal.TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=beta)
+    with patched_topk():
+        tl, tb, ts, fg, tgi = asg(t(pd_scores), t(pd_bboxes), t(anc), gl, gb, mg)
+    u = asg(t(pd_scores), t(pd_bboxes), t(anc), gl, gb, mg)
+    agree = bool(torch.equal(fg, u[3]) and torch.equal(tgi, u[4]))
+    ts_idx, ts_val = sparse_targets(ts.numpy())
+    recipe = dict(kind="assign", inputs=kind, B=B, nc=nc, img_hw=img_hw, M=M, topk=topk, seed=seed, crowd=crowd,
+                  alpha=alpha, beta=beta)
+    save(name, recipe, in_crc=np.int64(synth.checksum(gt, pd_scores, pd_bboxes, anc)),
+         target_labels=tl.numpy().astype(np.int16), target_bboxes_crc=np.int64(synth.checksum(tb.numpy())),
+         ts_idx=ts_idx, ts_val=ts_val, fg_mask=np.packbits(fg.numpy()), target_gt_idx=tgi.numpy().astype(np.int16),
+         unpatched_agrees=np.bool_(agree))
+
+
+# ---------------------------------------------------------------------------------------------- 2D loss
+class FakeModel(torch.nn.Module):
+    """The three attributes v8DetectionLoss.__init__ reads (loss.py:160-178)."""
+
+    def __init__(self, nc, strides, args):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self.args = args
+        head = types.SimpleNamespace(stride=torch.tensor(strides), nc=nc, no=nc + 64, reg_max=16)
+        self.model = [head]
+
+
+def case_loss(name, kind, B, nc, img_hw, M, seed, crowd=False):
+    lv = synth.levels(*img_hw)
+    gt = synth.gt2d(B, M, nc, img_hw, seed=seed + 1, crowd=crowd)
+    if kind == "random":
+        xm, xo = synth.head2d(B, nc, lv, seed=seed), synth.head2d(B, nc, lv, seed=seed + 7)
+    else:
+        xm = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 2, frac=0.05)
+        xo = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 3, frac=0.03)
+    batch = {k: t(v) for k, v in synth.batch_dict(gt, img_hw).items()}
+    fm = [t(f).requires_grad_(True) for f in synth.split_levels(xm, lv)]
+    fo = [t(f).requires_grad_(True) for f in synth.split_levels(xo, lv)]
+    model = FakeModel(nc, synth.STRIDES, types.SimpleNamespace(box=7.5, cls=0.5, dfl=1.5))
+    crit = ref_loss.v10DetectLoss(model)
+    with patched_topk():
+        total, items = crit({"one2many": fm, "one2one": fo}, batch)
+    total.backward()
+    gm = torch.cat([f.grad.view(B, nc + 64, -1) for f in fm], 2).numpy()
+    go = torch.cat([f.grad.view(B, nc + 64, -1) for f in fo], 2).numpy()
+    g = synth.rng(seed + 99)
+    pos = g.integers(0, gm.size, 4096)
+    # plus every position with a non-zero box-channel gradient of image 0 (fg anchors), capped
+    nzm = np.flatnonzero(gm[0, :64])[:4096]
+    nzo = np.flatnonzero(go[0, :64])[:4096]
+    recipe = dict(kind="loss", inputs=kind, B=B, nc=nc, img_hw=img_hw, M=M, seed=seed, crowd=crowd,
+                  gains=[7.5, 0.5, 1.5])
+    save(name, recipe, in_crc=np.int64(synth.checksum(gt, xm, xo)), total=np.float64(total.item()),
+         items=items.detach().numpy().astype(np.float64), grad_pos=pos, grad_m=gm.reshape(-1)[pos],
+         grad_o=go.reshape(-1)[pos], grad_m_abs_sum=np.float64(np.abs(gm).sum(dtype=np.float64)),
+         grad_o_abs_sum=np.float64(np.abs(go).sum(dtype=np.float64)), nz_m=nzm, nz_m_val=gm[0, :64].reshape(-1)[nzm],
+         nz_o=nzo, nz_o_val=go[0, :64].reshape(-1)[nzo])
+
+
+# ---------------------------------------------------------------------------------------------- 3D
+def head3d_ns(nc, strides):
+    ns = types.SimpleNamespace(nc=nc, no=nc + 35, dynamic=False, shape=None, export=False, format=None,
+                               stride=torch.tensor(strides), anchors=torch.empty(0), strides=torch.empty(0))
+    ns.decode = partial(v10Detect3d.decode, ns)
+    return ns
+
+
+def case_decode3d(name, B, nc, img_hw, D, seed):
+    lv = synth.levels(*img_hw)
+    x = synth.head3d(B, nc, lv, seed=seed)
+    feats = [t(f) for f in synth.split_levels(x, lv)]
+    ns = head3d_ns(nc, synth.STRIDES)
+    with torch.no_grad():
+        y, _ = v10Detect3d.inference(ns, feats)
+        with patched_topk():
+            reg, scores, labels = ref_ops.v10_3Dpostprocess(y.transpose(-1, -2), D, nc)
+        u = ref_ops.v10_3Dpostprocess(y.transpose(-1, -2), D, nc)
+    agree = bool(torch.equal(labels, u[2]) and torch.equal(scores, u[1]))
+    recipe = dict(kind="decode3d", B=B, nc=nc, img_hw=img_hw, D=D, seed=seed)
+    save(name, recipe, in_crc=np.int64(synth.checksum(x)), y=y.numpy(), reg=reg.numpy(), scores=scores.numpy(),
+         labels=labels.numpy(), unpatched_agrees=np.bool_(agree))
+    return torch.cat((reg, scores.unsqueeze(-1), labels.unsqueeze(-1)), -1).numpy()  # yolov10_3D/val.py:46-47
+
+
+def case_decode_preds(name, dets):
+    from ultralytics.data.datasets.kitti import KITTIDataset
+    from ultralytics.data.datasets.kitti_utils import Calibration
+
+    B, D, _ = dets.shape
+    g = synth.rng(77)
+    calibs, cal_arr = [], []
+    for b in range(B):
+        c = object.__new__(Calibration)
+        vals = np.array(synth.KITTI_CALIB) * (1 + 0.01 * g.standard_normal(6))
+        c.cu, c.cv, c.fu, c.fv, c.tx, c.ty = (float(v) for v in vals)
+        calibs.append(c)
+        cal_arr.append(vals)
+    inv = np.stack([np.array([[1.03 + 0.01 * b, 0.0, -3.0 + b], [0.0, 1.02, 2.5 - b]]) for b in range(B)])
+    ratio = np.stack([np.array([1.0 + 0.03 * b, 1.0 + 0.02 * b]) for b in range(B)])
+    ratio_pad = [(ratio[b], (0.0, 0.0)) for b in range(B)]
+    cms = np.array(synth.KITTI_MEAN_SIZES)
+    ds = types.SimpleNamespace(cls_mean_size=cms, use_camera_dis=False)
+    files = [f"im{b}" for b in range(B)]
+    res = KITTIDataset.decode_preds(ds, t(dets.copy()), calibs, files, ratio_pad, list(inv), undo_augment=True,
+                                    threshold=0.001)
+    rows = np.full((B, D, 14), np.nan)
+    counts = np.zeros(B, np.int32)
+    for b in range(B):
+        r = res[files[b]]
+        counts[b] = len(r)
+        if r:
+            rows[b, : len(r)] = np.array(r, dtype=np.float64)
+    recipe = dict(kind="decode_preds", note="rows are the kept detections in order; NaN padded")
+    save(name, recipe, dets=dets, calib=np.stack(cal_arr), inv_affine=inv, ratio=ratio, cls_mean_size=cms,
+         rows=rows, counts=counts)
+
+
+def case_assign3d(name, B, nc, img_hw, M, topk, seed, **kw):
+    lv = synth.levels(*img_hw)
+    x = synth.head3d(B, nc, lv, seed=seed)
+    gts = synth.gt3d(B, M, nc, img_hw, seed=seed + 1)
+    pd_scores, pd_bboxes, pd_3d, anc, st = synth.assigner3d_inputs_from_head(x, lv, nc)
+    # make ~3% of in-GT anchors 'trained': 2D box, 3D centre, depth, heading and class near the GT
+    g = synth.rng(seed + 5)
+    for b in range(B):
+        for m in range(M):
+            row = gts[b, m]
+            if row[1:5].sum() <= 0:
+                continue
+            ins = np.nonzero((anc[:, 0] > row[1]) & (anc[:, 0] < row[3]) & (anc[:, 1] > row[2]) & (anc[:, 1] < row[4]))[0]
+            if ins.size == 0:
+                continue
+            for a in g.choice(ins, size=min(ins.size, max(2, int(0.03 * ins.size))), replace=False):
+                pd_bboxes[b, a] = row[1:5] + g.standard_normal(4) * 3
+                pd_scores[b, a, int(row[0])] = 0.5 + 0.4 * g.random()
+                pd_3d[b, a, 0:2] = (row[9:11] - anc[a]) / st[a] + g.standard_normal(2) * 0.05
+                pd_3d[b, a, 2:5] = row[11:14] + g.standard_normal(3) * 0.05
+                pd_3d[b, a, 5 + int(row[15])] += 4.0
+                pd_3d[b, a, 17 + int(row[15])] = row[16] + g.standard_normal() * 0.05
+                pd_3d[b, a, 29] = row[14] + g.standard_normal() * 0.5
+    pd_scores, pd_bboxes, pd_3d = (np.ascontiguousarray(v, np.float32) for v in (pd_scores, pd_bboxes, pd_3d))
+    calibs = np.tile(np.array(synth.KITTI_CALIB, np.float32), (B, 1))
+    calibs[:, 0] += np.arange(B, dtype=np.float32)
+    ms = np.array(synth.KITTI_MEAN_SIZES, np.float32)
+    parts = np.split(gts, np.cumsum([1, 4, 2, 2, 2, 3, 1, 1])[:], axis=2)
+    gt_tuple = tuple(t(p) for p in parts)
+    mg = gt_tuple[1].sum(2, keepdim=True).gt_(0)
+    asg = ref_tal.TaskAlignedAssigner3d(topk=topk, num_classes=nc, **kw)
+    with patched_topk():
+        targets, fg, tgi, pk, gk = asg(t(pd_scores), t(pd_bboxes), t(pd_3d), t(anc), gt_tuple, mg, t(st[:, None]),
+                                       t(calibs), t(ms))
+    u = asg(t(pd_scores), t(pd_bboxes), t(pd_3d), t(anc), gt_tuple, mg, t(st[:, None]), t(calibs), t(ms))
+    agree = bool(torch.equal(fg, u[1]) and torch.equal(tgi, u[2]))
+    ts_idx, ts_val = sparse_targets(targets[1].numpy())
+    tv = torch.cat(targets[2:], -1).numpy()
+    recipe = dict(kind="assign3d", B=B, nc=nc, img_hw=img_hw, M=M, topk=topk, seed=seed, kw=kw)
+    save(name, recipe, in_crc=np.int64(synth.checksum(gts, pd_scores, pd_bboxes, pd_3d)),
+         pd_scores=pd_scores.astype(np.float32), pd_bboxes=pd_bboxes, pd_3d=pd_3d, gts=gts, calibs=calibs,
+         target_labels=targets[0].numpy().astype(np.int16), ts_idx=ts_idx, ts_val=ts_val,
+         target_vals_crc=np.int64(synth.checksum(tv)), fg_mask=np.packbits(fg.numpy()),
+         target_gt_idx=tgi.numpy().astype(np.int16), pd_kps_sample=pk.numpy()[:, ::37], gt_kps=gk.numpy(),
+         unpatched_agrees=np.bool_(agree))
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:] or None
+
+    def want(n):
+        return only is None or any(n.startswith(o) for o in only)
+
+    if want("decode"):
+        case_decode_post("decode_post_small", B=2, nc=8, img_hw=(160, 160), D=50, seed=10)
+        case_decode_post("decode_post_nc80", B=1, nc=80, img_hw=(256, 320), D=300, seed=11)
+        case_decode_post("decode_post_ties", B=2, nc=8, img_hw=(160, 160), D=100, seed=12, quantise=2)
+    if want("assign_"):
+        case_assign("assign_random_k10", "random", B=3, nc=8, img_hw=(160, 160), M=12, topk=10, seed=20)
+        case_assign("assign_trained_k10", "trained", B=3, nc=8, img_hw=(256, 320), M=12, topk=10, seed=21)
+        case_assign("assign_trained_k1", "trained", B=3, nc=8, img_hw=(256, 320), M=12, topk=1, seed=22)
+        case_assign("assign_trained_k13", "trained", B=2, nc=8, img_hw=(160, 160), M=6, topk=13, seed=23,
+                    alpha=1.0, beta=6.0)
+        case_assign("assign_ties_k10", "ties", B=3, nc=8, img_hw=(160, 160), M=12, topk=10, seed=24)
+        case_assign("assign_ties_k1", "ties", B=3, nc=8, img_hw=(160, 160), M=12, topk=1, seed=25)
+        case_assign("assign_crowd_k10", "trained", B=2, nc=8, img_hw=(256, 320), M=60, topk=10, seed=26, crowd=True)
+    if want("loss"):
+        case_loss("loss_random", "random", B=3, nc=8, img_hw=(160, 160), M=10, seed=30)
+        case_loss("loss_trained", "trained", B=3, nc=8, img_hw=(256, 320), M=12, seed=31)
+        case_loss("loss_crowd", "trained", B=2, nc=8, img_hw=(256, 320), M=60, seed=32, crowd=True)
+    if want("decode3d") or want("preds3d"):
+        dets = case_decode3d("decode3d_small", B=3, nc=3, img_hw=(96, 320), D=50, seed=40)
+        case_decode_preds("preds3d_small", dets)
+    if want("assign3d"):
+        case_assign3d("assign3d_k8", B=2, nc=3, img_hw=(96, 320), M=8, topk=8, seed=50, alpha=0.5, beta=1.0, gamma=1.0)
+        case_assign3d("assign3d_k1", B=2, nc=3, img_hw=(96, 320), M=8, topk=1, seed=51, alpha=0.5, beta=1.0, gamma=1.0)
+        case_assign3d("assign3d_l2_free", B=2, nc=3, img_hw=(96, 320), M=6, topk=8, seed=52, alpha=0.5, beta=3.0,
+                      gamma=3.0, kps_dist_metric="l2", constrain_anchors=False)
+        case_assign3d("assign3d_3donly", B=2, nc=3, img_hw=(96, 320), M=6, topk=8, seed=53, use_2d=False)
+        case_assign3d("assign3d_2donly", B=2, nc=3, img_hw=(96, 320), M=6, topk=8, seed=54, use_3d=False)

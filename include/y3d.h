@@ -1,0 +1,163 @@
+/*
+ * y3d.h -- C ABI of liby3d_b200.so: the B200 (sm_100a) implementation of the YOLOv10 / YOLOv10-3D
+ * detection-head hot path (head decode, NMS-free top-k, dual task-aligned assignment, loss partials).
+ *
+ * The reference (baldhat/yolov10-3D) is pure Python/PyTorch and has no FFI for this path; each entry point
+ * below replaces one reference *Python* function (cited per function, paths relative to the reference repo).
+ * The host-side mirror of those Python signatures lives in yolov10-3d_b200/ and binds this ABI with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer named d_* / without prefix in a "device" section is a DEVICE pointer; lvl_* geometry arrays
+ *    and the arrays of per-level pointers are small HOST arrays read during the call;
+ *  - all buffers (inputs, outputs, workspace) are owned by the caller; nothing is allocated, freed or retained;
+ *  - every function only enqueues work on `stream` (a cudaStream_t passed as void*; NULL = default stream),
+ *    never synchronises the device and keeps no global mutable state (re-entrant, one stream per thread is fine);
+ *  - return value: 0 = success; negative = Y3D_E* argument error (nothing was enqueued); positive = cudaError_t
+ *    of a failed launch; y3d_strerror() names both;
+ *  - fp32 only (the reference path is fp32; AMP callers up-cast), strides are in ELEMENTS;
+ *  - tie-breaking everywhere: lowest index first;
+ *  - workspace: query y3d_workspace_bytes(); contents need no initialisation; 256-byte alignment required.
+ */
+#ifndef Y3D_H_
+#define Y3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Y3D_MAX_LEVELS 4
+#define Y3D_MAX_TOPK 32      /* TAL top-k per GT (reference uses 10 / 13 / 8 / 1) */
+#define Y3D_MAX_DET 1024     /* max_det of the NMS-free top-k (reference: 300 / 50) */
+
+enum {
+    Y3D_OK = 0,
+    Y3D_EINVAL = -1,      /* bad shape / null pointer / bad flag */
+    Y3D_EUNSUPPORTED = -2, /* config outside the compiled limits (levels, topk, max_det, reg_max ...) */
+    Y3D_EALIGN = -3,      /* pointer / stride alignment the kernels need is not met */
+    Y3D_EWORKSPACE = -4   /* workspace missing or too small */
+};
+
+enum { /* `stage` of y3d_workspace_bytes */
+    Y3D_STAGE_POSTPROCESS = 1,
+    Y3D_STAGE_TAL_ASSIGN = 2,
+    Y3D_STAGE_V8_LOSS = 3,
+    Y3D_STAGE_TAL_ASSIGN3D = 4,
+    Y3D_STAGE_DECODE_TOPK = 5
+};
+
+const char *y3d_strerror(int rc);
+int y3d_abi_version(void);
+
+/* bytes of scratch a stage needs for the given sizes (unused dimensions may be 0) */
+size_t y3d_workspace_bytes(int stage, int B, int A, int nc, int M, int k, int D);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Head geometry.  The head emits one tensor per level, [B, C, h_l, w_l] (ultralytics/nn/modules/head.py:80-85).
+ * Level l, image b, channel c, cell i (= y*w_l + x) is at lvl_ptr[l][b*lvl_sB[l] + c*lvl_sC[l] + i].
+ * A concatenated x_cat [B, C, A] (head.py:56) is described with lvl_ptr[l] = x_cat + start_l, sB = C*A, sC = A.
+ * Anchors are never read: anchor (x+0.5, y+0.5) and stride are recomputed from the cell index
+ * (make_anchors, ultralytics/utils/tal.py:300-312).
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Detect.inference (head.py:53-79) = DFL softmax-integral (block.py:59-62) + dist2bbox (tal.py:315-325) * stride,
+ * cat with sigmoid(cls).  y: [B, 4+nc, A] contiguous; xywh=1 normal path, xywh=0 the export path (head.py:107). */
+int y3d_decode2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                 const float *lvl_stride, int nl, int B, int nc, int reg_max, int xywh, float *y, void *stream);
+
+/* ops.v10postprocess (ultralytics/utils/ops.py:852-865) when scores_first=0, nreg=4: preds[...,:4] boxes,
+ * preds[...,4:] scores;  ops.v10_3Dpostprocess (ops.py:867-880) when scores_first=1, nreg=35.
+ * preds element (b,a,ch) at preds[b*sB + a*sA + ch*sC] -- the reference passes a permuted view, so strides are
+ * honoured instead of forcing a copy.  Outputs: reg [B,D,nreg], scores [B,D], labels [B,D] int64 (reference dtype),
+ * anchor_idx [B,D] int32 (optional, may be NULL: the anchor each detection came from).  Requires 1 <= D <= min(A, Y3D_MAX_DET). */
+int y3d_postprocess(const float *preds, int64_t sB, int64_t sA, int64_t sC, int B, int A, int nc, int nreg,
+                    int scores_first, int D, float *reg, float *scores, int64_t *labels, int32_t *anchor_idx,
+                    void *ws, size_t ws_bytes, void *stream);
+
+/* v10Detect.forward export branch (head.py:526-531): decode (xyxy) + v10postprocess fused; the class scores of
+ * all anchors are never written and the box channels are only decoded for the D winners.
+ * out: [B, D, 6] = x1 y1 x2 y2 score label(as float); anchor_idx optional [B,D] int32. */
+int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                      const float *lvl_stride, int nl, int B, int nc, int reg_max, int xywh, int D, float *out,
+                      int32_t *anchor_idx, void *ws, size_t ws_bytes, void *stream);
+
+/* TaskAlignedAssigner.forward (ultralytics/utils/tal.py:44-94; get_pos_mask :96, get_box_metrics :108,
+ * select_topk_candidates :133, select_highest_overlaps :237, get_targets :169) with CIoU from
+ * ultralytics/utils/metrics.py:78-134.  M >= 1 (the M == 0 early-out of tal.py:68-76 is host-side glue).
+ *  pd_scores [B,A,nc] (already sigmoid; element strides ss_B, ss_A, ss_C), pd_bboxes [B,A,4] xyxy px contiguous,
+ *  anc_points [A,2] px, gt_labels [B,M], gt_bboxes [B,M,4] xyxy px, mask_gt [B,M] (0/1 floats).
+ *  lvl_hw / lvl_stride (HOST, may be NULL): when given, promise that anc_points == make_anchors(levels)*stride so
+ *  the candidate search walks each GT's rectangle instead of all A anchors (same results, less work).
+ * outputs (reference dtypes): target_labels [B,A] int64, target_bboxes [B,A,4], target_scores [B,A,nc],
+ *  fg_mask [B,A] uint8 (0/1; torch.bool storage), target_gt_idx [B,A] int64.  Any of target_labels / target_bboxes /
+ *  target_scores may be NULL to skip that write. */
+int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A, int64_t ss_C, const float *pd_bboxes,
+                   const float *anc_points, const float *gt_labels, const float *gt_bboxes, const float *mask_gt,
+                   int B, int A, int nc, int M, int topk, float alpha, float beta, float eps, const int *lvl_hw,
+                   const float *lvl_stride, int nl, int64_t *target_labels, float *target_bboxes,
+                   float *target_scores, uint8_t *fg_mask, int64_t *target_gt_idx, void *ws, size_t ws_bytes,
+                   void *stream);
+
+/* v8DetectionLoss.__call__ forward (ultralytics/utils/loss.py:206-257 with bbox_decode :197, BboxLoss :82-113)
+ * for ONE branch, fused: head levels in, three loss items out; pd_scores / target_scores are never materialised.
+ *  gt [B,M,5] = cls, xyxy px (the output of v8DetectionLoss.preprocess, loss.py:180-195; zero rows = padding), M >= 0.
+ *  gains = hyp.box, hyp.cls, hyp.dfl.  loss_items: DEVICE float[4] = box, cls, dfl (after gains), and
+ *  target_scores_sum (max(sum,1), loss.py:240).  partials (optional DEVICE double[4]): un-normalised
+ *  sum (1-ciou)*w, sum bce, sum dfl*w, sum target_scores -- what a multi-GPU caller all-reduces before
+ *  normalising; when `normalise` is 0 loss_items is left untouched.
+ *  v10DetectLoss (loss.py:727-737) = this with topk=10 on one2many + topk=1 on one2one.
+ *  dbg_fg_mask [B,A] u8 / dbg_target_gt_idx [B,A] i32 (optional, NULL in production): the assignment the fused
+ *  path used, for parity tests. */
+int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                    const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt, int M, int topk,
+                    float gain_box, float gain_cls, float gain_dfl, int normalise, float *loss_items,
+                    double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes,
+                    void *stream);
+
+/* v8DetectionLoss.bbox_decode (loss.py:197-204) + the permute/sigmoid of loss.py:214,232: head levels ->
+ * pd_bboxes [B,A,4] xyxy in GRID units (caller multiplies by stride, loss.py:233) and, optionally (may be NULL),
+ * pd_scores [B,A,nc] = sigmoid(class logits).  Same device arithmetic as the fused loss uses internally. */
+int y3d_train_decode(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                     const float *lvl_stride, int nl, int B, int nc, int reg_max, float *pd_bboxes, float *pd_scores,
+                     void *stream);
+
+/* turns all-reduced partials (see above) into loss items: DEVICE double[4] -> DEVICE float[4] */
+int y3d_v8_loss_finalize(const double *partials, float gain_box, float gain_cls, float gain_dfl, float *loss_items,
+                         void *stream);
+
+/* v10Detect3d.decode (head.py:755-764): [B, nc+35, A] levels -> y [B, nc+35, A] contiguous
+ * (cls logits | bbox xyxy px | center3d px | s3d | hd(24) | dep | dep_un). */
+int y3d_decode3d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                 const float *lvl_stride, int nl, int B, int nc, float *y, void *stream);
+
+/* KITTIDataset.decode_preds (ultralytics/data/datasets/kitti.py:519-576; bin2angle decode_helper.py:12,
+ * img_to_rect kitti_utils.py:241, alpha2ry :311, affine_transform :467), undo_augment=True.
+ *  dets [B,D,37] fp32 = bbox(4) c3d(2) s3d(3) hd(24) dep un score(logit) label (yolov10_3D/val.py:46-47);
+ *  calib [B,6] = cu cv fu fv tx ty, inv_affine [B,2,3], ratio [B,2], cls_mean_size [nc,3] -- all float64 like the
+ *  reference's numpy math.  rows [B,D,14] float64 = cls alpha x1 y1 x2 y2 h w l x y z ry score; valid [B,D] uint8
+ *  = !(score < threshold). */
+int y3d_decode_preds3d(const float *dets, int B, int D, int nc, const double *calib, const double *inv_affine,
+                       const double *ratio, const double *cls_mean_size, double threshold, double *rows,
+                       uint8_t *valid, void *stream);
+
+/* TaskAlignedAssigner3d.forward (ultralytics/utils/tal.py:391-452; keypoints utils/keypoint_utils.py:11-118).
+ *  pd_scores [B,A,nc] contiguous (sigmoid), pd_bboxes [B,A,4] px, pd_3d [B,A,31], anc_points [A,2] px,
+ *  stride [A], gts [B,M,17] packed (label bbox4 c2d2 s2d2 c3d2 s3d3 depth hbin hres), mask_gt [B,M],
+ *  calibs [B,6], mean_sizes [nc,3].  flags: bit0 use_2d, bit1 use_3d, bit2 kps l2 metric, bit3 constrain_anchors.
+ * outputs: target_labels [B,A] i64, target_scores [B,A,nc], target_vals [B,A,12] (c2d2 s2d2 c3d2 s3d3 dep hbin hres),
+ *  fg_mask [B,A] u8, target_gt_idx [B,A] i64, pd_keypoints [B,A,8,3], gt_keypoints [B,M,8,3]. */
+int y3d_tal_assign3d(const float *pd_scores, const float *pd_bboxes, const float *pd_3d, const float *anc_points,
+                     const float *stride, const float *gts, const float *mask_gt, const float *calibs,
+                     const float *mean_sizes, int B, int A, int nc, int M, int topk, float alpha, float beta,
+                     float gamma, float eps, int flags, const int *lvl_hw, const float *lvl_stride, int nl,
+                     int64_t *target_labels, float *target_scores, float *target_vals, uint8_t *fg_mask,
+                     int64_t *target_gt_idx, float *pd_keypoints, float *gt_keypoints, void *ws, size_t ws_bytes,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Y3D_H_ */

@@ -1,0 +1,81 @@
+"""CPU: the C-ABI library loads and exports every symbol include/y3d.h declares; host-side glue behaves like the
+reference's (GT packing, M == 0 early-out, loud failure instead of any CPU fallback).  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import yolov10_3d_b200 as y3d
+from oracle import oracle
+from tests import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "y3d.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(y3d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 13
+    handle = ctypes.CDLL(y3d._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/y3d.h but not exported"
+    assert set(names) == set(y3d._lib.SIGNATURES), "ctypes binding out of sync with include/y3d.h"
+    assert y3d.lib().y3d_abi_version() == 1
+    assert b"workspace" in y3d.lib().y3d_strerror(-4)
+    assert y3d._lib.workspace_bytes(y3d._lib.STAGE_TAL_ASSIGN, B=2, A=100, nc=4, M=3, k=10) > 0
+
+
+def test_argument_errors_come_back_as_codes_not_crashes():
+    lib = y3d.lib()
+    assert lib.y3d_postprocess(None, 0, 0, 0, 1, 10, 2, 4, 0, 5, None, None, None, None, None, 0, None) == -1
+    assert lib.y3d_v8_loss_finalize(None, 1.0, 1.0, 1.0, None, None) == -1
+    assert lib.y3d_decode_preds3d(None, 1, 1, 3, None, None, None, None, 0.1, None, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(y3d.Y3DError):
+        y3d.v10postprocess(torch.zeros(1, 10, 6), 5, 2)
+    with pytest.raises(y3d.Y3DError):
+        y3d.detect_inference([torch.zeros(1, 66, 4, 4)], [8.0], 2)
+    asg = y3d.TaskAlignedAssigner(topk=10, num_classes=4)
+    with pytest.raises(y3d.Y3DError):
+        asg(torch.rand(1, 20, 4), torch.rand(1, 20, 4), torch.rand(20, 2), torch.zeros(1, 2, 1), torch.rand(1, 2, 4),
+            torch.ones(1, 2, 1))
+
+
+def test_empty_gt_early_out_matches_reference_dtypes():
+    asg = y3d.TaskAlignedAssigner(topk=10, num_classes=4)
+    out = asg(torch.rand(2, 20, 4), torch.rand(2, 20, 4), torch.rand(20, 2), torch.zeros(2, 0, 1), torch.zeros(2, 0, 4),
+              torch.zeros(2, 0, 1))
+    assert [o.dtype for o in out] == [torch.float32] * 5  # tal.py:68-76
+    assert float(out[0][0, 0]) == 4.0 and out[1].shape == (2, 20, 4) and out[2].shape == (2, 20, 4)
+
+
+def test_pack_targets_matches_oracle_preprocess():
+    gt = synth.gt2d(4, 9, 5, (160, 224), seed=3)
+    gt[2] = 0  # an image without objects
+    bd = synth.batch_dict(gt, (160, 224))
+    perm = synth.rng(0).permutation(len(bd["batch_idx"]))  # rows of different images interleaved
+    bd = {k: v[perm] for k, v in bd.items()}
+    want = oracle.preprocess_targets(bd["batch_idx"], bd["cls"], bd["bboxes"], 4, (160, 224))
+    got = y3d.loss.pack_targets(torch.from_numpy(bd["batch_idx"]), torch.from_numpy(bd["cls"]),
+                                torch.from_numpy(bd["bboxes"]), 4, (160, 224), "cpu")
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-6, atol=1e-4)
+    empty = y3d.loss.pack_targets(torch.zeros(0), torch.zeros(0, 1), torch.zeros(0, 4), 3, (64, 64), "cpu")
+    assert empty.shape == (3, 0, 5)
+
+
+def test_make_anchors_matches_oracle():
+    lv = synth.levels(96, 320)
+    feats = [torch.zeros(1, 1, h, w) for h, w in lv]
+    anc, st = y3d.make_anchors(feats, synth.STRIDES)
+    oanc, ost = oracle.make_anchors(lv, synth.STRIDES)
+    assert np.array_equal(anc.numpy(), oanc) and np.array_equal(st.numpy()[:, 0], ost)

@@ -1,0 +1,370 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through the reference-shaped Python
+mirror -> ctypes -> the C ABI of liby3d_b200.so.  Checked against (a) the committed golden fixtures produced by the
+real reference and (b) the CPU oracle on the same seeded inputs.
+
+Bars: indices / masks / labels bit-exact; values within 1e-5 relative (boxes: relative to the
+box scale, i.e. 1e-4 px absolute).  Where the CUDA path and the oracle issue the same IEEE sequence (assignment
+metrics, 3D decode) values are compared for exact equality too.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from tests import cases, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def y3d():
+    import yolov10_3d_b200 as m
+
+    m.lib()  # fail loudly if the CUDA library is absent
+    return m
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def feats_of(x, lv):
+    return [dev(f) for f in synth.split_levels(x, lv)]
+
+
+# ------------------------------------------------------------------------------------------------ decode + top-k
+@pytest.mark.parametrize("name", cases.names("decode_post_"))
+def test_decode2d_vs_golden_and_oracle(y3d, name):
+    r, z = cases.load(name)
+    lv, x = cases.decode_post_inputs(r, z)
+    y, _ = y3d.detect_inference(feats_of(x, lv), synth.STRIDES, r["nc"])
+    y = y.cpu().numpy()
+    for ref in (z["y"], oracle.decode2d(x, lv, synth.STRIDES, r["nc"], xywh=True)):
+        np.testing.assert_allclose(y[:, :4], ref[:, :4], rtol=RTOL, atol=1e-4)
+        np.testing.assert_allclose(y[:, 4:], ref[:, 4:], rtol=RTOL, atol=1e-7)
+    # export variant (xyxy), and the concatenated-input description of the same tensor
+    from importlib import import_module
+
+    util = import_module("yolov10_3d_b200._util")
+    lvc = util.Levels.from_cat(dev(x), lv, synth.STRIDES)
+    y2 = y3d.detect_inference(lvc.feats, synth.STRIDES, r["nc"], export=True).cpu().numpy()
+    np.testing.assert_allclose(y2[:, :4], z["y_xyxy_box"], rtol=RTOL, atol=1e-4)
+    assert np.array_equal(y2[:, 4:], y[:, 4:])
+
+
+@pytest.mark.parametrize("name", cases.names("decode_post_"))
+def test_postprocess_bit_exact(y3d, name):
+    r, z = cases.load(name)
+    yref = dev(z["y"])
+    for preds in (yref.permute(0, 2, 1), yref.permute(0, 2, 1).contiguous()):  # permuted view and [B,A,C] contiguous
+        boxes, scores, labels = y3d.v10postprocess(preds, r["D"], r["nc"])
+        assert labels.dtype == torch.int64
+        assert np.array_equal(labels.cpu().numpy(), z["labels"])
+        assert np.array_equal(scores.cpu().numpy(), z["scores"])
+        assert np.array_equal(boxes.cpu().numpy(), z["boxes"])
+
+
+def test_postprocess_edge_cases(y3d):
+    g = synth.rng(5)
+    # D == A, all-equal scores (pure index order), NaN-free negative logits, nc = 1
+    for (B, A, nc, D) in ((1, 64, 1, 64), (2, 37, 3, 37), (3, 1000, 5, 1), (2, 300, 80, 300)):
+        p = g.standard_normal((B, A, 4 + nc)).astype(np.float32)
+        p[0, :, 4:] = 0.25  # image 0: every score ties
+        reg, sc, lab, aidx = oracle.postprocess(p, D, nc)
+        b2, s2, l2 = y3d.v10postprocess(dev(p), D, nc)
+        assert np.array_equal(l2.cpu().numpy(), lab)
+        assert np.array_equal(s2.cpu().numpy(), sc)
+        assert np.array_equal(b2.cpu().numpy(), reg)
+    with pytest.raises(RuntimeError):
+        y3d.v10postprocess(dev(np.zeros((1, 10, 6), np.float32)), 11, 2)
+    with pytest.raises(AssertionError):
+        y3d.v10postprocess(dev(np.zeros((1, 10, 6), np.float32)), 5, 3)
+
+
+def test_postprocess_full_size_vs_oracle(y3d):
+    # cfg1 / cfg4 shapes: A = 8400 (640^2) and 33600 (1280^2), nc = 80, D = 300
+    for (B, hw) in ((2, (640, 640)), (1, (1280, 1280))):
+        lv = synth.levels(*hw)
+        x = synth.head2d(B, 80, lv, seed=3)
+        y = oracle.decode2d(x, lv, synth.STRIDES, 80)
+        reg, sc, lab, aidx = oracle.postprocess(y.transpose(0, 2, 1), 300, 80)
+        b2, s2, l2 = y3d.v10postprocess(dev(y).permute(0, 2, 1), 300, 80)
+        assert np.array_equal(l2.cpu().numpy(), lab)
+        assert np.array_equal(s2.cpu().numpy(), sc)
+        assert np.array_equal(b2.cpu().numpy(), reg)
+        # sortedness (size-independent property)
+        s = s2.cpu().numpy()
+        assert (np.diff(s, axis=1) <= 0).all()
+
+
+@pytest.mark.parametrize("name", cases.names("decode_post_"))
+def test_fused_decode_topk(y3d, name):
+    r, z = cases.load(name)
+    lv, x = cases.decode_post_inputs(r, z)
+    feats = feats_of(x, lv)
+    out, aidx = y3d.v10detect_export_forward(feats, synth.STRIDES, r["nc"], r["D"], return_anchor_idx=True)
+    # == unfused path of this library, bit for bit (same device arithmetic)
+    y = y3d.detect_inference(feats, synth.STRIDES, r["nc"], export=True)
+    boxes, scores, labels = y3d.v10postprocess(y.permute(0, 2, 1), r["D"], r["nc"])
+    assert torch.equal(out[..., :4], boxes)
+    assert torch.equal(out[..., 4], scores)
+    assert torch.equal(out[..., 5], labels.float())
+    # vs the reference (export path = xyxy boxes): same winners unless two scores differ by < 1 ulp-ish
+    ref_lab = z["labels"]
+    same = (out[..., 5].cpu().numpy() == ref_lab)
+    assert same.mean() > 0.99
+    np.testing.assert_allclose(out[..., 4].cpu().numpy()[same], z["scores"][same], rtol=RTOL, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ 2D assigner
+def run_assign(y3d, inp, topk, alpha, beta, grid):
+    asg = y3d.TaskAlignedAssigner(topk=topk, num_classes=inp["pd_scores"].shape[-1], alpha=alpha, beta=beta,
+                                  grid=(inp["lvl_hw"], synth.STRIDES) if grid else None)
+    out = asg(dev(inp["pd_scores"]), dev(inp["pd_bboxes"]), dev(inp["anc"]), dev(inp["gt_labels"]),
+              dev(inp["gt_bboxes"]), dev(inp["mask_gt"]))
+    return [o.cpu().numpy() for o in out]
+
+
+@pytest.mark.parametrize("grid", [False, True])
+@pytest.mark.parametrize("name", cases.names("assign_"))
+def test_tal_assign_golden_and_oracle(y3d, name, grid):
+    r, z = cases.load(name)
+    inp = cases.assign_inputs(r, z)
+    B, A, nc = inp["pd_scores"].shape
+    tl, tb, ts, fg, tgi = run_assign(y3d, inp, r["topk"], r["alpha"], r["beta"], grid)
+    assert tl.dtype == np.int64 and tgi.dtype == np.int64 and fg.dtype == np.bool_ and ts.dtype == np.float32
+    # (a) the real reference
+    assert np.array_equal(fg, cases.unpack_mask(z, "fg_mask", B, A))
+    assert np.array_equal(tgi, z["target_gt_idx"].astype(np.int64))
+    assert np.array_equal(tl, z["target_labels"].astype(np.int64))
+    assert synth.checksum(tb) == int(z["target_bboxes_crc"])
+    np.testing.assert_allclose(ts, cases.dense_target_scores(z, B, A, nc), rtol=2e-5, atol=1e-7)
+    # (b) the oracle: same IEEE sequence -> exact equality, values included
+    o = oracle.tal_assign(inp["pd_scores"], inp["pd_bboxes"], inp["anc"], inp["gt_labels"], inp["gt_bboxes"],
+                          inp["mask_gt"], r["topk"], alpha=r["alpha"], beta=r["beta"])
+    assert np.array_equal(ts, o["target_scores"])
+    assert np.array_equal(tb, o["target_bboxes"])
+
+
+def _assign_case(B, hw, M, nc, seed, crowd, kind):
+    lv = synth.levels(*hw)
+    gt = synth.gt2d(B, M, nc, hw, seed=seed + 1, crowd=crowd)
+    x = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 2, frac=0.02) if kind == "trained" else \
+        synth.head2d(B, nc, lv, seed=seed)
+    pd_scores, pd_bboxes, anc = synth.assigner_inputs_from_head(x, lv, nc)
+    mask = (gt[..., 1:5].sum(-1, keepdims=True) > 0).astype(np.float32)
+    return dict(pd_scores=pd_scores, pd_bboxes=pd_bboxes, anc=anc, gt_labels=gt[..., :1].copy(),
+                gt_bboxes=gt[..., 1:5].copy(), mask_gt=mask, lvl_hw=lv)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=8, hw=(640, 640), M=100, nc=80, seed=100, crowd=False, kind="trained", topk=10),  # cfg2 shape
+    dict(B=8, hw=(640, 640), M=100, nc=80, seed=101, crowd=False, kind="trained", topk=1),
+    dict(B=4, hw=(640, 640), M=500, nc=80, seed=102, crowd=True, kind="trained", topk=10),   # cfg5 shape
+    dict(B=4, hw=(384, 1280), M=50, nc=3, seed=103, crowd=False, kind="random", topk=13),
+])
+def test_tal_assign_full_size_vs_oracle(y3d, cfg):
+    inp = _assign_case(cfg["B"], cfg["hw"], cfg["M"], cfg["nc"], cfg["seed"], cfg["crowd"], cfg["kind"])
+    o = oracle.tal_assign(inp["pd_scores"], inp["pd_bboxes"], inp["anc"], inp["gt_labels"], inp["gt_bboxes"],
+                          inp["mask_gt"], cfg["topk"], alpha=0.5, beta=6.0)
+    for grid in (True, False):
+        tl, tb, ts, fg, tgi = run_assign(y3d, inp, cfg["topk"], 0.5, 6.0, grid)
+        assert np.array_equal(fg, o["fg_mask"])
+        assert np.array_equal(tgi, o["target_gt_idx"])
+        assert np.array_equal(tl, o["target_labels"])
+        assert np.array_equal(tb, o["target_bboxes"])
+        assert np.array_equal(ts, o["target_scores"])
+    assert o["fg_mask"].sum() > cfg["B"]
+    # size-independent properties: one-hot rows, background rows are zero, scores in [0, 1]
+    assert ((ts > 0).sum(-1) <= 1).all() and (ts[~fg] == 0).all() and ts.max() <= 1.0 + 1e-6
+
+
+def test_tal_assign_edge_cases(y3d):
+    # M == 0 early-out keeps the reference's (float) dtypes, tal.py:68-76
+    asg = y3d.TaskAlignedAssigner(topk=10, num_classes=4)
+    ps, pb = torch.rand(2, 50, 4).cuda(), torch.rand(2, 50, 4).cuda()
+    out = asg(ps, pb, torch.rand(50, 2).cuda(), torch.zeros(2, 0, 1).cuda(), torch.zeros(2, 0, 4).cuda(),
+              torch.zeros(2, 0, 1).cuda())
+    assert out[0].dtype == torch.float32 and float(out[0][0, 0]) == 4.0 and out[2].shape == (2, 50, 4)
+    assert not out[3].any() and out[4].dtype == torch.float32
+    # an image with only padded GTs, a GT covering the whole image, a degenerate (zero-area) GT, topk == 1, B == 1
+    inp = _assign_case(2, (160, 160), 6, 5, 7, False, "trained")
+    inp["gt_bboxes"][1] = 0
+    inp["mask_gt"][1] = 0
+    inp["gt_bboxes"][0, 0] = (0, 0, 160, 160)
+    inp["gt_bboxes"][0, 1] = (40, 40, 40, 40)
+    inp["mask_gt"][0, :2] = 1
+    for topk in (1, 10, 32):
+        o = oracle.tal_assign(inp["pd_scores"], inp["pd_bboxes"], inp["anc"], inp["gt_labels"], inp["gt_bboxes"],
+                              inp["mask_gt"], topk)
+        for grid in (True, False):
+            tl, tb, ts, fg, tgi = run_assign(y3d, inp, topk, 0.5, 6.0, grid)
+            assert np.array_equal(fg, o["fg_mask"]) and np.array_equal(tgi, o["target_gt_idx"])
+            assert np.array_equal(tl, o["target_labels"]) and np.array_equal(ts, o["target_scores"])
+            assert not fg[1].any()
+    with pytest.raises(RuntimeError):
+        run_assign(y3d, inp, 33, 0.5, 6.0, False)  # > Y3D_MAX_TOPK: loud error, no fallback
+
+
+# ------------------------------------------------------------------------------------------------ fused loss
+class FakeModel(torch.nn.Module):
+    def __init__(self, nc, gains):
+        super().__init__()
+        import types
+
+        self.p = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+        self.args = types.SimpleNamespace(box=gains[0], cls=gains[1], dfl=gains[2])
+        self.model = [types.SimpleNamespace(stride=torch.tensor(synth.STRIDES), nc=nc, no=nc + 64, reg_max=16)]
+
+
+@pytest.mark.parametrize("name", cases.names("loss_"))
+def test_v10_loss_golden_and_oracle(y3d, name):
+    r, z = cases.load(name)
+    lv, gt, xm, xo = cases.loss_inputs(r, z)
+    bd = synth.batch_dict(gt, r["img_hw"])
+    batch = {k: torch.from_numpy(v) for k, v in bd.items()}  # dataloader tensors live on the host
+    crit = y3d.v10DetectLoss(FakeModel(r["nc"], r["gains"]))
+    total, items = crit({"one2many": feats_of(xm, lv), "one2one": feats_of(xo, lv)}, batch)
+    items = items.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(items, z["items"], rtol=2e-5)
+    np.testing.assert_allclose(float(total), float(z["total"]), rtol=2e-5)
+    packed = oracle.preprocess_targets(bd["batch_idx"], bd["cls"], bd["bboxes"], r["B"], r["img_hw"])
+    ototal, oitems = oracle.v10_loss(xm, xo, lv, synth.STRIDES, r["nc"], packed, gains=r["gains"])
+    np.testing.assert_allclose(items, oitems, rtol=2e-5)
+    # the packed targets themselves (GT packing is host-side glue in torch)
+    lossmod = __import__("yolov10_3d_b200").loss
+    mine = lossmod.pack_targets(batch["batch_idx"], batch["cls"], batch["bboxes"], r["B"], r["img_hw"], "cuda")
+    np.testing.assert_allclose(mine.cpu().numpy(), packed, rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("topk", [10, 1])
+def test_fused_loss_assignment_bit_exact(y3d, topk):
+    """The assignment inside the fused loss == the oracle assigner run on the decode the fused path uses."""
+    B, nc, hw, M = 4, 80, (640, 640), 40
+    lv = synth.levels(*hw)
+    gt = synth.gt2d(B, M, nc, hw, seed=11)
+    x = synth.train_like_head2d(B, nc, lv, gt, seed=12, frac=0.02)
+    feats = feats_of(x, lv)
+    lossmod, util, lib = (__import__("yolov10_3d_b200").loss, __import__("yolov10_3d_b200")._util,
+                          __import__("yolov10_3d_b200")._lib)
+    items, partials, dbg = lossmod.v8_loss_forward(feats, synth.STRIDES, nc, dev(gt), topk, (7.5, 0.5, 1.5), debug=True)
+    levels = util.Levels(feats, synth.STRIDES)
+    A = levels.A
+    pb = torch.empty((B, A, 4), device="cuda")
+    ps = torch.empty((B, A, nc), device="cuda")
+    lib.check(lib.lib().y3d_train_decode(*levels.args(), B, nc, 16, util.ptr(pb), util.ptr(ps), util.stream_ptr()))
+    anc, st = synth.anchors_px(lv)
+    pb_px = (pb.cpu().numpy() * st[None, :, None]).astype(np.float32)
+    mask = (gt[..., 1:5].sum(-1, keepdims=True) > 0).astype(np.float32)
+    o = oracle.tal_assign(ps.cpu().numpy(), pb_px, anc, gt[..., :1], gt[..., 1:5], mask, topk)
+    assert np.array_equal(dbg["fg_mask"].cpu().numpy(), o["fg_mask"])
+    assert np.array_equal(dbg["target_gt_idx"].cpu().numpy().astype(np.int64), o["target_gt_idx"])
+    # train decode vs oracle decode (values)
+    ob = oracle.bbox_decode(np.ascontiguousarray(x[:, :64].transpose(0, 2, 1)), anc / st[:, None])
+    np.testing.assert_allclose(pb.cpu().numpy(), ob, rtol=RTOL, atol=1e-5)
+    assert float(partials[3]) > 1.0 and o["fg_mask"].sum() > 0
+
+
+def test_loss_no_targets(y3d):
+    lv = synth.levels(160, 160)
+    x = synth.head2d(2, 8, lv, seed=1)
+    lossmod = __import__("yolov10_3d_b200").loss
+    items, partials, _ = lossmod.v8_loss_forward(feats_of(x, lv), synth.STRIDES, 8, torch.zeros(2, 0, 5), 10,
+                                                 (7.5, 0.5, 1.5))
+    oi, _, _ = oracle.v8_loss(x, lv, synth.STRIDES, 8, np.zeros((2, 0, 5), np.float32), 10)
+    np.testing.assert_allclose(items[:3].cpu().numpy(), oi, rtol=2e-5)
+    assert float(items[0]) == 0.0 and float(items[2]) == 0.0 and float(items[3]) == 1.0
+
+
+# ------------------------------------------------------------------------------------------------ 3D
+@pytest.mark.parametrize("name", cases.names("decode3d_"))
+def test_decode3d_and_postprocess(y3d, name):
+    r, z = cases.load(name)
+    lv, x = cases.decode3d_inputs(r, z)
+    y, _ = y3d.detect3d_decode(feats_of(x, lv), synth.STRIDES, r["nc"])
+    np.testing.assert_allclose(y.cpu().numpy(), z["y"], rtol=RTOL, atol=1e-4)
+    assert np.array_equal(y.cpu().numpy(), oracle.decode3d(x, lv, synth.STRIDES, r["nc"]))  # same IEEE sequence
+    reg, scores, labels = y3d.v10_3Dpostprocess(dev(z["y"]).transpose(-1, -2), r["D"], r["nc"])
+    assert np.array_equal(labels.cpu().numpy(), z["labels"])
+    assert np.array_equal(scores.cpu().numpy(), z["scores"])
+    assert np.array_equal(reg.cpu().numpy(), z["reg"])
+    dets = y3d.detect3d_postprocess(dev(z["y"]), r["D"], r["nc"])
+    assert dets.shape == (r["B"], r["D"], 37)
+
+
+def test_decode_preds(y3d):
+    r, z = cases.load("preds3d_small")
+    B = z["dets"].shape[0]
+    cal = [type("C", (), dict(cu=c[0], cv=c[1], fu=c[2], fv=c[3], tx=c[4], ty=c[5]))() for c in z["calib"]]
+    files = [f"im{b}" for b in range(B)]
+    res = y3d.kitti.decode_preds(dev(z["dets"]), cal, files, [(z["ratio"][b], (0.0, 0.0)) for b in range(B)],
+                                 list(z["inv_affine"]), z["cls_mean_size"])
+    for b in range(B):
+        n = int(z["counts"][b])
+        got = np.array(res[files[b]], dtype=np.float64).reshape(-1, 14)
+        assert got.shape[0] == n
+        np.testing.assert_allclose(got, z["rows"][b, :n], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("grid", [False, True])
+@pytest.mark.parametrize("name", cases.names("assign3d_"))
+def test_tal_assign3d(y3d, name, grid):
+    r, z = cases.load(name)
+    B, nc, M = r["B"], r["nc"], r["M"]
+    lv = synth.levels(*r["img_hw"])
+    anc, st = synth.anchors_px(lv)
+    A = anc.shape[0]
+    gts = z["gts"]
+    mask_gt = (gts[..., 1:5].sum(-1, keepdims=True) > 0).astype(np.float32)
+    ms = np.array(synth.KITTI_MEAN_SIZES, np.float32)
+    kw = dict(alpha=0.5, beta=3.0, gamma=3.0)
+    kw.update(r["kw"])
+    asg = y3d.TaskAlignedAssigner3d(topk=r["topk"], num_classes=nc, grid=(lv, synth.STRIDES) if grid else None, **kw)
+    parts = np.split(gts, np.cumsum([1, 4, 2, 2, 2, 3, 1, 1]), axis=2)
+    targets, fg, tgi, pk, gk = asg(dev(z["pd_scores"]), dev(z["pd_bboxes"]), dev(z["pd_3d"]), dev(anc),
+                                   tuple(dev(p) for p in parts), dev(mask_gt), dev(st[:, None]), dev(z["calibs"]),
+                                   dev(ms))
+    fg, tgi = fg.cpu().numpy(), tgi.cpu().numpy()
+    ts = targets[1].cpu().numpy()
+    tv = torch.cat(targets[2:], -1).cpu().numpy()
+    # (a) the real reference
+    np.testing.assert_allclose(gk.cpu().numpy(), z["gt_kps"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(pk.cpu().numpy()[:, ::37], z["pd_kps_sample"], rtol=1e-4, atol=2e-5)
+    assert np.array_equal(fg, cases.unpack_mask(z, "fg_mask", B, A))
+    assert np.array_equal(tgi, z["target_gt_idx"].astype(np.int64))
+    assert np.array_equal(targets[0].cpu().numpy(), z["target_labels"].astype(np.int64))
+    assert synth.checksum(tv) == int(z["target_vals_crc"])
+    np.testing.assert_allclose(ts, cases.dense_target_scores(z, B, A, nc), rtol=5e-5, atol=1e-7)
+    # (b) the oracle, exactly
+    o = oracle.tal_assign3d(z["pd_scores"], z["pd_bboxes"], z["pd_3d"], anc, st, gts, mask_gt[..., 0], z["calibs"],
+                            ms, r["topk"], **kw)
+    assert np.array_equal(pk.cpu().numpy(), o["pd_keypoints"])
+    assert np.array_equal(gk.cpu().numpy(), o["gt_keypoints"])
+    assert np.array_equal(ts, o["target_scores"])
+    assert np.array_equal(tv, o["target_vals"])
+
+
+def test_tal_assign3d_kitti_shape_vs_oracle(y3d):
+    # cfg3 shape: 384x1280 -> A = 10080, nc = 3, M = 50, top-k 8 and 1
+    B, nc, M, hw = 4, 3, 50, (384, 1280)
+    lv = synth.levels(*hw)
+    x = synth.head3d(B, nc, lv, seed=60)
+    gts = synth.gt3d(B, M, nc, hw, seed=61)
+    ps, pb, p3, anc, st = synth.assigner3d_inputs_from_head(x, lv, nc)
+    mask_gt = (gts[..., 1:5].sum(-1) > 0).astype(np.float32)
+    cal = np.tile(np.array(synth.KITTI_CALIB, np.float32), (B, 1))
+    ms = np.array(synth.KITTI_MEAN_SIZES, np.float32)
+    parts = np.split(gts, np.cumsum([1, 4, 2, 2, 2, 3, 1, 1]), axis=2)
+    for topk in (8, 1):
+        o = oracle.tal_assign3d(ps, pb, p3, anc, st, gts, mask_gt, cal, ms, topk, alpha=0.5, beta=1.0, gamma=1.0)
+        asg = y3d.TaskAlignedAssigner3d(topk=topk, num_classes=nc, alpha=0.5, beta=1.0, gamma=1.0,
+                                        grid=(lv, synth.STRIDES))
+        targets, fg, tgi, pk, gk = asg(dev(ps), dev(pb), dev(p3), dev(anc), tuple(dev(p) for p in parts),
+                                       dev(mask_gt[..., None]), dev(st[:, None]), dev(cal), dev(ms))
+        assert np.array_equal(fg.cpu().numpy(), o["fg_mask"])
+        assert np.array_equal(tgi.cpu().numpy(), o["target_gt_idx"])
+        assert np.array_equal(targets[1].cpu().numpy(), o["target_scores"])
+        assert np.array_equal(pk.cpu().numpy(), o["pd_keypoints"])
+        assert o["fg_mask"].sum() > 0

@@ -1,0 +1,469 @@
+// assign.cu -- task-aligned assigners (sm_100a), API-faithful entry points.
+//   y3d_tal_assign    TaskAlignedAssigner.forward    reference ultralytics/utils/tal.py:44-264
+//   y3d_tal_assign3d  TaskAlignedAssigner3d.forward  reference ultralytics/utils/tal.py:391-700
+//                     get_3d_keypoints               reference ultralytics/utils/keypoint_utils.py:11-118
+// The core (candidate walk, per-GT top-k, conflict resolution) is documented in assign.cuh.
+// Algorithmic bytes of the API-faithful 2D assigner per image and branch:
+//   read 4*A*(nc+6) + 24*M, write A*(8 + 16 + 4*nc + 1 + 8); the dense target_scores write dominates.
+#include "assign.cuh"
+
+namespace y3d {
+
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAssignWarps * 32) tal_topk_kernel(AssignCtx c) {
+    __shared__ int queue[kAssignWarps][64];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kAssignWarps + wid;
+    if (gw >= (long long)c.B * c.M) return;
+    const int b = (int)(gw / c.M), m = (int)(gw % c.M);
+    const GtRec g = load_gt(c, b, m);
+    if (!g.valid) return;  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104)
+    const int k = c.k;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // lane-distributed sorted top-k list; sentinel loses against any real entry (metrics are >= 0)
+    float tk_m = -1.0f;
+    int tk_i = 0x7fffffff;
+    int tk_in = 0;
+
+    auto process = [&](bool has, float cm, int ci, int cin) {
+        for (;;) {
+            float kth_m = __shfl_sync(0xffffffffu, tk_m, k - 1);
+            int kth_i = __shfl_sync(0xffffffffu, tk_i, k - 1);
+            bool qual = has && better(cm, ci, kth_m, kth_i);
+            unsigned mk = __ballot_sync(0xffffffffu, qual);
+            if (!mk) break;
+            int src = __ffs(mk) - 1;
+            float xm = __shfl_sync(0xffffffffu, cm, src);
+            int xi = __shfl_sync(0xffffffffu, ci, src);
+            int xin = __shfl_sync(0xffffffffu, cin, src);
+            bool hb = better(tk_m, tk_i, xm, xi);
+            int pos = __popc(__ballot_sync(0xffffffffu, hb && lane < k));
+            float um = __shfl_up_sync(0xffffffffu, tk_m, 1);
+            int ui = __shfl_up_sync(0xffffffffu, tk_i, 1);
+            int uin = __shfl_up_sync(0xffffffffu, tk_in, 1);
+            if (lane == pos) {
+                tk_m = xm; tk_i = xi; tk_in = xin;
+            } else if (lane > pos) {
+                tk_m = um; tk_i = ui; tk_in = uin;
+            }
+            if (lane == src) has = false;
+        }
+    };
+
+    auto eval_and_process = [&](bool has, int a, bool force) {
+        // `force`: anchors 0..k-1 enter the list even when outside the GT (metric 0), see header comment
+        float metric = 0.0f, ovl = 0.0f;
+        int cin = 0;
+        if (has) {
+            float ax, ay, st;
+            anchor_px(c, a, ax, ay, st);
+            bool ing = dm::in_gt(ax, ay, g.box);
+            cin = c.constrain ? (int)ing : 1;
+            if (cin) pair_eval(c, b, m, g, a, metric, ovl);
+        }
+        bool go = has && (force || metric > 0.0f);
+        process(go, metric, a, cin);
+    };
+
+    // phase 0: the first k anchors
+    eval_and_process(lane < k && lane < c.A, lane, true);
+
+    // phase 1: enumerate candidates (anchors >= k inside the GT) into the warp queue, evaluate 32 at a time
+    int qn = 0;
+    auto push = [&](bool cand, int a) {
+        unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (bal) {
+            if (cand) queue[wid][qn + __popc(bal & lt_mask)] = a;
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32) {
+                int a2 = queue[wid][lane];
+                int rest = qn - 32;
+                int carry = lane < rest ? queue[wid][32 + lane] : 0;
+                __syncwarp();
+                if (lane < rest) queue[wid][lane] = carry;
+                __syncwarp();
+                qn = rest;
+                eval_and_process(true, a2, false);
+            }
+        }
+    };
+
+    if (c.use_grid && c.constrain) {
+        for (int l = 0; l < c.t.nl; ++l) {
+            const float st = c.t.stride[l];
+            const int w = c.t.w[l], h = c.t.h[l];
+            // conservative cell range: the exact fp32 in-GT test below decides (tal.py:218-235)
+            float fx0 = fmaxf(floorf(g.box.x / st - 0.5f) - 1.0f, 0.0f);
+            float fy0 = fmaxf(floorf(g.box.y / st - 0.5f) - 1.0f, 0.0f);
+            float fx1 = fminf(ceilf(g.box.z / st - 0.5f) + 1.0f, (float)(w - 1));
+            float fy1 = fminf(ceilf(g.box.w / st - 0.5f) + 1.0f, (float)(h - 1));
+            if (!(fx0 <= fx1) || !(fy0 <= fy1)) continue;
+            const int c0 = (int)fx0, r0 = (int)fy0;
+            const int ncols = (int)fx1 - c0 + 1, nrows = (int)fy1 - r0 + 1;
+            const int cells = ncols * nrows;
+            for (int i0 = 0; i0 < cells; i0 += 32) {
+                int i = i0 + lane;
+                bool cand = false;
+                int a = 0;
+                if (i < cells) {
+                    int r = i / ncols, cc = i - r * ncols;
+                    a = c.t.start[l] + (r0 + r) * w + c0 + cc;
+                    float ax = dm::mul((float)(c0 + cc) + 0.5f, st), ay = dm::mul((float)(r0 + r) + 0.5f, st);
+                    cand = a >= k && dm::in_gt(ax, ay, g.box);
+                }
+                push(cand, a);
+            }
+        }
+    } else {
+        for (int a0 = 0; a0 < c.A; a0 += 32) {
+            int a = a0 + lane;
+            bool cand = false;
+            if (a < c.A && a >= k) {
+                if (c.constrain) {
+                    float ax, ay, st;
+                    anchor_px(c, a, ax, ay, st);
+                    cand = dm::in_gt(ax, ay, g.box);
+                } else {
+                    cand = true;
+                }
+            }
+            push(cand, a);
+        }
+    }
+    if (qn > 0) {
+        int a2 = lane < qn ? queue[wid][lane] : 0;
+        eval_and_process(lane < qn, a2, false);
+    }
+
+    // claims: mask_pos = mask_topk * mask_in_gts * mask_gt (tal.py:104)
+    if (lane < k && tk_i != 0x7fffffff && tk_in) {
+        long long o = (long long)b * c.A + tk_i;
+        atomicAdd(c.claim_cnt + o, 1);
+        atomicMin(c.claim_gt + o, m);
+    }
+}
+
+// grid (ceil(A/256), B); dynamic smem: M GtRec
+__global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GtRec *gts = reinterpret_cast<GtRec *>(smem_raw);
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    // does any anchor of this block need the all-GT scan?
+    long long o = (long long)b * c.A + a;
+    int cnt = a < c.A ? c.claim_cnt[o] : 0;
+    int any_multi = __syncthreads_or(cnt > 1);
+    if (any_multi) {
+        for (int m = threadIdx.x; m < c.M; m += blockDim.x) gts[m] = load_gt(c, b, m);
+        __syncthreads();
+    }
+    if (a >= c.A) return;
+    int gi = -1;
+    float alignv = 0.0f;
+    if (cnt > 0) {
+        float ax, ay, st;
+        anchor_px(c, a, ax, ay, st);
+        if (cnt == 1) {
+            gi = c.claim_gt[o];
+        } else {  // select_highest_overlaps tal.py:252-263: argmax over all GTs, first maximum
+            float bv = -1.0f;
+            for (int m = 0; m < c.M; ++m) {
+                const GtRec g = gts[m];
+                float metric = 0.0f, ovl = 0.0f;
+                bool sel = g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box));
+                if (sel) pair_eval(c, b, m, g, a, metric, ovl);
+                if (ovl > bv) { bv = ovl; gi = m; }
+            }
+        }
+        const GtRec g = cnt > 1 ? gts[gi] : load_gt(c, b, gi);
+        float metric = 0.0f, ovl = 0.0f;
+        bool sel = g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box));
+        if (sel) pair_eval(c, b, gi, g, a, metric, ovl);
+        alignv = metric;
+        atomicMax(c.pos_align + (long long)b * c.M + gi, __float_as_int(metric));  // values >= 0: int order == float order
+        atomicMax(c.pos_ov + (long long)b * c.M + gi, __float_as_int(ovl));
+    }
+    c.tgi[o] = gi;
+    c.alignv[o] = alignv;
+}
+
+
+// enqueue: init + top-k + resolve.  After this c.tgi / c.alignv / c.pos_* are final.
+int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync((char *)ws + w.off_cnt, 0, w.zero_bytes, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync((char *)ws + w.off_cgt, 0x7f, sizeof(int) * (size_t)c.B * c.A, s);
+    if (e != cudaSuccess) return (int)e;
+    long long warps = (long long)c.B * c.M;
+    tal_topk_kernel<<<(unsigned)((warps + kAssignWarps - 1) / kAssignWarps), kAssignWarps * 32, 0, s>>>(c);
+    Y3D_CHECK_LAUNCH();
+    size_t smem = sizeof(GtRec) * (size_t)c.M;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(tal_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((c.A + 255) / 256, c.B);
+    tal_resolve_kernel<<<grid, 256, smem, s>>>(c);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ emit kernels
+// get_targets (tal.py:169-216 / 651-700) + normalisation (tal.py:88-92): per-anchor small outputs
+__global__ void __launch_bounds__(256) tal_emit_small_kernel(AssignCtx c, int64_t *__restrict__ t_lab,
+                                                             float *__restrict__ t_box, uint8_t *__restrict__ fg,
+                                                             int64_t *__restrict__ t_gi, float *__restrict__ norm_ws,
+                                                             int *__restrict__ lab_ws, const float *__restrict__ gts17,
+                                                             float *__restrict__ t_vals) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)c.B * c.A) return;
+    const int b = (int)(i / c.A);
+    const int gi = c.tgi[i];
+    const bool isfg = gi >= 0;
+    const long long gm = (long long)b * c.M + (isfg ? gi : 0);  // background anchors index GT 0 (argmax of zeros)
+    long long lab = (long long)c.gt_labels[gm * c.gl_stride];
+    lab = lab < 0 ? 0 : lab;  // target_labels.clamp_(0)
+    const float norm = isfg ? assigned_norm(c, b, gi, c.alignv[i]) : 0.0f;
+    norm_ws[i] = norm;
+    lab_ws[i] = isfg ? (int)lab : -1;
+    if (t_lab) t_lab[i] = lab;
+    if (t_box) {
+        const float *g = c.gt_bboxes + gm * c.gb_stride;
+        *reinterpret_cast<float4 *>(t_box + 4 * i) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    if (t_vals) {
+        const float *g = gts17 + gm * 17 + 5;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) t_vals[i * 12 + j] = g[j];
+    }
+    fg[i] = (uint8_t)isfg;
+    t_gi[i] = isfg ? gi : 0;
+}
+
+// dense target_scores [B,A,nc] = one_hot(label) * fg * norm: 128-bit streaming stores
+template <int VEC>
+__global__ void __launch_bounds__(256) tal_emit_scores_kernel(const float *__restrict__ norm_ws,
+                                                              const int *__restrict__ lab_ws, int nc, long long total,
+                                                              float *__restrict__ t_sc) {
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long e0 = f * VEC;
+    if (e0 >= total) return;
+    long long i = e0 / nc;
+    int c0 = (int)(e0 - i * nc);
+    if constexpr (VEC == 4) {  // nc % 4 == 0: the four elements belong to one anchor
+        int lab = lab_ws[i];
+        float nv = norm_ws[i];
+        int d = lab - c0;
+        float4 v = make_float4(d == 0 ? nv : 0.f, d == 1 ? nv : 0.f, d == 2 ? nv : 0.f, d == 3 ? nv : 0.f);
+        stg_stream4(t_sc + e0, v);
+    } else {
+        t_sc[e0] = (lab_ws[i] == c0) ? norm_ws[i] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 3D keypoints
+// get_3d_keypoints (keypoint_utils.py:11-118) for one box; op order identical to oracle/y3d_oracle.c::y3d_o_keypoints
+__device__ __forceinline__ void keypoints24(float c3x, float c3y, float dep, float s_h, float s_w, float s_l, int hbin,
+                                            float hres, const float *cal, float *out) {
+    using namespace dm;
+    const float kPi = 3.14159265358979323846f, k2Pi = 6.283185307179586f;
+    const float cu = cal[0], cv = cal[1], fu = cal[2], fv = cal[3], tx = cal[4], ty = cal[5];
+    const float lx = add(div(mul(sub(c3x, cu), dep), fu), tx);  // img_to_rect :113-119
+    const float ly = add(div(mul(sub(c3y, cv), dep), fv), ty);
+    const float lz = dep;
+    float alpha = add(mul((float)hbin, 0.5235987755982988f), hres);  // class2angle :42-47
+    if (alpha > kPi) alpha = sub(alpha, k2Pi);
+    float ry = add(alpha, atan2_(sub(c3x, cu), fu));  // alpha2ry :94-101
+    if (ry > kPi) ry = sub(ry, k2Pi);
+    if (ry < -kPi) ry = add(ry, k2Pi);
+    float sx, cx, sy, cy;  // to_egoc_rot_mat :87-91  R = Rx(pi/2) @ Ry(-ry)
+    sincos_(1.5707963267948966f, &sx, &cx);
+    sincos_(-ry, &sy, &cy);
+    const float R00 = cy, R01 = 0.0f, R02 = sy;
+    const float R10 = mul(sx, sy), R11 = cx, R12 = -mul(sx, cy);
+    const float R20 = -mul(cx, sy), R21 = sx, R22 = mul(cx, cy);
+    const float hl = div(s_l, 2.0f), hw = div(s_w, 2.0f), hh = div(s_h, 2.0f);  // get_box_corners :20-26
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float px = (k & 2) ? -hl : hl;
+        const float py = (k & 1) ? -hw : hw;
+        const float pz = (k & 4) ? hh : -hh;
+        out[3 * k + 0] = add(add(add(mul(px, R00), mul(py, R10)), mul(pz, R20)), lx);  // transform_to_camera :104-110
+        out[3 * k + 1] = add(add(add(mul(px, R01), mul(py, R11)), mul(pz, R21)), ly);
+        out[3 * k + 2] = add(add(add(mul(px, R02), mul(py, R12)), mul(pz, R22)), lz);
+    }
+}
+
+__global__ void __launch_bounds__(128) kps_pred_kernel(const float *__restrict__ pd_scores,
+                                                       const float *__restrict__ pd_3d, const float *__restrict__ anc,
+                                                       const float *__restrict__ stride,
+                                                       const float *__restrict__ calibs,
+                                                       const float *__restrict__ mean_sizes, int B, int A, int nc,
+                                                       float *__restrict__ pd_kps) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * A) return;
+    const int b = (int)(i / A), a = (int)(i % A);
+    const float *p = pd_3d + i * 31;
+    const float *s = pd_scores + i * nc;
+    const float st = stride[a];
+    const float c3x = dm::add(anc[2 * a], dm::mul(p[0], st));  // decode_3d_center tal.py:454-456
+    const float c3y = dm::add(anc[2 * a + 1], dm::mul(p[1], st));
+    int cls = 0;  // decode_3d_size tal.py:458-462 (argmax, first max)
+    float best = s[0];
+    for (int c = 1; c < nc; ++c) {
+        float v = s[c];
+        if (v > best) { best = v; cls = c; }
+    }
+    const float sh_ = dm::add(mean_sizes[3 * cls], p[2]), sw_ = dm::add(mean_sizes[3 * cls + 1], p[3]),
+                sl_ = dm::add(mean_sizes[3 * cls + 2], p[4]);
+    int hb = 0;
+    float hbv = p[5];
+    for (int j = 1; j < 12; ++j) {
+        float v = p[5 + j];
+        if (v > hbv) { hbv = v; hb = j; }
+    }
+    float out[24];
+    keypoints24(c3x, c3y, p[29], sh_, sw_, sl_, hb, p[5 + 12 + hb], calibs + 6 * b, out);
+    float4 *o = reinterpret_cast<float4 *>(pd_kps + i * 24);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o[j] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+}
+
+__global__ void kps_gt_kernel(const float *__restrict__ gts, const float *__restrict__ calibs,
+                              const float *__restrict__ mean_sizes, int B, int M, int nc,
+                              float *__restrict__ gt_kps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * M) return;
+    const int b = i / M;
+    const float *g = gts + (long long)i * 17;
+    int lab = (int)g[0];
+    lab = lab < 0 ? 0 : (lab >= nc ? nc - 1 : lab);
+    const float sh_ = dm::add(mean_sizes[3 * lab], g[11]), sw_ = dm::add(mean_sizes[3 * lab + 1], g[12]),
+                sl_ = dm::add(mean_sizes[3 * lab + 2], g[13]);  // add_cls_mean_size tal.py:605-609
+    float out[24];
+    keypoints24(g[9], g[10], g[14], sh_, sw_, sl_, (int)g[15], g[16], calibs + 6 * b, out);
+    for (int j = 0; j < 24; ++j) gt_kps[(long long)i * 24 + j] = out[j];
+}
+
+static int run_emit(const AssignCtx &c, void *ws, const AssignWs &w, int64_t *t_lab, float *t_box, float *t_sc,
+                    uint8_t *fg, int64_t *t_gi, const float *gts17, float *t_vals, cudaStream_t s) {
+    float *norm_ws = (float *)((char *)ws + w.off_norm);
+    int *lab_ws = (int *)((char *)ws + w.off_lab);
+    long long n = (long long)c.B * c.A;
+    tal_emit_small_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c, t_lab, t_box, fg, t_gi, norm_ws, lab_ws, gts17,
+                                                                      t_vals);
+    Y3D_CHECK_LAUNCH();
+    if (t_sc) {
+        long long total = n * c.nc;
+        if (c.nc % 4 == 0 && ((uintptr_t)t_sc) % 16 == 0) {
+            long long th = total / 4;
+            tal_emit_scores_kernel<4><<<(unsigned)((th + 255) / 256), 256, 0, s>>>(norm_ws, lab_ws, c.nc, total, t_sc);
+        } else {
+            tal_emit_scores_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(norm_ws, lab_ws, c.nc, total, t_sc);
+        }
+        Y3D_CHECK_LAUNCH();
+    }
+    return Y3D_OK;
+}
+
+size_t assign_workspace_bytes(int B, int A, int M) { return assign_ws_layout(B, A, M).total; }
+
+}  // namespace y3d
+
+using namespace y3d;
+
+extern "C" int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A, int64_t ss_C,
+                              const float *pd_bboxes, const float *anc_points, const float *gt_labels,
+                              const float *gt_bboxes, const float *mask_gt, int B, int A, int nc, int M, int topk,
+                              float alpha, float beta, float eps, const int *lvl_hw, const float *lvl_stride, int nl,
+                              int64_t *target_labels, float *target_bboxes, float *target_scores, uint8_t *fg_mask,
+                              int64_t *target_gt_idx, void *ws, size_t ws_bytes, void *stream) {
+    if (!pd_scores || !pd_bboxes || !gt_labels || !gt_bboxes || !mask_gt || !fg_mask || !target_gt_idx)
+        return Y3D_EINVAL;
+    if (B < 0 || A < 1 || nc < 1 || M < 1 || topk < 1 || topk > A) return Y3D_EINVAL;
+    if (topk > Y3D_MAX_TOPK) return Y3D_EUNSUPPORTED;
+    if (((uintptr_t)pd_bboxes) % 16 || (target_bboxes && ((uintptr_t)target_bboxes) % 16)) return Y3D_EALIGN;
+    AssignCtx c{};
+    if (lvl_hw && lvl_stride && nl > 0) {
+        int a = make_level_table(c.t, nullptr, nullptr, nullptr, lvl_hw, lvl_stride, nl);
+        if (a != A) return Y3D_EINVAL;
+        c.use_grid = 1;
+    } else {
+        if (!anc_points) return Y3D_EINVAL;
+        if (((uintptr_t)anc_points) % 8) return Y3D_EALIGN;
+        c.use_grid = 0;
+    }
+    AssignWs w = assign_ws_layout(B, A, M);
+    if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
+    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    if (B == 0) return Y3D_OK;
+    c.score_mode = 0;
+    c.pd_scores = pd_scores; c.ssB = ss_B; c.ssA = ss_A; c.ssC = ss_C;
+    c.pd_bboxes = pd_bboxes; c.box_grid_units = 0;
+    c.anc = anc_points;
+    c.gt_labels = gt_labels; c.gl_stride = 1;
+    c.gt_bboxes = gt_bboxes; c.gb_stride = 4;
+    c.mask_gt = mask_gt;
+    c.B = B; c.A = A; c.nc = nc; c.M = M; c.k = topk;
+    c.alpha = alpha; c.beta = beta; c.gamma = 1.0f; c.eps = eps;
+    c.use_2d = 1; c.use_3d = 0; c.kps_l2 = 0; c.constrain = 1;
+    assign_bind_ws(c, ws, w);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = assign_run_core(c, ws, w, s);
+    if (rc) return rc;
+    return run_emit(c, ws, w, target_labels, target_bboxes, target_scores, fg_mask, target_gt_idx, nullptr, nullptr, s);
+}
+
+extern "C" int y3d_tal_assign3d(const float *pd_scores, const float *pd_bboxes, const float *pd_3d,
+                                const float *anc_points, const float *stride, const float *gts,
+                                const float *mask_gt, const float *calibs, const float *mean_sizes, int B, int A,
+                                int nc, int M, int topk, float alpha, float beta, float gamma, float eps, int flags,
+                                const int *lvl_hw, const float *lvl_stride, int nl, int64_t *target_labels,
+                                float *target_scores, float *target_vals, uint8_t *fg_mask, int64_t *target_gt_idx,
+                                float *pd_keypoints, float *gt_keypoints, void *ws, size_t ws_bytes, void *stream) {
+    if (!pd_scores || !pd_bboxes || !pd_3d || !anc_points || !stride || !gts || !mask_gt || !calibs || !mean_sizes ||
+        !fg_mask || !target_gt_idx || !pd_keypoints || !gt_keypoints)
+        return Y3D_EINVAL;
+    if (B < 0 || A < 1 || nc < 1 || M < 1 || topk < 1 || topk > A) return Y3D_EINVAL;
+    if (topk > Y3D_MAX_TOPK) return Y3D_EUNSUPPORTED;
+    const int use_2d = flags & 1, use_3d = (flags >> 1) & 1, kps_l2 = (flags >> 2) & 1, constrain = (flags >> 3) & 1;
+    if (!use_2d && !use_3d) return Y3D_EINVAL;  // tal.py:486 RuntimeError
+    if (((uintptr_t)pd_bboxes) % 16 || ((uintptr_t)pd_keypoints) % 16 || ((uintptr_t)gt_keypoints) % 16 ||
+        ((uintptr_t)anc_points) % 8)
+        return Y3D_EALIGN;
+    AssignCtx c{};
+    if (lvl_hw && lvl_stride && nl > 0) {
+        int a = make_level_table(c.t, nullptr, nullptr, nullptr, lvl_hw, lvl_stride, nl);
+        if (a != A) return Y3D_EINVAL;
+        c.use_grid = 1;
+    }
+    AssignWs w = assign_ws_layout(B, A, M);
+    if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
+    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    if (B == 0) return Y3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long n = (long long)B * A;
+    kps_pred_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pd_scores, pd_3d, anc_points, stride, calibs, mean_sizes,
+                                                               B, A, nc, pd_keypoints);
+    Y3D_CHECK_LAUNCH();
+    kps_gt_kernel<<<(B * M + 127) / 128, 128, 0, s>>>(gts, calibs, mean_sizes, B, M, nc, gt_keypoints);
+    Y3D_CHECK_LAUNCH();
+    c.score_mode = 0;
+    c.pd_scores = pd_scores; c.ssB = (long long)A * nc; c.ssA = nc; c.ssC = 1;
+    c.pd_bboxes = pd_bboxes; c.box_grid_units = 0;
+    c.anc = anc_points;
+    c.gt_labels = gts; c.gl_stride = 17;
+    c.gt_bboxes = gts + 1; c.gb_stride = 17;
+    c.mask_gt = mask_gt;
+    c.B = B; c.A = A; c.nc = nc; c.M = M; c.k = topk;
+    c.alpha = alpha; c.beta = beta; c.gamma = gamma; c.eps = eps;
+    c.use_2d = use_2d; c.use_3d = use_3d; c.kps_l2 = kps_l2; c.constrain = constrain;
+    c.pd_kps = pd_keypoints; c.gt_kps = gt_keypoints;
+    assign_bind_ws(c, ws, w);
+    int rc = assign_run_core(c, ws, w, s);
+    if (rc) return rc;
+    return run_emit(c, ws, w, target_labels, nullptr, target_scores, fg_mask, target_gt_idx, gts, target_vals, s);
+}

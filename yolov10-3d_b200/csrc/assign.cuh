@@ -1,0 +1,187 @@
+// assign.cuh -- task-aligned assignment core shared by assign.cu (API-faithful assigners) and loss.cu (fused loss).
+//
+// Restates TaskAlignedAssigner / TaskAlignedAssigner3d (reference ultralytics/utils/tal.py:44-264, 391-700) without
+// ever materialising the reference's dense [B, M, A] tensors:
+//
+//   tal_topk_kernel    one warp per (image, GT): walks the anchors inside the GT's rectangle (or all A anchors when
+//                      no grid is promised), evaluates score^alpha * CIoU^beta (* sim^gamma) for the in-GT anchors
+//                      32 at a time through a warp queue, keeps the per-GT top-k as a lane-distributed sorted list
+//                      (value desc, index asc) and claims the winners with two atomics per (GT, anchor).
+//                      Zero-metric ties are exact: anchors 0..k-1 always enter the list (they are what a dense
+//                      stable top-k would pick among zeros), zero-metric anchors >= k can never be selected.
+//   tal_resolve_kernel one thread per (image, anchor): 0 claims -> background; 1 claim -> that GT; >1 claims ->
+//                      argmax over ALL M GTs of the overlap (select_highest_overlaps, tal.py:252-263, including its
+//                      quirk that a GT which never selected the anchor can win); then the pair's (align, overlap)
+//                      is recomputed and folded into per-GT maxima with integer atomicMax (values are >= 0).
+//   emit kernels       norm = align * pos_overlap / (pos_align + eps) (tal.py:88-92) and the reference-format outputs.
+#pragma once
+#include "y3d_common.cuh"
+
+namespace y3d {
+
+constexpr int kAssignWarps = 8;
+constexpr int kNoClaim = 0x7f7f7f7f;
+
+struct AssignCtx {
+    // predictions
+    int score_mode;              // 0: pd_scores tensor of probabilities; 1: head-level logits (sigmoid on the fly)
+    const float *pd_scores;      // mode 0
+    long long ssB, ssA, ssC;     // mode 0 element strides
+    int cls_ch0;                 // mode 1: first class channel in the head tensor (4*reg_max)
+    const float *pd_bboxes;      // [B,A,4]; px when box_grid_units == 0, grid units (multiplied by stride here) otherwise
+    int box_grid_units;
+    const float *anc;            // [A,2] px, or nullptr when use_grid
+    LevelTable t;                // geometry (use_grid) and head pointers (score_mode 1)
+    int use_grid;
+    // ground truth, generic strides so that packed [B,M,5] / [B,M,17] rows work too
+    const float *gt_labels; long long gl_stride;   // label of (b,m) at gt_labels[(b*M+m)*gl_stride]
+    const float *gt_bboxes; long long gb_stride;   // box of (b,m) at gt_bboxes[(b*M+m)*gb_stride .. +4]
+    const float *mask_gt;                          // [B,M] or nullptr => valid iff sum(box) > 0 (loss.py:226)
+    int B, A, nc, M, k;
+    float alpha, beta, gamma, eps;
+    // 3D extras (TaskAlignedAssigner3d)
+    int use_2d, use_3d, kps_l2, constrain;
+    const float *pd_kps;  // [B,A,24]
+    const float *gt_kps;  // [B,M,24]
+    // workspace
+    int *claim_cnt;    // [B,A] zero-initialised
+    int *claim_gt;     // [B,A] initialised to kNoClaim
+    int *pos_align;    // [B,M] float bits, zero-initialised
+    int *pos_ov;       // [B,M] float bits, zero-initialised
+    int *tgi;          // [B,A] out of resolve: assigned GT or -1
+    float *alignv;     // [B,A] out of resolve: align_metric of the assigned pair
+};
+
+struct GtRec {
+    float4 box;
+    float at1;
+    int label;
+    int valid;
+};
+
+__device__ __forceinline__ GtRec load_gt(const AssignCtx &c, int b, int m) {
+    GtRec g;
+    long long i = (long long)b * c.M + m;
+    const float *pb = c.gt_bboxes + i * c.gb_stride;
+    g.box = make_float4(pb[0], pb[1], pb[2], pb[3]);
+    g.label = (int)c.gt_labels[i * c.gl_stride];
+    if (c.mask_gt)
+        g.valid = c.mask_gt[i] != 0.0f;
+    else
+        g.valid = dm::add(dm::add(dm::add(g.box.x, g.box.y), g.box.z), g.box.w) > 0.0f;
+    g.at1 = dm::box1_atan(g.box);
+    return g;
+}
+
+__device__ __forceinline__ void anchor_px(const AssignCtx &c, int a, float &ax, float &ay, float &st) {
+    if (c.use_grid) {
+        int l = level_of(c.t, a);
+        int cell = a - c.t.start[l];
+        int w = c.t.w[l];
+        st = c.t.stride[l];
+        ax = dm::mul((float)(cell % w) + 0.5f, st);
+        ay = dm::mul((float)(cell / w) + 0.5f, st);
+    } else {
+        float2 p = *reinterpret_cast<const float2 *>(c.anc + 2 * (long long)a);
+        ax = p.x;
+        ay = p.y;
+        st = 1.0f;
+    }
+}
+
+__device__ __forceinline__ float pair_score(const AssignCtx &c, int b, int a, int label) {
+    if (c.score_mode == 0) return c.pd_scores[b * c.ssB + a * c.ssA + (long long)label * c.ssC];
+    int l = level_of(c.t, a);
+    const float *p = c.t.ptr[l] + (long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + label) * c.t.sC[l] + (a - c.t.start[l]);
+    return 1.0f / (1.0f + expf(-*p));  // pred_scores.detach().sigmoid() loss.py:232
+}
+
+__device__ __forceinline__ float4 pair_box(const AssignCtx &c, int b, int a) {
+    float4 p = *reinterpret_cast<const float4 *>(c.pd_bboxes + ((long long)b * c.A + a) * 4);
+    if (c.box_grid_units) {  // pred_bboxes.detach() * stride_tensor loss.py:233
+        float st = c.t.stride[level_of(c.t, a)];
+        p.x = dm::mul(p.x, st); p.y = dm::mul(p.y, st); p.z = dm::mul(p.z, st); p.w = dm::mul(p.w, st);
+    }
+    return p;
+}
+
+// get_box_metrics (tal.py:108-127) / get_box_kp_metrics / get_keypoint_metrics (tal.py:553-603) for one in-mask pair.
+// ovl is what the reference calls `overlaps` downstream: CIoU for the 2D assigner, the 3D similarity when use_3d.
+__device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, float &metric,
+                                          float &ovl) {
+    float s = pair_score(c, b, a, g.label);
+    metric = dm::pow_(s, c.alpha);
+    ovl = 0.0f;
+    if (c.use_2d) {
+        float o = dm::ciou(g.box, pair_box(c, b, a), g.at1);
+        o = o < 0.0f ? 0.0f : o;  // clamp_(0) tal.py:131
+        metric = dm::mul(metric, dm::pow_(o, c.beta));
+        ovl = o;
+    }
+    if (c.use_3d) {  // keypoint_distance_3d tal.py:464-470
+        const float4 *pk = reinterpret_cast<const float4 *>(c.pd_kps + ((long long)b * c.A + a) * 24);
+        const float4 *gk = reinterpret_cast<const float4 *>(c.gt_kps + ((long long)b * c.M + m) * 24);
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            float4 p = pk[j], q = __ldg(gk + j);
+            float d0 = dm::sub(p.x, q.x), d1 = dm::sub(p.y, q.y), d2 = dm::sub(p.z, q.z), d3 = dm::sub(p.w, q.w);
+            if (c.kps_l2) {
+                acc = dm::add(acc, dm::mul(d0, d0)); acc = dm::add(acc, dm::mul(d1, d1));
+                acc = dm::add(acc, dm::mul(d2, d2)); acc = dm::add(acc, dm::mul(d3, d3));
+            } else {
+                acc = dm::add(acc, fabsf(d0)); acc = dm::add(acc, fabsf(d1));
+                acc = dm::add(acc, fabsf(d2)); acc = dm::add(acc, fabsf(d3));
+            }
+        }
+        float dist = dm::div(acc, 24.0f);
+        float sim = dm::div(1.0f, dm::exp_(c.kps_l2 ? dm::mul(0.5f, dist) : dist));
+        metric = dm::mul(metric, dm::pow_(sim, c.gamma));
+        ovl = sim;  // tal.py:602-603
+    }
+}
+
+__device__ __forceinline__ bool better(float am, int ai, float bm, int bi) {
+    return am > bm || (am == bm && ai < bi);
+}
+
+// norm_align_metric of an assigned anchor (tal.py:89-92)
+__device__ __forceinline__ float assigned_norm(const AssignCtx &c, int b, int gi, float alignv) {
+    float pa = __int_as_float(c.pos_align[(long long)b * c.M + gi]);
+    float po = __int_as_float(c.pos_ov[(long long)b * c.M + gi]);
+    return dm::div(dm::mul(alignv, po), dm::add(pa, c.eps));
+}
+
+// host helpers --------------------------------------------------------------------------------------------------
+struct AssignWs {
+    size_t off_cnt, off_pa, off_po, off_cgt, off_tgi, off_align, off_norm, off_lab, total, zero_bytes;
+};
+inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+inline AssignWs assign_ws_layout(int B, int A, int M) {
+    AssignWs w;
+    size_t ba = a256(sizeof(int) * (size_t)B * A), bm = a256(sizeof(int) * (size_t)B * (M > 0 ? M : 1));
+    w.off_cnt = 0;
+    w.off_pa = ba;
+    w.off_po = ba + bm;
+    w.zero_bytes = ba + 2 * bm;  // claim_cnt | pos_align | pos_ov are zero-filled with one memset
+    w.off_cgt = w.zero_bytes;
+    w.off_tgi = w.off_cgt + ba;
+    w.off_align = w.off_tgi + ba;
+    w.off_norm = w.off_align + ba;
+    w.off_lab = w.off_norm + ba;
+    w.total = w.off_lab + ba;
+    return w;
+}
+inline void assign_bind_ws(AssignCtx &c, void *ws, const AssignWs &w) {
+    char *p = (char *)ws;
+    c.claim_cnt = (int *)(p + w.off_cnt);
+    c.pos_align = (int *)(p + w.off_pa);
+    c.pos_ov = (int *)(p + w.off_po);
+    c.claim_gt = (int *)(p + w.off_cgt);
+    c.tgi = (int *)(p + w.off_tgi);
+    c.alignv = (float *)(p + w.off_align);
+}
+// enqueue: init + top-k + resolve (defined in assign.cu).  After this c.tgi / c.alignv / c.pos_* are final.
+int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s);
+
+}  // namespace y3d

@@ -1,0 +1,431 @@
+// topk.cu -- NMS-free two-stage top-k (sm_100a).
+//   y3d_postprocess    ops.v10postprocess / ops.v10_3Dpostprocess   reference ultralytics/utils/ops.py:852-880
+//   y3d_decode_topk2d  v10Detect.forward export branch               reference ultralytics/nn/modules/head.py:526-531
+//
+// Stage 0 (streaming, many CTAs): per-anchor class max  -> keys [B,A]           (scores.amax(-1), ops.py:855)
+// Stage 1 (one CTA per image)   : exact top-D of the A keys by 4-pass MSB radix select on order-preserving
+//                                 uint32 keys, ties resolved lowest-index-first, then a bitonic sort of the D
+//                                 winners on (key desc, index asc)                 (torch.topk, ops.py:856)
+// Stage 2 (same CTA)            : the D x nc scores of the winners are gathered into shared memory, the same
+//                                 select + sort runs over the flattened index i*nc + c (ops.py:861), then
+//                                 labels = idx % nc, anchor = winners[idx // nc], gather of the regression channels.
+// Results are identical to a stable descending sort (lowest index wins ties) -- the order BASELINE.json mandates.
+#include "y3d_common.cuh"
+
+namespace y3d {
+
+constexpr int kTopkThreads = 1024;
+constexpr int kKeys2SmemCap = 40960;  // uint32 keys of stage 2 kept in shared memory (160 KB)
+
+__device__ __forceinline__ uint32_t float_key(float x) {
+    if (x != x) return 0xFFFFFFFFu;  // NaN sorts first, like torch.topk
+    x = x + 0.0f;                    // -0 -> +0 (equal values must tie)
+    uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(u);
+}
+
+struct TopkSrc {
+    int mode;  // 0: strided preds tensor; 1: head levels (sigmoid + DFL decode on the fly)
+    const float *preds;
+    long long sB, sA, sC;
+    int soff, roff;  // first score / first regression channel
+    LevelTable t;
+    int xywh;
+};
+
+__device__ __forceinline__ float sigmoid_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ float src_score(const TopkSrc &s, int b, int a, int c) {
+    if (s.mode == 0) return s.preds[b * s.sB + a * s.sA + (long long)(s.soff + c) * s.sC];
+    int l = level_of(s.t, a);
+    const float *p = s.t.ptr[l] + (long long)b * s.t.sB[l] + (a - s.t.start[l]);
+    return sigmoid_(p[(long long)(64 + c) * s.t.sC[l]]);
+}
+
+// decode of one anchor's box from the head (same arithmetic as decode2d_kernel)
+__device__ __forceinline__ void src_box(const TopkSrc &s, int b, int a, float out[4]) {
+    int l = level_of(s.t, a);
+    int cell = a - s.t.start[l];
+    const float *p = s.t.ptr[l] + (long long)b * s.t.sB[l] + cell;
+    const long long cs = s.t.sC[l];
+    float d[4];
+    for (int side = 0; side < 4; ++side) {
+        float x[16];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            x[j] = p[(long long)(side * 16 + j) * cs];
+            m = fmaxf(m, x[j]);
+        }
+        float sum = 0.f, acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float e = expf(x[j] - m);
+            sum += e;
+            acc += (float)j * e;
+        }
+        d[side] = acc / sum;
+    }
+    const int w = s.t.w[l];
+    const float st = s.t.stride[l];
+    float ax = (float)(cell % w) + 0.5f, ay = (float)(cell / w) + 0.5f;
+    float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    if (s.xywh) {
+        out[0] = ((x1 + x2) / 2.0f) * st;
+        out[1] = ((y1 + y2) / 2.0f) * st;
+        out[2] = (x2 - x1) * st;
+        out[3] = (y2 - y1) * st;
+    } else {
+        out[0] = x1 * st; out[1] = y1 * st; out[2] = x2 * st; out[3] = y2 * st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ stage 0 kernels
+// generic strided amax: one warp per anchor, lanes over classes (coalesced when sC == 1)
+__global__ void amax_warp_kernel(const float *__restrict__ preds, long long sB, long long sA, long long sC, int soff,
+                                 int B, int A, int nc, float *__restrict__ keys) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * A) return;
+    int b = warp / A, a = warp % A;
+    const float *p = preds + b * sB + a * sA + (long long)soff * sC;
+    float m = -INFINITY;
+    bool nan = false;
+    for (int c = lane; c < nc; c += 32) {
+        float v = p[c * sC];
+        nan |= (v != v);
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    nan = __any_sync(0xffffffffu, nan);
+    if (lane == 0) keys[warp] = nan ? NAN : m;
+}
+// anchor-contiguous amax (sA == 1, the reference's permuted view of [B, C, A]): one thread per anchor
+__global__ void amax_anchor_kernel(const float *__restrict__ preds, long long sB, long long sC, int soff, int B, int A,
+                                   int nc, float *__restrict__ keys) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (a >= A) return;
+    const float *p = preds + b * sB + a + (long long)soff * sC;
+    float m = -INFINITY;
+    bool nan = false;
+    int c = 0;
+    for (; c + 4 <= nc; c += 4) {
+        float v0 = ldg_stream1(p + (c + 0) * sC), v1 = ldg_stream1(p + (c + 1) * sC);
+        float v2 = ldg_stream1(p + (c + 2) * sC), v3 = ldg_stream1(p + (c + 3) * sC);
+        nan |= (v0 != v0) | (v1 != v1) | (v2 != v2) | (v3 != v3);
+        m = fmaxf(fmaxf(m, fmaxf(v0, v1)), fmaxf(v2, v3));
+    }
+    for (; c < nc; ++c) {
+        float v = ldg_stream1(p + c * sC);
+        nan |= (v != v);
+        m = fmaxf(m, v);
+    }
+    keys[(long long)b * A + a] = nan ? NAN : m;
+}
+// head levels -> max_c sigmoid(logit): 4 anchors per thread, 128-bit loads; class channels only are read
+template <int VEC>
+__global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total, int nc, int A,
+                                                      float *__restrict__ keys) {
+    // quads are enumerated level by level
+    int q = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (q >= nq_total) return;
+    int l = 0, qs = 0;
+    for (int i = 0; i < t.nl; ++i) {
+        int nq = t.h[i] * t.w[i] / VEC;
+        if (q >= qs + nq) { qs += nq; l = i + 1; }
+    }
+    int cell = (q - qs) * VEC;
+    const float *p = t.ptr[l] + (long long)b * t.sB[l] + cell + 64LL * t.sC[l];
+    const long long cs = t.sC[l];
+    float m[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) m[e] = -INFINITY;
+    bool nan = false;
+    for (int c = 0; c < nc; ++c) {
+        if constexpr (VEC == 4) {
+            float4 v = ldg_stream4(p + c * cs);
+            float s0 = sigmoid_(v.x), s1 = sigmoid_(v.y), s2 = sigmoid_(v.z), s3 = sigmoid_(v.w);
+            nan |= (s0 != s0) | (s1 != s1) | (s2 != s2) | (s3 != s3);
+            m[0] = fmaxf(m[0], s0); m[1] = fmaxf(m[1], s1); m[2] = fmaxf(m[2], s2); m[3] = fmaxf(m[3], s3);
+        } else {
+            float s0 = sigmoid_(ldg_stream1(p + c * cs));
+            nan |= (s0 != s0);
+            m[0] = fmaxf(m[0], s0);
+        }
+    }
+    float *o = keys + (long long)b * A + t.start[l] + cell;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) o[e] = nan ? NAN : m[e];  // (NaN handling is per quad; NaN inputs are unsupported)
+}
+
+// ------------------------------------------------------------------------------------------ block select
+struct SelShared {
+    unsigned hist[256];
+    unsigned warp_tot[32];
+    unsigned prefix, need, n_gt, n_eq, eq_base, cnt;
+};
+
+// Exact top-D of n keys by (key desc, index asc).  key_at(i) must be pure.  Writes D composites
+// (key << 32 | ~index) into out[0..D) (unordered), out[D..Dpad) = 0, then sorts descending.
+template <class KeyAt>
+__device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long long *out, SelShared &sh) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { sh.prefix = 0; sh.need = D; }
+    unsigned mask = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int i = tid; i < 256; i += nt) sh.hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = sh.prefix;
+        for (int i0 = 0; i0 < n; i0 += nt) {
+            int i = i0 + tid;
+            bool on = i < n;
+            unsigned k = on ? key_at(i) : 0u;
+            on = on && ((k & mask) == prefix);
+            unsigned digit = (k >> shift) & 255u;
+            // warp-aggregated shared atomics: one add per distinct digit per warp
+            unsigned act = __ballot_sync(0xffffffffu, on);
+            if (on) {
+                unsigned peers = __match_any_sync(act, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&sh.hist[digit], (unsigned)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (wid == 0) {  // lane l owns digits 255-8l .. 248-8l (descending)
+            unsigned loc[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = sh.hist[255 - 8 * lane - j]; s += loc[j]; }
+            unsigned inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            unsigned exc = inc - s, need = sh.need;
+            if (exc < need && need <= inc) {
+                unsigned cum = exc;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum < need && need <= cum + loc[j]) {
+                        sh.prefix = prefix | ((unsigned)(255 - 8 * lane - j) << shift);
+                        sh.need = need - cum;
+                        sh.n_eq = loc[j];
+                    }
+                    cum += loc[j];
+                }
+            }
+        }
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    const unsigned T = sh.prefix, need_eq = sh.need, n_eq = sh.n_eq, n_gt = D - need_eq;
+    if (tid == 0) { sh.cnt = 0; sh.eq_base = 0; }
+    for (int i = D + tid; i < Dpad; i += nt) out[i] = 0ull;
+    __syncthreads();
+    const bool take_all_eq = (n_eq == need_eq);
+    // keys > T (and all == T when no boundary tie): unordered append, warp-aggregated
+    for (int i0 = 0; i0 < n; i0 += nt) {
+        int i = i0 + tid;
+        unsigned k = i < n ? key_at(i) : 0u;
+        bool sel = i < n && (k > T || (take_all_eq && k == T));
+        unsigned bal = __ballot_sync(0xffffffffu, sel);
+        if (bal) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&sh.cnt, (unsigned)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sel) out[base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)k << 32) | (0xFFFFFFFFu - (unsigned)i);
+        }
+    }
+    if (!take_all_eq) {  // boundary tie: the first need_eq keys == T in index order
+        for (int i0 = 0; i0 < n; i0 += nt) {
+            __syncthreads();
+            if (sh.eq_base >= need_eq) break;
+            int i = i0 + tid;
+            bool eq = i < n && key_at(i) == T;
+            unsigned bal = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) sh.warp_tot[wid] = __popc(bal);
+            __syncthreads();
+            unsigned before = 0, total = 0;
+            for (int w = 0; w < (nt >> 5); ++w) {
+                unsigned v = sh.warp_tot[w];
+                before += (w < wid) ? v : 0u;
+                total += v;
+            }
+            unsigned rank = sh.eq_base + before + __popc(bal & ((1u << lane) - 1u));
+            if (eq && rank < need_eq) out[n_gt + rank] = ((unsigned long long)T << 32) | (0xFFFFFFFFu - (unsigned)i);
+            __syncthreads();
+            if (tid == 0) sh.eq_base += total;
+        }
+    }
+    __syncthreads();
+    // bitonic sort, descending
+    for (int k = 2; k <= Dpad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < Dpad; i += nt) {
+                int p = i ^ j;
+                if (p > i) {
+                    unsigned long long x = out[i], y = out[p];
+                    bool desc = (i & k) == 0;
+                    if (desc ? (x < y) : (x > y)) { out[i] = y; out[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// one CTA per image
+__global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, const float *__restrict__ keys, int A,
+                                                                    int nc, int nreg, int D, int Dpad, int keys2_smem,
+                                                                    uint32_t *__restrict__ keys2_ws, float *reg,
+                                                                    float *scores, int64_t *labels,
+                                                                    int32_t *anchor_idx, int out_mode) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *win1 = (unsigned long long *)smem_raw;
+    unsigned long long *win2 = win1 + Dpad;
+    uint32_t *k2s = (uint32_t *)(win2 + Dpad);
+    __shared__ SelShared sh;
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const float *kb = keys + (long long)b * A;
+    block_topk([&](int i) { return float_key(kb[i]); }, A, D, Dpad, win1, sh);
+    // stage 2: D x nc candidate scores, flattened index j = i*nc + c   (ops.py:858-861)
+    const int n2 = D * nc;
+    uint32_t *k2 = keys2_smem ? k2s : keys2_ws + (long long)b * n2;
+    for (int j = tid; j < n2; j += nt) {
+        int i = j / nc, c = j - i * nc;
+        int a = (int)(0xFFFFFFFFu - (unsigned)(win1[i] & 0xFFFFFFFFull));
+        k2[j] = float_key(src_score(src, b, a, c));
+    }
+    __syncthreads();
+    block_topk([&](int j) { return k2[j]; }, n2, D, Dpad, win2, sh);
+    for (int r = tid; r < D; r += nt) {
+        unsigned long long w = win2[r];
+        int j = (int)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull));
+        int i = j / nc, c = j - i * nc;
+        int a = (int)(0xFFFFFFFFu - (unsigned)(win1[i] & 0xFFFFFFFFull));
+        float sc = key_float((uint32_t)(w >> 32));
+        long long o = (long long)b * D + r;
+        if (anchor_idx) anchor_idx[o] = a;
+        if (out_mode == 0) {
+            scores[o] = sc;
+            labels[o] = c;
+        } else {  // fused export layout [B,D,6] = box, score, label (head.py:531)
+            float bx[4];
+            src_box(src, b, a, bx);
+            float *q = reg + o * 6;
+            q[0] = bx[0]; q[1] = bx[1]; q[2] = bx[2]; q[3] = bx[3]; q[4] = sc; q[5] = (float)c;
+        }
+    }
+    if (out_mode == 0) {
+        for (int e = tid; e < D * nreg; e += nt) {
+            int r = e / nreg, rr = e - r * nreg;
+            unsigned long long w = win2[r];
+            int j = (int)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull));
+            int a = (int)(0xFFFFFFFFu - (unsigned)(win1[j / nc] & 0xFFFFFFFFull));
+            reg[((long long)b * D + r) * nreg + rr] =
+                src.preds[b * src.sB + a * src.sA + (long long)(src.roff + rr) * src.sC];
+        }
+    }
+}
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t topk_workspace_bytes(int B, int A, int nc, int D) {
+    size_t keys = align256(sizeof(float) * (size_t)B * A);
+    size_t k2 = (D * nc > kKeys2SmemCap) ? align256(sizeof(uint32_t) * (size_t)B * D * nc) : 0;
+    return keys + k2;
+}
+
+static int launch_select(const TopkSrc &src, const float *keys, int B, int A, int nc, int nreg, int D, float *reg,
+                         float *scores, int64_t *labels, int32_t *anchor_idx, int out_mode, uint32_t *keys2_ws,
+                         cudaStream_t s) {
+    int Dpad = next_pow2(D);
+    int n2 = D * nc;
+    int k2smem = n2 <= kKeys2SmemCap;
+    size_t smem = sizeof(unsigned long long) * 2 * (size_t)Dpad + (k2smem ? sizeof(uint32_t) * (size_t)n2 : 0);
+    cudaError_t e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    topk_select_kernel<<<B, kTopkThreads, smem, s>>>(src, keys, A, nc, nreg, D, Dpad, k2smem, keys2_ws, reg, scores,
+                                                    labels, anchor_idx, out_mode);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
+}
+
+}  // namespace y3d
+
+using namespace y3d;
+
+extern "C" int y3d_postprocess(const float *preds, int64_t sB, int64_t sA, int64_t sC, int B, int A, int nc, int nreg,
+                               int scores_first, int D, float *reg, float *scores, int64_t *labels,
+                               int32_t *anchor_idx, void *ws, size_t ws_bytes, void *stream) {
+    if (!preds || !reg || !scores || !labels || B < 0 || A < 1 || nc < 1 || nreg < 0) return Y3D_EINVAL;
+    if (D < 1 || D > A) return Y3D_EINVAL;  // torch.topk raises when k > A (ops.py:856)
+    if (D > Y3D_MAX_DET) return Y3D_EUNSUPPORTED;
+    size_t need = topk_workspace_bytes(B, A, nc, D);
+    if (!ws || ws_bytes < need) return Y3D_EWORKSPACE;
+    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    if (B == 0) return Y3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    float *keys = (float *)ws;
+    uint32_t *k2 = (uint32_t *)((char *)ws + align256(sizeof(float) * (size_t)B * A));
+    const int soff = scores_first ? 0 : nreg, roff = scores_first ? nc : 0;
+    if (sA == 1) {
+        dim3 grid((A + 255) / 256, B);
+        amax_anchor_kernel<<<grid, 256, 0, s>>>(preds, sB, sC, soff, B, A, nc, keys);
+    } else {
+        long long threads = (long long)B * A * 32;
+        amax_warp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(preds, sB, sA, sC, soff, B, A, nc, keys);
+    }
+    Y3D_CHECK_LAUNCH();
+    TopkSrc src{};
+    src.mode = 0;
+    src.preds = preds;
+    src.sB = sB; src.sA = sA; src.sC = sC;
+    src.soff = soff; src.roff = roff;
+    return launch_select(src, keys, B, A, nc, nreg, D, reg, scores, labels, anchor_idx, 0, k2, s);
+}
+
+extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
+                                 const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
+                                 int xywh, int D, float *out, int32_t *anchor_idx, void *ws, size_t ws_bytes,
+                                 void *stream) {
+    if (!lvl_ptr || !lvl_sB || !lvl_sC || !out || B < 0 || nc < 1) return Y3D_EINVAL;
+    if (reg_max != 16) return Y3D_EUNSUPPORTED;
+    TopkSrc src{};
+    int A = make_level_table(src.t, lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl);
+    if (A < 0) return A;
+    for (int l = 0; l < nl; ++l)
+        if (!lvl_ptr[l]) return Y3D_EINVAL;
+    if (D < 1 || D > A) return Y3D_EINVAL;
+    if (D > Y3D_MAX_DET) return Y3D_EUNSUPPORTED;
+    size_t need = topk_workspace_bytes(B, A, nc, D);
+    if (!ws || ws_bytes < need) return Y3D_EWORKSPACE;
+    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    if (B == 0) return Y3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    float *keys = (float *)ws;
+    uint32_t *k2 = (uint32_t *)((char *)ws + align256(sizeof(float) * (size_t)B * A));
+    bool v4 = true;
+    for (int l = 0; l < nl; ++l)
+        v4 = v4 && (src.t.h[l] * src.t.w[l]) % 4 == 0 && ((uintptr_t)lvl_ptr[l]) % 16 == 0 && lvl_sB[l] % 4 == 0 &&
+             lvl_sC[l] % 4 == 0;
+    if (v4) {
+        int nq = A / 4;
+        dim3 grid((nq + 127) / 128, B);
+        cls_max_kernel<4><<<grid, 128, 0, s>>>(src.t, nq, nc, A, keys);
+    } else {
+        dim3 grid((A + 127) / 128, B);
+        cls_max_kernel<1><<<grid, 128, 0, s>>>(src.t, A, nc, A, keys);
+    }
+    Y3D_CHECK_LAUNCH();
+    src.mode = 1;
+    src.xywh = xywh;
+    return launch_select(src, keys, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s);
+}

@@ -1,0 +1,12 @@
+"""Import alias: the package directory is ``yolov10-3d_b200/`` (a hyphen cannot be imported), so this module
+loads it under the importable name ``yolov10_3d_b200``."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "yolov10-3d_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -403,6 +403,7 @@ static void assign_core(int A, int nc, int M, int k, float alpha, float beta, fl
     int *tk_idx = (int *)malloc(sizeof(int) * (size_t)k);
     float *tk_val = (float *)malloc(sizeof(float) * (size_t)k);
     int8_t *count = (int8_t *)malloc((size_t)A);
+    kv_t *scratch = k > 16 ? (kv_t *)malloc(sizeof(kv_t) * (size_t)A) : NULL;
     for (int m = 0; m < M; ++m) {
         const float *g = gb + 4 * m;
         int lab = (int)(int64_t)gl[m];
@@ -436,7 +437,7 @@ static void assign_core(int A, int nc, int M, int k, float alpha, float beta, fl
         /* select_topk_candidates tal.py:133-167 */
         memset(count, 0, (size_t)A);
         if (valid) {
-            stable_topk(align + (long)m * A, A, k, tk_idx, tk_val, NULL);
+            stable_topk(align + (long)m * A, A, k, tk_idx, tk_val, scratch);
             for (int j = 0; j < k; ++j) count[tk_idx[j]] += 1;
         } else {
             count[0] = (int8_t)k; /* indices forced to 0 */
@@ -494,7 +495,7 @@ static void assign_core(int A, int nc, int M, int k, float alpha, float beta, fl
         if (fg[a]) t_sc[(long)a * nc + lab] = norm;
     }
     free(align); free(ov); free(in_gts); free(mpos); free(tk_idx); free(tk_val); free(count);
-    free(pos_align); free(pos_ov);
+    free(pos_align); free(pos_ov); free(scratch);
 }
 
 int y3d_o_tal_assign(const float *pd_scores, const float *pd_bboxes, const float *anc, const float *gt_labels,

@@ -133,9 +133,8 @@ __global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total
     int q = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (q >= nq_total) return;
     int l = 0, qs = 0;
-    for (int i = 0; i < t.nl; ++i) {
-        int nq = t.h[i] * t.w[i] / VEC;
-        if (q >= qs + nq) { qs += nq; l = i + 1; }
+    for (int i = 0; i + 1 < t.nl; ++i) {  // levels are enumerated in order; start[] is in anchors = VEC * quads
+        if (q >= t.start[i + 1] / VEC) { l = i + 1; qs = t.start[i + 1] / VEC; }
     }
     int cell = (q - qs) * VEC;
     const float *p = t.ptr[l] + (long long)b * t.sB[l] + cell + 64LL * t.sC[l];

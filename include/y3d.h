@@ -110,12 +110,15 @@ int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A, int64_t s
  *  normalising; when `normalise` is 0 loss_items is left untouched.
  *  v10DetectLoss (loss.py:727-737) = this with topk=10 on one2many + topk=1 on one2one.
  *  dbg_fg_mask [B,A] u8 / dbg_target_gt_idx [B,A] i32 (optional, NULL in production): the assignment the fused
- *  path used, for parity tests. */
+ *  path used, for parity tests.
+ *  prof_events (optional HOST array of 6 cudaEvent_t, NULL in production): recorded on `stream` before the first
+ *  kernel and after each stage -- [0] start, [1] head streaming pass, [2] per-GT top-k, [3] conflict resolve,
+ *  [4] foreground loss terms, [5] finalize -- so a benchmark can time each kernel inside the fused call. */
 int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
                     const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt, int M, int topk,
                     float gain_box, float gain_cls, float gain_dfl, int normalise, float *loss_items,
-                    double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes,
-                    void *stream);
+                    double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx, void *const *prof_events,
+                    void *ws, size_t ws_bytes, void *stream);
 
 /* v8DetectionLoss.bbox_decode (loss.py:197-204) + the permute/sigmoid of loss.py:214,232: head levels ->
  * pd_bboxes [B,A,4] xyxy in GRID units (caller multiplies by stride, loss.py:233) and, optionally (may be NULL),

@@ -6,7 +6,7 @@ Everything computes in liby3d_b200.so (hand-written CUDA, C ABI in include/y3d.h
 fallback -- a missing library raises at the first call.
 """
 from . import _lib  # noqa: F401
-from . import head, kitti, loss, ops, tal  # noqa: F401
+from . import dist, head, kitti, loss, ops, tal  # noqa: F401
 from ._lib import Y3DError, lib  # noqa: F401
 from .head import V10DetectDecoder, detect3d_decode, detect3d_postprocess, detect_inference, v10detect_export_forward  # noqa: F401
 from .loss import v8DetectionLoss, v10DetectLoss  # noqa: F401

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx c) {
 
 
 // enqueue: init + top-k + resolve.  After this c.tgi / c.alignv / c.pos_* are final.
-int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s) {
+int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s, cudaEvent_t after_topk) {
     cudaError_t e = cudaMemsetAsync((char *)ws + w.off_cnt, 0, w.zero_bytes, s);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync((char *)ws + w.off_cgt, 0x7f, sizeof(int) * (size_t)c.B * c.A, s);
@@ -199,6 +199,7 @@ int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_
     long long warps = (long long)c.B * c.M;
     tal_topk_kernel<<<(unsigned)((warps + kAssignWarps - 1) / kAssignWarps), kAssignWarps * 32, 0, s>>>(c);
     Y3D_CHECK_LAUNCH();
+    if (after_topk) cudaEventRecord(after_topk, s);
     size_t smem = sizeof(GtRec) * (size_t)c.M;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(tal_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

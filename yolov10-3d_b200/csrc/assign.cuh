@@ -182,6 +182,7 @@ inline void assign_bind_ws(AssignCtx &c, void *ws, const AssignWs &w) {
     c.alignv = (float *)(p + w.off_align);
 }
 // enqueue: init + top-k + resolve (defined in assign.cu).  After this c.tgi / c.alignv / c.pos_* are final.
-int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s);
+int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s,
+                    cudaEvent_t after_topk = nullptr);
 
 }  // namespace y3d

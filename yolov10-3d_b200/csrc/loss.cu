@@ -331,7 +331,8 @@ extern "C" int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
                                const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
                                const float *gt, int M, int topk, float gain_box, float gain_cls, float gain_dfl,
                                int normalise, float *loss_items, double *partials, uint8_t *dbg_fg_mask,
-                               int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes, void *stream) {
+                               int32_t *dbg_target_gt_idx, void *const *prof_events, void *ws, size_t ws_bytes,
+                               void *stream) {
     if (!lvl_ptr || !lvl_sB || !lvl_sC || B < 1 || nc < 1 || M < 0 || (M > 0 && !gt)) return Y3D_EINVAL;
     if (!loss_items && !partials) return Y3D_EINVAL;
     if (reg_max != kR) return Y3D_EUNSUPPORTED;
@@ -353,8 +354,13 @@ extern "C" int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
     double *part_bce = (double *)(p + w.off_pbce);
     double *part_fg = (double *)(p + w.off_pfg);
     int nbx = 0;
+    auto mark = [&](int i) {
+        if (prof_events && prof_events[i]) cudaEventRecord((cudaEvent_t)prof_events[i], s);
+    };
+    mark(0);
     int rc = launch_stream(c.t, B, nc, A, pd_bboxes, nullptr, part_bce, &nbx, s);
     if (rc) return rc;
+    mark(1);
     const int n_bce = nbx * B;
     if (M > 0) {
         c.score_mode = 1;
@@ -368,18 +374,22 @@ extern "C" int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
         c.alpha = 0.5f; c.beta = 6.0f; c.gamma = 1.0f; c.eps = 1e-9f;  // loss.py:176
         c.use_2d = 1; c.use_3d = 0; c.kps_l2 = 0; c.constrain = 1;
         assign_bind_ws(c, ws, w.aw);
-        rc = assign_run_core(c, ws, w.aw, s);
+        rc = assign_run_core(c, ws, w.aw, s, prof_events ? (cudaEvent_t)prof_events[2] : nullptr);
         if (rc) return rc;
+        mark(3);
         dim3 grid((A + 255) / 256, B);
         loss_fg_kernel<<<grid, 256, 0, s>>>(c, gt, part_fg, dbg_fg_mask, dbg_target_gt_idx);
         Y3D_CHECK_LAUNCH();
+        mark(4);
     } else {
+        mark(2); mark(3); mark(4);
         if (dbg_fg_mask) cudaMemsetAsync(dbg_fg_mask, 0, (size_t)B * A, s);
         if (dbg_target_gt_idx) cudaMemsetAsync(dbg_target_gt_idx, 0, sizeof(int32_t) * (size_t)B * A, s);
     }
     loss_finalize_kernel<<<1, 256, 0, s>>>(part_bce, n_bce, M > 0 ? part_fg : nullptr, w.nb_fg, gain_box, gain_cls,
                                            gain_dfl, normalise, partials, loss_items);
     Y3D_CHECK_LAUNCH();
+    mark(5);
     return Y3D_OK;
 }
 

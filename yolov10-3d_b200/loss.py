@@ -43,9 +43,10 @@ def pack_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device, extra=Non
     return out
 
 
-def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, debug=False):
+def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, debug=False, prof_events=None):
     """One branch through ``y3d_v8_loss_fwd``.  Returns (items[4] = box, cls, dfl, target_scores_sum  -- or ``None``
-    when not normalising --, partials float64[4], debug dict or None).  Nothing synchronises."""
+    when not normalising --, partials float64[4], debug dict or None).  Nothing synchronises.
+    ``prof_events``: optional ctypes array of 6 cudaEvent_t handles (see include/y3d.h), for benchmarks."""
     lv = Levels(feats, strides)
     if lv.C != 4 * REG_MAX + nc:
         raise ValueError(f"expected {4 * REG_MAX + nc} channels, got {lv.C}")
@@ -62,7 +63,7 @@ def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, 
     _lib.check(_lib.lib().y3d_v8_loss_fwd(
         *lv.args(), lv.B, nc, REG_MAX, ptr(gt) if M > 0 else None, M, int(topk), float(gains[0]), float(gains[1]),
         float(gains[2]), int(normalise), ptr(items), ptr(partials), ptr(dbg["fg_mask"]) if debug else None,
-        ptr(dbg["target_gt_idx"]) if debug else None, ptr(ws), ws.numel(), stream_ptr(dev)))
+        ptr(dbg["target_gt_idx"]) if debug else None, prof_events, ptr(ws), ws.numel(), stream_ptr(dev)))
     return items, partials, dbg
 
 

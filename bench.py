@@ -171,15 +171,15 @@ def main_cuda(args):
     strides = list(synth.STRIDES)
     K, W = args.steps, args.warmup
 
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(2 * K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
     for row in ev:
         for e in row:
             e.record()  # forces creation of the underlying cudaEvent_t
     torch.cuda.synchronize()
-    ev_c = [(ctypes.c_void_p * 6)(*[e.cuda_event for e in row]) for row in ev]
+    ev_c = [(ctypes.c_void_p * 5)(*[e.cuda_event for e in row]) for row in ev]
 
     def step(i=None):
-        pe = (ev_c[2 * i], ev_c[2 * i + 1]) if i is not None else (None, None)
+        pe = ev_c[i] if i is not None else None
         return y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=pe)
 
     for _ in range(W):
@@ -201,11 +201,11 @@ def main_cuda(args):
         dist.barrier()
     ms_total = t_start.elapsed_time(t_stop)
     sampler.stop()
-    stage_ms = np.zeros(5)
+    stage_ms = np.zeros(4)
     for row in ev:
-        for s in range(5):
+        for s in range(4):
             stage_ms[s] += row[s].elapsed_time(row[s + 1])
-    stage_ms /= (2 * K)  # per launch (two branches per step)
+    stage_ms /= K  # per launch: every kernel covers both branches
 
     # e2e: public API, pinned host inputs, H2D + D2H inside the timed region
     model = _fake_model(torch, nc, gains, dev)
@@ -238,12 +238,12 @@ def main_cuda(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = 4.0 * (64 + nc) * A * B  # 4*(4R+nc)*A per image and branch, one branch per launch
+        alg_bytes = 2 * 4.0 * (64 + nc) * A * B  # 2*4*(4R+nc)*A per image; one launch covers both branches
         achieved = alg_bytes / (stage_ms[0] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("loss_stream_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("loss_stream_tma_kernel_dram_bytes_per_launch")
         h2d = sum(f.numel() * 4 for f in host_m + host_o)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -257,15 +257,14 @@ def main_cuda(args):
             "config": {"workload": WORKLOAD, "global_batch": B * world, "sharding": f"by image, {B}/GPU",
                        "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed",
                        "collective": "all_reduce of 8 float64 loss partials per step" if world > 1 else "none"},
-            "roofline": {"bound": "hbm", "kernel": "loss_stream_kernel<4>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "loss_stream_tma_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(stage_ms[0]),
-                         "stage_ms_per_launch": {"stream": float(stage_ms[0]), "gt_topk": float(stage_ms[1]),
-                                                 "resolve": float(stage_ms[2]), "fg_loss": float(stage_ms[3]),
-                                                 "finalize": float(stage_ms[4])}},
+                         "stage_ms_per_launch": {"memset+stream": float(stage_ms[0]), "gt_topk": float(stage_ms[1]),
+                                                 "resolve": float(stage_ms[2]), "fg_loss+finalize": float(stage_ms[3])}},
             "e2e": {"value": B * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 24, "steps": Ke},
-            "gpu_launches": 10 * K,
+            "gpu_launches": 4 * K,
             "clocks": sampler.summary(),
             "loss_items": [float(v) for v in items.cpu()],
         }

@@ -111,14 +111,26 @@ int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A, int64_t s
  *  v10DetectLoss (loss.py:727-737) = this with topk=10 on one2many + topk=1 on one2one.
  *  dbg_fg_mask [B,A] u8 / dbg_target_gt_idx [B,A] i32 (optional, NULL in production): the assignment the fused
  *  path used, for parity tests.
- *  prof_events (optional HOST array of 6 cudaEvent_t, NULL in production): recorded on `stream` before the first
- *  kernel and after each stage -- [0] start, [1] head streaming pass, [2] per-GT top-k, [3] conflict resolve,
- *  [4] foreground loss terms, [5] finalize -- so a benchmark can time each kernel inside the fused call. */
+ *  prof_events (optional HOST array of 5 cudaEvent_t, NULL in production): recorded on `stream` before the first
+ *  operation and after each stage -- [0] start, [1] head streaming pass, [2] per-GT top-k, [3] conflict resolve,
+ *  [4] foreground loss terms + final reduction -- so a benchmark can time each kernel inside the fused call. */
 int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
                     const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt, int M, int topk,
                     float gain_box, float gain_cls, float gain_dfl, int normalise, float *loss_items,
                     double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx, void *const *prof_events,
                     void *ws, size_t ws_bytes, void *stream);
+
+/* v10DetectLoss.__call__ forward (loss.py:727-737): BOTH branches of the consistent dual assignment in the same
+ * launches -- one2many (top-k topk_o2m = 10) and one2one (top-k topk_o2o = 1) share the level geometry, the GT set
+ * and the gains.  loss_items: DEVICE float[8] = (box, cls, dfl, target_scores_sum) x (one2many, one2one);
+ * partials: DEVICE double[8] likewise; dbg_fg_mask [2,B,A] / dbg_target_gt_idx [2,B,A].  Other arguments as in
+ * y3d_v8_loss_fwd.  total loss of the reference = (items[0..2] + items[4..6]).sum() * B. */
+int y3d_v10_loss_fwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC,
+                     const float *const *o2o_ptr, const int64_t *o2o_sB, const int64_t *o2o_sC, const int *lvl_hw,
+                     const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt, int M,
+                     int topk_o2m, int topk_o2o, float gain_box, float gain_cls, float gain_dfl, int normalise,
+                     float *loss_items, double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx,
+                     void *const *prof_events, void *ws, size_t ws_bytes, void *stream);
 
 /* v8DetectionLoss.bbox_decode (loss.py:197-204) + the permute/sigmoid of loss.py:214,232: head levels ->
  * pd_bboxes [B,A,4] xyxy in GRID units (caller multiplies by stride, loss.py:233) and, optionally (may be NULL),
@@ -127,9 +139,9 @@ int y3d_train_decode(const float *const *lvl_ptr, const int64_t *lvl_sB, const i
                      const float *lvl_stride, int nl, int B, int nc, int reg_max, float *pd_bboxes, float *pd_scores,
                      void *stream);
 
-/* turns all-reduced partials (see above) into loss items: DEVICE double[4] -> DEVICE float[4] */
-int y3d_v8_loss_finalize(const double *partials, float gain_box, float gain_cls, float gain_dfl, float *loss_items,
-                         void *stream);
+/* turns all-reduced partials (see above) into loss items: DEVICE double[4*n_branch] -> DEVICE float[4*n_branch] */
+int y3d_v8_loss_finalize(const double *partials, int n_branch, float gain_box, float gain_cls, float gain_dfl,
+                         float *loss_items, void *stream);
 
 /* v10Detect3d.decode (head.py:755-764): [B, nc+35, A] levels -> y [B, nc+35, A] contiguous
  * (cls logits | bbox xyxy px | center3d px | s3d | hd(24) | dep | dep_un). */

@@ -23,7 +23,7 @@ def declared_symbols():
 
 def test_library_exports_every_declared_symbol():
     names = declared_symbols()
-    assert len(names) >= 13
+    assert len(names) >= 14
     handle = ctypes.CDLL(y3d._lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/y3d.h but not exported"
@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 def test_argument_errors_come_back_as_codes_not_crashes():
     lib = y3d.lib()
     assert lib.y3d_postprocess(None, 0, 0, 0, 1, 10, 2, 4, 0, 5, None, None, None, None, None, 0, None) == -1
-    assert lib.y3d_v8_loss_finalize(None, 1.0, 1.0, 1.0, None, None) == -1
+    assert lib.y3d_v8_loss_finalize(None, 1, 1.0, 1.0, 1.0, None, None) == -1
     assert lib.y3d_decode_preds3d(None, 1, 1, 3, None, None, None, None, 0.1, None, None, None) == -1
 
 

@@ -250,6 +250,13 @@ def test_fused_loss_assignment_bit_exact(y3d, topk):
     lossmod, util, lib = (__import__("yolov10_3d_b200").loss, __import__("yolov10_3d_b200")._util,
                           __import__("yolov10_3d_b200")._lib)
     items, partials, dbg = lossmod.v8_loss_forward(feats, synth.STRIDES, nc, dev(gt), topk, (7.5, 0.5, 1.5), debug=True)
+    # the two-branch entry point runs the same kernels: branch 0 = top-k 10, branch 1 = top-k 1
+    items2, partials2, dbg2 = lossmod.v10_loss_forward(feats, feats, synth.STRIDES, nc, dev(gt), (7.5, 0.5, 1.5),
+                                                       debug=True)
+    z = 0 if topk == 10 else 1
+    assert torch.equal(dbg2["fg_mask"][z], dbg["fg_mask"]) and torch.equal(dbg2["target_gt_idx"][z], dbg["target_gt_idx"])
+    # (partial sums are grouped per CTA, and the tile -> CTA map differs between the 1- and 2-branch launches)
+    assert torch.allclose(items2[4 * z:4 * z + 4], items, rtol=1e-6) and torch.allclose(partials2[4 * z:4 * z + 4], partials, rtol=1e-9)
     levels = util.Levels(feats, synth.STRIDES)
     A = levels.A
     pb = torch.empty((B, A, 4), device="cuda")

@@ -10,14 +10,17 @@
 namespace y3d {
 
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kAssignWarps * 32) tal_topk_kernel(AssignCtx c) {
-    __shared__ int queue[kAssignWarps][64];
+// grid (B*M, 1, n_branch), block kTopkWarps*32: one CTA per (image, GT)
+__global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc) {
+    __shared__ int queue[kTopkWarps][64];
+    __shared__ float mrg_m[kTopkWarps][32];
+    __shared__ int mrg_i[kTopkWarps][32];
+    __shared__ int mrg_in[kTopkWarps][32];
+    const AssignCtx &c = cc.c[blockIdx.z];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long gw = (long long)blockIdx.x * kAssignWarps + wid;
-    if (gw >= (long long)c.B * c.M) return;
-    const int b = (int)(gw / c.M), m = (int)(gw % c.M);
+    const int b = blockIdx.x / c.M, m = blockIdx.x % c.M;
     const GtRec g = load_gt(c, b, m);
-    if (!g.valid) return;  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104)
+    if (!g.valid) return;  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104); whole CTA exits
     const int k = c.k;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(kAssignWarps * 32) tal_topk_kernel(AssignCtx c
     };
 
     auto eval_and_process = [&](bool has, int a, bool force) {
-        // `force`: anchors 0..k-1 enter the list even when outside the GT (metric 0), see header comment
+        // `force`: anchors 0..k-1 enter the list even when outside the GT (metric 0), see assign.cuh
         float metric = 0.0f, ovl = 0.0f;
         int cin = 0;
         if (has) {
@@ -66,10 +69,10 @@ __global__ void __launch_bounds__(kAssignWarps * 32) tal_topk_kernel(AssignCtx c
         process(go, metric, a, cin);
     };
 
-    // phase 0: the first k anchors
-    eval_and_process(lane < k && lane < c.A, lane, true);
+    // phase 0 (warp 0): the first k anchors
+    if (wid == 0) eval_and_process(lane < k && lane < c.A, lane, true);
 
-    // phase 1: enumerate candidates (anchors >= k inside the GT) into the warp queue, evaluate 32 at a time
+    // phase 1: candidates (anchors >= k inside the GT) -> warp queue -> evaluated 32 at a time
     int qn = 0;
     auto push = [&](bool cand, int a) {
         unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -103,21 +106,21 @@ __global__ void __launch_bounds__(kAssignWarps * 32) tal_topk_kernel(AssignCtx c
             const int c0 = (int)fx0, r0 = (int)fy0;
             const int ncols = (int)fx1 - c0 + 1, nrows = (int)fy1 - r0 + 1;
             const int cells = ncols * nrows;
-            for (int i0 = 0; i0 < cells; i0 += 32) {
+            for (int i0 = wid * 32; i0 < cells; i0 += kTopkWarps * 32) {
                 int i = i0 + lane;
                 bool cand = false;
                 int a = 0;
                 if (i < cells) {
-                    int r = i / ncols, cc = i - r * ncols;
-                    a = c.t.start[l] + (r0 + r) * w + c0 + cc;
-                    float ax = dm::mul((float)(c0 + cc) + 0.5f, st), ay = dm::mul((float)(r0 + r) + 0.5f, st);
+                    int r = i / ncols, cc_ = i - r * ncols;
+                    a = c.t.start[l] + (r0 + r) * w + c0 + cc_;
+                    float ax = dm::mul((float)(c0 + cc_) + 0.5f, st), ay = dm::mul((float)(r0 + r) + 0.5f, st);
                     cand = a >= k && dm::in_gt(ax, ay, g.box);
                 }
                 push(cand, a);
             }
         }
     } else {
-        for (int a0 = 0; a0 < c.A; a0 += 32) {
+        for (int a0 = wid * 32; a0 < c.A; a0 += kTopkWarps * 32) {
             int a = a0 + lane;
             bool cand = false;
             if (a < c.A && a >= k) {
@@ -137,24 +140,31 @@ __global__ void __launch_bounds__(kAssignWarps * 32) tal_topk_kernel(AssignCtx c
         eval_and_process(lane < qn, a2, false);
     }
 
-    // claims: mask_pos = mask_topk * mask_in_gts * mask_gt (tal.py:104)
-    if (lane < k && tk_i != 0x7fffffff && tk_in) {
-        long long o = (long long)b * c.A + tk_i;
-        atomicAdd(c.claim_cnt + o, 1);
-        atomicMin(c.claim_gt + o, m);
+    // merge the per-warp lists into warp 0's
+    mrg_m[wid][lane] = tk_m; mrg_i[wid][lane] = tk_i; mrg_in[wid][lane] = tk_in;
+    __syncthreads();
+    if (wid != 0) return;
+#pragma unroll
+    for (int w = 1; w < kTopkWarps; ++w) {
+        int ci = mrg_i[w][lane];
+        process(lane < k && ci != 0x7fffffff, mrg_m[w][lane], ci, mrg_in[w][lane]);
     }
+    // claims: mask_pos = mask_topk * mask_in_gts * mask_gt (tal.py:104)
+    if (lane < k && tk_i != 0x7fffffff && tk_in)
+        atomicAdd(c.claim + (long long)b * c.A + tk_i, (1ull << 32) | (unsigned long long)m);
 }
 
-// grid (ceil(A/256), B); dynamic smem: M GtRec
-__global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx c) {
+// grid (ceil(A/256), B, n_branch); dynamic smem: M GtRec
+__global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GtRec *gts = reinterpret_cast<GtRec *>(smem_raw);
+    const AssignCtx &c = cc.c[blockIdx.z];
     const int b = blockIdx.y;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    // does any anchor of this block need the all-GT scan?
-    long long o = (long long)b * c.A + a;
-    int cnt = a < c.A ? c.claim_cnt[o] : 0;
-    int any_multi = __syncthreads_or(cnt > 1);
+    const long long o = (long long)b * c.A + a;
+    const unsigned long long cl = a < c.A ? c.claim[o] : 0ull;
+    const int cnt = (int)(cl >> 32);
+    const int any_multi = __syncthreads_or(cnt > 1);  // does any anchor of this block need the all-GT scan?
     if (any_multi) {
         for (int m = threadIdx.x; m < c.M; m += blockDim.x) gts[m] = load_gt(c, b, m);
         __syncthreads();
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx c) {
         float ax, ay, st;
         anchor_px(c, a, ax, ay, st);
         if (cnt == 1) {
-            gi = c.claim_gt[o];
+            gi = (int)(cl & 0xffffffffull);
         } else {  // select_highest_overlaps tal.py:252-263: argmax over all GTs, first maximum
             float bv = -1.0f;
             for (int m = 0; m < c.M; ++m) {
@@ -189,28 +199,22 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx c) {
     c.alignv[o] = alignv;
 }
 
-
-// enqueue: init + top-k + resolve.  After this c.tgi / c.alignv / c.pos_* are final.
-int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s, cudaEvent_t after_topk) {
-    cudaError_t e = cudaMemsetAsync((char *)ws + w.off_cnt, 0, w.zero_bytes, s);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync((char *)ws + w.off_cgt, 0x7f, sizeof(int) * (size_t)c.B * c.A, s);
-    if (e != cudaSuccess) return (int)e;
-    long long warps = (long long)c.B * c.M;
-    tal_topk_kernel<<<(unsigned)((warps + kAssignWarps - 1) / kAssignWarps), kAssignWarps * 32, 0, s>>>(c);
+int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk) {
+    const AssignCtx &c = cc.c[0];
+    dim3 gt_grid((unsigned)((long long)c.B * c.M), 1, n);
+    tal_topk_kernel<<<gt_grid, kTopkWarps * 32, 0, s>>>(cc);
     Y3D_CHECK_LAUNCH();
     if (after_topk) cudaEventRecord(after_topk, s);
     size_t smem = sizeof(GtRec) * (size_t)c.M;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(tal_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tal_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 grid((c.A + 255) / 256, c.B);
-    tal_resolve_kernel<<<grid, 256, smem, s>>>(c);
+    dim3 grid((c.A + 255) / 256, c.B, n);
+    tal_resolve_kernel<<<grid, 256, smem, s>>>(cc);
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }
-
 
 // ------------------------------------------------------------------------------------------------ emit kernels
 // get_targets (tal.py:169-216 / 651-700) + normalisation (tal.py:88-92): per-anchor small outputs
@@ -413,7 +417,11 @@ extern "C" int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A
     c.use_2d = 1; c.use_3d = 0; c.kps_l2 = 0; c.constrain = 1;
     assign_bind_ws(c, ws, w);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = assign_run_core(c, ws, w, s);
+    cudaError_t e = cudaMemsetAsync((char *)ws + w.off_cnt, 0, w.zero_bytes, s);
+    if (e != cudaSuccess) return (int)e;
+    AssignCtx2 cc{};
+    cc.c[0] = c;
+    int rc = assign_run_core(cc, 1, s);
     if (rc) return rc;
     return run_emit(c, ws, w, target_labels, target_bboxes, target_scores, fg_mask, target_gt_idx, nullptr, nullptr, s);
 }
@@ -464,7 +472,11 @@ extern "C" int y3d_tal_assign3d(const float *pd_scores, const float *pd_bboxes, 
     c.use_2d = use_2d; c.use_3d = use_3d; c.kps_l2 = kps_l2; c.constrain = constrain;
     c.pd_kps = pd_keypoints; c.gt_kps = gt_keypoints;
     assign_bind_ws(c, ws, w);
-    int rc = assign_run_core(c, ws, w, s);
+    cudaError_t e = cudaMemsetAsync((char *)ws + w.off_cnt, 0, w.zero_bytes, s);
+    if (e != cudaSuccess) return (int)e;
+    AssignCtx2 cc{};
+    cc.c[0] = c;
+    int rc = assign_run_core(cc, 1, s);
     if (rc) return rc;
     return run_emit(c, ws, w, target_labels, nullptr, target_scores, fg_mask, target_gt_idx, gts, target_vals, s);
 }

@@ -6,7 +6,9 @@
 //   tal_topk_kernel    one warp per (image, GT): walks the anchors inside the GT's rectangle (or all A anchors when
 //                      no grid is promised), evaluates score^alpha * CIoU^beta (* sim^gamma) for the in-GT anchors
 //                      32 at a time through a warp queue, keeps the per-GT top-k as a lane-distributed sorted list
-//                      (value desc, index asc) and claims the winners with two atomics per (GT, anchor).
+//                      (value desc, index asc) and claims the winners with one 64-bit atomic per (GT, anchor).
+//                      A CTA of kTopkWarps warps shares one GT: each warp takes every kTopkWarps-th chunk of 32 cells
+//                      and keeps its own list; warp 0 merges the lists.
 //                      Zero-metric ties are exact: anchors 0..k-1 always enter the list (they are what a dense
 //                      stable top-k would pick among zeros), zero-metric anchors >= k can never be selected.
 //   tal_resolve_kernel one thread per (image, anchor): 0 claims -> background; 1 claim -> that GT; >1 claims ->
@@ -19,8 +21,7 @@
 
 namespace y3d {
 
-constexpr int kAssignWarps = 8;
-constexpr int kNoClaim = 0x7f7f7f7f;
+constexpr int kTopkWarps = 4;
 
 struct AssignCtx {
     // predictions
@@ -44,8 +45,8 @@ struct AssignCtx {
     const float *pd_kps;  // [B,A,24]
     const float *gt_kps;  // [B,M,24]
     // workspace
-    int *claim_cnt;    // [B,A] zero-initialised
-    int *claim_gt;     // [B,A] initialised to kNoClaim
+    unsigned long long *claim;  // [B,A] zero-initialised; += (1<<32 | m) per claim: count in the high word and,
+                                // when the count is 1, the claiming GT in the low word
     int *pos_align;    // [B,M] float bits, zero-initialised
     int *pos_ov;       // [B,M] float bits, zero-initialised
     int *tgi;          // [B,A] out of resolve: assigned GT or -1
@@ -152,20 +153,24 @@ __device__ __forceinline__ float assigned_norm(const AssignCtx &c, int b, int gi
     return dm::div(dm::mul(alignv, po), dm::add(pa, c.eps));
 }
 
+// up to two branches (one2many / one2one of v10DetectLoss) run in the same launches, selected by blockIdx.z
+struct AssignCtx2 {
+    AssignCtx c[2];
+};
+
 // host helpers --------------------------------------------------------------------------------------------------
 struct AssignWs {
-    size_t off_cnt, off_pa, off_po, off_cgt, off_tgi, off_align, off_norm, off_lab, total, zero_bytes;
+    size_t off_cnt, off_pa, off_po, off_tgi, off_align, off_norm, off_lab, total, zero_bytes;
 };
 inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline AssignWs assign_ws_layout(int B, int A, int M) {
     AssignWs w;
     size_t ba = a256(sizeof(int) * (size_t)B * A), bm = a256(sizeof(int) * (size_t)B * (M > 0 ? M : 1));
     w.off_cnt = 0;
-    w.off_pa = ba;
-    w.off_po = ba + bm;
-    w.zero_bytes = ba + 2 * bm;  // claim_cnt | pos_align | pos_ov are zero-filled with one memset
-    w.off_cgt = w.zero_bytes;
-    w.off_tgi = w.off_cgt + ba;
+    w.off_pa = 2 * ba;
+    w.off_po = 2 * ba + bm;
+    w.zero_bytes = 2 * ba + 2 * bm;  // claim | pos_align | pos_ov are zero-filled with one memset
+    w.off_tgi = w.zero_bytes;
     w.off_align = w.off_tgi + ba;
     w.off_norm = w.off_align + ba;
     w.off_lab = w.off_norm + ba;
@@ -174,15 +179,15 @@ inline AssignWs assign_ws_layout(int B, int A, int M) {
 }
 inline void assign_bind_ws(AssignCtx &c, void *ws, const AssignWs &w) {
     char *p = (char *)ws;
-    c.claim_cnt = (int *)(p + w.off_cnt);
+    c.claim = (unsigned long long *)(p + w.off_cnt);
     c.pos_align = (int *)(p + w.off_pa);
     c.pos_ov = (int *)(p + w.off_po);
-    c.claim_gt = (int *)(p + w.off_cgt);
     c.tgi = (int *)(p + w.off_tgi);
     c.alignv = (float *)(p + w.off_align);
 }
-// enqueue: init + top-k + resolve (defined in assign.cu).  After this c.tgi / c.alignv / c.pos_* are final.
-int assign_run_core(const AssignCtx &c, void *ws, const AssignWs &w, cudaStream_t s,
-                    cudaEvent_t after_topk = nullptr);
+// enqueue top-k + resolve for n (1 or 2) branches of identical B, A, M (defined in assign.cu).  The caller has
+// zero-filled [off_cnt, off_cnt + zero_bytes) of every branch's workspace.  After this c.tgi / c.alignv / c.pos_*
+// are final.
+int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk = nullptr);
 
 }  // namespace y3d

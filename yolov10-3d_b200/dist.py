@@ -38,13 +38,6 @@ def all_gather_detections(dets_local, group=None):
     return torch.cat([o[:s] for o, s in zip(out, sizes)])
 
 
-def finalize_items(partials, gains):
-    """partials float64[4] = sum (1-ciou)w, sum bce, sum dfl w, sum target_scores -> items float32[3] (loss.py:240-256)."""
-    tss = torch.clamp(partials[3], min=1.0)
-    g = torch.tensor([gains[0], gains[1], gains[2]], dtype=torch.float64, device=partials.device)
-    return (partials[:3] / tss * g).float()
-
-
 def reduce_partials(partials, group=None):
     """Sum the per-rank loss partials (any shape, float64) over the group, in place."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -52,14 +45,16 @@ def reduce_partials(partials, group=None):
     return partials
 
 
-def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_batch, group=None, prof_events=(None, None)):
+def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_batch, group=None, prof_events=None):
     """``v10DetectLoss`` (loss.py:727-737) on this rank's image shard, normalised over the GLOBAL batch.
 
-    Returns ``(total, items[6])`` identical on every rank and equal to the single-process result on the full batch."""
-    _, pm, _ = _loss.v8_loss_forward(feats_o2m, strides, nc, gt_local, 10, gains, normalise=False,
-                                     prof_events=prof_events[0])
-    _, po, _ = _loss.v8_loss_forward(feats_o2o, strides, nc, gt_local, 1, gains, normalise=False,
-                                     prof_events=prof_events[1])
-    parts = reduce_partials(torch.stack([pm, po]), group)
-    items = torch.cat([finalize_items(parts[0], gains), finalize_items(parts[1], gains)])
+    Returns ``(total, items[6])`` identical on every rank and equal to the single-process result on the full batch.
+    One rank: the kernels normalise directly.  Several ranks: un-normalised partials -> one all_reduce of 8 doubles
+    -> ``y3d_v8_loss_finalize``."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    items, parts, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains, normalise=not multi,
+                                             prof_events=prof_events)
+    if multi:
+        items = _loss.finalize_partials(reduce_partials(parts, group), gains)
+    items = items.view(2, 4)[:, :3].reshape(6)
     return items.sum() * global_batch, items

@@ -67,6 +67,44 @@ def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, 
     return items, partials, dbg
 
 
+def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(10, 1), normalise=True, debug=False,
+                     prof_events=None):
+    """Both branches of ``v10DetectLoss`` through ONE call of ``y3d_v10_loss_fwd`` (same launches for both).
+
+    Returns (items float32[8] = (box, cls, dfl, target_scores_sum) x (one2many, one2one) or ``None`` when not
+    normalising, partials float64[8], debug dict or None).  Nothing synchronises."""
+    lm, lo = Levels(feats_o2m, strides), Levels(feats_o2o, strides)
+    if lm.C != 4 * REG_MAX + nc or lo.C != lm.C:
+        raise ValueError(f"expected {4 * REG_MAX + nc} channels, got {lm.C} / {lo.C}")
+    if lm.hw != lo.hw or lm.B != lo.B:
+        raise ValueError("one2many and one2one heads must share batch size and level shapes")
+    dev = lm.device
+    gt = gt_packed.to(dev, torch.float32).contiguous()
+    M = int(gt.shape[1])
+    items = torch.empty(8, dtype=torch.float32, device=dev) if normalise else None
+    partials = torch.empty(8, dtype=torch.float64, device=dev)
+    dbg = None
+    if debug:
+        dbg = dict(fg_mask=torch.empty((2, lm.B, lm.A), dtype=torch.bool, device=dev),
+                   target_gt_idx=torch.empty((2, lm.B, lm.A), dtype=torch.int32, device=dev))
+    ws = workspace(_lib.workspace_bytes(_lib.STAGE_V8_LOSS, B=lm.B, A=lm.A, nc=nc, M=M, k=max(topk)), dev)
+    _lib.check(_lib.lib().y3d_v10_loss_fwd(
+        lm.c_ptr, lm.c_sB, lm.c_sC, lo.c_ptr, lo.c_sB, lo.c_sC, lm.c_hw, lm.c_stride, lm.nl, lm.B, nc, REG_MAX,
+        ptr(gt) if M > 0 else None, M, int(topk[0]), int(topk[1]), float(gains[0]), float(gains[1]), float(gains[2]),
+        int(normalise), ptr(items), ptr(partials), ptr(dbg["fg_mask"]) if debug else None,
+        ptr(dbg["target_gt_idx"]) if debug else None, prof_events, ptr(ws), ws.numel(), stream_ptr(dev)))
+    return items, partials, dbg
+
+
+def finalize_partials(partials, gains):
+    """All-reduced partials float64[4*n] -> items float32[4*n] (``y3d_v8_loss_finalize``)."""
+    n = partials.numel() // 4
+    items = torch.empty(4 * n, dtype=torch.float32, device=partials.device)
+    _lib.check(_lib.lib().y3d_v8_loss_finalize(ptr(partials), n, float(gains[0]), float(gains[1]), float(gains[2]),
+                                               ptr(items), stream_ptr(partials.device)))
+    return items
+
+
 class v8DetectionLoss:
     """loss.py:157-257.  ``model.args`` must provide ``box, cls, dfl``; ``model.model[-1]`` the head (``stride, nc,
     no, reg_max``)."""
@@ -107,8 +145,12 @@ class v10DetectLoss:
         self.one2one = v8DetectionLoss(model, tal_topk=1)
 
     def __call__(self, preds, batch):
-        one2many = preds["one2many"]
-        loss_one2many = self.one2many(one2many, batch)
-        one2one = preds["one2one"]
-        loss_one2one = self.one2one(one2one, batch)
-        return loss_one2many[0] + loss_one2one[0], torch.cat((loss_one2many[1], loss_one2one[1]))
+        one2many, one2one = preds["one2many"], preds["one2one"]
+        fm = one2many[1] if isinstance(one2many, tuple) else one2many  # loss.py:209
+        fo = one2one[1] if isinstance(one2one, tuple) else one2one
+        o = self.one2many
+        gt = o._targets(fm, batch)
+        items, _, _ = v10_loss_forward(fm, fo, [float(s) for s in o.stride], o.nc, gt,
+                                       (o.hyp.box, o.hyp.cls, o.hyp.dfl), topk=(o.topk, self.one2one.topk))
+        loss = items.view(2, 4)[:, :3].reshape(6)  # box_om cls_om dfl_om box_oo cls_oo dfl_oo (yolov10/train.py:10)
+        return loss.sum() * fm[0].shape[0], loss.detach()

@@ -10,7 +10,7 @@ batch 64 per GPU at 640x640 (A = 8400 anchors, 80 classes), synthetic GT up to 1
 
 One JSON line on stdout (rank 0).  ``value``: images/s with the head tensors resident in HBM.  ``e2e``: the same
 step through the public Python API (yolov10_3d_b200.v10DetectLoss) with pinned HOST head tensors, H2D copies and the
-D2H read of the loss items inside the timed region.  ``roofline``: the dominant kernel (loss_stream_kernel, the one
+D2H read of the loss items inside the timed region.  ``roofline``: the dominant kernel (head_stream_kernel, the one
 pass over the head tensor) timed with CUDA events recorded by the library on the launching stream.
 """
 import argparse
@@ -171,12 +171,12 @@ def main_cuda(args):
     strides = list(synth.STRIDES)
     K, W = args.steps, args.warmup
 
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     for row in ev:
         for e in row:
             e.record()  # forces creation of the underlying cudaEvent_t
     torch.cuda.synchronize()
-    ev_c = [(ctypes.c_void_p * 5)(*[e.cuda_event for e in row]) for row in ev]
+    ev_c = [(ctypes.c_void_p * 4)(*[e.cuda_event for e in row]) for row in ev]
 
     def step(i=None):
         pe = ev_c[i] if i is not None else None
@@ -201,9 +201,9 @@ def main_cuda(args):
         dist.barrier()
     ms_total = t_start.elapsed_time(t_stop)
     sampler.stop()
-    stage_ms = np.zeros(4)
+    stage_ms = np.zeros(3)
     for row in ev:
-        for s in range(4):
+        for s in range(3):
             stage_ms[s] += row[s].elapsed_time(row[s + 1])
     stage_ms /= K  # per launch: every kernel covers both branches
 
@@ -243,7 +243,7 @@ def main_cuda(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("loss_stream_tma_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("head_stream_kernel_dram_bytes_per_launch")
         h2d = sum(f.numel() * 4 for f in host_m + host_o)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -257,14 +257,14 @@ def main_cuda(args):
             "config": {"workload": WORKLOAD, "global_batch": B * world, "sharding": f"by image, {B}/GPU",
                        "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed",
                        "collective": "all_reduce of 8 float64 loss partials per step" if world > 1 else "none"},
-            "roofline": {"bound": "hbm", "kernel": "loss_stream_tma_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "head_stream_kernel<4>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(stage_ms[0]),
-                         "stage_ms_per_launch": {"memset+stream": float(stage_ms[0]), "gt_topk": float(stage_ms[1]),
-                                                 "resolve": float(stage_ms[2]), "fg_loss+finalize": float(stage_ms[3])}},
+                         "stage_ms_per_launch": {"head_stream": float(stage_ms[0]), "gt_topk": float(stage_ms[1]),
+                                                 "finish(resolve+fg_loss+reduce)": float(stage_ms[2])}},
             "e2e": {"value": B * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 24, "steps": Ke},
-            "gpu_launches": 4 * K,
+            "gpu_launches": 3 * K,
             "clocks": sampler.summary(),
             "loss_items": [float(v) for v in items.cpu()],
         }

@@ -111,9 +111,10 @@ int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A, int64_t s
  *  v10DetectLoss (loss.py:727-737) = this with topk=10 on one2many + topk=1 on one2one.
  *  dbg_fg_mask [B,A] u8 / dbg_target_gt_idx [B,A] i32 (optional, NULL in production): the assignment the fused
  *  path used, for parity tests.
- *  prof_events (optional HOST array of 5 cudaEvent_t, NULL in production): recorded on `stream` before the first
- *  operation and after each stage -- [0] start, [1] head streaming pass, [2] per-GT top-k, [3] conflict resolve,
- *  [4] foreground loss terms + final reduction -- so a benchmark can time each kernel inside the fused call. */
+ *  prof_events (optional HOST array of 4 cudaEvent_t, NULL in production): recorded on `stream` before the first
+ *  operation and after each kernel -- [0] start, [1] head streaming pass, [2] per-GT top-k + claims,
+ *  [3] conflict resolution + foreground loss terms + final reduction -- so a benchmark can time each kernel inside
+ *  the fused call. */
 int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
                     const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt, int M, int topk,
                     float gain_box, float gain_cls, float gain_dfl, int normalise, float *loss_items,

@@ -4,7 +4,7 @@
 namespace y3d {
 size_t topk_workspace_bytes(int B, int A, int nc, int D);
 size_t assign_workspace_bytes(int B, int A, int M);
-size_t loss_workspace_bytes(int B, int A, int M);
+size_t loss_workspace_bytes(int B, int A, int M, int k);
 }  // namespace y3d
 
 extern "C" const char *y3d_strerror(int rc) {
@@ -23,13 +23,12 @@ extern "C" const char *y3d_strerror(int rc) {
 extern "C" int y3d_abi_version(void) { return 1; }
 
 extern "C" size_t y3d_workspace_bytes(int stage, int B, int A, int nc, int M, int k, int D) {
-    (void)k;
     switch (stage) {
         case Y3D_STAGE_POSTPROCESS:
         case Y3D_STAGE_DECODE_TOPK: return y3d::topk_workspace_bytes(B, A, nc, D) + 256;
         case Y3D_STAGE_TAL_ASSIGN:
         case Y3D_STAGE_TAL_ASSIGN3D: return y3d::assign_workspace_bytes(B, A, M) + 256;
-        case Y3D_STAGE_V8_LOSS: return y3d::loss_workspace_bytes(B, A, M) + 256;
+        case Y3D_STAGE_V8_LOSS: return y3d::loss_workspace_bytes(B, A, M, k) + 256;
         default: return 0;
     }
 }

@@ -10,19 +10,21 @@
 namespace y3d {
 
 // ----------------------------------------------------------------------------------------------------------------
-// grid (B*M, 1, n_branch), block kTopkWarps*32: one CTA per (image, GT)
-__global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc) {
-    __shared__ int queue[kTopkWarps][64];
+// grid (ceil(B*M*wpg / kTopkWarps), 1, n_branch), block kTopkWarps*32.  wpg = warps per GT: 1 (rectangle walk) or
+// kTopkWarps (all-anchor scan; the warps' lists are merged through shared memory).
+__global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc, int wpg) {
     __shared__ float mrg_m[kTopkWarps][32];
     __shared__ int mrg_i[kTopkWarps][32];
     __shared__ int mrg_in[kTopkWarps][32];
     const AssignCtx &c = cc.c[blockIdx.z];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int b = blockIdx.x / c.M, m = blockIdx.x % c.M;
+    const long long gt_id = wpg == 1 ? (long long)blockIdx.x * kTopkWarps + wid : (long long)blockIdx.x;
+    const int wsub = wpg == 1 ? 0 : wid;  // this warp's share of the GT's chunks
+    if (gt_id >= (long long)c.B * c.M) return;
+    const int b = (int)(gt_id / c.M), m = (int)(gt_id % c.M);
     const GtRec g = load_gt(c, b, m);
-    if (!g.valid) return;  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104); whole CTA exits
+    if (!g.valid) return;  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104); all its warps exit
     const int k = c.k;
-    const unsigned lt_mask = (1u << lane) - 1u;
 
     // lane-distributed sorted top-k list; sentinel loses against any real entry (metrics are >= 0)
     float tk_m = -1.0f;
@@ -54,104 +56,106 @@ __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc
         }
     };
 
-    auto eval_and_process = [&](bool has, int a, bool force) {
-        // `force`: anchors 0..k-1 enter the list even when outside the GT (metric 0), see assign.cuh
-        float metric = 0.0f, ovl = 0.0f;
+    // two candidates per lane: loads of both first, then the arithmetic, then the list updates.
+    // `force`: anchors 0..k-1 enter the list even when outside the GT (metric 0), see assign.cuh
+    auto eval2 = [&](bool h0, int a0, int in0, bool h1, int a1, int in1, bool force) {
+        PairRaw r0{}, r1{};
+        if (h0 && in0) r0 = pair_load(c, b, a0, g.label);
+        if (h1 && in1) r1 = pair_load(c, b, a1, g.label);
+        float m0 = 0.0f, m1 = 0.0f, ov;
+        if (h0 && in0) pair_eval(c, b, m, g, a0, r0, m0, ov);
+        if (h1 && in1) pair_eval(c, b, m, g, a1, r1, m1, ov);
+        process(h0 && (force || m0 > 0.0f), m0, a0, in0);
+        process(h1 && (force || m1 > 0.0f), m1, a1, in1);
+    };
+
+    // phase 0 (first warp of the GT): the first k anchors
+    if (wsub == 0) {
+        const bool has = lane < k && lane < c.A;
         int cin = 0;
         if (has) {
             float ax, ay, st;
-            anchor_px(c, a, ax, ay, st);
-            bool ing = dm::in_gt(ax, ay, g.box);
-            cin = c.constrain ? (int)ing : 1;
-            if (cin) pair_eval(c, b, m, g, a, metric, ovl);
+            anchor_px(c, lane, ax, ay, st);
+            cin = c.constrain ? (int)dm::in_gt(ax, ay, g.box) : 1;
         }
-        bool go = has && (force || metric > 0.0f);
-        process(go, metric, a, cin);
-    };
+        eval2(has, lane, cin, false, 0, 0, true);
+    }
 
-    // phase 0 (warp 0): the first k anchors
-    if (wid == 0) eval_and_process(lane < k && lane < c.A, lane, true);
-
-    // phase 1: candidates (anchors >= k inside the GT) -> warp queue -> evaluated 32 at a time
-    int qn = 0;
-    auto push = [&](bool cand, int a) {
-        unsigned bal = __ballot_sync(0xffffffffu, cand);
-        if (bal) {
-            if (cand) queue[wid][qn + __popc(bal & lt_mask)] = a;
-            qn += __popc(bal);
-            __syncwarp();
-            if (qn >= 32) {
-                int a2 = queue[wid][lane];
-                int rest = qn - 32;
-                int carry = lane < rest ? queue[wid][32 + lane] : 0;
-                __syncwarp();
-                if (lane < rest) queue[wid][lane] = carry;
-                __syncwarp();
-                qn = rest;
-                eval_and_process(true, a2, false);
-            }
-        }
-    };
-
+    // phase 1: candidates = anchors >= k inside the GT
     if (c.use_grid && c.constrain) {
-        for (int l = 0; l < c.t.nl; ++l) {
-            const float st = c.t.stride[l];
-            const int w = c.t.w[l], h = c.t.h[l];
-            // conservative cell range: the exact fp32 in-GT test below decides (tal.py:218-235)
-            float fx0 = fmaxf(floorf(g.box.x / st - 0.5f) - 1.0f, 0.0f);
-            float fy0 = fmaxf(floorf(g.box.y / st - 0.5f) - 1.0f, 0.0f);
-            float fx1 = fminf(ceilf(g.box.z / st - 0.5f) + 1.0f, (float)(w - 1));
-            float fy1 = fminf(ceilf(g.box.w / st - 0.5f) + 1.0f, (float)(h - 1));
-            if (!(fx0 <= fx1) || !(fy0 <= fy1)) continue;
-            const int c0 = (int)fx0, r0 = (int)fy0;
-            const int ncols = (int)fx1 - c0 + 1, nrows = (int)fy1 - r0 + 1;
-            const int cells = ncols * nrows;
-            for (int i0 = wid * 32; i0 < cells; i0 += kTopkWarps * 32) {
-                int i = i0 + lane;
-                bool cand = false;
-                int a = 0;
-                if (i < cells) {
-                    int r = i / ncols, cc_ = i - r * ncols;
-                    a = c.t.start[l] + (r0 + r) * w + c0 + cc_;
-                    float ax = dm::mul((float)(c0 + cc_) + 0.5f, st), ay = dm::mul((float)(r0 + r) + 0.5f, st);
-                    cand = a >= k && dm::in_gt(ax, ay, g.box);
+        // conservative cell rectangle per level (one cell of margin; the exact fp32 in-GT test decides, tal.py:218-235)
+        int c0[Y3D_MAX_LEVELS], r0[Y3D_MAX_LEVELS], ncols[Y3D_MAX_LEVELS], cum[Y3D_MAX_LEVELS + 1];
+        cum[0] = 0;
+#pragma unroll
+        for (int l = 0; l < Y3D_MAX_LEVELS; ++l) {
+            int cells = 0;
+            c0[l] = r0[l] = 0;
+            ncols[l] = 1;
+            if (l < c.t.nl) {
+                const float st = c.t.stride[l];
+                // exact bounds are floor(.)+1 and ceil(.)-1: one cell of slack absorbs the rounding of x / st - 0.5
+                const float fx0 = fmaxf(floorf(g.box.x / st - 0.5f), 0.0f);
+                const float fy0 = fmaxf(floorf(g.box.y / st - 0.5f), 0.0f);
+                const float fx1 = fminf(ceilf(g.box.z / st - 0.5f), (float)(c.t.w[l] - 1));
+                const float fy1 = fminf(ceilf(g.box.w / st - 0.5f), (float)(c.t.h[l] - 1));
+                if (fx0 <= fx1 && fy0 <= fy1) {
+                    c0[l] = (int)fx0; r0[l] = (int)fy0;
+                    ncols[l] = (int)fx1 - c0[l] + 1;
+                    cells = ncols[l] * ((int)fy1 - r0[l] + 1);
                 }
-                push(cand, a);
             }
+            cum[l + 1] = cum[l] + cells;
+        }
+        const int total = cum[Y3D_MAX_LEVELS];
+        auto locate = [&](int i, int &a) -> bool {
+            if (i >= total) return false;
+            int l = 0;
+#pragma unroll
+            for (int q = 1; q < Y3D_MAX_LEVELS; ++q) l += (i >= cum[q]) ? 1 : 0;
+            const int j = i - cum[l];
+            const int r = j / ncols[l], cc_ = j - r * ncols[l];
+            const int col = c0[l] + cc_, row = r0[l] + r;
+            a = c.t.start[l] + row * c.t.w[l] + col;
+            const float st = c.t.stride[l];
+            const float ax = dm::mul((float)col + 0.5f, st), ay = dm::mul((float)row + 0.5f, st);
+            return a >= k && dm::in_gt(ax, ay, g.box);
+        };
+        for (int i0 = wsub * 64; i0 < total; i0 += wpg * 64) {
+            int a0 = 0, a1 = 0;
+            const bool h0 = locate(i0 + lane, a0), h1 = locate(i0 + 32 + lane, a1);
+            if (__ballot_sync(0xffffffffu, h0 || h1)) eval2(h0, a0, 1, h1, a1, 1, false);
         }
     } else {
-        for (int a0 = wid * 32; a0 < c.A; a0 += kTopkWarps * 32) {
-            int a = a0 + lane;
-            bool cand = false;
-            if (a < c.A && a >= k) {
-                if (c.constrain) {
-                    float ax, ay, st;
-                    anchor_px(c, a, ax, ay, st);
-                    cand = dm::in_gt(ax, ay, g.box);
-                } else {
-                    cand = true;
-                }
+        for (int i0 = wsub * 64; i0 < c.A; i0 += wpg * 64) {
+            const int a0 = i0 + lane, a1 = i0 + 32 + lane;
+            bool h0 = a0 < c.A && a0 >= k, h1 = a1 < c.A && a1 >= k;
+            if (c.constrain) {
+                float ax, ay, st;
+                if (h0) { anchor_px(c, a0, ax, ay, st); h0 = dm::in_gt(ax, ay, g.box); }
+                if (h1) { anchor_px(c, a1, ax, ay, st); h1 = dm::in_gt(ax, ay, g.box); }
             }
-            push(cand, a);
+            if (__ballot_sync(0xffffffffu, h0 || h1)) eval2(h0, a0, 1, h1, a1, 1, false);
         }
     }
-    if (qn > 0) {
-        int a2 = lane < qn ? queue[wid][lane] : 0;
-        eval_and_process(lane < qn, a2, false);
-    }
 
-    // merge the per-warp lists into warp 0's
-    mrg_m[wid][lane] = tk_m; mrg_i[wid][lane] = tk_i; mrg_in[wid][lane] = tk_in;
-    __syncthreads();
-    if (wid != 0) return;
-#pragma unroll
-    for (int w = 1; w < kTopkWarps; ++w) {
-        int ci = mrg_i[w][lane];
-        process(lane < k && ci != 0x7fffffff, mrg_m[w][lane], ci, mrg_in[w][lane]);
+    if (wpg > 1) {  // merge the per-warp lists into the first warp's
+        mrg_m[wid][lane] = tk_m; mrg_i[wid][lane] = tk_i; mrg_in[wid][lane] = tk_in;
+        __syncthreads();
+        if (wid != 0) return;
+        for (int w = 1; w < wpg; ++w) {
+            int ci = mrg_i[w][lane];
+            process(lane < k && ci != 0x7fffffff, mrg_m[w][lane], ci, mrg_in[w][lane]);
+        }
     }
     // claims: mask_pos = mask_topk * mask_in_gts * mask_gt (tal.py:104)
-    if (lane < k && tk_i != 0x7fffffff && tk_in)
-        atomicAdd(c.claim + (long long)b * c.A + tk_i, (1ull << 32) | (unsigned long long)m);
+    if (lane < k && tk_i != 0x7fffffff && tk_in) {
+        const unsigned long long old =
+            atomicAdd(c.claim + (long long)b * c.A + tk_i, (1ull << 32) | (unsigned long long)m);
+        if (c.list_a && (old >> 32) == 0) {  // first claim of this anchor: publish it
+            const int pos = atomicAdd(c.list_count + b, 1);
+            if (pos < c.list_cap) c.list_a[(long long)b * c.list_cap + pos] = tk_i;
+        }
+    }
 }
 
 // grid (ceil(A/256), B, n_branch); dynamic smem: M GtRec
@@ -199,11 +203,20 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
     c.alignv[o] = alignv;
 }
 
+int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s) {
+    const AssignCtx &c = cc.c[0];
+    const int wpg = (c.use_grid && c.constrain) ? 1 : kTopkWarps;
+    const long long warps = (long long)c.B * c.M * wpg;
+    dim3 gt_grid((unsigned)((warps + kTopkWarps - 1) / kTopkWarps), 1, n);
+    tal_topk_kernel<<<gt_grid, kTopkWarps * 32, 0, s>>>(cc, wpg);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
+}
+
 int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk) {
     const AssignCtx &c = cc.c[0];
-    dim3 gt_grid((unsigned)((long long)c.B * c.M), 1, n);
-    tal_topk_kernel<<<gt_grid, kTopkWarps * 32, 0, s>>>(cc);
-    Y3D_CHECK_LAUNCH();
+    int rc0 = assign_run_topk(cc, n, s);
+    if (rc0) return rc0;
     if (after_topk) cudaEventRecord(after_topk, s);
     size_t smem = sizeof(GtRec) * (size_t)c.M;
     if (smem > 48 * 1024) {

@@ -3,12 +3,11 @@
 // Restates TaskAlignedAssigner / TaskAlignedAssigner3d (reference ultralytics/utils/tal.py:44-264, 391-700) without
 // ever materialising the reference's dense [B, M, A] tensors:
 //
-//   tal_topk_kernel    one warp per (image, GT): walks the anchors inside the GT's rectangle (or all A anchors when
-//                      no grid is promised), evaluates score^alpha * CIoU^beta (* sim^gamma) for the in-GT anchors
-//                      32 at a time through a warp queue, keeps the per-GT top-k as a lane-distributed sorted list
+//   tal_topk_kernel    one warp per (image, GT) -- or kTopkWarps warps per GT when every anchor is a candidate
+//                      (no grid promised / constrain_anchors off): walks the cells of the GT's rectangle 64 at a time
+//                      (loads of both halves issued before any arithmetic), evaluates score^alpha * CIoU^beta
+//                      (* sim^gamma) for the in-GT anchors, keeps the per-GT top-k as a lane-distributed sorted list
 //                      (value desc, index asc) and claims the winners with one 64-bit atomic per (GT, anchor).
-//                      A CTA of kTopkWarps warps shares one GT: each warp takes every kTopkWarps-th chunk of 32 cells
-//                      and keeps its own list; warp 0 merges the lists.
 //                      Zero-metric ties are exact: anchors 0..k-1 always enter the list (they are what a dense
 //                      stable top-k would pick among zeros), zero-metric anchors >= k can never be selected.
 //   tal_resolve_kernel one thread per (image, anchor): 0 claims -> background; 1 claim -> that GT; >1 claims ->
@@ -21,7 +20,7 @@
 
 namespace y3d {
 
-constexpr int kTopkWarps = 4;
+constexpr int kTopkWarps = 4;  // warps (= GTs) per CTA of tal_topk_kernel
 
 struct AssignCtx {
     // predictions
@@ -29,8 +28,10 @@ struct AssignCtx {
     const float *pd_scores;      // mode 0
     long long ssB, ssA, ssC;     // mode 0 element strides
     int cls_ch0;                 // mode 1: first class channel in the head tensor (4*reg_max)
-    const float *pd_bboxes;      // [B,A,4]; px when box_grid_units == 0, grid units (multiplied by stride here) otherwise
+    const float *pd_bboxes;      // [B,A,4] (box_soa == 0) or [B,4,A] (box_soa == 1); px when box_grid_units == 0,
+                                 // grid units (multiplied by stride here) otherwise
     int box_grid_units;
+    int box_soa;
     const float *anc;            // [A,2] px, or nullptr when use_grid
     LevelTable t;                // geometry (use_grid) and head pointers (score_mode 1)
     int use_grid;
@@ -51,6 +52,11 @@ struct AssignCtx {
     int *pos_ov;       // [B,M] float bits, zero-initialised
     int *tgi;          // [B,A] out of resolve: assigned GT or -1
     float *alignv;     // [B,A] out of resolve: align_metric of the assigned pair
+    // optional (fused loss path): the first GT to claim an anchor appends it to the image's list, so that the
+    // finishing kernel touches only claimed anchors.  list_count [B] zero-initialised, list_a [B, list_cap].
+    int *list_count;
+    int *list_a;
+    int list_cap;
 };
 
 struct GtRec {
@@ -90,15 +96,37 @@ __device__ __forceinline__ void anchor_px(const AssignCtx &c, int a, float &ax, 
     }
 }
 
-__device__ __forceinline__ float pair_score(const AssignCtx &c, int b, int a, int label) {
-    if (c.score_mode == 0) return c.pd_scores[b * c.ssB + a * c.ssA + (long long)label * c.ssC];
-    int l = level_of(c.t, a);
-    const float *p = c.t.ptr[l] + (long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + label) * c.t.sC[l] + (a - c.t.start[l]);
-    return 1.0f / (1.0f + expf(-*p));  // pred_scores.detach().sigmoid() loss.py:232
+// The raw loads of one (GT, anchor) pair are split from the arithmetic so that callers can issue the loads of
+// several pairs before evaluating any of them (memory-level parallelism: these are latency-bound gathers).
+struct PairRaw {
+    float4 box;  // as stored (grid units when c.box_grid_units)
+    float s;     // probability (score_mode 0) or logit (score_mode 1)
+};
+
+__device__ __forceinline__ PairRaw pair_load(const AssignCtx &c, int b, int a, int label) {
+    PairRaw r;
+    if (c.score_mode == 0) {
+        r.s = c.pd_scores[b * c.ssB + a * c.ssA + (long long)label * c.ssC];
+    } else {
+        int l = level_of(c.t, a);
+        r.s = c.t.ptr[l][(long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + label) * c.t.sC[l] + (a - c.t.start[l])];
+    }
+    if (c.box_soa) {
+        const float *p = c.pd_bboxes + (long long)b * 4 * c.A + a;
+        r.box = make_float4(p[0], p[c.A], p[2 * (long long)c.A], p[3 * (long long)c.A]);
+    } else {
+        r.box = *reinterpret_cast<const float4 *>(c.pd_bboxes + ((long long)b * c.A + a) * 4);
+    }
+    return r;
 }
 
-__device__ __forceinline__ float4 pair_box(const AssignCtx &c, int b, int a) {
-    float4 p = *reinterpret_cast<const float4 *>(c.pd_bboxes + ((long long)b * c.A + a) * 4);
+__device__ __forceinline__ float pair_score(const AssignCtx &c, const PairRaw &r) {
+    if (c.score_mode == 0) return r.s;
+    return 1.0f / (1.0f + expf(-r.s));  // pred_scores.detach().sigmoid() loss.py:232
+}
+
+__device__ __forceinline__ float4 pair_box(const AssignCtx &c, const PairRaw &r, int a) {
+    float4 p = r.box;
     if (c.box_grid_units) {  // pred_bboxes.detach() * stride_tensor loss.py:233
         float st = c.t.stride[level_of(c.t, a)];
         p.x = dm::mul(p.x, st); p.y = dm::mul(p.y, st); p.z = dm::mul(p.z, st); p.w = dm::mul(p.w, st);
@@ -108,13 +136,13 @@ __device__ __forceinline__ float4 pair_box(const AssignCtx &c, int b, int a) {
 
 // get_box_metrics (tal.py:108-127) / get_box_kp_metrics / get_keypoint_metrics (tal.py:553-603) for one in-mask pair.
 // ovl is what the reference calls `overlaps` downstream: CIoU for the 2D assigner, the 3D similarity when use_3d.
-__device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, float &metric,
-                                          float &ovl) {
-    float s = pair_score(c, b, a, g.label);
+__device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, const PairRaw &raw,
+                                          float &metric, float &ovl) {
+    float s = pair_score(c, raw);
     metric = dm::pow_(s, c.alpha);
     ovl = 0.0f;
     if (c.use_2d) {
-        float o = dm::ciou(g.box, pair_box(c, b, a), g.at1);
+        float o = dm::ciou(g.box, pair_box(c, raw, a), g.at1);
         o = o < 0.0f ? 0.0f : o;  // clamp_(0) tal.py:131
         metric = dm::mul(metric, dm::pow_(o, c.beta));
         ovl = o;
@@ -140,6 +168,11 @@ __device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, cons
         metric = dm::mul(metric, dm::pow_(sim, c.gamma));
         ovl = sim;  // tal.py:602-603
     }
+}
+
+__device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, float &metric,
+                                          float &ovl) {
+    pair_eval(c, b, m, g, a, pair_load(c, b, a, g.label), metric, ovl);
 }
 
 __device__ __forceinline__ bool better(float am, int ai, float bm, int bi) {
@@ -189,5 +222,7 @@ inline void assign_bind_ws(AssignCtx &c, void *ws, const AssignWs &w) {
 // zero-filled [off_cnt, off_cnt + zero_bytes) of every branch's workspace.  After this c.tgi / c.alignv / c.pos_*
 // are final.
 int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk = nullptr);
+// top-k + claims only (the fused loss path finishes with its own kernel)
+int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s);
 
 }  // namespace y3d

@@ -46,7 +46,7 @@ def pack_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device, extra=Non
 def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, debug=False, prof_events=None):
     """One branch through ``y3d_v8_loss_fwd``.  Returns (items[4] = box, cls, dfl, target_scores_sum  -- or ``None``
     when not normalising --, partials float64[4], debug dict or None).  Nothing synchronises.
-    ``prof_events``: optional ctypes array of 6 cudaEvent_t handles (see include/y3d.h), for benchmarks."""
+    ``prof_events``: optional ctypes array of 4 cudaEvent_t handles (see include/y3d.h), for benchmarks."""
     lv = Levels(feats, strides)
     if lv.C != 4 * REG_MAX + nc:
         raise ValueError(f"expected {4 * REG_MAX + nc} channels, got {lv.C}")

@@ -10,12 +10,34 @@
 namespace y3d {
 
 // ----------------------------------------------------------------------------------------------------------------
+// Top-k entries are 64-bit keys: metric bits (>= 0, so integer order == float order) | 0x7fffffff - anchor | in-GT bit.
+// A larger key is a better entry (value desc, index asc); 0 is the empty slot.
+__device__ __forceinline__ unsigned long long tk_key(float metric, int a, int in) {
+    return ((unsigned long long)__float_as_uint(metric) << 32) | ((unsigned long long)(0x7fffffff - a) << 1) |
+           (unsigned long long)(in & 1);
+}
+__device__ __forceinline__ int tk_anchor(unsigned long long key) { return 0x7fffffff - (int)((key & 0xffffffffull) >> 1); }
+
 // grid (ceil(B*M*wpg / kTopkWarps), 1, n_branch), block kTopkWarps*32.  wpg = warps per GT: 1 (rectangle walk) or
 // kTopkWarps (all-anchor scan; the warps' lists are merged through shared memory).
+//
+// The kernel is a chain of latency-bound gathers, so it is organised around few, fat memory round trips, and its
+// code is kept small (one call site per stage, heavy arithmetic out of line) because hundreds of divergent warps
+// share the instruction cache:
+//  * at GT start the class-score rows of the GT's rectangles are pulled into L2 (prefetch, fire-and-forget);
+//  * stage 1 walks the candidate cells 128 at a time (4 per lane): exact in-GT test, then the score and box gathers of
+//    all four cells are issued together.  sb = score^alpha bounds the metric from above (CIoU^beta, sim^gamma <= 1): a
+//    candidate whose sb is below the current k-th metric can never enter the list and is dropped before any box
+//    arithmetic.  Survivors are compacted into a per-warp queue;
+//  * stage 2 pops 32 at a time (full lanes, no loads): CIoU / keypoint similarity and the sorted-list update.
+constexpr int kTopkU = 4;             // cells per lane and round trip
+constexpr int kTopkQ = 32 * kTopkU + 32;  // queue slots per warp
+
 __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc, int wpg) {
-    __shared__ float mrg_m[kTopkWarps][32];
-    __shared__ int mrg_i[kTopkWarps][32];
-    __shared__ int mrg_in[kTopkWarps][32];
+    __shared__ int q_a[kTopkWarps][kTopkQ];
+    __shared__ float q_s[kTopkWarps][kTopkQ];
+    __shared__ float4 q_b[kTopkWarps][kTopkQ];
+    __shared__ unsigned long long mrg[kTopkWarps][32];
     const AssignCtx &c = cc.c[blockIdx.z];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long gt_id = wpg == 1 ? (long long)blockIdx.x * kTopkWarps + wid : (long long)blockIdx.x;
@@ -25,135 +47,223 @@ __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc
     const GtRec g = load_gt(c, b, m);
     if (!g.valid) return;  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104); all its warps exit
     const int k = c.k;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool prune = c.beta >= 0.0f && c.gamma >= 0.0f;  // the upper bound needs non-negative exponents
+    const bool rect = c.use_grid && c.constrain;
 
-    // lane-distributed sorted top-k list; sentinel loses against any real entry (metrics are >= 0)
-    float tk_m = -1.0f;
-    int tk_i = 0x7fffffff;
-    int tk_in = 0;
-
-    auto process = [&](bool has, float cm, int ci, int cin) {
-        for (;;) {
-            float kth_m = __shfl_sync(0xffffffffu, tk_m, k - 1);
-            int kth_i = __shfl_sync(0xffffffffu, tk_i, k - 1);
-            bool qual = has && better(cm, ci, kth_m, kth_i);
-            unsigned mk = __ballot_sync(0xffffffffu, qual);
-            if (!mk) break;
-            int src = __ffs(mk) - 1;
-            float xm = __shfl_sync(0xffffffffu, cm, src);
-            int xi = __shfl_sync(0xffffffffu, ci, src);
-            int xin = __shfl_sync(0xffffffffu, cin, src);
-            bool hb = better(tk_m, tk_i, xm, xi);
-            int pos = __popc(__ballot_sync(0xffffffffu, hb && lane < k));
-            float um = __shfl_up_sync(0xffffffffu, tk_m, 1);
-            int ui = __shfl_up_sync(0xffffffffu, tk_i, 1);
-            int uin = __shfl_up_sync(0xffffffffu, tk_in, 1);
-            if (lane == pos) {
-                tk_m = xm; tk_i = xi; tk_in = xin;
-            } else if (lane > pos) {
-                tk_m = um; tk_i = ui; tk_in = uin;
-            }
-            if (lane == src) has = false;
-        }
+    // conservative cell rectangle of level l (exact bounds are floor(.)+1 and ceil(.)-1: one cell of slack absorbs the
+    // rounding of x / st - 0.5); the exact fp32 in-GT test decides (tal.py:218-235)
+    int c0 = 0, r0 = 0, ncols = 1, nrows = 0;
+    auto rect_of = [&](int l) -> bool {
+        const float st = c.t.stride[l];
+        const float fx0 = fmaxf(floorf(g.box.x / st - 0.5f), 0.0f);
+        const float fy0 = fmaxf(floorf(g.box.y / st - 0.5f), 0.0f);
+        const float fx1 = fminf(ceilf(g.box.z / st - 0.5f), (float)(c.t.w[l] - 1));
+        const float fy1 = fminf(ceilf(g.box.w / st - 0.5f), (float)(c.t.h[l] - 1));
+        if (!(fx0 <= fx1 && fy0 <= fy1)) return false;
+        c0 = (int)fx0; r0 = (int)fy0;
+        ncols = (int)fx1 - c0 + 1; nrows = (int)fy1 - r0 + 1;
+        return true;
     };
-
-    // two candidates per lane: loads of both first, then the arithmetic, then the list updates.
-    // `force`: anchors 0..k-1 enter the list even when outside the GT (metric 0), see assign.cuh
-    auto eval2 = [&](bool h0, int a0, int in0, bool h1, int a1, int in1, bool force) {
-        PairRaw r0{}, r1{};
-        if (h0 && in0) r0 = pair_load(c, b, a0, g.label);
-        if (h1 && in1) r1 = pair_load(c, b, a1, g.label);
-        float m0 = 0.0f, m1 = 0.0f, ov;
-        if (h0 && in0) pair_eval(c, b, m, g, a0, r0, m0, ov);
-        if (h1 && in1) pair_eval(c, b, m, g, a1, r1, m1, ov);
-        process(h0 && (force || m0 > 0.0f), m0, a0, in0);
-        process(h1 && (force || m1 > 0.0f), m1, a1, in1);
-    };
-
-    // phase 0 (first warp of the GT): the first k anchors
-    if (wsub == 0) {
-        const bool has = lane < k && lane < c.A;
-        int cin = 0;
-        if (has) {
-            float ax, ay, st;
-            anchor_px(c, lane, ax, ay, st);
-            cin = c.constrain ? (int)dm::in_gt(ax, ay, g.box) : 1;
+    if (rect && c.score_mode == 1 && wsub == 0) {  // pull the label-channel rows of every rectangle into L2
+#pragma unroll 1
+        for (int l = 0; l < c.t.nl; ++l) {
+            if (!rect_of(l)) continue;
+            const float *row0 = c.t.ptr[l] + (long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + g.label) * c.t.sC[l];
+            for (int j = lane; j < 2 * nrows; j += 32)  // first and last cell of each row segment
+                prefetch_l2(row0 + (long long)(r0 + (j >> 1)) * c.t.w[l] + c0 + ((j & 1) ? ncols - 1 : 0));
         }
-        eval2(has, lane, cin, false, 0, 0, true);
     }
 
-    // phase 1: candidates = anchors >= k inside the GT
-    if (c.use_grid && c.constrain) {
-        // conservative cell rectangle per level (one cell of margin; the exact fp32 in-GT test decides, tal.py:218-235)
-        int c0[Y3D_MAX_LEVELS], r0[Y3D_MAX_LEVELS], ncols[Y3D_MAX_LEVELS], cum[Y3D_MAX_LEVELS + 1];
-        cum[0] = 0;
+    unsigned long long tk = 0ull;   // lane-distributed sorted list (descending), lanes >= k unused
+    unsigned long long thr = 0ull;  // key of the k-th entry (warp-uniform)
+
+    auto process = [&](unsigned long long ck) {  // ck: this lane's candidate key, 0 = none
+        for (;;) {
+            const unsigned mk = __ballot_sync(0xffffffffu, ck > thr);
+            if (!mk) break;
+            const int src = __ffs(mk) - 1;
+            const unsigned long long x = __shfl_sync(0xffffffffu, ck, src);
+            const int pos = __popc(__ballot_sync(0xffffffffu, tk > x && lane < k));
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, tk, 1);
+            if (lane == pos) tk = x;
+            else if (lane > pos) tk = up;
+            thr = __shfl_sync(0xffffffffu, tk, k - 1);
+            if (lane == src) ck = 0ull;
+        }
+    };
+
+    // phase 0 (first warp of the GT): the first k anchors enter the list even when outside the GT or at metric 0
+    // (they are what a dense stable top-k picks among zeros), see assign.cuh
+    unsigned long long key0 = 0ull;
+    if (wsub == 0 && lane < k && lane < c.A) {
+        float ax, ay, st;
+        anchor_px(c, lane, ax, ay, st);
+        const int cin = c.constrain ? (int)dm::in_gt(ax, ay, g.box) : 1;
+        float metric = 0.0f, ovl;
+        if (cin) pair_eval(c, b, m, g, lane, metric, ovl);
+        key0 = tk_key(metric, lane, cin);
+    }
+
+    // phase 1: candidates = anchors >= k inside the GT.  One loop body serves both walks: `more` trips, then the flush.
+    int qn = 0;
+    int l = -1, i0 = 0, cells = 0, w = 1, start = 0;
+    float st = 1.0f, inv = 1.0f;
+    if (!rect) { cells = c.A; i0 = wsub * (32 * kTopkU); l = 0; }
+    bool done = false;
+    for (bool first = true;; first = false) {
+        unsigned long long key = 0ull;
+        if (first) {
+            key = key0;
+        } else if (qn < 32 && !done) {
+            // ---- advance to the next chunk of candidate cells (only while the queue cannot fill a warp)
+            bool more = true;
+            if (rect) {
+                while (l < 0 || i0 >= cells) {
+                    if (++l >= c.t.nl) { more = false; break; }
+                    cells = 0;
+                    if (!rect_of(l)) continue;
+                    cells = ncols * nrows;
+                    st = c.t.stride[l]; w = c.t.w[l]; start = c.t.start[l];
+                    inv = __frcp_rn((float)ncols);
+                    i0 = wsub * (32 * kTopkU);
+                }
+            } else {
+                more = i0 < cells;
+            }
+            if (!more) done = true;
+            if (more) {
+                // ---- stage 1: locate, in-GT test, one round trip for the gathers of up to kTopkU candidates per lane
+                bool h[kTopkU];
+                int a[kTopkU];
+                bool any = false;
 #pragma unroll
-        for (int l = 0; l < Y3D_MAX_LEVELS; ++l) {
-            int cells = 0;
-            c0[l] = r0[l] = 0;
-            ncols[l] = 1;
-            if (l < c.t.nl) {
-                const float st = c.t.stride[l];
-                // exact bounds are floor(.)+1 and ceil(.)-1: one cell of slack absorbs the rounding of x / st - 0.5
-                const float fx0 = fmaxf(floorf(g.box.x / st - 0.5f), 0.0f);
-                const float fy0 = fmaxf(floorf(g.box.y / st - 0.5f), 0.0f);
-                const float fx1 = fminf(ceilf(g.box.z / st - 0.5f), (float)(c.t.w[l] - 1));
-                const float fy1 = fminf(ceilf(g.box.w / st - 0.5f), (float)(c.t.h[l] - 1));
-                if (fx0 <= fx1 && fy0 <= fy1) {
-                    c0[l] = (int)fx0; r0[l] = (int)fy0;
-                    ncols[l] = (int)fx1 - c0[l] + 1;
-                    cells = ncols[l] * ((int)fy1 - r0[l] + 1);
+                for (int u = 0; u < kTopkU; ++u) {
+                    const int j = i0 + u * 32 + lane;
+                    h[u] = false;
+                    a[u] = 0;
+                    if (j < cells) {
+                        float ax, ay, s_;
+                        if (rect) {
+                            int r = (int)(((float)j + 0.5f) * inv);  // j / ncols; fixed up if the product rounded across
+                            int cc_ = j - r * ncols;
+                            if (cc_ < 0) { --r; cc_ += ncols; }
+                            else if (cc_ >= ncols) { ++r; cc_ -= ncols; }
+                            const int col = c0 + cc_, row = r0 + r;
+                            a[u] = start + row * w + col;
+                            ax = dm::mul((float)col + 0.5f, st); ay = dm::mul((float)row + 0.5f, st);
+                            h[u] = a[u] >= k && dm::in_gt(ax, ay, g.box);
+                        } else {
+                            a[u] = j;
+                            h[u] = j >= k;
+                            if (h[u] && c.constrain) {
+                                anchor_px(c, j, ax, ay, s_);
+                                h[u] = dm::in_gt(ax, ay, g.box);
+                            }
+                        }
+                    }
+                    any |= h[u];
+                }
+                i0 += wpg * (32 * kTopkU);
+                if (__ballot_sync(0xffffffffu, any)) {
+                    float x[kTopkU];
+                    float4 bx[kTopkU];
+#pragma unroll
+                    for (int u = 0; u < kTopkU; ++u) {
+                        x[u] = 0.f;
+                        bx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (h[u]) {
+                            x[u] = pair_load_score(c, b, a[u], g.label);
+                            bx[u] = pair_load_box(c, b, a[u]).box;
+                        }
+                    }
+                    const unsigned tm = prune ? (unsigned)(thr >> 32) : 0u;
+#pragma unroll
+                    for (int u = 0; u < kTopkU; ++u) {
+                        const float sb = h[u] ? dm::pow_(pair_score(c, x[u]), c.alpha) : 0.f;
+                        const bool pass = h[u] && sb > 0.0f && __float_as_uint(sb) >= tm;
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass) {
+                            const int pos = qn + __popc(bal & lt_mask);
+                            q_a[wid][pos] = a[u];
+                            q_s[wid][pos] = sb;
+                            q_b[wid][pos] = bx[u];
+                        }
+                        qn += __popc(bal);
+                    }
+                    __syncwarp();
                 }
             }
-            cum[l + 1] = cum[l] + cells;
-        }
-        const int total = cum[Y3D_MAX_LEVELS];
-        auto locate = [&](int i, int &a) -> bool {
-            if (i >= total) return false;
-            int l = 0;
-#pragma unroll
-            for (int q = 1; q < Y3D_MAX_LEVELS; ++q) l += (i >= cum[q]) ? 1 : 0;
-            const int j = i - cum[l];
-            const int r = j / ncols[l], cc_ = j - r * ncols[l];
-            const int col = c0[l] + cc_, row = r0[l] + r;
-            a = c.t.start[l] + row * c.t.w[l] + col;
-            const float st = c.t.stride[l];
-            const float ax = dm::mul((float)col + 0.5f, st), ay = dm::mul((float)row + 0.5f, st);
-            return a >= k && dm::in_gt(ax, ay, g.box);
-        };
-        for (int i0 = wsub * 64; i0 < total; i0 += wpg * 64) {
-            int a0 = 0, a1 = 0;
-            const bool h0 = locate(i0 + lane, a0), h1 = locate(i0 + 32 + lane, a1);
-            if (__ballot_sync(0xffffffffu, h0 || h1)) eval2(h0, a0, 1, h1, a1, 1, false);
-        }
-    } else {
-        for (int i0 = wsub * 64; i0 < c.A; i0 += wpg * 64) {
-            const int a0 = i0 + lane, a1 = i0 + 32 + lane;
-            bool h0 = a0 < c.A && a0 >= k, h1 = a1 < c.A && a1 >= k;
-            if (c.constrain) {
-                float ax, ay, st;
-                if (h0) { anchor_px(c, a0, ax, ay, st); h0 = dm::in_gt(ax, ay, g.box); }
-                if (h1) { anchor_px(c, a1, ax, ay, st); h1 = dm::in_gt(ax, ay, g.box); }
+            continue;
+        } else if (qn > 0) {
+            // ---- stage 2: pop full lanes while trips remain, the rest at the end (no loads: pure arithmetic)
+            const int take = qn < 32 ? qn : 32;
+            qn -= take;
+            if (lane < take) {
+                const int a2 = q_a[wid][qn + lane];
+                const float s2 = q_s[wid][qn + lane];
+                if (!prune || __float_as_uint(s2) >= (unsigned)(thr >> 32)) {
+                    PairRaw raw;
+                    raw.box = q_b[wid][qn + lane];
+                    raw.s = 0.0f;
+                    float ovl;
+                    const float metric = pair_metric(c, b, m, g, a2, raw, s2, ovl);
+                    if (metric > 0.0f) key = tk_key(metric, a2, 1);
+                }
             }
-            if (__ballot_sync(0xffffffffu, h0 || h1)) eval2(h0, a0, 1, h1, a1, 1, false);
+            __syncwarp();
+        } else {
+            break;
         }
+        process(key);
     }
 
     if (wpg > 1) {  // merge the per-warp lists into the first warp's
-        mrg_m[wid][lane] = tk_m; mrg_i[wid][lane] = tk_i; mrg_in[wid][lane] = tk_in;
+        mrg[wid][lane] = lane < k ? tk : 0ull;
         __syncthreads();
         if (wid != 0) return;
-        for (int w = 1; w < wpg; ++w) {
-            int ci = mrg_i[w][lane];
-            process(lane < k && ci != 0x7fffffff, mrg_m[w][lane], ci, mrg_in[w][lane]);
+        unsigned long long km = 0ull;
+        for (int w2 = 1; w2 < wpg; ++w2) {  // one call site: k insertions per foreign list at most
+            km = mrg[w2][lane];
+            for (;;) {
+                const unsigned mk = __ballot_sync(0xffffffffu, km > thr);
+                if (!mk) break;
+                const int src = __ffs(mk) - 1;
+                const unsigned long long x = __shfl_sync(0xffffffffu, km, src);
+                const int pos = __popc(__ballot_sync(0xffffffffu, tk > x && lane < k));
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, tk, 1);
+                if (lane == pos) tk = x;
+                else if (lane > pos) tk = up;
+                thr = __shfl_sync(0xffffffffu, tk, k - 1);
+                if (lane == src) km = 0ull;
+            }
         }
     }
     // claims: mask_pos = mask_topk * mask_in_gts * mask_gt (tal.py:104)
-    if (lane < k && tk_i != 0x7fffffff && tk_in) {
-        const unsigned long long old =
-            atomicAdd(c.claim + (long long)b * c.A + tk_i, (1ull << 32) | (unsigned long long)m);
-        if (c.list_a && (old >> 32) == 0) {  // first claim of this anchor: publish it
-            const int pos = atomicAdd(c.list_count + b, 1);
-            if (pos < c.list_cap) c.list_a[(long long)b * c.list_cap + pos] = tk_i;
+    if (lane < k && tk != 0ull && (tk & 1ull)) {
+        const int a = tk_anchor(tk);
+        const unsigned long long old = atomicAdd(c.claim + (long long)b * c.A + a, (1ull << 32) | (unsigned long long)m);
+        if (c.list_a) {
+            if ((old >> 32) == 0) {  // first claim of this anchor: publish it
+                const int pos = atomicAdd(c.list_count + b, 1);
+                if (pos < c.list_cap) c.list_a[(long long)b * c.list_cap + pos] = a;
+            }
+            if (c.score_mode == 1 && c.cls_ch0 == 64) {
+                // the finishing kernel will gather the two DFL bins around each target distance (loss.py:99-113):
+                // start pulling them into L2 now
+                const int lv = level_of(c.t, a);
+                const int cell = a - c.t.start[lv];
+                const float sv = c.t.stride[lv];
+                const float ax = (float)(cell % c.t.w[lv]) + 0.5f, ay = (float)(cell / c.t.w[lv]) + 0.5f;
+                const float ltrb[4] = {ax - g.box.x / sv, ay - g.box.y / sv, g.box.z / sv - ax, g.box.w / sv - ay};
+                const float *hp = c.t.ptr[lv] + (long long)b * c.t.sB[lv] + cell;
+#pragma unroll
+                for (int side = 0; side < 4; ++side) {
+                    const int tl = (int)fminf(fmaxf(ltrb[side], 0.0f), 14.99f);
+                    prefetch_l2(hp + (long long)(side * 16 + tl) * c.t.sC[lv]);
+                    prefetch_l2(hp + (long long)(side * 16 + tl + 1) * c.t.sC[lv]);
+                }
+            }
         }
     }
 }

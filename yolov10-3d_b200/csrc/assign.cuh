@@ -103,14 +103,15 @@ struct PairRaw {
     float s;     // probability (score_mode 0) or logit (score_mode 1)
 };
 
-__device__ __forceinline__ PairRaw pair_load(const AssignCtx &c, int b, int a, int label) {
+__device__ __forceinline__ float pair_load_score(const AssignCtx &c, int b, int a, int label) {
+    if (c.score_mode == 0) return c.pd_scores[b * c.ssB + a * c.ssA + (long long)label * c.ssC];
+    const int l = level_of(c.t, a);
+    return c.t.ptr[l][(long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + label) * c.t.sC[l] + (a - c.t.start[l])];
+}
+
+__device__ __forceinline__ PairRaw pair_load_box(const AssignCtx &c, int b, int a) {
     PairRaw r;
-    if (c.score_mode == 0) {
-        r.s = c.pd_scores[b * c.ssB + a * c.ssA + (long long)label * c.ssC];
-    } else {
-        int l = level_of(c.t, a);
-        r.s = c.t.ptr[l][(long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + label) * c.t.sC[l] + (a - c.t.start[l])];
-    }
+    r.s = 0.0f;
     if (c.box_soa) {
         const float *p = c.pd_bboxes + (long long)b * 4 * c.A + a;
         r.box = make_float4(p[0], p[c.A], p[2 * (long long)c.A], p[3 * (long long)c.A]);
@@ -120,9 +121,15 @@ __device__ __forceinline__ PairRaw pair_load(const AssignCtx &c, int b, int a, i
     return r;
 }
 
-__device__ __forceinline__ float pair_score(const AssignCtx &c, const PairRaw &r) {
-    if (c.score_mode == 0) return r.s;
-    return 1.0f / (1.0f + expf(-r.s));  // pred_scores.detach().sigmoid() loss.py:232
+__device__ __forceinline__ PairRaw pair_load(const AssignCtx &c, int b, int a, int label) {
+    PairRaw r = pair_load_box(c, b, a);
+    r.s = pair_load_score(c, b, a, label);
+    return r;
+}
+
+__device__ __forceinline__ float pair_score(const AssignCtx &c, float raw) {
+    if (c.score_mode == 0) return raw;
+    return 1.0f / (1.0f + expf(-raw));  // pred_scores.detach().sigmoid() loss.py:232
 }
 
 __device__ __forceinline__ float4 pair_box(const AssignCtx &c, const PairRaw &r, int a) {
@@ -134,28 +141,30 @@ __device__ __forceinline__ float4 pair_box(const AssignCtx &c, const PairRaw &r,
     return p;
 }
 
-// get_box_metrics (tal.py:108-127) / get_box_kp_metrics / get_keypoint_metrics (tal.py:553-603) for one in-mask pair.
-// ovl is what the reference calls `overlaps` downstream: CIoU for the 2D assigner, the 3D similarity when use_3d.
-__device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, const PairRaw &raw,
-                                          float &metric, float &ovl) {
-    float s = pair_score(c, raw);
-    metric = dm::pow_(s, c.alpha);
-    ovl = 0.0f;
-    if (c.use_2d) {
-        float o = dm::ciou(g.box, pair_box(c, raw, a), g.at1);
+// get_box_metrics (tal.py:108-127) / get_box_kp_metrics / get_keypoint_metrics (tal.py:553-603) for one in-mask pair,
+// given sb = score^alpha.  ovl is what the reference calls `overlaps` downstream: CIoU for the 2D assigner, the 3D
+// similarity when use_3d.
+// Out of line on purpose, with scalar arguments only (a reference to the kernel parameters would force a local
+// copy): one copy of the CIoU / atan / pow / keypoint code per kernel keeps the instruction-cache footprint small.
+// flags: bit0 use_2d, bit1 use_3d, bit2 kps_l2.
+static __device__ __noinline__ float pair_metric_core(float4 gbox, float gat1, float4 pbox, float sb, float beta,
+                                                      float gamma, int flags, const float4 *pk, const float4 *gk,
+                                                      float *ovl_out) {
+    float metric = sb;
+    float ovl = 0.0f;
+    if (flags & 1) {
+        float o = dm::ciou(gbox, pbox, gat1);
         o = o < 0.0f ? 0.0f : o;  // clamp_(0) tal.py:131
-        metric = dm::mul(metric, dm::pow_(o, c.beta));
+        metric = dm::mul(metric, dm::pow_(o, beta));
         ovl = o;
     }
-    if (c.use_3d) {  // keypoint_distance_3d tal.py:464-470
-        const float4 *pk = reinterpret_cast<const float4 *>(c.pd_kps + ((long long)b * c.A + a) * 24);
-        const float4 *gk = reinterpret_cast<const float4 *>(c.gt_kps + ((long long)b * c.M + m) * 24);
+    if (flags & 2) {  // keypoint_distance_3d tal.py:464-470
         float acc = 0.0f;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             float4 p = pk[j], q = __ldg(gk + j);
             float d0 = dm::sub(p.x, q.x), d1 = dm::sub(p.y, q.y), d2 = dm::sub(p.z, q.z), d3 = dm::sub(p.w, q.w);
-            if (c.kps_l2) {
+            if (flags & 4) {
                 acc = dm::add(acc, dm::mul(d0, d0)); acc = dm::add(acc, dm::mul(d1, d1));
                 acc = dm::add(acc, dm::mul(d2, d2)); acc = dm::add(acc, dm::mul(d3, d3));
             } else {
@@ -164,10 +173,28 @@ __device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, cons
             }
         }
         float dist = dm::div(acc, 24.0f);
-        float sim = dm::div(1.0f, dm::exp_(c.kps_l2 ? dm::mul(0.5f, dist) : dist));
-        metric = dm::mul(metric, dm::pow_(sim, c.gamma));
+        float sim = dm::div(1.0f, dm::exp_((flags & 4) ? dm::mul(0.5f, dist) : dist));
+        metric = dm::mul(metric, dm::pow_(sim, gamma));
         ovl = sim;  // tal.py:602-603
     }
+    *ovl_out = ovl;
+    return metric;
+}
+
+__device__ __forceinline__ float pair_metric(const AssignCtx &c, int b, int m, const GtRec &g, int a,
+                                             const PairRaw &raw, float sb, float &ovl) {
+    const int flags = (c.use_2d ? 1 : 0) | (c.use_3d ? 2 : 0) | (c.kps_l2 ? 4 : 0);
+    const float4 *pk = nullptr, *gk = nullptr;
+    if (c.use_3d) {
+        pk = reinterpret_cast<const float4 *>(c.pd_kps + ((long long)b * c.A + a) * 24);
+        gk = reinterpret_cast<const float4 *>(c.gt_kps + ((long long)b * c.M + m) * 24);
+    }
+    return pair_metric_core(g.box, g.at1, pair_box(c, raw, a), sb, c.beta, c.gamma, flags, pk, gk, &ovl);
+}
+
+__device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, const PairRaw &raw,
+                                          float &metric, float &ovl) {
+    metric = pair_metric(c, b, m, g, a, raw, dm::pow_(pair_score(c, raw.s), c.alpha), ovl);
 }
 
 __device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, float &metric,

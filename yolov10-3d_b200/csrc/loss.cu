@@ -28,7 +28,7 @@ namespace y3d {
 
 constexpr int kR = 16;
 constexpr int kStreamThreads = 128;  // 32 anchor-quads x 4 channel parts
-constexpr int kFinishThreads = 512;
+constexpr int kFinishThreads = 1024;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -46,12 +46,12 @@ __device__ __forceinline__ float lg2_approx(float x) {
 __device__ __forceinline__ float sigmoid_acc(float v) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v))); }
 
 template <int V>
-__device__ __forceinline__ void ldv(const float *p, float (&o)[V]) {
+__device__ __forceinline__ void ldv(const float *p, float (&o)[V], unsigned long long pol) {
     if constexpr (V == 4) {
-        const float4 r = ldg_stream4(p);
+        const float4 r = ldg_stream4(p, pol);
         o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
     } else {
-        o[0] = ldg_stream1(p);
+        o[0] = ldg_stream1(p, pol);
     }
 }
 template <int V>
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
     const int q = blockIdx.x * 32 + lane;
     const LevelTable &t = P.t[z];
     const int A = P.A;
+    const unsigned long long pol = l2_evict_first_policy();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (P.list_count[z]) P.list_count[z][b] = 0;
         if (b == 0 && z == 0 && P.counter) *P.counter = 0u;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
             float x[kR][V];
             const float *pb = base + (long long)(part * kR) * cs;
 #pragma unroll
-            for (int j = 0; j < kR; ++j) ldv<V>(pb + (long long)j * cs, x[j]);
+            for (int j = 0; j < kR; ++j) ldv<V>(pb + (long long)j * cs, x[j], pol);
             const int w = t.w[l];
             int cx = cell % w, cy = cell / w;
             float ob[V], ol[V];
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
             for (; c + 4 <= s1; c += 4) {
                 float v[4][V];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) ldv<V>(pc + (long long)(c + jj) * cs, v[jj]);
+                for (int jj = 0; jj < 4; ++jj) ldv<V>(pc + (long long)(c + jj) * cs, v[jj], pol);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
             }
             for (; c < s1; ++c) {
                 float v[V];
-                ldv<V>(pc + (long long)c * cs, v);
+                ldv<V>(pc + (long long)c * cs, v, pol);
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
                     const float tt = ex2_approx(-fabsf(v[i]) * kLog2e);
@@ -257,19 +258,28 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         float ax, ay, st;
         anchor_px(c, a, ax, ay, st);
         int gi = (int)(cl & 0xffffffffull);
-        if (cnt > 1) {  // argmax over ALL GTs of the overlap, first maximum
+        const PairRaw raw = pair_load_box(c, b, a);
+        float x = 0.0f;
+        if (cnt == 1) x = pair_load_score(c, b, a, gts[gi].label);  // in flight together with the box
+        if (cnt > 1) {  // argmax over ALL GTs of the overlap, first maximum: pure arithmetic, GTs from shared memory
+            const float4 pbox = pair_box(c, raw, a);
             float bv = -1.0f;
             gi = 0;
             for (int m = 0; m < M; ++m) {
                 const GtRec g = gts[m];
-                float metric = 0.0f, ovl = 0.0f;
-                if (g.valid && dm::in_gt(ax, ay, g.box)) pair_eval(c, b, m, g, a, metric, ovl);
+                float ovl = 0.0f;
+                if (g.valid && dm::in_gt(ax, ay, g.box)) {
+                    ovl = dm::ciou(g.box, pbox, g.at1);
+                    ovl = ovl < 0.0f ? 0.0f : ovl;
+                }
                 if (ovl > bv) { bv = ovl; gi = m; }
             }
+            x = pair_load_score(c, b, a, gts[gi].label);
         }
         const GtRec g = gts[gi];
         float metric = 0.0f, ovl = 0.0f;
-        if (g.valid && dm::in_gt(ax, ay, g.box)) pair_eval(c, b, gi, g, a, metric, ovl);
+        if (g.valid && dm::in_gt(ax, ay, g.box))
+            metric = pair_metric(c, b, gi, g, a, raw, dm::pow_(pair_score(c, x), c.alpha), ovl);
         lgi[e] = gi;
         lal[e] = metric;
         atomicMax(pos_a + gi, __float_as_int(metric));  // values >= 0: int order == float order

@@ -83,7 +83,26 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// 128-bit streaming loads / stores: the head tensor and the big outputs are touched exactly once.
+// 128-bit streaming loads: the head tensor is touched exactly once per pass, so it bypasses L1 and is marked
+// evict-first in L2 -- the small intermediates (boxes, claims, lists) written next to it are what later kernels
+// gather from and should be the lines that survive in the 126 MB L2.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float *p, unsigned long long pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float *p, unsigned long long pol) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -100,6 +119,8 @@ __device__ __forceinline__ void stg_stream4(float *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+// fire-and-forget pull of one line into L2 (latency-bound gathers of a later phase / kernel then hit L2)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // --------------------------------------------------------------------------------------------- dm:: math
 namespace dm {
@@ -228,6 +249,8 @@ __device__ __forceinline__ float exp_(float x) {
     return mul(mul(p, a), b);
 }
 
+static __device__ __noinline__ float pow_generic(float x, float e) { return powf(x, e); }
+
 // pow with the path's exponents explicit (see oracle/y3d_oracle.c::y3d_powf); other exponents -> powf.
 __device__ __forceinline__ float pow_(float x, float e) {
     if (e == 0.5f) return sqrt_(x);
@@ -244,7 +267,7 @@ __device__ __forceinline__ float pow_(float x, float e) {
         return mul(x4, x2);
     }
     if (e == 0.0f) return 1.0f;
-    return powf(x, e);
+    return pow_generic(x, e);
 }
 
 // atan(w/h) term of a box, h already has +eps (metrics.py:103-104,126)

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Developer tool: per-CTA phase timestamps of loss_finish_kernel (library built with -DY3D_TIMING).
+
+    python tools/phase_timing.py build     # here (nvcc)   -> tools/liby3d_timing.so
+    python tools/phase_timing.py run       # on the GPU box
+"""
+import ctypes
+import glob
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tools", "liby3d_timing.so")
+
+if sys.argv[1] == "build":
+    src = sorted(glob.glob(os.path.join(ROOT, "yolov10-3d_b200", "csrc", "*.cu")))
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-DY3D_TIMING",
+                           "-o", OUT, *src])
+    print(OUT)
+    sys.exit(0)
+
+import numpy as np
+import torch
+
+import yolov10_3d_b200 as y3d
+from yolov10_3d_b200 import _lib
+
+_lib.LIB_PATH = OUT
+import bench
+
+lv, gt, xm, xo = bench.make_inputs(seed=0)
+from tests import synth
+
+dev = torch.device("cuda", 0)
+fm = [torch.from_numpy(f).to(dev) for f in synth.split_levels(xm, lv)]
+fo = [torch.from_numpy(f).to(dev) for f in synth.split_levels(xo, lv)]
+gtd = torch.from_numpy(gt).to(dev)
+for _ in range(5):
+    y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
+torch.cuda.synchronize()
+n = 128 * 8
+buf = (ctypes.c_ulonglong * n)()
+h = _lib.lib()
+h.y3d_debug_read_stamps.argtypes = [ctypes.c_void_p, ctypes.c_int]
+assert h.y3d_debug_read_stamps(buf, n) == 0
+t = np.array(buf, dtype=np.uint64).reshape(128, 8).astype(np.int64)
+t0 = t[:, 0].min()
+valid = (gt[..., 1:5].sum(-1) > 0).sum(1)
+print("cta(b,z) nGT  start  gts  resolve  fg  reduce  (us, relative to first CTA start; phases = durations)")
+d = np.diff(t[:, :5], axis=1) / 1e3
+for i in list(range(0, 6)) + list(range(64, 70)):
+    print(i % 64, i // 64, valid[i % 64], round((t[i, 0] - t0) / 1e3, 1), d[i].round(1))
+print("mean phase durations (us):", d.mean(0).round(2), " max:", d.max(0).round(2))
+print("kernel span (us): first start -> last CTA end", (t[:, :5].max() - t0) / 1e3, " final-reduce stamp", (t[:, 5].max() - t0) / 1e3)

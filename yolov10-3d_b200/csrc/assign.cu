@@ -33,19 +33,37 @@ __device__ __forceinline__ int tk_anchor(unsigned long long key) { return 0x7fff
 constexpr int kTopkU = 4;             // cells per lane and round trip
 constexpr int kTopkQ = 32 * kTopkU + 32;  // queue slots per warp
 
-__global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc, int wpg) {
+__global__ void __launch_bounds__(kTopkWarps * 32, 5) tal_topk_kernel(AssignCtx2 cc, int wpg, int n_branch) {
     __shared__ int q_a[kTopkWarps][kTopkQ];
     __shared__ float q_s[kTopkWarps][kTopkQ];
     __shared__ float4 q_b[kTopkWarps][kTopkQ];
     __shared__ unsigned long long mrg[kTopkWarps][32];
-    const AssignCtx &c = cc.c[blockIdx.z];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long gt_id = wpg == 1 ? (long long)blockIdx.x * kTopkWarps + wid : (long long)blockIdx.x;
+    const long long per_branch = (long long)cc.c[0].B * cc.c[0].M;
+    const long long total = per_branch * n_branch;
     const int wsub = wpg == 1 ? 0 : wid;  // this warp's share of the GT's chunks
-    if (gt_id >= (long long)c.B * c.M) return;
+    // Work items = (branch, image, GT).  One warp per GT: persistent warps pull items from a global counter (padded
+    // GTs cost one load, big GTs do not stall a whole wave).  Several warps per GT: one item per CTA, static.
+    bool static_done = false;
+    for (long long item = (long long)blockIdx.x;;) {
+    if (wpg == 1) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(cc.work_counter, 1);
+        item = __shfl_sync(0xffffffffu, it, 0);
+    } else {
+        if (static_done) break;  // static mapping: a single pass
+        static_done = true;
+    }
+    if (item >= total) break;
+    const int z = (int)(item / per_branch);
+    const long long gt_id = item - z * per_branch;
+    const AssignCtx &c = cc.c[z];
     const int b = (int)(gt_id / c.M), m = (int)(gt_id % c.M);
     const GtRec g = load_gt(c, b, m);
-    if (!g.valid) return;  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104); all its warps exit
+    if (!g.valid) {  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104)
+        if (wpg == 1) continue;
+        break;
+    }
     const int k = c.k;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool prune = c.beta >= 0.0f && c.gamma >= 0.0f;  // the upper bound needs non-negative exponents
@@ -107,8 +125,13 @@ __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc
 
     // phase 1: candidates = anchors >= k inside the GT.  One loop body serves both walks: `more` trips, then the flush.
     int qn = 0;
-    int l = -1, i0 = 0, cells = 0, w = 1, start = 0;
+    int l = -1, i0 = 0, cells = 0, w = 1, start = 0, rmid = 0, cmid = 0;
     float st = 1.0f, inv = 1.0f;
+    const float *srow = nullptr;  // rect walk, score_mode 1: label-channel row of this image and level, minus `start`
+    // centre-out order inside the rectangle: the best candidates tend to sit near the GT centre, so visiting them
+    // first raises the k-th metric early and later candidates fail the cheap threshold tests (the result does not
+    // depend on the order: keys are totally ordered)
+    auto centre_out = [](int i, int mid) { return (i & 1) ? mid + ((i + 1) >> 1) : mid - (i >> 1); };
     if (!rect) { cells = c.A; i0 = wsub * (32 * kTopkU); l = 0; }
     bool done = false;
     for (bool first = true;; first = false) {
@@ -126,6 +149,9 @@ __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc
                     cells = ncols * nrows;
                     st = c.t.stride[l]; w = c.t.w[l]; start = c.t.start[l];
                     inv = __frcp_rn((float)ncols);
+                    rmid = (nrows - 1) >> 1; cmid = (ncols - 1) >> 1;
+                    if (c.score_mode == 1)
+                        srow = c.t.ptr[l] + (long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + g.label) * c.t.sC[l] - start;
                     i0 = wsub * (32 * kTopkU);
                 }
             } else {
@@ -149,7 +175,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc
                             int cc_ = j - r * ncols;
                             if (cc_ < 0) { --r; cc_ += ncols; }
                             else if (cc_ >= ncols) { ++r; cc_ -= ncols; }
-                            const int col = c0 + cc_, row = r0 + r;
+                            const int col = c0 + centre_out(cc_, cmid), row = r0 + centre_out(r, rmid);
                             a[u] = start + row * w + col;
                             ax = dm::mul((float)col + 0.5f, st); ay = dm::mul((float)row + 0.5f, st);
                             h[u] = a[u] >= k && dm::in_gt(ax, ay, g.box);
@@ -173,7 +199,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc
                         x[u] = 0.f;
                         bx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (h[u]) {
-                            x[u] = pair_load_score(c, b, a[u], g.label);
+                            x[u] = srow ? srow[a[u]] : pair_load_score(c, b, a[u], g.label);
                             bx[u] = pair_load_box(c, b, a[u]).box;
                         }
                     }
@@ -266,6 +292,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32) tal_topk_kernel(AssignCtx2 cc
             }
         }
     }
+    __syncwarp();
+    }  // item loop
 }
 
 // grid (ceil(A/256), B, n_branch); dynamic smem: M GtRec
@@ -315,10 +343,16 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
 
 int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s) {
     const AssignCtx &c = cc.c[0];
-    const int wpg = (c.use_grid && c.constrain) ? 1 : kTopkWarps;
-    const long long warps = (long long)c.B * c.M * wpg;
-    dim3 gt_grid((unsigned)((warps + kTopkWarps - 1) / kTopkWarps), 1, n);
-    tal_topk_kernel<<<gt_grid, kTopkWarps * 32, 0, s>>>(cc, wpg);
+    const int wpg = (c.use_grid && c.constrain && cc.work_counter) ? 1 : kTopkWarps;
+    const long long items = (long long)c.B * c.M * n;
+    long long blocks = wpg == 1 ? (items + kTopkWarps - 1) / kTopkWarps : items;
+    if (wpg == 1) {  // persistent: no more CTAs than fit at once
+        int dev = 0, sms = kNumSMs;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (blocks > 5LL * sms) blocks = 5LL * sms;
+    }
+    tal_topk_kernel<<<(unsigned)blocks, kTopkWarps * 32, 0, s>>>(cc, wpg, n);
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }
@@ -544,6 +578,7 @@ extern "C" int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A
     if (e != cudaSuccess) return (int)e;
     AssignCtx2 cc{};
     cc.c[0] = c;
+    cc.work_counter = (int *)((char *)ws + w.off_work);
     int rc = assign_run_core(cc, 1, s);
     if (rc) return rc;
     return run_emit(c, ws, w, target_labels, target_bboxes, target_scores, fg_mask, target_gt_idx, nullptr, nullptr, s);
@@ -599,6 +634,7 @@ extern "C" int y3d_tal_assign3d(const float *pd_scores, const float *pd_bboxes, 
     if (e != cudaSuccess) return (int)e;
     AssignCtx2 cc{};
     cc.c[0] = c;
+    cc.work_counter = (int *)((char *)ws + w.off_work);
     int rc = assign_run_core(cc, 1, s);
     if (rc) return rc;
     return run_emit(c, ws, w, target_labels, nullptr, target_scores, fg_mask, target_gt_idx, gts, target_vals, s);

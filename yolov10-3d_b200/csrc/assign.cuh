@@ -216,11 +216,12 @@ __device__ __forceinline__ float assigned_norm(const AssignCtx &c, int b, int gi
 // up to two branches (one2many / one2one of v10DetectLoss) run in the same launches, selected by blockIdx.z
 struct AssignCtx2 {
     AssignCtx c[2];
+    int *work_counter;  // zero-initialised: dynamic (branch, image, GT) work distribution of tal_topk_kernel
 };
 
 // host helpers --------------------------------------------------------------------------------------------------
 struct AssignWs {
-    size_t off_cnt, off_pa, off_po, off_tgi, off_align, off_norm, off_lab, total, zero_bytes;
+    size_t off_cnt, off_pa, off_po, off_work, off_tgi, off_align, off_norm, off_lab, total, zero_bytes;
 };
 inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline AssignWs assign_ws_layout(int B, int A, int M) {
@@ -229,7 +230,8 @@ inline AssignWs assign_ws_layout(int B, int A, int M) {
     w.off_cnt = 0;
     w.off_pa = 2 * ba;
     w.off_po = 2 * ba + bm;
-    w.zero_bytes = 2 * ba + 2 * bm;  // claim | pos_align | pos_ov are zero-filled with one memset
+    w.zero_bytes = 2 * ba + 2 * bm + 256;  // claim | pos_align | pos_ov | work counter: zero-filled with one memset
+    w.off_work = 2 * ba + 2 * bm;
     w.off_tgi = w.zero_bytes;
     w.off_align = w.off_tgi + ba;
     w.off_norm = w.off_align + ba;

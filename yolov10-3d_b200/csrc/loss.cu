@@ -71,13 +71,13 @@ struct StreamParams {
     float *pd_scores[2];   // optional [B,A,nc] sigmoid (y3d_train_decode only)
     unsigned long long *claim[2];  // optional [B,A], zeroed here
     int *list_count[2];    // optional [B], zeroed here
-    unsigned *counter;     // optional ticket of the finishing kernel, zeroed here
+    unsigned *counter;     // optional ticket of the finishing kernel (+1: work counter of the top-k kernel), zeroed here
     double *part_bce;      // [n_branch][gridDim.x * B] or nullptr
     int n_branch, B, nc, A, box_aos;
 };
 
 // grid (ceil(A/V/32), B, n_branch), block 128 = 32 units of V anchors x 4 channel parts (warp = part)
-template <int V>
+template <int V, bool PS>
 __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamParams P) {
     __shared__ double red[4];
     const int z = blockIdx.z, b = blockIdx.y;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
     const unsigned long long pol = l2_evict_first_policy();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (P.list_count[z]) P.list_count[z][b] = 0;
-        if (b == 0 && z == 0 && P.counter) *P.counter = 0u;
+        if (b == 0 && z == 0 && P.counter) { P.counter[0] = 0u; P.counter[1] = 0u; }
     }
     float bce = 0.f;
     if (q * V < A) {
@@ -147,8 +147,6 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
         // single log1p per anchor and segment replaces one log per element.  Segments of 64 keep u < 2^64.
         const int cpp = (P.nc + 3) >> 2;
         const int c_lo = part * cpp, c_hi = min(P.nc, c_lo + cpp);
-        const float *pc = base + (long long)(4 * kR) * cs;
-        float *ps = P.pd_scores[z];
         float tot[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) tot[i] = 0.f;
@@ -157,31 +155,29 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
             float u[V], pos[V];
 #pragma unroll
             for (int i = 0; i < V; ++i) u[i] = pos[i] = 0.f;
-            int c = s0;
-            for (; c + 4 <= s1; c += 4) {
-                float v[4][V];
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) ldv<V>(pc + (long long)(c + jj) * cs, v[jj], pol);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int i = 0; i < V; ++i) {
-                        const float tt = ex2_approx(-fabsf(v[jj][i]) * kLog2e);
-                        u[i] = __fmaf_rn(u[i], tt, u[i] + tt);
-                        pos[i] += fmaxf(v[jj][i], 0.f);
-                        if (ps) ps[((long long)b * A + a0 + i) * P.nc + c + jj] = sigmoid_acc(v[jj][i]);
-                    }
-            }
-            for (; c < s1; ++c) {
-                float v[V];
-                ldv<V>(pc + (long long)c * cs, v, pol);
+            const float *pc = base + (long long)(4 * kR + s0) * cs;
+            auto fold = [&](const float (&v)[V], int c) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
                     const float tt = ex2_approx(-fabsf(v[i]) * kLog2e);
                     u[i] = __fmaf_rn(u[i], tt, u[i] + tt);
                     pos[i] += fmaxf(v[i], 0.f);
-                    if (ps) ps[((long long)b * A + a0 + i) * P.nc + c] = sigmoid_acc(v[i]);
+                    if constexpr (PS) P.pd_scores[z][((long long)b * A + a0 + i) * P.nc + c] = sigmoid_acc(v[i]);
                 }
+            };
+            int c = s0;
+            constexpr int CB = 10;  // channel rows in flight per thread (nc = 80: two batches)
+            for (; c + CB <= s1; c += CB, pc += CB * cs) {
+                float v[CB][V];
+#pragma unroll
+                for (int jj = 0; jj < CB; ++jj) ldv<V>(pc + jj * cs, v[jj], pol);
+#pragma unroll
+                for (int jj = 0; jj < CB; ++jj) fold(v[jj], c + jj);
+            }
+            for (; c < s1; ++c, pc += cs) {
+                float v[V];
+                ldv<V>(pc, v, pol);
+                fold(v, c);
             }
 #pragma unroll
             for (int i = 0; i < V; ++i) tot[i] += pos[i] + log1pf(u[i]);
@@ -205,13 +201,13 @@ struct FinishParams {
     int *list_gi[2];           // [B,cap] scratch
     float *list_al[2];         // [B,cap] scratch
     const double *part_bce;    // [n_branch][n_bce]
-    double *part_fg;           // [n_branch][B][4]
+    double *part_fg;           // [n_branch][B][5]: iou, dfl, target_scores, x*t, softplus
     unsigned *counter;         // zeroed by the stream kernel
     double *partials;          // optional out [n_branch][4]
     float *loss_items;         // optional out [n_branch][4]
     uint8_t *dbg_fg[2];
     int32_t *dbg_gi[2];
-    int n_bce, n_branch, normalise;
+    int n_bce_x, n_branch, normalise;  // n_bce_x: BCE partials per image (= gridDim.x of the stream kernel)
     float gain_box, gain_cls, gain_dfl;
 };
 
@@ -223,16 +219,47 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
     return v;
 }
 
-// grid (B, n_branch), block 512; dynamic smem: M GtRec + 2*M int
+#ifdef Y3D_TIMING
+__device__ unsigned long long g_y3d_stamps[2 * 1024 * 8];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define Y3D_STAMP(i)                                                                                  \
+    do {                                                                                              \
+        __syncthreads();                                                                              \
+        if (threadIdx.x == 0) g_y3d_stamps[((blockIdx.y * gridDim.x + blockIdx.x) & 2047) * 8 + (i)] = gtimer(); \
+    } while (0)
+#else
+#define Y3D_STAMP(i)
+#endif
+
+constexpr int kConfMax = 1024;  // multiply-claimed anchors resolved cooperatively per image (more: serial fallback)
+constexpr int kFinishWarps = kFinishThreads / 32;
+
+struct FinishSmem {  // dynamic shared memory of loss_finish_kernel, followed by GtRec[M], int pos_a[M], int pos_o[M]
+    float4 conf_box[kConfMax];            // predicted box (px) of a conflicted anchor
+    unsigned long long conf_best[kConfMax];  // (overlap bits << 32) | (0xffffffff - m): atomicMax = first maximum
+    float2 conf_xy[kConfMax];             // its anchor point (px)
+    int2 queue[kFinishWarps][64];         // per-warp compaction queue of in-GT (conflict, GT) pairs
+    long long redl[4][kFinishWarps];
+    double redd[kFinishWarps];
+    double fin[2][5];
+    int n_conf;
+    unsigned ticket;
+};
+size_t finish_smem_bytes(int M) { return sizeof(FinishSmem) + (sizeof(GtRec) + 2 * sizeof(int)) * (size_t)M; }
+
+// grid (B, n_branch), block 1024; one CTA per (image, branch) over the image's claimed anchors only
 __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 cc, FinishParams F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ long long redl[4][kFinishThreads / 32];
-    __shared__ double redd[5][kFinishThreads];
-    __shared__ unsigned s_ticket;
+    FinishSmem &S = *reinterpret_cast<FinishSmem *>(smem_raw);
     const int z = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AssignCtx &c = cc.c[z];
     const int M = c.M, A = c.A;
-    GtRec *gts = reinterpret_cast<GtRec *>(smem_raw);
+    Y3D_STAMP(0);
+    GtRec *gts = reinterpret_cast<GtRec *>(smem_raw + sizeof(FinishSmem));
     int *pos_a = reinterpret_cast<int *>(gts + M);
     int *pos_o = pos_a + M;
     for (int m = tid; m < M; m += kFinishThreads) {
@@ -240,6 +267,7 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         pos_a[m] = 0;
         pos_o[m] = 0;
     }
+    if (tid == 0) S.n_conf = 0;
     if (F.dbg_fg[z])
         for (int a = tid; a < A; a += kFinishThreads) {
             F.dbg_fg[z][(long long)b * A + a] = 0;
@@ -250,7 +278,19 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
     int *lgi = F.list_gi[z] + (long long)b * c.list_cap;
     float *lal = F.list_al[z] + (long long)b * c.list_cap;
     __syncthreads();
-    // ---- resolve the claimed anchors (select_highest_overlaps tal.py:237-264) and fold the per-GT maxima
+    Y3D_STAMP(1);
+    // ---- resolve, step 1: singly-claimed anchors are final; multiply-claimed ones (select_highest_overlaps
+    //      tal.py:237-264: argmax over ALL GTs of the overlap, first maximum) are parked for the cooperative step
+    auto settle = [&](int e, int a, int gi, float ax, float ay, const PairRaw &raw, float x) {
+        const GtRec g = gts[gi];
+        float metric = 0.0f, ovl = 0.0f;
+        if (g.valid && dm::in_gt(ax, ay, g.box))
+            metric = pair_metric(c, b, gi, g, a, raw, dm::pow_(pair_score(c, x), c.alpha), ovl);
+        lgi[e] = gi;
+        lal[e] = metric;
+        atomicMax(pos_a + gi, __float_as_int(metric));  // values >= 0: int order == float order
+        atomicMax(pos_o + gi, __float_as_int(ovl));
+    };
     for (int e = tid; e < n; e += kFinishThreads) {
         const int a = __ldcg(la + e);
         const unsigned long long cl = __ldcg(c.claim + (long long)b * A + a);
@@ -259,11 +299,17 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         anchor_px(c, a, ax, ay, st);
         int gi = (int)(cl & 0xffffffffull);
         const PairRaw raw = pair_load_box(c, b, a);
-        float x = 0.0f;
-        if (cnt == 1) x = pair_load_score(c, b, a, gts[gi].label);  // in flight together with the box
-        if (cnt > 1) {  // argmax over ALL GTs of the overlap, first maximum: pure arithmetic, GTs from shared memory
+        if (cnt > 1) {
             const float4 pbox = pair_box(c, raw, a);
-            float bv = -1.0f;
+            const int ci = atomicAdd(&S.n_conf, 1);
+            if (ci < kConfMax) {
+                S.conf_box[ci] = pbox;
+                S.conf_xy[ci] = make_float2(ax, ay);
+                S.conf_best[ci] = 0xffffffffull;  // overlap 0 at GT 0: what the scan starts from
+                lgi[e] = -1 - ci;
+                continue;
+            }
+            float bv = -1.0f;  // overflow of the cooperative buffers: serial scan
             gi = 0;
             for (int m = 0; m < M; ++m) {
                 const GtRec g = gts[m];
@@ -274,18 +320,60 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
                 }
                 if (ovl > bv) { bv = ovl; gi = m; }
             }
-            x = pair_load_score(c, b, a, gts[gi].label);
         }
-        const GtRec g = gts[gi];
-        float metric = 0.0f, ovl = 0.0f;
-        if (g.valid && dm::in_gt(ax, ay, g.box))
-            metric = pair_metric(c, b, gi, g, a, raw, dm::pow_(pair_score(c, x), c.alpha), ovl);
-        lgi[e] = gi;
-        lal[e] = metric;
-        atomicMax(pos_a + gi, __float_as_int(metric));  // values >= 0: int order == float order
-        atomicMax(pos_o + gi, __float_as_int(ovl));
+        settle(e, a, gi, ax, ay, raw, pair_load_score(c, b, a, gts[gi].label));
     }
     __syncthreads();
+    // ---- resolve, step 2: warp w takes conflicts w, w+32, ...; lanes test the GTs, in-GT pairs are compacted and
+    //      their CIoU evaluated on full lanes
+    const int n_conf = min(S.n_conf, kConfMax);
+    if (n_conf > 0) {
+        int qn = 0;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        auto drain = [&](int take) {
+            qn -= take;
+            if (lane < take) {
+                const int2 pr = S.queue[wid][qn + lane];
+                const GtRec g = gts[pr.y];
+                float ovl = dm::ciou(g.box, S.conf_box[pr.x], g.at1);
+                if (ovl > 0.0f)
+                    atomicMax(&S.conf_best[pr.x],
+                              ((unsigned long long)__float_as_uint(ovl) << 32) | (unsigned long long)(0xffffffffu - (unsigned)pr.y));
+            }
+            __syncwarp();
+        };
+        for (int ci = wid; ci < n_conf; ci += kFinishWarps) {
+            const float2 xy = S.conf_xy[ci];
+            for (int m0 = 0; m0 < M; m0 += 32) {
+                const int m = m0 + lane;
+                bool in = false;
+                if (m < M) {
+                    const GtRec g = gts[m];
+                    in = g.valid && dm::in_gt(xy.x, xy.y, g.box);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) S.queue[wid][qn + __popc(bal & lt_mask)] = make_int2(ci, m);
+                qn += __popc(bal);
+                __syncwarp();
+                if (qn >= 32) drain(32);
+            }
+        }
+        if (qn > 0) drain(qn);
+    }
+    __syncthreads();
+    // ---- resolve, step 3: settle the conflicted anchors on their winning GT
+    if (n_conf > 0)
+        for (int e = tid; e < n; e += kFinishThreads) {
+            const int code = lgi[e];
+            if (code >= 0) continue;
+            const int ci = -1 - code;
+            const int a = __ldcg(la + e);
+            const int gi = (int)(0xffffffffu - (unsigned)(S.conf_best[ci] & 0xffffffffull));
+            const float2 xy = S.conf_xy[ci];
+            settle(e, a, gi, xy.x, xy.y, pair_load_box(c, b, a), pair_load_score(c, b, a, gts[gi].label));
+        }
+    __syncthreads();
+    Y3D_STAMP(2);
     // ---- loss terms of the foreground anchors (BboxLoss.forward loss.py:82-113; BCE correction -x[label]*t)
     long long s_iou = 0, s_dfl = 0, s_ts = 0, s_xt = 0;
     for (int e = tid; e < n; e += kFinishThreads) {
@@ -334,51 +422,68 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
             F.dbg_gi[z][(long long)b * A + a] = gi;
         }
     }
+    Y3D_STAMP(3);
+    // ---- per-image partials: exact integer sums of the foreground terms + this image's BCE partials (fixed order)
     s_iou = warp_sum_ll(s_iou); s_dfl = warp_sum_ll(s_dfl); s_ts = warp_sum_ll(s_ts); s_xt = warp_sum_ll(s_xt);
-    if (lane == 0) { redl[0][wid] = s_iou; redl[1][wid] = s_dfl; redl[2][wid] = s_ts; redl[3][wid] = s_xt; }
+    double bce = 0.0;
+    for (int i = tid; i < F.n_bce_x; i += kFinishThreads)
+        bce += __ldcg(F.part_bce + ((long long)z * gridDim.x + b) * F.n_bce_x + i);
+    bce = warp_sum(bce);
+    if (lane == 0) {
+        S.redl[0][wid] = s_iou; S.redl[1][wid] = s_dfl; S.redl[2][wid] = s_ts; S.redl[3][wid] = s_xt;
+        S.redd[wid] = bce;
+    }
     __syncthreads();
+    double *pimg = F.part_fg + ((long long)z * gridDim.x + b) * 5;
     if (tid < 4) {
         long long s = 0;
-        for (int i = 0; i < kFinishThreads / 32; ++i) s += redl[tid][i];
-        F.part_fg[((long long)z * gridDim.x + b) * 4 + tid] = (double)s / kFix;
+        for (int i = 0; i < kFinishWarps; ++i) s += S.redl[tid][i];
+        pimg[tid] = (double)s / kFix;
+    } else if (tid == 4) {
+        double s = 0.0;
+        for (int i = 0; i < kFinishWarps; ++i) s += S.redd[i];
+        pimg[4] = s;
     }
-    // last CTA done: fixed-order reduction of every partial (deterministic whichever CTA it is)
+    // last CTA done: fixed-order reduction of the per-image partials (deterministic whichever CTA it is)
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(F.counter, 1u);
+    if (tid == 0) S.ticket = atomicAdd(F.counter, 1u);
     __syncthreads();
-    if (s_ticket != gridDim.x * gridDim.y - 1) return;
+    Y3D_STAMP(4);
+    if (S.ticket != gridDim.x * gridDim.y - 1) return;
     __threadfence();
     const int B = gridDim.x;
-    for (int zz = 0; zz < F.n_branch; ++zz) {
-        double acc[5] = {0, 0, 0, 0, 0};
-        for (int i = tid; i < F.n_bce; i += kFinishThreads) acc[0] += __ldcg(F.part_bce + (long long)zz * F.n_bce + i);
-        for (int i = tid; i < B; i += kFinishThreads)
-            for (int k = 0; k < 4; ++k) acc[1 + k] += __ldcg(F.part_fg + ((long long)zz * B + i) * 4 + k);
-        __syncthreads();
-        for (int k = 0; k < 5; ++k) redd[k][tid] = acc[k];
-        __syncthreads();
-        for (int s = kFinishThreads / 2; s > 0; s >>= 1) {
-            if (tid < s)
-                for (int k = 0; k < 5; ++k) redd[k][tid] += redd[k][tid + s];
-            __syncthreads();
+    if (wid < 5 * F.n_branch) {  // warp (zz, k): sum over the images, lane-strided then a fixed shuffle tree
+        const int zz = wid / 5, k = wid % 5;
+        double acc = 0.0;
+        for (int i = lane; i < B; i += 32) acc += __ldcg(F.part_fg + ((long long)zz * B + i) * 5 + k);
+        acc = warp_sum(acc);
+        if (lane == 0) S.fin[zz][k] = acc;
+    }
+    __syncthreads();
+    if (tid < F.n_branch) {
+        const int zz = tid;
+        const double s_i = S.fin[zz][0], s_d = S.fin[zz][1], s_t = S.fin[zz][2];
+        const double bce_t = S.fin[zz][4] - S.fin[zz][3];
+        if (F.partials) {
+            F.partials[4 * zz + 0] = s_i; F.partials[4 * zz + 1] = bce_t;
+            F.partials[4 * zz + 2] = s_d; F.partials[4 * zz + 3] = s_t;
         }
-        if (tid == 0) {
-            const double bce = redd[0][0] - redd[4][0], s_i = redd[1][0], s_d = redd[2][0], s_t = redd[3][0];
-            if (F.partials) {
-                F.partials[4 * zz + 0] = s_i; F.partials[4 * zz + 1] = bce;
-                F.partials[4 * zz + 2] = s_d; F.partials[4 * zz + 3] = s_t;
-            }
-            if (F.normalise && F.loss_items) {
-                const double tss = s_t > 1.0 ? s_t : 1.0;  // max(target_scores.sum(), 1) loss.py:240
-                F.loss_items[4 * zz + 0] = (float)(s_i / tss * F.gain_box);
-                F.loss_items[4 * zz + 1] = (float)(bce / tss * F.gain_cls);
-                F.loss_items[4 * zz + 2] = (float)(s_d / tss * F.gain_dfl);
-                F.loss_items[4 * zz + 3] = (float)tss;
-            }
+        if (F.normalise && F.loss_items) {
+            const double tss = s_t > 1.0 ? s_t : 1.0;  // max(target_scores.sum(), 1) loss.py:240
+            F.loss_items[4 * zz + 0] = (float)(s_i / tss * F.gain_box);
+            F.loss_items[4 * zz + 1] = (float)(bce_t / tss * F.gain_cls);
+            F.loss_items[4 * zz + 2] = (float)(s_d / tss * F.gain_dfl);
+            F.loss_items[4 * zz + 3] = (float)tss;
         }
     }
+    Y3D_STAMP(5);
 }
+#ifdef Y3D_TIMING
+extern "C" int y3d_debug_read_stamps(unsigned long long *host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_y3d_stamps, sizeof(unsigned long long) * n);
+}
+#endif
 
 __global__ void loss_finalize_partials_kernel(const double *__restrict__ partials, int n_branch, float gain_box,
                                               float gain_cls, float gain_dfl, float *__restrict__ loss_items) {
@@ -423,7 +528,7 @@ static LossWs loss_ws_layout(int nb, int B, int A, int M, int k) {
     w.per_branch = o;
     w.off_counter = (size_t)nb * w.per_branch;
     w.off_pfg = w.off_counter + 256;
-    w.off_pbce = w.off_pfg + a256(sizeof(double) * 4 * (size_t)nb * B);
+    w.off_pbce = w.off_pfg + a256(sizeof(double) * 5 * (size_t)nb * B);
     w.n_bce = stream_blocks_x(A) * B;
     w.total = w.off_pbce + a256(sizeof(double) * (size_t)nb * w.n_bce);
     return w;
@@ -436,10 +541,15 @@ static int launch_stream(const StreamParams &P, int *n_bce, cudaStream_t s) {
     const int units = v4 ? P.A / 4 : P.A;
     dim3 grid((units + 31) / 32, P.B, P.n_branch);
     *n_bce = (int)(grid.x * grid.y);
-    if (v4)
-        head_stream_kernel<4><<<grid, kStreamThreads, 0, s>>>(P);
+    const bool ps = P.pd_scores[0] != nullptr;
+    if (v4 && !ps)
+        head_stream_kernel<4, false><<<grid, kStreamThreads, 0, s>>>(P);
+    else if (v4)
+        head_stream_kernel<4, true><<<grid, kStreamThreads, 0, s>>>(P);
+    else if (!ps)
+        head_stream_kernel<1, false><<<grid, kStreamThreads, 0, s>>>(P);
     else
-        head_stream_kernel<1><<<grid, kStreamThreads, 0, s>>>(P);
+        head_stream_kernel<1, true><<<grid, kStreamThreads, 0, s>>>(P);
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }
@@ -475,8 +585,8 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     const LossWs w = loss_ws_layout(nb, B, A, M, kmax);
     if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
     if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
-    const size_t fin_smem = (sizeof(GtRec) + 2 * sizeof(int)) * (size_t)M;
-    if (fin_smem > 200 * 1024) return Y3D_EUNSUPPORTED;
+    const size_t fin_smem = finish_smem_bytes(M);
+    if (fin_smem > 220 * 1024) return Y3D_EUNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     char *p = (char *)ws;
     auto mark = [&](int i) {
@@ -520,6 +630,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     int rc = launch_stream(P, &n_bce, s);
     if (rc) return rc;
     mark(1);
+    cc.work_counter = (int *)(P.counter + 1);
     if (M > 0) {
         rc = assign_run_topk(cc, nb, s);
         if (rc) return rc;
@@ -531,9 +642,9 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     F.counter = P.counter;
     F.partials = partials;
     F.loss_items = loss_items;
-    F.n_bce = n_bce; F.n_branch = nb; F.normalise = normalise;
+    F.n_bce_x = n_bce / B; F.n_branch = nb; F.normalise = normalise;
     F.gain_box = gain_box; F.gain_cls = gain_cls; F.gain_dfl = gain_dfl;
-    if (fin_smem > 48 * 1024) {
+    {
         cudaError_t e = cudaFuncSetAttribute(loss_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
         if (e != cudaSuccess) return (int)e;
     }

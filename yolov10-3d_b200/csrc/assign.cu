@@ -18,30 +18,63 @@ __device__ __forceinline__ unsigned long long tk_key(float metric, int a, int in
 }
 __device__ __forceinline__ int tk_anchor(unsigned long long key) { return 0x7fffffff - (int)((key & 0xffffffffull) >> 1); }
 
-// grid (ceil(B*M*wpg / kTopkWarps), 1, n_branch), block kTopkWarps*32.  wpg = warps per GT: 1 (rectangle walk) or
-// kTopkWarps (all-anchor scan; the warps' lists are merged through shared memory).
+// grid: persistent CTAs (rectangle walk) or one CTA per (branch, image, GT) (all-anchor scan); block kTopkWarps*32.
+// wpg = warps per GT: 1 (rectangle walk) or kTopkWarps (all-anchor scan; the warps' lists are merged through shared
+// memory).
 //
-// The kernel is a chain of latency-bound gathers, so it is organised around few, fat memory round trips, and its
-// code is kept small (one call site per stage, heavy arithmetic out of line) because hundreds of divergent warps
-// share the instruction cache:
-//  * at GT start the class-score rows of the GT's rectangles are pulled into L2 (prefetch, fire-and-forget);
-//  * stage 1 walks the candidate cells 128 at a time (4 per lane): exact in-GT test, then the score and box gathers of
-//    all four cells are issued together.  sb = score^alpha bounds the metric from above (CIoU^beta, sim^gamma <= 1): a
-//    candidate whose sb is below the current k-th metric can never enter the list and is dropped before any box
-//    arithmetic.  Survivors are compacted into a per-warp queue;
-//  * stage 2 pops 32 at a time (full lanes, no loads): CIoU / keypoint similarity and the sorted-list update.
+// The kernel is instruction-issue bound (about 1.6 M (GT, anchor) pairs at cfg2, each an exactly rounded CIoU), so it is
+// organised to evaluate as few pairs exactly as possible, on full lanes, with a small code footprint (one call site
+// per stage, heavy arithmetic out of line: hundreds of divergent warps share the instruction cache):
+//  * the in-GT test (tal.py:218-235) is separable and monotone in the column / row index, so the exact set of in-GT
+//    cells of a level is a rectangle whose four edges are found with the reference's own fp32 comparisons -- no
+//    per-cell test, no wasted lanes; the rectangles of all levels form one flat index space, walked centre-out
+//    128 cells at a time (4 per lane, their score and box gathers issued together);
+//  * two upper bounds drop a candidate before any exact arithmetic: sb = score^alpha (CIoU^beta, sim^gamma <= 1) and
+//    sb * IoU^beta with a fast IoU (CIoU <= IoU); a candidate whose bound is below the current k-th metric can never
+//    enter the list.  Survivors are compacted into a per-warp queue;
+//  * stage 2 pops 32 at a time (full lanes, no loads): exact CIoU / keypoint similarity and the sorted-list update.
 constexpr int kTopkU = 4;             // cells per lane and round trip
 constexpr int kTopkQ = 32 * kTopkU + 32;  // queue slots per warp
 
-__global__ void __launch_bounds__(kTopkWarps * 32, 5) tal_topk_kernel(AssignCtx2 cc, int wpg, int n_branch) {
+// score^alpha of a candidate and an upper bound of its metric: sb * IoU^beta with a fast IoU (CIoU <= IoU; the factor
+// 1.0001 covers the fast arithmetic and the eps terms of the exact expression).  beta < 0: no IoU bound.  Out of line:
+// one copy for the four candidates of a round trip.
+static __device__ __noinline__ float2 cand_bounds(float x, int score_mode, float alpha, float4 box, float st,
+                                                  float4 gbox, float g_area, float beta) {
+    const float s = score_mode == 0 ? x : 1.0f / (1.0f + expf(-x));  // pred_scores.detach().sigmoid() loss.py:232
+    const float sb = dm::pow_(s, alpha);
+    float ub = sb;
+    if (beta >= 0.0f) {
+        const float4 p = make_float4(box.x * st, box.y * st, box.z * st, box.w * st);
+        const float iw = fmaxf(fminf(gbox.z, p.z) - fmaxf(gbox.x, p.x), 0.f);
+        const float ih = fmaxf(fminf(gbox.w, p.w) - fmaxf(gbox.y, p.y), 0.f);
+        const float inter = iw * ih;
+        const float uni = g_area + (p.z - p.x) * (p.w - p.y) - inter;
+        const float iou = fminf(__fdividef(inter, fmaxf(uni, 1e-30f)) * 1.0001f, 1.0f);
+        ub = sb * dm::pow_(iou, beta) * 1.0001f;
+    }
+    return make_float2(sb, ub);
+}
+
+struct LvlWalk {  // one level's exact in-GT rectangle (per warp, shared memory)
+    int off, ncols, c0, r0;        // first flat index, columns, first column / row
+    int w, start, cmid, rmid;      // grid width, first anchor of the level, centre-out pivots
+    float inv, st;                 // 1 / ncols, stride
+    const float *srow;             // score_mode 1: label-channel row of this image and level, minus `start`
+};
+
+__global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2 cc, int wpg, int n_branch) {
     __shared__ int q_a[kTopkWarps][kTopkQ];
     __shared__ float q_s[kTopkWarps][kTopkQ];
+    __shared__ float q_u[kTopkWarps][kTopkQ];
     __shared__ float4 q_b[kTopkWarps][kTopkQ];
+    __shared__ LvlWalk walk[kTopkWarps][Y3D_MAX_LEVELS];
     __shared__ unsigned long long mrg[kTopkWarps][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long per_branch = (long long)cc.c[0].B * cc.c[0].M;
     const long long total = per_branch * n_branch;
     const int wsub = wpg == 1 ? 0 : wid;  // this warp's share of the GT's chunks
+    const unsigned lt_mask = (1u << lane) - 1u;
     // Work items = (branch, image, GT).  One warp per GT: persistent warps pull items from a global counter (padded
     // GTs cost one load, big GTs do not stall a whole wave).  Several warps per GT: one item per CTA, static.
     bool static_done = false;
@@ -65,51 +98,50 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 5) tal_topk_kernel(AssignCtx2
         break;
     }
     const int k = c.k;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const bool prune = c.beta >= 0.0f && c.gamma >= 0.0f;  // the upper bound needs non-negative exponents
     const bool rect = c.use_grid && c.constrain;
+    const bool prune = c.beta >= 0.0f && c.gamma >= 0.0f;  // the upper bounds need non-negative exponents
+    const bool iou_bound = prune && c.use_2d &&
+                           (c.beta == 1.0f || c.beta == 2.0f || c.beta == 3.0f || c.beta == 4.0f || c.beta == 6.0f);
+    const float g_area = (g.box.z - g.box.x) * (g.box.w - g.box.y);
 
-    // conservative cell rectangle of level l (exact bounds are floor(.)+1 and ceil(.)-1: one cell of slack absorbs the
-    // rounding of x / st - 0.5); the exact fp32 in-GT test decides (tal.py:218-235)
-    int c0 = 0, r0 = 0, ncols = 1, nrows = 0;
-    auto rect_of = [&](int l) -> bool {
-        const float st = c.t.stride[l];
-        const float fx0 = fmaxf(floorf(g.box.x / st - 0.5f), 0.0f);
-        const float fy0 = fmaxf(floorf(g.box.y / st - 0.5f), 0.0f);
-        const float fx1 = fminf(ceilf(g.box.z / st - 0.5f), (float)(c.t.w[l] - 1));
-        const float fy1 = fminf(ceilf(g.box.w / st - 0.5f), (float)(c.t.h[l] - 1));
-        if (!(fx0 <= fx1 && fy0 <= fy1)) return false;
-        c0 = (int)fx0; r0 = (int)fy0;
-        ncols = (int)fx1 - c0 + 1; nrows = (int)fy1 - r0 + 1;
-        return true;
-    };
-    if (rect && c.score_mode == 1 && wsub == 0) {  // pull the label-channel rows of every rectangle into L2
-#pragma unroll 1
+    int cells = c.A;  // candidates in the flat index space
+    int off1 = 0x7fffffff, off2 = 0x7fffffff, off3 = 0x7fffffff;
+    if (rect) {
+        // exact in-GT rectangle of every level: in_gt(ax, ay) = min(ax-x1, ay-y1, x2-ax, y2-ay) > 1e-9 splits into four
+        // monotone edge tests; each edge is located with the very comparison the dense test uses, starting one cell
+        // outside the real-valued estimate (all lanes do the same scalar work)
+        cells = 0;
         for (int l = 0; l < c.t.nl; ++l) {
-            if (!rect_of(l)) continue;
-            const float *row0 = c.t.ptr[l] + (long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + g.label) * c.t.sC[l];
-            for (int j = lane; j < 2 * nrows; j += 32)  // first and last cell of each row segment
-                prefetch_l2(row0 + (long long)(r0 + (j >> 1)) * c.t.w[l] + c0 + ((j & 1) ? ncols - 1 : 0));
+            const float st = c.t.stride[l];
+            const int w = c.t.w[l], h = c.t.h[l];
+            int cA = max((int)floorf(g.box.x / st - 0.5f) - 1, 0);
+            int cB = min((int)ceilf(g.box.z / st - 0.5f) + 1, w - 1);
+            int rA = max((int)floorf(g.box.y / st - 0.5f) - 1, 0);
+            int rB = min((int)ceilf(g.box.w / st - 0.5f) + 1, h - 1);
+            while (cA <= cB && !(dm::sub(dm::mul((float)cA + 0.5f, st), g.box.x) > 1e-9f)) ++cA;
+            while (cB >= cA && !(dm::sub(g.box.z, dm::mul((float)cB + 0.5f, st)) > 1e-9f)) --cB;
+            while (rA <= rB && !(dm::sub(dm::mul((float)rA + 0.5f, st), g.box.y) > 1e-9f)) ++rA;
+            while (rB >= rA && !(dm::sub(g.box.w, dm::mul((float)rB + 0.5f, st)) > 1e-9f)) --rB;
+            const int ncols = cB >= cA ? cB - cA + 1 : 0, nrows = rB >= rA ? rB - rA + 1 : 0;
+            if (lane == 0) {
+                LvlWalk &L = walk[wid][l];
+                L.off = cells; L.ncols = ncols > 0 ? ncols : 1; L.c0 = cA; L.r0 = rA;
+                L.w = w; L.start = c.t.start[l]; L.cmid = (ncols - 1) >> 1; L.rmid = (nrows - 1) >> 1;
+                L.inv = __frcp_rn((float)(ncols > 0 ? ncols : 1)); L.st = st;
+                L.srow = c.score_mode == 1 ? c.t.ptr[l] + (long long)b * c.t.sB[l] +
+                                                 (long long)(c.cls_ch0 + g.label) * c.t.sC[l] - c.t.start[l]
+                                           : nullptr;
+            }
+            cells += ncols * nrows;
+            if (l == 0) off1 = cells;
+            else if (l == 1) off2 = cells;
+            else if (l == 2) off3 = cells;
         }
+        __syncwarp();
     }
 
     unsigned long long tk = 0ull;   // lane-distributed sorted list (descending), lanes >= k unused
     unsigned long long thr = 0ull;  // key of the k-th entry (warp-uniform)
-
-    auto process = [&](unsigned long long ck) {  // ck: this lane's candidate key, 0 = none
-        for (;;) {
-            const unsigned mk = __ballot_sync(0xffffffffu, ck > thr);
-            if (!mk) break;
-            const int src = __ffs(mk) - 1;
-            const unsigned long long x = __shfl_sync(0xffffffffu, ck, src);
-            const int pos = __popc(__ballot_sync(0xffffffffu, tk > x && lane < k));
-            const unsigned long long up = __shfl_up_sync(0xffffffffu, tk, 1);
-            if (lane == pos) tk = x;
-            else if (lane > pos) tk = up;
-            thr = __shfl_sync(0xffffffffu, tk, k - 1);
-            if (lane == src) ck = 0ull;
-        }
-    };
 
     // phase 0 (first warp of the GT): the first k anchors enter the list even when outside the GT or at metric 0
     // (they are what a dense stable top-k picks among zeros), see assign.cuh
@@ -123,103 +155,81 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 5) tal_topk_kernel(AssignCtx2
         key0 = tk_key(metric, lane, cin);
     }
 
-    // phase 1: candidates = anchors >= k inside the GT.  One loop body serves both walks: `more` trips, then the flush.
+    // phase 1: candidates = anchors >= k inside the GT.  One loop body: first entry, then trips while the queue cannot
+    // fill a warp, pops otherwise, the remainder at the end.
     int qn = 0;
-    int l = -1, i0 = 0, cells = 0, w = 1, start = 0, rmid = 0, cmid = 0;
-    float st = 1.0f, inv = 1.0f;
-    const float *srow = nullptr;  // rect walk, score_mode 1: label-channel row of this image and level, minus `start`
-    // centre-out order inside the rectangle: the best candidates tend to sit near the GT centre, so visiting them
-    // first raises the k-th metric early and later candidates fail the cheap threshold tests (the result does not
-    // depend on the order: keys are totally ordered)
-    auto centre_out = [](int i, int mid) { return (i & 1) ? mid + ((i + 1) >> 1) : mid - (i >> 1); };
-    if (!rect) { cells = c.A; i0 = wsub * (32 * kTopkU); l = 0; }
+    int i0 = wsub * (32 * kTopkU);
     bool done = false;
     for (bool first = true;; first = false) {
         unsigned long long key = 0ull;
         if (first) {
             key = key0;
         } else if (qn < 32 && !done) {
-            // ---- advance to the next chunk of candidate cells (only while the queue cannot fill a warp)
-            bool more = true;
-            if (rect) {
-                while (l < 0 || i0 >= cells) {
-                    if (++l >= c.t.nl) { more = false; break; }
-                    cells = 0;
-                    if (!rect_of(l)) continue;
-                    cells = ncols * nrows;
-                    st = c.t.stride[l]; w = c.t.w[l]; start = c.t.start[l];
-                    inv = __frcp_rn((float)ncols);
-                    rmid = (nrows - 1) >> 1; cmid = (ncols - 1) >> 1;
-                    if (c.score_mode == 1)
-                        srow = c.t.ptr[l] + (long long)b * c.t.sB[l] + (long long)(c.cls_ch0 + g.label) * c.t.sC[l] - start;
-                    i0 = wsub * (32 * kTopkU);
-                }
-            } else {
-                more = i0 < cells;
-            }
-            if (!more) done = true;
-            if (more) {
-                // ---- stage 1: locate, in-GT test, one round trip for the gathers of up to kTopkU candidates per lane
-                bool h[kTopkU];
-                int a[kTopkU];
-                bool any = false;
+            if (i0 >= cells) { done = true; continue; }
+            // ---- stage 1: locate, one round trip for the gathers of up to kTopkU candidates per lane, bounds
+            bool h[kTopkU];
+            int a[kTopkU];
+            float x[kTopkU];
+            float4 bx[kTopkU];
 #pragma unroll
-                for (int u = 0; u < kTopkU; ++u) {
-                    const int j = i0 + u * 32 + lane;
-                    h[u] = false;
-                    a[u] = 0;
-                    if (j < cells) {
-                        float ax, ay, s_;
-                        if (rect) {
-                            int r = (int)(((float)j + 0.5f) * inv);  // j / ncols; fixed up if the product rounded across
-                            int cc_ = j - r * ncols;
-                            if (cc_ < 0) { --r; cc_ += ncols; }
-                            else if (cc_ >= ncols) { ++r; cc_ -= ncols; }
-                            const int col = c0 + centre_out(cc_, cmid), row = r0 + centre_out(r, rmid);
-                            a[u] = start + row * w + col;
-                            ax = dm::mul((float)col + 0.5f, st); ay = dm::mul((float)row + 0.5f, st);
-                            h[u] = a[u] >= k && dm::in_gt(ax, ay, g.box);
-                        } else {
-                            a[u] = j;
-                            h[u] = j >= k;
-                            if (h[u] && c.constrain) {
-                                anchor_px(c, j, ax, ay, s_);
-                                h[u] = dm::in_gt(ax, ay, g.box);
-                            }
+            for (int u = 0; u < kTopkU; ++u) {
+                const int j = i0 + u * 32 + lane;
+                h[u] = false;
+                a[u] = 0;
+                x[u] = 0.f;
+                bx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < cells) {
+                    if (rect) {
+                        const int l = (j >= off1 ? 1 : 0) + (j >= off2 ? 1 : 0) + (j >= off3 ? 1 : 0);
+                        const LvlWalk &L = walk[wid][l];
+                        const int jj = j - L.off;
+                        int r = (int)(((float)jj + 0.5f) * L.inv);  // jj / ncols; fixed up if the product rounded across
+                        int cc_ = jj - r * L.ncols;
+                        if (cc_ < 0) { --r; cc_ += L.ncols; }
+                        else if (cc_ >= L.ncols) { ++r; cc_ -= L.ncols; }
+                        // centre-out inside the rectangle: good candidates first raise the k-th metric early
+                        const int col = L.c0 + ((cc_ & 1) ? L.cmid + ((cc_ + 1) >> 1) : L.cmid - (cc_ >> 1));
+                        const int row = L.r0 + ((r & 1) ? L.rmid + ((r + 1) >> 1) : L.rmid - (r >> 1));
+                        a[u] = L.start + row * L.w + col;
+                        h[u] = a[u] >= k;
+                        if (h[u]) x[u] = L.srow ? L.srow[a[u]] : pair_load_score(c, b, a[u], g.label);
+                    } else {
+                        a[u] = j;
+                        h[u] = j >= k;
+                        if (h[u] && c.constrain) {
+                            float ax, ay, s_;
+                            anchor_px(c, j, ax, ay, s_);
+                            h[u] = dm::in_gt(ax, ay, g.box);
                         }
+                        if (h[u]) x[u] = pair_load_score(c, b, j, g.label);
                     }
-                    any |= h[u];
-                }
-                i0 += wpg * (32 * kTopkU);
-                if (__ballot_sync(0xffffffffu, any)) {
-                    float x[kTopkU];
-                    float4 bx[kTopkU];
-#pragma unroll
-                    for (int u = 0; u < kTopkU; ++u) {
-                        x[u] = 0.f;
-                        bx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (h[u]) {
-                            x[u] = srow ? srow[a[u]] : pair_load_score(c, b, a[u], g.label);
-                            bx[u] = pair_load_box(c, b, a[u]).box;
-                        }
-                    }
-                    const unsigned tm = prune ? (unsigned)(thr >> 32) : 0u;
-#pragma unroll
-                    for (int u = 0; u < kTopkU; ++u) {
-                        const float sb = h[u] ? dm::pow_(pair_score(c, x[u]), c.alpha) : 0.f;
-                        const bool pass = h[u] && sb > 0.0f && __float_as_uint(sb) >= tm;
-                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass) {
-                            const int pos = qn + __popc(bal & lt_mask);
-                            q_a[wid][pos] = a[u];
-                            q_s[wid][pos] = sb;
-                            q_b[wid][pos] = bx[u];
-                        }
-                        qn += __popc(bal);
-                    }
-                    __syncwarp();
+                    if (h[u]) bx[u] = pair_load_box(c, b, a[u]).box;
                 }
             }
+            i0 += wpg * (32 * kTopkU);
+            const unsigned tm = prune ? (unsigned)(thr >> 32) : 0u;
+#pragma unroll
+            for (int u = 0; u < kTopkU; ++u) {
+                float sb = 0.f, ub = 0.f;  // score^alpha and the upper bound of the metric
+                if (__any_sync(0xffffffffu, h[u])) {
+                    const float stv_ = c.box_grid_units ? c.t.stride[level_of(c.t, a[u])] : 1.0f;
+                    const float2 r2 = cand_bounds(x[u], c.score_mode, c.alpha, bx[u], stv_, g.box, g_area,
+                                                  iou_bound ? c.beta : -1.0f);
+                    sb = h[u] ? r2.x : 0.f;
+                    ub = r2.y;
+                }
+                const bool pass = h[u] && sb > 0.0f && __float_as_uint(ub) >= tm;
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const int pos = qn + __popc(bal & lt_mask);
+                    q_a[wid][pos] = a[u];
+                    q_s[wid][pos] = sb;
+                    q_u[wid][pos] = ub;
+                    q_b[wid][pos] = bx[u];
+                }
+                qn += __popc(bal);
+            }
+            __syncwarp();
             continue;
         } else if (qn > 0) {
             // ---- stage 2: pop full lanes while trips remain, the rest at the end (no loads: pure arithmetic)
@@ -227,13 +237,12 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 5) tal_topk_kernel(AssignCtx2
             qn -= take;
             if (lane < take) {
                 const int a2 = q_a[wid][qn + lane];
-                const float s2 = q_s[wid][qn + lane];
-                if (!prune || __float_as_uint(s2) >= (unsigned)(thr >> 32)) {
+                if (!prune || __float_as_uint(q_u[wid][qn + lane]) >= (unsigned)(thr >> 32)) {
                     PairRaw raw;
                     raw.box = q_b[wid][qn + lane];
                     raw.s = 0.0f;
                     float ovl;
-                    const float metric = pair_metric(c, b, m, g, a2, raw, s2, ovl);
+                    const float metric = pair_metric(c, b, m, g, a2, raw, q_s[wid][qn + lane], ovl);
                     if (metric > 0.0f) key = tk_key(metric, a2, 1);
                 }
             }
@@ -241,24 +250,35 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 5) tal_topk_kernel(AssignCtx2
         } else {
             break;
         }
-        process(key);
+        // ---- sorted-list update with this lane's candidate key (0 = none)
+        for (;;) {
+            const unsigned mk = __ballot_sync(0xffffffffu, key > thr);
+            if (!mk) break;
+            const int src = __ffs(mk) - 1;
+            const unsigned long long xk = __shfl_sync(0xffffffffu, key, src);
+            const int pos = __popc(__ballot_sync(0xffffffffu, tk > xk && lane < k));
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, tk, 1);
+            if (lane == pos) tk = xk;
+            else if (lane > pos) tk = up;
+            thr = __shfl_sync(0xffffffffu, tk, k - 1);
+            if (lane == src) key = 0ull;
+        }
     }
 
     if (wpg > 1) {  // merge the per-warp lists into the first warp's
         mrg[wid][lane] = lane < k ? tk : 0ull;
         __syncthreads();
         if (wid != 0) return;
-        unsigned long long km = 0ull;
-        for (int w2 = 1; w2 < wpg; ++w2) {  // one call site: k insertions per foreign list at most
-            km = mrg[w2][lane];
+        for (int w2 = 1; w2 < wpg; ++w2) {
+            unsigned long long km = mrg[w2][lane];
             for (;;) {
                 const unsigned mk = __ballot_sync(0xffffffffu, km > thr);
                 if (!mk) break;
                 const int src = __ffs(mk) - 1;
-                const unsigned long long x = __shfl_sync(0xffffffffu, km, src);
-                const int pos = __popc(__ballot_sync(0xffffffffu, tk > x && lane < k));
+                const unsigned long long xk = __shfl_sync(0xffffffffu, km, src);
+                const int pos = __popc(__ballot_sync(0xffffffffu, tk > xk && lane < k));
                 const unsigned long long up = __shfl_up_sync(0xffffffffu, tk, 1);
-                if (lane == pos) tk = x;
+                if (lane == pos) tk = xk;
                 else if (lane > pos) tk = up;
                 thr = __shfl_sync(0xffffffffu, tk, k - 1);
                 if (lane == src) km = 0ull;
@@ -350,7 +370,7 @@ int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s) {
         int dev = 0, sms = kNumSMs;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (blocks > 5LL * sms) blocks = 5LL * sms;
+        if (blocks > 6LL * sms) blocks = 6LL * sms;
     }
     tal_topk_kernel<<<(unsigned)blocks, kTopkWarps * 32, 0, s>>>(cc, wpg, n);
     Y3D_CHECK_LAUNCH();

@@ -114,10 +114,15 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         for (int l = 0; l < c.t.nl; ++l) {
             const float st = c.t.stride[l];
             const int w = c.t.w[l], h = c.t.h[l];
-            int cA = max((int)floorf(g.box.x / st - 0.5f) - 1, 0);
-            int cB = min((int)ceilf(g.box.z / st - 0.5f) + 1, w - 1);
-            int rA = max((int)floorf(g.box.y / st - 0.5f) - 1, 0);
-            int rB = min((int)ceilf(g.box.w / st - 0.5f) + 1, h - 1);
+            int cA = max((int)floorf(g.box.x / st - 0.5f), 0);
+            int cB = min((int)ceilf(g.box.z / st - 0.5f), w - 1);
+            int rA = max((int)floorf(g.box.y / st - 0.5f), 0);
+            int rB = min((int)ceilf(g.box.w / st - 0.5f), h - 1);
+            // (if rounding put a start inside the range, step outwards first)
+            while (cA > 0 && dm::sub(dm::mul((float)(cA - 1) + 0.5f, st), g.box.x) > 1e-9f) --cA;
+            while (cB < w - 1 && dm::sub(g.box.z, dm::mul((float)(cB + 1) + 0.5f, st)) > 1e-9f) ++cB;
+            while (rA > 0 && dm::sub(dm::mul((float)(rA - 1) + 0.5f, st), g.box.y) > 1e-9f) --rA;
+            while (rB < h - 1 && dm::sub(g.box.w, dm::mul((float)(rB + 1) + 0.5f, st)) > 1e-9f) ++rB;
             while (cA <= cB && !(dm::sub(dm::mul((float)cA + 0.5f, st), g.box.x) > 1e-9f)) ++cA;
             while (cB >= cA && !(dm::sub(g.box.z, dm::mul((float)cB + 0.5f, st)) > 1e-9f)) --cB;
             while (rA <= rB && !(dm::sub(dm::mul((float)rA + 0.5f, st), g.box.y) > 1e-9f)) ++rA;
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
 
     // phase 1: candidates = anchors >= k inside the GT.  One loop body: first entry, then trips while the queue cannot
     // fill a warp, pops otherwise, the remainder at the end.
-    int qn = 0;
+    int qn = 0, qh = 0;  // FIFO ring: candidates are evaluated in walk order (centre first)
     int i0 = wsub * (32 * kTopkU);
     bool done = false;
     for (bool first = true;; first = false) {
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
             // ---- stage 1: locate, one round trip for the gathers of up to kTopkU candidates per lane, bounds
             bool h[kTopkU];
             int a[kTopkU];
-            float x[kTopkU];
+            float x[kTopkU], sv[kTopkU];
             float4 bx[kTopkU];
 #pragma unroll
             for (int u = 0; u < kTopkU; ++u) {
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                 h[u] = false;
                 a[u] = 0;
                 x[u] = 0.f;
+                sv[u] = 1.0f;
                 bx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < cells) {
                     if (rect) {
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                         const int col = L.c0 + ((cc_ & 1) ? L.cmid + ((cc_ + 1) >> 1) : L.cmid - (cc_ >> 1));
                         const int row = L.r0 + ((r & 1) ? L.rmid + ((r + 1) >> 1) : L.rmid - (r >> 1));
                         a[u] = L.start + row * L.w + col;
+                        sv[u] = L.st;
                         h[u] = a[u] >= k;
                         if (h[u]) x[u] = L.srow ? L.srow[a[u]] : pair_load_score(c, b, a[u], g.label);
                     } else {
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                             h[u] = dm::in_gt(ax, ay, g.box);
                         }
                         if (h[u]) x[u] = pair_load_score(c, b, j, g.label);
+                        if (h[u] && c.box_grid_units) sv[u] = c.t.stride[level_of(c.t, j)];
                     }
                     if (h[u]) bx[u] = pair_load_box(c, b, a[u]).box;
                 }
@@ -212,8 +220,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
             for (int u = 0; u < kTopkU; ++u) {
                 float sb = 0.f, ub = 0.f;  // score^alpha and the upper bound of the metric
                 if (__any_sync(0xffffffffu, h[u])) {
-                    const float stv_ = c.box_grid_units ? c.t.stride[level_of(c.t, a[u])] : 1.0f;
-                    const float2 r2 = cand_bounds(x[u], c.score_mode, c.alpha, bx[u], stv_, g.box, g_area,
+                    const float2 r2 = cand_bounds(x[u], c.score_mode, c.alpha, bx[u],
+                                                  c.box_grid_units ? sv[u] : 1.0f, g.box, g_area,
                                                   iou_bound ? c.beta : -1.0f);
                     sb = h[u] ? r2.x : 0.f;
                     ub = r2.y;
@@ -221,7 +229,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                 const bool pass = h[u] && sb > 0.0f && __float_as_uint(ub) >= tm;
                 const unsigned bal = __ballot_sync(0xffffffffu, pass);
                 if (pass) {
-                    const int pos = qn + __popc(bal & lt_mask);
+                    int pos = qh + qn + __popc(bal & lt_mask);
+                    if (pos >= kTopkQ) pos -= kTopkQ;
                     q_a[wid][pos] = a[u];
                     q_s[wid][pos] = sb;
                     q_u[wid][pos] = ub;
@@ -234,18 +243,22 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         } else if (qn > 0) {
             // ---- stage 2: pop full lanes while trips remain, the rest at the end (no loads: pure arithmetic)
             const int take = qn < 32 ? qn : 32;
-            qn -= take;
+            int qi = qh + lane;
+            if (qi >= kTopkQ) qi -= kTopkQ;
             if (lane < take) {
-                const int a2 = q_a[wid][qn + lane];
-                if (!prune || __float_as_uint(q_u[wid][qn + lane]) >= (unsigned)(thr >> 32)) {
+                const int a2 = q_a[wid][qi];
+                if (!prune || __float_as_uint(q_u[wid][qi]) >= (unsigned)(thr >> 32)) {
                     PairRaw raw;
-                    raw.box = q_b[wid][qn + lane];
+                    raw.box = q_b[wid][qi];
                     raw.s = 0.0f;
                     float ovl;
-                    const float metric = pair_metric(c, b, m, g, a2, raw, q_s[wid][qn + lane], ovl);
+                    const float metric = pair_metric(c, b, m, g, a2, raw, q_s[wid][qi], ovl);
                     if (metric > 0.0f) key = tk_key(metric, a2, 1);
                 }
             }
+            qn -= take;
+            qh += take;
+            if (qh >= kTopkQ) qh -= kTopkQ;
             __syncwarp();
         } else {
             break;

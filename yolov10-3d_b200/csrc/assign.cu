@@ -71,14 +71,14 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     __shared__ LvlWalk walk[kTopkWarps][Y3D_MAX_LEVELS];
     __shared__ unsigned long long mrg[kTopkWarps][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long per_branch = (long long)cc.c[0].B * cc.c[0].M;
-    const long long total = per_branch * n_branch;
+    const int per_branch = cc.c[0].B * cc.c[0].M;  // host checks n_branch * B * M < 2^31
+    const int total = per_branch * n_branch;
     const int wsub = wpg == 1 ? 0 : wid;  // this warp's share of the GT's chunks
     const unsigned lt_mask = (1u << lane) - 1u;
     // Work items = (branch, image, GT).  One warp per GT: persistent warps pull items from a global counter (padded
     // GTs cost one load, big GTs do not stall a whole wave).  Several warps per GT: one item per CTA, static.
     bool static_done = false;
-    for (long long item = (long long)blockIdx.x;;) {
+    for (int item = (int)blockIdx.x;;) {
     if (wpg == 1) {
         int it = 0;
         if (lane == 0) it = atomicAdd(cc.work_counter, 1);
@@ -88,15 +88,15 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         static_done = true;
     }
     if (item >= total) break;
-    const int z = (int)(item / per_branch);
-    const long long gt_id = item - z * per_branch;
+    const int z = item >= per_branch ? 1 : 0;
+    const int gt_id = item - z * per_branch;
     const AssignCtx &c = cc.c[z];
-    const int b = (int)(gt_id / c.M), m = (int)(gt_id % c.M);
-    const GtRec g = load_gt(c, b, m);
-    if (!g.valid) {  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104)
+    const int b = gt_id / c.M, m = gt_id - b * c.M;
+    if (!gt_valid(c, b, m)) {  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104)
         if (wpg == 1) continue;
         break;
     }
+    const GtRec g = load_gt(c, b, m);
     const int k = c.k;
     const bool rect = c.use_grid && c.constrain;
     const bool prune = c.beta >= 0.0f && c.gamma >= 0.0f;  // the upper bounds need non-negative exponents
@@ -114,19 +114,33 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         for (int l = 0; l < c.t.nl; ++l) {
             const float st = c.t.stride[l];
             const int w = c.t.w[l], h = c.t.h[l];
-            int cA = max((int)floorf(g.box.x / st - 0.5f), 0);
-            int cB = min((int)ceilf(g.box.z / st - 0.5f), w - 1);
-            int rA = max((int)floorf(g.box.y / st - 0.5f), 0);
-            int rB = min((int)ceilf(g.box.w / st - 0.5f), h - 1);
-            // (if rounding put a start inside the range, step outwards first)
-            while (cA > 0 && dm::sub(dm::mul((float)(cA - 1) + 0.5f, st), g.box.x) > 1e-9f) --cA;
-            while (cB < w - 1 && dm::sub(g.box.z, dm::mul((float)(cB + 1) + 0.5f, st)) > 1e-9f) ++cB;
-            while (rA > 0 && dm::sub(dm::mul((float)(rA - 1) + 0.5f, st), g.box.y) > 1e-9f) --rA;
-            while (rB < h - 1 && dm::sub(g.box.w, dm::mul((float)(rB + 1) + 0.5f, st)) > 1e-9f) ++rB;
-            while (cA <= cB && !(dm::sub(dm::mul((float)cA + 0.5f, st), g.box.x) > 1e-9f)) ++cA;
-            while (cB >= cA && !(dm::sub(g.box.z, dm::mul((float)cB + 0.5f, st)) > 1e-9f)) --cB;
-            while (rA <= rB && !(dm::sub(dm::mul((float)rA + 0.5f, st), g.box.y) > 1e-9f)) ++rA;
-            while (rB >= rA && !(dm::sub(g.box.w, dm::mul((float)rB + 0.5f, st)) > 1e-9f)) --rB;
+            // lo edge: first index i with (i + 0.5) * st - lo > 1e-9; hi edge: last index with hi - (i + 0.5) * st > 1e-9.
+            // The real-valued estimate is off by at most one cell, so a window of four cells around it brackets the
+            // flip of the (monotone) comparison; anything else falls back to a linear search.
+            auto lo_edge = [&](float lo, int n) {
+                const int f = (int)floorf(lo / st - 0.5f);
+                auto ok = [&](int i) { return dm::sub(dm::mul((float)i + 0.5f, st), lo) > 1e-9f; };
+                int e = f - 1 + (ok(f - 1) ? 0 : 1) + (ok(f) ? 0 : 1) + (ok(f + 1) ? 0 : 1) + (ok(f + 2) ? 0 : 1);
+                if (ok(f - 1) || !ok(f + 2)) {  // flip not inside the window
+                    e = f - 1;
+                    while (e > 0 && ok(e - 1)) --e;
+                    while (e < n && !ok(e)) ++e;
+                }
+                return max(e, 0);
+            };
+            auto hi_edge = [&](float hi, int n) {
+                const int f = (int)ceilf(hi / st - 0.5f);
+                auto ok = [&](int i) { return dm::sub(hi, dm::mul((float)i + 0.5f, st)) > 1e-9f; };
+                int e = f + 1 - (ok(f + 1) ? 0 : 1) - (ok(f) ? 0 : 1) - (ok(f - 1) ? 0 : 1) - (ok(f - 2) ? 0 : 1);
+                if (ok(f + 1) || !ok(f - 2)) {
+                    e = f + 1;
+                    while (e < n - 1 && ok(e + 1)) ++e;
+                    while (e >= 0 && !ok(e)) --e;
+                }
+                return min(e, n - 1);
+            };
+            const int cA = lo_edge(g.box.x, w), cB = hi_edge(g.box.z, w);
+            const int rA = lo_edge(g.box.y, h), rB = hi_edge(g.box.w, h);
             const int ncols = cB >= cA ? cB - cA + 1 : 0, nrows = rB >= rA ? rB - rA + 1 : 0;
             if (lane == 0) {
                 LvlWalk &L = walk[wid][l];
@@ -378,6 +392,7 @@ int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s) {
     const AssignCtx &c = cc.c[0];
     const int wpg = (c.use_grid && c.constrain && cc.work_counter) ? 1 : kTopkWarps;
     const long long items = (long long)c.B * c.M * n;
+    if (items >= 0x7fffffffLL) return Y3D_EUNSUPPORTED;
     long long blocks = wpg == 1 ? (items + kTopkWarps - 1) / kTopkWarps : items;
     if (wpg == 1) {  // persistent: no more CTAs than fit at once
         int dev = 0, sms = kNumSMs;

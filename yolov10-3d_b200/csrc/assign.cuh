@@ -66,6 +66,14 @@ struct GtRec {
     int valid;
 };
 
+// validity of a GT row alone (padded rows are skipped before any other work)
+__device__ __forceinline__ bool gt_valid(const AssignCtx &c, int b, int m) {
+    const long long i = (long long)b * c.M + m;
+    if (c.mask_gt) return c.mask_gt[i] != 0.0f;
+    const float *pb = c.gt_bboxes + i * c.gb_stride;
+    return dm::add(dm::add(dm::add(pb[0], pb[1]), pb[2]), pb[3]) > 0.0f;
+}
+
 __device__ __forceinline__ GtRec load_gt(const AssignCtx &c, int b, int m) {
     GtRec g;
     long long i = (long long)b * c.M + m;

@@ -133,6 +133,28 @@ int y3d_v10_loss_fwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const i
                      float *loss_items, double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx,
                      void *const *prof_events, void *ws, size_t ws_bytes, void *stream);
 
+/* Backward of y3d_v8_loss_fwd / y3d_v10_loss_fwd: what autograd produces in the reference for loss.py:206-257
+ * (BCEWithLogits :240, BboxLoss.forward :82-96, _df_loss :99-113, bbox_decode :197-204; CIoU metrics.py:78-134 with
+ * alpha under no_grad :128-129; the assigner, tal.py:44, is @torch.no_grad and therefore a constant).
+ *  Call right after the forward call with the SAME geometry, gt, M, topk and the SAME, untouched workspace (the
+ *  forward leaves the claimed-anchor lists with assigned GT and alignment weight in it).
+ *  grad_ptr / grad_sB / grad_sC: one gradient tensor per level, indexed like the head tensors; every element is
+ *  written (box rows of background anchors are zero).  loss_items: DEVICE float[4 * n_branch] of the forward pass
+ *  (after y3d_v8_loss_finalize in the multi-GPU case: the batch-global target_scores_sum must be in [4z+3]).
+ *  grad_items: DEVICE float[3 * n_branch] = d total / d (box, cls, dfl) item of each branch; the reference's
+ *  total = sum(items) * batch_size gives batch_size for each. */
+int y3d_v8_loss_bwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, float *const *grad_ptr,
+                    const int64_t *grad_sB, const int64_t *grad_sC, const int *lvl_hw, const float *lvl_stride, int nl,
+                    int B, int nc, int reg_max, const float *gt, int M, int topk, float gain_box, float gain_cls,
+                    float gain_dfl, const float *loss_items, const float *grad_items, const void *ws, size_t ws_bytes,
+                    void *stream);
+int y3d_v10_loss_bwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC, float *const *o2m_grad,
+                     const int64_t *o2m_gsB, const int64_t *o2m_gsC, const float *const *o2o_ptr, const int64_t *o2o_sB,
+                     const int64_t *o2o_sC, float *const *o2o_grad, const int64_t *o2o_gsB, const int64_t *o2o_gsC,
+                     const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt,
+                     int M, int topk_o2m, int topk_o2o, float gain_box, float gain_cls, float gain_dfl,
+                     const float *loss_items, const float *grad_items, const void *ws, size_t ws_bytes, void *stream);
+
 /* v8DetectionLoss.bbox_decode (loss.py:197-204) + the permute/sigmoid of loss.py:214,232: head levels ->
  * pd_bboxes [B,A,4] xyxy in GRID units (caller multiplies by stride, loss.py:233) and, optionally (may be NULL),
  * pd_scores [B,A,nc] = sigmoid(class logits).  Same device arithmetic as the fused loss uses internally. */

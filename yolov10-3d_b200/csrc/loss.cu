@@ -22,11 +22,10 @@
 //        (select_highest_overlaps), per-GT maxima in shared memory, CIoU / DFL-CE / BCE-correction terms, exact
 //        (fixed-point, order-independent) block sums; the last CTA reduces all partials in a fixed order and
 //        writes the loss items.
-#include "assign.cuh"
+#include "loss.cuh"
 
 namespace y3d {
 
-constexpr int kR = 16;
 constexpr int kStreamThreads = 128;  // 32 anchor-quads x 4 channel parts
 constexpr int kFinishThreads = 1024;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -200,6 +199,7 @@ struct FinishParams {
     const float *lse[2];       // [B,4,A]
     int *list_gi[2];           // [B,cap] scratch
     float *list_al[2];         // [B,cap] scratch
+    float *list_w[2];          // [B,cap] out: normalised alignment weight of each entry (read by the backward pass)
     const double *part_bce;    // [n_branch][n_bce]
     double *part_fg;           // [n_branch][B][5]: iou, dfl, target_scores, x*t, softplus
     unsigned *counter;         // zeroed by the stream kernel
@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         const float alv = lal[e];
         const float pa = __int_as_float(pos_a[gi]), po = __int_as_float(pos_o[gi]);
         const float wgt = dm::div(dm::mul(alv, po), dm::add(pa, c.eps));  // = target_scores.sum(-1), tal.py:89-92
+        F.list_w[z][(long long)b * c.list_cap + e] = wgt;  // kept for the backward pass
         const int l = level_of(c.t, a);
         const int cell = a - c.t.start[l];
         const float st = c.t.stride[l];
@@ -507,32 +508,6 @@ static bool vec4_ok(const LevelTable &t) {
     return true;
 }
 
-struct LossWs {  // all offsets 256-byte aligned; per-branch blocks are contiguous
-    size_t claim, boxes, lse, list_a, list_gi, list_al, list_count, per_branch;
-    size_t off_counter, off_pfg, off_pbce, total;
-    int cap, n_bce;
-};
-static int stream_blocks_x(int A) { return (A + 31) / 32; }  // upper bound (the scalar path)
-static LossWs loss_ws_layout(int nb, int B, int A, int M, int k) {
-    LossWs w;
-    long long cap = (long long)(M > 0 ? M : 1) * (k > 0 ? k : 1);
-    w.cap = (int)(cap < A ? cap : A);
-    size_t o = 0;
-    w.claim = o;      o += a256(sizeof(unsigned long long) * (size_t)B * A);
-    w.boxes = o;      o += a256(sizeof(float) * 4 * (size_t)B * A);
-    w.lse = o;        o += a256(sizeof(float) * 4 * (size_t)B * A);
-    w.list_a = o;     o += a256(sizeof(int) * (size_t)B * w.cap);
-    w.list_gi = o;    o += a256(sizeof(int) * (size_t)B * w.cap);
-    w.list_al = o;    o += a256(sizeof(float) * (size_t)B * w.cap);
-    w.list_count = o; o += a256(sizeof(int) * (size_t)B);
-    w.per_branch = o;
-    w.off_counter = (size_t)nb * w.per_branch;
-    w.off_pfg = w.off_counter + 256;
-    w.off_pbce = w.off_pfg + a256(sizeof(double) * 5 * (size_t)nb * B);
-    w.n_bce = stream_blocks_x(A) * B;
-    w.total = w.off_pbce + a256(sizeof(double) * (size_t)nb * w.n_bce);
-    return w;
-}
 size_t loss_workspace_bytes(int B, int A, int M, int k) { return loss_ws_layout(2, B, A, M, k > 0 ? k : Y3D_MAX_TOPK).total; }
 
 // returns the number of BCE partials per branch through *n_bce
@@ -623,6 +598,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         F.lse[z] = P.lse[z];
         F.list_gi[z] = (int *)(q + w.list_gi);
         F.list_al[z] = (float *)(q + w.list_al);
+        F.list_w[z] = (float *)(q + w.list_w);
         F.dbg_fg[z] = dbg_fg_mask ? dbg_fg_mask + (size_t)z * B * A : nullptr;
         F.dbg_gi[z] = dbg_target_gt_idx ? dbg_target_gt_idx + (size_t)z * B * A : nullptr;
     }

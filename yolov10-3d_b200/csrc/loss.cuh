@@ -1,0 +1,40 @@
+// loss.cuh -- declarations shared by loss.cu (fused forward) and loss_bwd.cu (backward): constants and the
+// workspace layout.  The backward pass reads what the forward pass left in the caller-owned workspace (claimed-anchor
+// lists with their assigned GT and alignment weight), so both sides must agree on the layout.
+#pragma once
+#include "assign.cuh"
+
+namespace y3d {
+
+constexpr int kR = 16;  // reg_max (head.py:37)
+
+struct LossWs {  // all offsets 256-byte aligned; per-branch blocks are contiguous
+    size_t claim, boxes, lse, list_a, list_gi, list_al, list_w, list_count, per_branch;
+    size_t off_counter, off_pfg, off_pbce, total;
+    int cap, n_bce;
+};
+inline int stream_blocks_x(int A) { return (A + 31) / 32; }  // upper bound (the scalar path)
+inline LossWs loss_ws_layout(int nb, int B, int A, int M, int k) {
+    LossWs w;
+    long long cap = (long long)(M > 0 ? M : 1) * (k > 0 ? k : 1);
+    w.cap = (int)(cap < A ? cap : A);
+    size_t o = 0;
+    w.claim = o;      o += a256(sizeof(unsigned long long) * (size_t)B * A);
+    w.boxes = o;      o += a256(sizeof(float) * 4 * (size_t)B * A);
+    w.lse = o;        o += a256(sizeof(float) * 4 * (size_t)B * A);
+    w.list_a = o;     o += a256(sizeof(int) * (size_t)B * w.cap);
+    w.list_gi = o;    o += a256(sizeof(int) * (size_t)B * w.cap);
+    w.list_al = o;    o += a256(sizeof(float) * (size_t)B * w.cap);
+    w.list_w = o;     o += a256(sizeof(float) * (size_t)B * w.cap);
+    w.list_count = o; o += a256(sizeof(int) * (size_t)B);
+    w.per_branch = o;
+    w.off_counter = (size_t)nb * w.per_branch;
+    w.off_pfg = w.off_counter + 256;
+    w.off_pbce = w.off_pfg + a256(sizeof(double) * 5 * (size_t)nb * B);
+    w.n_bce = stream_blocks_x(A) * B;
+    w.total = w.off_pbce + a256(sizeof(double) * (size_t)nb * w.n_bce);
+    return w;
+}
+
+
+}  // namespace y3d

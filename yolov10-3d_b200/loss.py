@@ -1,7 +1,8 @@
 """``v8DetectionLoss`` / ``v10DetectLoss`` mirrors (reference ultralytics/utils/loss.py:157-257, 727-737): same
 constructor (``model`` with ``.args`` and a head as ``model.model[-1]``), same ``__call__(preds, batch)`` and the
-same ``(loss.sum() * batch_size, loss.detach())`` return.  One branch = one call into csrc/loss.cu, which reads the
-head tensors once and never materialises ``pd_scores`` / ``target_scores``."""
+same ``(loss.sum() * batch_size, loss.detach())`` return -- the first element carries an autograd graph whose
+backward is csrc/loss_bwd.cu.  The forward (csrc/loss.cu) reads the head tensors once and never materialises
+``pd_scores`` / ``target_scores``."""
 import torch
 
 from . import _lib
@@ -43,28 +44,46 @@ def pack_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device, extra=Non
     return out
 
 
+def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_events):
+    """Shared body of the one- and two-branch forward calls.  ``levels``: list of 1 or 2 ``Levels``.  Returns a dict with
+    ``items`` (float32[4n] or None), ``partials`` (float64[4n]), ``dbg``, and what the backward pass needs (``ws``,
+    ``gt``, ``M``)."""
+    n = len(levels)
+    l0 = levels[0]
+    for lv in levels:
+        if lv.C != 4 * REG_MAX + nc:
+            raise ValueError(f"expected {4 * REG_MAX + nc} channels, got {lv.C}")
+        if lv.hw != l0.hw or lv.B != l0.B:
+            raise ValueError("one2many and one2one heads must share batch size and level shapes")
+    dev = l0.device
+    gt = gt_packed.to(dev, torch.float32).contiguous()
+    M = int(gt.shape[1])
+    items = torch.empty(4 * n, dtype=torch.float32, device=dev) if normalise else None
+    partials = torch.empty(4 * n, dtype=torch.float64, device=dev)
+    dbg = None
+    if debug:
+        shape = (l0.B, l0.A) if n == 1 else (n, l0.B, l0.A)
+        dbg = dict(fg_mask=torch.empty(shape, dtype=torch.bool, device=dev),
+                   target_gt_idx=torch.empty(shape, dtype=torch.int32, device=dev))
+    ws = workspace(_lib.workspace_bytes(_lib.STAGE_V8_LOSS, B=l0.B, A=l0.A, nc=nc, M=M, k=max(topk)), dev)
+    tail = (ptr(gt) if M > 0 else None, M, *[int(k) for k in topk], float(gains[0]), float(gains[1]), float(gains[2]),
+            int(normalise), ptr(items), ptr(partials), ptr(dbg["fg_mask"]) if debug else None,
+            ptr(dbg["target_gt_idx"]) if debug else None, prof_events, ptr(ws), ws.numel(), stream_ptr(dev))
+    if n == 1:
+        _lib.check(_lib.lib().y3d_v8_loss_fwd(*l0.args(), l0.B, nc, REG_MAX, *tail))
+    else:
+        l1 = levels[1]
+        _lib.check(_lib.lib().y3d_v10_loss_fwd(l0.c_ptr, l0.c_sB, l0.c_sC, l1.c_ptr, l1.c_sB, l1.c_sC, l0.c_hw,
+                                               l0.c_stride, l0.nl, l0.B, nc, REG_MAX, *tail))
+    return dict(items=items, partials=partials, dbg=dbg, ws=ws, gt=gt, M=M)
+
+
 def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, debug=False, prof_events=None):
     """One branch through ``y3d_v8_loss_fwd``.  Returns (items[4] = box, cls, dfl, target_scores_sum  -- or ``None``
     when not normalising --, partials float64[4], debug dict or None).  Nothing synchronises.
     ``prof_events``: optional ctypes array of 4 cudaEvent_t handles (see include/y3d.h), for benchmarks."""
-    lv = Levels(feats, strides)
-    if lv.C != 4 * REG_MAX + nc:
-        raise ValueError(f"expected {4 * REG_MAX + nc} channels, got {lv.C}")
-    dev = lv.device
-    gt = gt_packed.to(dev, torch.float32).contiguous()
-    M = int(gt.shape[1])
-    items = torch.empty(4, dtype=torch.float32, device=dev) if normalise else None
-    partials = torch.empty(4, dtype=torch.float64, device=dev)
-    dbg = None
-    if debug:
-        dbg = dict(fg_mask=torch.empty((lv.B, lv.A), dtype=torch.bool, device=dev),
-                   target_gt_idx=torch.empty((lv.B, lv.A), dtype=torch.int32, device=dev))
-    ws = workspace(_lib.workspace_bytes(_lib.STAGE_V8_LOSS, B=lv.B, A=lv.A, nc=nc, M=M, k=topk), dev)
-    _lib.check(_lib.lib().y3d_v8_loss_fwd(
-        *lv.args(), lv.B, nc, REG_MAX, ptr(gt) if M > 0 else None, M, int(topk), float(gains[0]), float(gains[1]),
-        float(gains[2]), int(normalise), ptr(items), ptr(partials), ptr(dbg["fg_mask"]) if debug else None,
-        ptr(dbg["target_gt_idx"]) if debug else None, prof_events, ptr(ws), ws.numel(), stream_ptr(dev)))
-    return items, partials, dbg
+    r = _branch_forward([Levels(feats, strides)], nc, gt_packed, (topk,), gains, normalise, debug, prof_events)
+    return r["items"], r["partials"], r["dbg"]
 
 
 def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(10, 1), normalise=True, debug=False,
@@ -73,27 +92,52 @@ def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(
 
     Returns (items float32[8] = (box, cls, dfl, target_scores_sum) x (one2many, one2one) or ``None`` when not
     normalising, partials float64[8], debug dict or None).  Nothing synchronises."""
-    lm, lo = Levels(feats_o2m, strides), Levels(feats_o2o, strides)
-    if lm.C != 4 * REG_MAX + nc or lo.C != lm.C:
-        raise ValueError(f"expected {4 * REG_MAX + nc} channels, got {lm.C} / {lo.C}")
-    if lm.hw != lo.hw or lm.B != lo.B:
-        raise ValueError("one2many and one2one heads must share batch size and level shapes")
-    dev = lm.device
-    gt = gt_packed.to(dev, torch.float32).contiguous()
-    M = int(gt.shape[1])
-    items = torch.empty(8, dtype=torch.float32, device=dev) if normalise else None
-    partials = torch.empty(8, dtype=torch.float64, device=dev)
-    dbg = None
-    if debug:
-        dbg = dict(fg_mask=torch.empty((2, lm.B, lm.A), dtype=torch.bool, device=dev),
-                   target_gt_idx=torch.empty((2, lm.B, lm.A), dtype=torch.int32, device=dev))
-    ws = workspace(_lib.workspace_bytes(_lib.STAGE_V8_LOSS, B=lm.B, A=lm.A, nc=nc, M=M, k=max(topk)), dev)
-    _lib.check(_lib.lib().y3d_v10_loss_fwd(
-        lm.c_ptr, lm.c_sB, lm.c_sC, lo.c_ptr, lo.c_sB, lo.c_sC, lm.c_hw, lm.c_stride, lm.nl, lm.B, nc, REG_MAX,
-        ptr(gt) if M > 0 else None, M, int(topk[0]), int(topk[1]), float(gains[0]), float(gains[1]), float(gains[2]),
-        int(normalise), ptr(items), ptr(partials), ptr(dbg["fg_mask"]) if debug else None,
-        ptr(dbg["target_gt_idx"]) if debug else None, prof_events, ptr(ws), ws.numel(), stream_ptr(dev)))
-    return items, partials, dbg
+    r = _branch_forward([Levels(feats_o2m, strides), Levels(feats_o2o, strides)], nc, gt_packed, topk, gains,
+                        normalise, debug, prof_events)
+    return r["items"], r["partials"], r["dbg"]
+
+
+def _branch_backward(levels, nc, fwd, topk, gains, items, grad_items):
+    """``y3d_v8_loss_bwd`` / ``y3d_v10_loss_bwd`` on the workspace the forward call left behind.  Returns one fp32
+    gradient tensor per level and branch, shaped like the (contiguous) head tensors."""
+    n = len(levels)
+    l0 = levels[0]
+    grads = [[torch.empty_like(f) for f in lv.feats] for lv in levels]
+    gl = [Levels(g, l0.strides) for g in grads]
+    gi = grad_items.to(l0.device, torch.float32).contiguous()
+    tail = (l0.c_hw, l0.c_stride, l0.nl, l0.B, nc, REG_MAX, ptr(fwd["gt"]) if fwd["M"] > 0 else None, fwd["M"],
+            *[int(k) for k in topk], float(gains[0]), float(gains[1]), float(gains[2]), ptr(items), ptr(gi),
+            ptr(fwd["ws"]), fwd["ws"].numel(), stream_ptr(l0.device))
+    if n == 1:
+        _lib.check(_lib.lib().y3d_v8_loss_bwd(l0.c_ptr, l0.c_sB, l0.c_sC, gl[0].c_ptr, gl[0].c_sB, gl[0].c_sC, *tail))
+    else:
+        l1 = levels[1]
+        _lib.check(_lib.lib().y3d_v10_loss_bwd(l0.c_ptr, l0.c_sB, l0.c_sC, gl[0].c_ptr, gl[0].c_sB, gl[0].c_sC,
+                                               l1.c_ptr, l1.c_sB, l1.c_sC, gl[1].c_ptr, gl[1].c_sB, gl[1].c_sC, *tail))
+    return grads
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """autograd node of the fused loss: forward = the three forward kernels, backward = the two backward kernels.
+    Inputs: the per-level head tensors of every branch; output: the 3 loss items of every branch."""
+
+    @staticmethod
+    def forward(ctx, cfg, *feats):
+        strides, nc, gt, topk, gains = cfg
+        n = len(topk)
+        nl = len(feats) // n
+        levels = [Levels(feats[i * nl:(i + 1) * nl], strides) for i in range(n)]
+        fwd = _branch_forward(levels, nc, gt, topk, gains, True, False, None)
+        ctx.levels, ctx.fwd, ctx.cfg = levels, fwd, cfg
+        ctx.in_dtypes = [f.dtype for f in feats]
+        return fwd["items"].view(n, 4)[:, :3].reshape(3 * n)
+
+    @staticmethod
+    def backward(ctx, grad_items):
+        strides, nc, gt, topk, gains = ctx.cfg
+        grads = _branch_backward(ctx.levels, nc, ctx.fwd, topk, gains, ctx.fwd["items"], grad_items)
+        flat = [g for br in grads for g in br]
+        return (None, *[g.to(dt) for g, dt in zip(flat, ctx.in_dtypes)])
 
 
 def finalize_partials(partials, gains):
@@ -132,8 +176,7 @@ class v8DetectionLoss:
         feats = preds[1] if isinstance(preds, tuple) else preds  # loss.py:209
         gt = self._targets(feats, batch)
         gains = (self.hyp.box, self.hyp.cls, self.hyp.dfl)
-        items, _, _ = v8_loss_forward(feats, [float(s) for s in self.stride], self.nc, gt, self.topk, gains)
-        loss = items[:3]
+        loss = _FusedLossFn.apply(([float(s) for s in self.stride], self.nc, gt, (self.topk,), gains), *feats)
         return loss.sum() * feats[0].shape[0], loss.detach()  # loss.py:257
 
 
@@ -150,7 +193,7 @@ class v10DetectLoss:
         fo = one2one[1] if isinstance(one2one, tuple) else one2one
         o = self.one2many
         gt = o._targets(fm, batch)
-        items, _, _ = v10_loss_forward(fm, fo, [float(s) for s in o.stride], o.nc, gt,
-                                       (o.hyp.box, o.hyp.cls, o.hyp.dfl), topk=(o.topk, self.one2one.topk))
-        loss = items.view(2, 4)[:, :3].reshape(6)  # box_om cls_om dfl_om box_oo cls_oo dfl_oo (yolov10/train.py:10)
+        loss = _FusedLossFn.apply(([float(s) for s in o.stride], o.nc, gt, (o.topk, self.one2one.topk),
+                                   (o.hyp.box, o.hyp.cls, o.hyp.dfl)), *fm, *fo)
+        # box_om cls_om dfl_om box_oo cls_oo dfl_oo (yolov10/train.py:10)
         return loss.sum() * fm[0].shape[0], loss.detach()

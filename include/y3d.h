@@ -46,7 +46,8 @@ enum { /* `stage` of y3d_workspace_bytes */
     Y3D_STAGE_TAL_ASSIGN = 2,
     Y3D_STAGE_V8_LOSS = 3,
     Y3D_STAGE_TAL_ASSIGN3D = 4,
-    Y3D_STAGE_DECODE_TOPK = 5
+    Y3D_STAGE_DECODE_TOPK = 5,
+    Y3D_STAGE_DD_LOSS = 6
 };
 
 const char *y3d_strerror(int rc);
@@ -194,6 +195,26 @@ int y3d_tal_assign3d(const float *pd_scores, const float *pd_bboxes, const float
                      int64_t *target_labels, float *target_scores, float *target_vals, uint8_t *fg_mask,
                      int64_t *target_gt_idx, float *pd_keypoints, float *gt_keypoints, void *ws, size_t ws_bytes,
                      void *stream);
+
+/* DDDetectionLoss.__call__ forward (ultralytics/utils/loss.py:821-900; bbox_decode :812-819, compute_box2d_loss
+ * :913-926, compute_box3d_loss :928-963, laplacian_aleatoric_uncertainty_loss_new :1112-1119, compute_heading_loss
+ * :1122-1136) for ONE branch of DetectLoss3d (loss.py:741-771), fused with TaskAlignedAssigner3d (tal.py:391-700).
+ *  head levels [B, nc+35, h, w] = cls(nc) | o2d(2) s2d(2) o3d(2) s3d(3) hd(24) dep dep_un;
+ *  gts [B,M,17] = label, bbox xyxy px, center_2d(2), size_2d(2), center_3d(2), size_3d(3), depth, heading_bin,
+ *  heading_res -- the output of DDDetectionLoss.preprocess (loss.py:795-810), zero rows = padding; calibs [B,6],
+ *  mean_sizes [nc,3] (DEVICE).  flags as y3d_tal_assign3d.  gains: HOST float[6] = hyp.loss2d, cls, depth, offset3d,
+ *  size3d, heading.  loss_items: DEVICE float[8] = the six loss items, target_scores_sum, number of foreground anchors
+ *  (all zero when M == 0, as the reference's early return).  partials: DEVICE double[11] (required) = un-normalised
+ *  sums: softplus, |offset2d|, |size2d|, depth, |offset3d|, |size3d|, heading CE, heading L1, x[label]*t,
+ *  sum target_scores, n_fg -- what a multi-GPU caller all-reduces before y3d_dd_loss_finalize.
+ *  dbg_target_gt_idx (optional) [B,A] int32: the assigned GT of every anchor, -1 = background.
+ *  The distillation / foreground-depth-map terms of the fork (loss.py:792,890-895) are out of scope. */
+int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                    const float *lvl_stride, int nl, int B, int nc, const float *gts, int M, const float *calibs,
+                    const float *mean_sizes, int topk, float alpha, float beta, float gamma, int flags,
+                    const float *gains, int normalise, float *loss_items, double *partials,
+                    int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes, void *stream);
+int y3d_dd_loss_finalize(const double *partials, int M, const float *gains, float *loss_items, void *stream);
 
 #ifdef __cplusplus
 }

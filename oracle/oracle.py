@@ -266,6 +266,67 @@ def tal_assign3d(pd_scores, pd_bboxes, pd_3d, anc_points, stride, gts_packed, ma
     return out
 
 
+def dd_loss(xcat, lvl_hw, lvl_stride, nc, gts_packed, calibs, mean_sizes, topk, gains=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0),
+            alpha=0.5, beta=1.0, gamma=1.0, use_2d=True, use_3d=True, kps_dist_metric="l1", constrain_anchors=True):
+    """DDDetectionLoss.__call__ loss.py:821-900 for one branch (distillation off).  ``xcat`` [B, nc+35, A] =
+    cls | o2d(2) s2d(2) o3d(2) s3d(3) hd(24) dep dep_un; ``gts_packed`` [B,M,17] is the output of
+    DDDetectionLoss.preprocess (loss.py:795-810; bbox xyxy px).  ``gains`` = hyp.loss2d, cls, depth, offset3d, size3d,
+    heading.  Returns (items float64[6], target_scores_sum, n_fg, assignment dict).  The assigner is the C oracle; the
+    loss terms are float64 numpy restatements of compute_box2d_loss :913-926, compute_box3d_loss :928-963,
+    laplacian_aleatoric_uncertainty_loss_new :1112-1119 and compute_heading_loss :1122-1136."""
+    x = _f32(xcat)
+    B, Cc, A = x.shape
+    assert Cc == nc + 35
+    gts = _f32(gts_packed)
+    M = gts.shape[1]
+    if M == 0:  # loss.py:873-876: the 5-tuple of the empty-GT assigner cannot be unpacked -> zero loss
+        return np.zeros(6), 1.0, 0, None
+    anc_g, st = make_anchors(lvl_hw, lvl_stride)  # grid units, [A,2] / [A]
+    st = st.reshape(-1)
+    t = np.ascontiguousarray(x.transpose(0, 2, 1))  # [B,A,C]
+    logits = t[..., :nc]
+    pd_scores = (np.float32(1.0) / (np.float32(1.0) + np.exp(-logits, dtype=np.float32))).astype(np.float32)
+    centers = (anc_g[None] + t[..., nc:nc + 2]).astype(np.float32)  # bbox_decode loss.py:812-819
+    half = (t[..., nc + 2:nc + 4] * np.float32(0.5)).astype(np.float32)
+    pd_bboxes = (np.concatenate([centers - half, centers + half], -1).astype(np.float32) *
+                 st[None, :, None]).astype(np.float32)
+    pd_3d = np.ascontiguousarray(t[..., nc + 4:])
+    anc_px = (anc_g * st[:, None]).astype(np.float32)
+    mask_gt = (gts[..., 1:5].sum(-1) > 0).astype(np.float32)
+    asg = tal_assign3d(pd_scores, pd_bboxes, pd_3d, anc_px, st, gts, mask_gt, calibs, mean_sizes, topk, alpha=alpha,
+                       beta=beta, gamma=gamma, use_2d=use_2d, use_3d=use_3d, kps_dist_metric=kps_dist_metric,
+                       constrain_anchors=constrain_anchors)
+    fg = asg["fg_mask"]
+    ts = asg["target_scores"].astype(np.float64)
+    tv = asg["target_vals"].astype(np.float64)  # c2d2 s2d2 c3d2 s3d3 dep hbin hres
+    tss = max(ts.sum(), 1.0)
+    n_fg = int(fg.sum())
+    z = logits.astype(np.float64)
+    bce = (np.maximum(z, 0) - z * ts + np.log1p(np.exp(-np.abs(z)))).sum()
+    p = t.astype(np.float64)[fg]  # [n_fg, C]
+    tvf = tv[fg]
+    stf = np.broadcast_to(st[None, :], fg.shape)[fg].astype(np.float64)[:, None]
+    ancf = np.broadcast_to(anc_px[None], fg.shape + (2,))[fg].astype(np.float64)
+    l1 = lambda a, b: np.abs(a - b)  # noqa: E731
+    off2d = l1(p[:, nc:nc + 2] * stf, tvf[:, 0:2] - ancf).mean() if n_fg else np.nan
+    size2d = l1(p[:, nc + 2:nc + 4] * stf, tvf[:, 2:4]).mean() if n_fg else np.nan
+    dep, un = p[:, nc + 33], p[:, nc + 34]
+    depth = (1.4142 * np.exp(-0.5 * un) * np.abs(dep - tvf[:, 9]) + 0.5 * un).sum()
+    off3d = l1(p[:, nc + 4:nc + 6] * stf, tvf[:, 4:6] - ancf).mean() if n_fg else np.nan
+    size3d = l1(p[:, nc + 6:nc + 9], tvf[:, 6:9]).sum()
+    hd = p[:, nc + 9:nc + 33]
+    tb = tvf[:, 10].astype(np.int64)
+    hb = hd[:, :12]
+    mx = hb.max(1, keepdims=True)
+    lse = (mx + np.log(np.exp(hb - mx).sum(1, keepdims=True)))[:, 0]
+    rows = np.arange(n_fg)
+    hd_ce = (lse - hb[rows, tb]).sum()
+    hd_l1 = np.abs(hd[rows, 12 + tb] - tvf[:, 11]).sum()
+    items = np.array([(size2d + off2d) / tss * gains[0], bce / tss * gains[1], depth / tss * gains[2],
+                      off3d / tss * gains[3], size3d / tss * gains[4], (hd_ce + hd_l1) / tss * gains[5]])
+    return items, tss, n_fg, asg
+
+
 def decode_preds(dets, calib, inv_affine, ratio, cls_mean_size, threshold=0.001):
     """KITTIDataset.decode_preds kitti.py:519-576.  dets [B,D,37] float32; calib [B,6], inv_affine [B,2,3],
     ratio [B,2], cls_mean_size [nc,3] float64.  Returns (rows [B,D,14] float64, valid [B,D] bool)."""

@@ -78,6 +78,24 @@ def loss_inputs(r, z):
     return lv, gt, xm, xo
 
 
+def loss3d_inputs(r, z):
+    """Same construction as tests/golden/make_golden.py::case_loss3d."""
+    B, nc, img_hw, M, seed = r["B"], r["nc"], r["img_hw"], r["M"], r["seed"]
+    lv = synth.levels(*img_hw)
+    gts = synth.gt3d(B, M, nc, img_hw, seed=seed + 1)
+    x = synth.train_like_head3d(B, nc, lv, gts, seed=seed)
+    assert synth.checksum(gts, x) == int(z["in_crc"]), "regenerated inputs differ"
+    ms = np.array(synth.KITTI_MEAN_SIZES, np.float32)
+    return lv, gts, x, z["calibs"].astype(np.float32), ms
+
+
+def loss3d_kwargs(r):
+    kw = r["kw"]
+    return dict(alpha=kw.get("alpha", 0.5), beta=kw.get("beta", 1.0), gamma=kw.get("gamma", 1.0),
+                use_2d=kw.get("use_2d", True), use_3d=kw.get("use_3d", True),
+                kps_dist_metric=kw.get("kps_dist_metric", "l1"), constrain_anchors=kw.get("constrain_anchors", True))
+
+
 def decode3d_inputs(r, z):
     lv = synth.levels(*r["img_hw"])
     x = synth.head3d(r["B"], r["nc"], lv, seed=r["seed"])

@@ -286,6 +286,45 @@ def case_assign3d(name, B, nc, img_hw, M, topk, seed, **kw):
          unpatched_agrees=np.bool_(agree))
 
 
+def case_loss3d(name, B, nc, img_hw, M, topk, seed, **kw):
+    """The REAL DDDetectionLoss (loss.py:775-900) on CPU.  compute_heading_loss calls ``.cuda()`` on a fresh one-hot
+    (loss.py:1132); ``torch.Tensor.cuda`` is patched to the identity for the duration of the call -- no reference file
+    is touched."""
+    lv = synth.levels(*img_hw)
+    gts = synth.gt3d(B, M, nc, img_hw, seed=seed + 1)
+    x = synth.train_like_head3d(B, nc, lv, gts, seed=seed)
+    calibs = np.tile(np.array(synth.KITTI_CALIB, np.float32), (B, 1))
+    calibs[:, 0] += np.arange(B, dtype=np.float32)
+    ms = np.array(synth.KITTI_MEAN_SIZES, np.float32)
+    gains = dict(loss2d=1.3, cls=0.7, depth=1.1, offset3d=0.9, size3d=1.2, heading=0.8)
+    args = types.SimpleNamespace(distillation=False, tal_topk=topk, tal_alpha=kw.get("alpha", 0.5),
+                                 tal_beta=kw.get("beta", 1.0), tal_gamma=kw.get("gamma", 1.0),
+                                 tal_2d=kw.get("use_2d", True), tal_3d=kw.get("use_3d", True),
+                                 kps_dist_metric=kw.get("kps_dist_metric", "l1"),
+                                 constrain_anchors=kw.get("constrain_anchors", True), **gains)
+    model = FakeModel(nc, synth.STRIDES, args)
+    model.model[0].no = nc + 35
+    crit = ref_loss.DDDetectionLoss(model, tal_topk=topk)
+    feats = [t(f) for f in synth.split_levels(x, lv)]
+    batch = {k: t(v) for k, v in synth.batch_dict3d(gts, img_hw, calibs, ms).items()}
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with patched_topk():
+            total, items = crit(feats, batch, embeddings=None)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    # the packed targets the loss built internally (preprocess loss.py:795-810), for the GT-packing glue test
+    imgsz = torch.tensor(feats[0].shape[2:], dtype=torch.float32) * synth.STRIDES[0]
+    g_in = torch.cat((batch["batch_idx"].view(-1, 1), batch["cls"].view(-1, 1), batch["bboxes"], batch["center_2d"],
+                      batch["size_2d"], batch["center_3d"], batch["size_3d"], batch["depth"].view(-1, 1),
+                      batch["heading_bin"].view(-1, 1), batch["heading_res"].view(-1, 1)), 1)
+    packed = crit.preprocess(g_in, B, scale_tensor=imgsz[[1, 0, 1, 0]]).numpy()
+    recipe = dict(kind="loss3d", B=B, nc=nc, img_hw=img_hw, M=M, topk=topk, seed=seed, kw=kw, gains=list(gains.values()))
+    save(name, recipe, in_crc=np.int64(synth.checksum(gts, x)), calibs=calibs, packed=packed,
+         total=np.float64(total.item()), items=items.detach().numpy().astype(np.float64))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:] or None
 
@@ -312,6 +351,11 @@ if __name__ == "__main__":
     if want("decode3d") or want("preds3d"):
         dets = case_decode3d("decode3d_small", B=3, nc=3, img_hw=(96, 320), D=50, seed=40)
         case_decode_preds("preds3d_small", dets)
+    if want("loss3d"):
+        case_loss3d("loss3d_k8", B=2, nc=3, img_hw=(96, 320), M=8, topk=8, seed=60)
+        case_loss3d("loss3d_k1", B=2, nc=3, img_hw=(96, 320), M=8, topk=1, seed=61)
+        case_loss3d("loss3d_free_l2", B=2, nc=3, img_hw=(96, 320), M=6, topk=8, seed=62, beta=3.0, gamma=3.0,
+                    kps_dist_metric="l2", constrain_anchors=False)
     if want("assign3d"):
         case_assign3d("assign3d_k8", B=2, nc=3, img_hw=(96, 320), M=8, topk=8, seed=50, alpha=0.5, beta=1.0, gamma=1.0)
         case_assign3d("assign3d_k1", B=2, nc=3, img_hw=(96, 320), M=8, topk=1, seed=51, alpha=0.5, beta=1.0, gamma=1.0)

@@ -201,3 +201,50 @@ def assigner3d_inputs_from_head(xcat, lvl_hw, nc):
     pd_bboxes = (np.concatenate([centers - size / 2, centers + size / 2], -1) * st[None, :, None]).astype(np.float32)
     pd_3d = np.ascontiguousarray(t[..., nc + 4:])
     return pd_scores, pd_bboxes, pd_3d, anc, st
+
+
+def train_like_head3d(B, nc, lv, gts, seed, frac=0.05):
+    """head3d with ~frac of the in-GT anchors of every GT made 'trained' (2D box, 3D centre, size, depth, heading and
+    class close to the GT), so that positive metrics, conflicts and non-trivial loss terms occur."""
+    x = head3d(B, nc, lv, seed=seed)
+    anc, st = anchors_px(lv)
+    g = rng(seed + 5)
+    for b in range(B):
+        for m in range(gts.shape[1]):
+            row = gts[b, m]
+            if row[1:5].sum() <= 0:
+                continue
+            ins = np.nonzero((anc[:, 0] > row[1]) & (anc[:, 0] < row[3]) & (anc[:, 1] > row[2]) & (anc[:, 1] < row[4]))[0]
+            if ins.size == 0:
+                continue
+            for a in g.choice(ins, size=min(ins.size, max(2, int(frac * ins.size))), replace=False):
+                s_ = st[a]
+                x[b, int(row[0]), a] = 1.0 + 2.0 * g.random()
+                x[b, nc + 0:nc + 2, a] = (row[5:7] - anc[a]) / s_ + g.standard_normal(2) * 0.3
+                x[b, nc + 2:nc + 4, a] = row[7:9] / s_ + g.standard_normal(2) * 0.3
+                x[b, nc + 4:nc + 6, a] = (row[9:11] - anc[a]) / s_ + g.standard_normal(2) * 0.05
+                x[b, nc + 6:nc + 9, a] = row[11:14] + g.standard_normal(3) * 0.05
+                x[b, nc + 9 + int(row[15]), a] += 4.0
+                x[b, nc + 21 + int(row[15]), a] = row[16] + g.standard_normal() * 0.05
+                x[b, nc + 33, a] = row[14] + g.standard_normal() * 0.5
+    return np.ascontiguousarray(x, np.float32)
+
+
+def batch_dict3d(gts, img_hw, calibs, mean_sizes):
+    """The batch keys DDDetectionLoss.__call__ reads (loss.py:848-856) for packed GT rows [B,M,17] (bbox xyxy px);
+    numpy arrays."""
+    h, w = img_hw
+    rows, bi = [], []
+    for b in range(gts.shape[0]):
+        for m in range(gts.shape[1]):
+            if gts[b, m, 1:5].sum() > 0:
+                rows.append(gts[b, m])
+                bi.append(b)
+    r = np.array(rows, np.float32).reshape(-1, 17)
+    x1, y1, x2, y2 = r[:, 1], r[:, 2], r[:, 3], r[:, 4]
+    bb = np.stack([(x1 + x2) / 2 / w, (y1 + y2) / 2 / h, (x2 - x1) / w, (y2 - y1) / h], 1).astype(np.float32)
+    c = np.ascontiguousarray
+    return dict(batch_idx=np.array(bi, np.float32), cls=c(r[:, 0:1]), bboxes=bb, center_2d=c(r[:, 5:7]),
+                size_2d=c(r[:, 7:9]), center_3d=c(r[:, 9:11]), size_3d=c(r[:, 11:14]), depth=c(r[:, 14]),
+                heading_bin=c(r[:, 15]), heading_res=c(r[:, 16]), calib=np.asarray(calibs, np.float32),
+                mean_sizes=np.asarray(mean_sizes, np.float32))

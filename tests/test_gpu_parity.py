@@ -364,6 +364,66 @@ def test_decode3d_and_postprocess(y3d, name):
     assert dets.shape == (r["B"], r["D"], 37)
 
 
+class FakeModel3d(torch.nn.Module):
+    def __init__(self, nc, r, topk):
+        super().__init__()
+        import types
+
+        kw = cases.loss3d_kwargs(r)
+        g = r["gains"]
+        self.p = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+        self.args = types.SimpleNamespace(
+            distillation=False, fgdm_loss=False, fgdm_supervision=False, tal_topk=topk, tal_alpha=kw["alpha"],
+            tal_beta=kw["beta"], tal_gamma=kw["gamma"], tal_2d=kw["use_2d"], tal_3d=kw["use_3d"],
+            kps_dist_metric=kw["kps_dist_metric"], constrain_anchors=kw["constrain_anchors"], loss2d=g[0], cls=g[1],
+            depth=g[2], offset3d=g[3], size3d=g[4], heading=g[5])
+        self.model = [types.SimpleNamespace(stride=torch.tensor(synth.STRIDES), nc=nc, no=nc + 35)]
+
+
+@pytest.mark.parametrize("name", cases.names("loss3d_"))
+def test_dd_loss_golden_and_oracle(y3d, name):
+    """DDDetectionLoss through the public mirror against the REAL reference (fixture) and the oracle, and the
+    assignment inside the fused call against the oracle assigner bit for bit."""
+    r, z = cases.load(name)
+    lv, gts, x, calibs, ms = cases.loss3d_inputs(r, z)
+    batch = {k: torch.from_numpy(v) for k, v in synth.batch_dict3d(gts, r["img_hw"], calibs, ms).items()}
+    crit = y3d.DDDetectionLoss(FakeModel3d(r["nc"], r, r["topk"]), tal_topk=r["topk"])
+    total, items = crit(feats_of(x, lv), batch, embeddings=None)
+    np.testing.assert_allclose(items.cpu().numpy().astype(np.float64), z["items"], rtol=3e-5)
+    np.testing.assert_allclose(float(total), float(z["total"]), rtol=3e-5)
+    oitems, tss, n_fg, asg = oracle.dd_loss(x, lv, synth.STRIDES, r["nc"], z["packed"], calibs, ms, r["topk"],
+                                            gains=r["gains"], **cases.loss3d_kwargs(r))
+    it8, parts, tgi = y3d.loss3d.dd_loss_forward(feats_of(x, lv), list(synth.STRIDES), r["nc"], dev(z["packed"]),
+                                                 dev(calibs), dev(ms), r["topk"], r["gains"], debug=True,
+                                                 **cases.loss3d_kwargs(r))
+    it8 = it8.cpu().numpy()
+    np.testing.assert_allclose(it8[:6], oitems, rtol=3e-5)
+    assert int(it8[7]) == n_fg and abs(it8[6] - tss) <= 1e-5 * tss
+    tgi = tgi.cpu().numpy()
+    assert np.array_equal(tgi >= 0, asg["fg_mask"])
+    assert np.array_equal(tgi[tgi >= 0], asg["target_gt_idx"][asg["fg_mask"]])
+
+
+def test_dd_loss_no_targets_and_dual(y3d):
+    r, z = cases.load("loss3d_k8")
+    lv, gts, x, calibs, ms = cases.loss3d_inputs(r, z)
+    f = feats_of(x, lv)
+    it8, parts, _ = y3d.loss3d.dd_loss_forward(f, list(synth.STRIDES), r["nc"], torch.zeros(r["B"], 0, 17), dev(calibs),
+                                               dev(ms), 8, r["gains"])
+    assert not it8[:6].cpu().numpy().any()  # loss.py:873-876: zero loss when the batch has no targets
+    batch = {k: torch.from_numpy(v) for k, v in synth.batch_dict3d(gts, r["img_hw"], calibs, ms).items()}
+    model = FakeModel3d(r["nc"], r, 8)
+    dual = y3d.DetectLoss3d(model)
+    tot, items = dual({"one2many": f, "one2one": f, "o2m_embs": None, "o2o_embs": None}, batch)
+    assert items.shape == (12,)
+    t8, i8 = y3d.DDDetectionLoss(model, tal_topk=8)(f, batch)
+    t1, i1 = y3d.DDDetectionLoss(model, tal_topk=1)(f, batch)
+    np.testing.assert_allclose(items.cpu().numpy(), torch.cat((i8, i1)).cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(float(tot), float(t8 + t1), rtol=1e-6)
+    tot1, items1 = dual({"one2one": f, "o2o_embs": None}, batch)  # eval: only the one2one branch (loss.py:771)
+    assert float(tot1) == 0.0 and items1.shape == (6,)
+
+
 def test_decode_preds(y3d):
     r, z = cases.load("preds3d_small")
     B = z["dets"].shape[0]

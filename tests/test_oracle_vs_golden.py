@@ -98,3 +98,21 @@ def test_tal_assign3d(name):
     assert synth.checksum(out["target_vals"]) == int(z["target_vals_crc"])
     np.testing.assert_allclose(out["target_scores"], cases.dense_target_scores(z, B, A, nc), rtol=5e-5, atol=1e-7)
     assert out["fg_mask"].sum() > 0
+
+
+@pytest.mark.parametrize("name", cases.names("loss3d_"))
+def test_dd_loss_oracle_vs_reference(name):
+    """oracle.dd_loss against the REAL DDDetectionLoss (loss.py:821-900) run on CPU by make_golden.py, including the
+    GT packing of DDDetectionLoss.preprocess (loss.py:795-810)."""
+    r, z = cases.load(name)
+    lv, gts, x, calibs, ms = cases.loss3d_inputs(r, z)
+    bd = synth.batch_dict3d(gts, r["img_hw"], calibs, ms)
+    extra = np.concatenate([bd["center_2d"], bd["size_2d"], bd["center_3d"], bd["size_3d"], bd["depth"][:, None],
+                            bd["heading_bin"][:, None], bd["heading_res"][:, None]], 1)
+    packed = oracle.preprocess_targets(bd["batch_idx"], bd["cls"], bd["bboxes"], r["B"], r["img_hw"], extra=extra)
+    np.testing.assert_allclose(packed, z["packed"], rtol=1e-6, atol=1e-4)
+    items, tss, n_fg, asg = oracle.dd_loss(x, lv, synth.STRIDES, r["nc"], z["packed"], calibs, ms, r["topk"],
+                                           gains=r["gains"], **cases.loss3d_kwargs(r))
+    assert n_fg > 0
+    np.testing.assert_allclose(items, z["items"], rtol=2e-5)
+    np.testing.assert_allclose(items.sum() * r["B"], float(z["total"]), rtol=2e-5)

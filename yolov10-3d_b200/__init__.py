@@ -6,10 +6,11 @@ Everything computes in liby3d_b200.so (hand-written CUDA, C ABI in include/y3d.h
 fallback -- a missing library raises at the first call.
 """
 from . import _lib  # noqa: F401
-from . import dist, head, kitti, loss, ops, tal  # noqa: F401
+from . import dist, head, kitti, loss, loss3d, ops, tal  # noqa: F401
 from ._lib import Y3DError, lib  # noqa: F401
 from .head import V10DetectDecoder, detect3d_decode, detect3d_postprocess, detect_inference, v10detect_export_forward  # noqa: F401
 from .loss import v8DetectionLoss, v10DetectLoss  # noqa: F401
+from .loss3d import DDDetectionLoss, DetectLoss3d  # noqa: F401
 from .ops import v10_3Dpostprocess, v10postprocess, xywh2xyxy  # noqa: F401
 from .tal import TaskAlignedAssigner, TaskAlignedAssigner3d, make_anchors  # noqa: F401
 

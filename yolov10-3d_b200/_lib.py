@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liby3d_b200.so")
 
-STAGE_POSTPROCESS, STAGE_TAL_ASSIGN, STAGE_V8_LOSS, STAGE_TAL_ASSIGN3D, STAGE_DECODE_TOPK = 1, 2, 3, 4, 5
+STAGE_POSTPROCESS, STAGE_TAL_ASSIGN, STAGE_V8_LOSS, STAGE_TAL_ASSIGN3D, STAGE_DECODE_TOPK, STAGE_DD_LOSS = 1, 2, 3, 4, 5, 6
 MAX_LEVELS, MAX_TOPK, MAX_DET = 4, 32, 1024
 
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
@@ -32,6 +32,8 @@ SIGNATURES = {
     "y3d_v8_loss_finalize": (_i, [_vp, _i, _f, _f, _f, _vp, _vp]),
     "y3d_v8_loss_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "y3d_v10_loss_bwd": (_i, [_vp] * 14 + [_i, _i, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "y3d_dd_loss_fwd": (_i, _LEVELS + [_i, _i, _vp, _i, _vp, _vp, _i, _f, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "y3d_dd_loss_finalize": (_i, [_vp, _i, _vp, _vp, _vp]),
     "y3d_decode3d": (_i, _LEVELS + [_i, _i, _vp, _vp]),
     "y3d_decode_preds3d": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp]),
     "y3d_tal_assign3d": (_i, [_vp] * 9 + [_i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp, _vp, _i] + [_vp] * 7 +

@@ -5,6 +5,7 @@ namespace y3d {
 size_t topk_workspace_bytes(int B, int A, int nc, int D);
 size_t assign_workspace_bytes(int B, int A, int M);
 size_t loss_workspace_bytes(int B, int A, int M, int k);
+size_t dd_loss_workspace_bytes(int B, int A, int M);
 }  // namespace y3d
 
 extern "C" const char *y3d_strerror(int rc) {
@@ -29,6 +30,7 @@ extern "C" size_t y3d_workspace_bytes(int stage, int B, int A, int nc, int M, in
         case Y3D_STAGE_TAL_ASSIGN:
         case Y3D_STAGE_TAL_ASSIGN3D: return y3d::assign_workspace_bytes(B, A, M) + 256;
         case Y3D_STAGE_V8_LOSS: return y3d::loss_workspace_bytes(B, A, M, k) + 256;
+        case Y3D_STAGE_DD_LOSS: return y3d::dd_loss_workspace_bytes(B, A, M) + 256;
         default: return 0;
     }
 }

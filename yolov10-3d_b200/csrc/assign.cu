@@ -475,38 +475,7 @@ __global__ void __launch_bounds__(256) tal_emit_scores_kernel(const float *__res
 }
 
 // ------------------------------------------------------------------------------------------------ 3D keypoints
-// get_3d_keypoints (keypoint_utils.py:11-118) for one box; op order identical to oracle/y3d_oracle.c::y3d_o_keypoints
-__device__ __forceinline__ void keypoints24(float c3x, float c3y, float dep, float s_h, float s_w, float s_l, int hbin,
-                                            float hres, const float *cal, float *out) {
-    using namespace dm;
-    const float kPi = 3.14159265358979323846f, k2Pi = 6.283185307179586f;
-    const float cu = cal[0], cv = cal[1], fu = cal[2], fv = cal[3], tx = cal[4], ty = cal[5];
-    const float lx = add(div(mul(sub(c3x, cu), dep), fu), tx);  // img_to_rect :113-119
-    const float ly = add(div(mul(sub(c3y, cv), dep), fv), ty);
-    const float lz = dep;
-    float alpha = add(mul((float)hbin, 0.5235987755982988f), hres);  // class2angle :42-47
-    if (alpha > kPi) alpha = sub(alpha, k2Pi);
-    float ry = add(alpha, atan2_(sub(c3x, cu), fu));  // alpha2ry :94-101
-    if (ry > kPi) ry = sub(ry, k2Pi);
-    if (ry < -kPi) ry = add(ry, k2Pi);
-    float sx, cx, sy, cy;  // to_egoc_rot_mat :87-91  R = Rx(pi/2) @ Ry(-ry)
-    sincos_(1.5707963267948966f, &sx, &cx);
-    sincos_(-ry, &sy, &cy);
-    const float R00 = cy, R01 = 0.0f, R02 = sy;
-    const float R10 = mul(sx, sy), R11 = cx, R12 = -mul(sx, cy);
-    const float R20 = -mul(cx, sy), R21 = sx, R22 = mul(cx, cy);
-    const float hl = div(s_l, 2.0f), hw = div(s_w, 2.0f), hh = div(s_h, 2.0f);  // get_box_corners :20-26
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float px = (k & 2) ? -hl : hl;
-        const float py = (k & 1) ? -hw : hw;
-        const float pz = (k & 4) ? hh : -hh;
-        out[3 * k + 0] = add(add(add(mul(px, R00), mul(py, R10)), mul(pz, R20)), lx);  // transform_to_camera :104-110
-        out[3 * k + 1] = add(add(add(mul(px, R01), mul(py, R11)), mul(pz, R21)), ly);
-        out[3 * k + 2] = add(add(add(mul(px, R02), mul(py, R12)), mul(pz, R22)), lz);
-    }
-}
-
+// keypoints24(): assign.cuh
 __global__ void __launch_bounds__(128) kps_pred_kernel(const float *__restrict__ pd_scores,
                                                        const float *__restrict__ pd_3d, const float *__restrict__ anc,
                                                        const float *__restrict__ stride,
@@ -580,6 +549,13 @@ static int run_emit(const AssignCtx &c, void *ws, const AssignWs &w, int64_t *t_
 }
 
 size_t assign_workspace_bytes(int B, int A, int M) { return assign_ws_layout(B, A, M).total; }
+
+int launch_kps_gt(const float *gts, const float *calibs, const float *mean_sizes, int B, int M, int nc, float *gt_kps,
+                  cudaStream_t s) {
+    kps_gt_kernel<<<(B * M + 127) / 128, 128, 0, s>>>(gts, calibs, mean_sizes, B, M, nc, gt_kps);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
+}
 
 }  // namespace y3d
 

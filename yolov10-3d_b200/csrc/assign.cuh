@@ -221,6 +221,39 @@ __device__ __forceinline__ float assigned_norm(const AssignCtx &c, int b, int gi
     return dm::div(dm::mul(alignv, po), dm::add(pa, c.eps));
 }
 
+// get_3d_keypoints (keypoint_utils.py:11-118) for one box; op order identical to oracle/y3d_oracle.c::y3d_o_keypoints
+__device__ __forceinline__ void keypoints24(float c3x, float c3y, float dep, float s_h, float s_w, float s_l, int hbin,
+                                            float hres, const float *cal, float *out) {
+    using namespace dm;
+    const float kPi = 3.14159265358979323846f, k2Pi = 6.283185307179586f;
+    const float cu = cal[0], cv = cal[1], fu = cal[2], fv = cal[3], tx = cal[4], ty = cal[5];
+    const float lx = add(div(mul(sub(c3x, cu), dep), fu), tx);  // img_to_rect :113-119
+    const float ly = add(div(mul(sub(c3y, cv), dep), fv), ty);
+    const float lz = dep;
+    float alpha = add(mul((float)hbin, 0.5235987755982988f), hres);  // class2angle :42-47
+    if (alpha > kPi) alpha = sub(alpha, k2Pi);
+    float ry = add(alpha, atan2_(sub(c3x, cu), fu));  // alpha2ry :94-101
+    if (ry > kPi) ry = sub(ry, k2Pi);
+    if (ry < -kPi) ry = add(ry, k2Pi);
+    float sx, cx, sy, cy;  // to_egoc_rot_mat :87-91  R = Rx(pi/2) @ Ry(-ry)
+    sincos_(1.5707963267948966f, &sx, &cx);
+    sincos_(-ry, &sy, &cy);
+    const float R00 = cy, R01 = 0.0f, R02 = sy;
+    const float R10 = mul(sx, sy), R11 = cx, R12 = -mul(sx, cy);
+    const float R20 = -mul(cx, sy), R21 = sx, R22 = mul(cx, cy);
+    const float hl = div(s_l, 2.0f), hw = div(s_w, 2.0f), hh = div(s_h, 2.0f);  // get_box_corners :20-26
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float px = (k & 2) ? -hl : hl;
+        const float py = (k & 1) ? -hw : hw;
+        const float pz = (k & 4) ? hh : -hh;
+        out[3 * k + 0] = add(add(add(mul(px, R00), mul(py, R10)), mul(pz, R20)), lx);  // transform_to_camera :104-110
+        out[3 * k + 1] = add(add(add(mul(px, R01), mul(py, R11)), mul(pz, R21)), ly);
+        out[3 * k + 2] = add(add(add(mul(px, R02), mul(py, R12)), mul(pz, R22)), lz);
+    }
+}
+
+
 // up to two branches (one2many / one2one of v10DetectLoss) run in the same launches, selected by blockIdx.z
 struct AssignCtx2 {
     AssignCtx c[2];
@@ -259,6 +292,9 @@ inline void assign_bind_ws(AssignCtx &c, void *ws, const AssignWs &w) {
 // zero-filled [off_cnt, off_cnt + zero_bytes) of every branch's workspace.  After this c.tgi / c.alignv / c.pos_*
 // are final.
 int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk = nullptr);
+// GT keypoints [B,M,24] from packed [B,M,17] rows (add_cls_mean_size tal.py:605-609 + get_3d_keypoints)
+int launch_kps_gt(const float *gts, const float *calibs, const float *mean_sizes, int B, int M, int nc, float *gt_kps,
+                  cudaStream_t s);
 // top-k + claims only (the fused loss path finishes with its own kernel)
 int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s);
 

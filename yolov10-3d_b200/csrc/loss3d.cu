@@ -1,0 +1,303 @@
+// loss3d.cu -- fused forward of the fork's 3D detection loss (sm_100a).
+//   y3d_dd_loss_fwd   DDDetectionLoss.__call__   reference ultralytics/utils/loss.py:821-900
+//                     bbox_decode                reference ultralytics/utils/loss.py:812-819
+//                     compute_box2d_loss         reference ultralytics/utils/loss.py:913-926
+//                     compute_box3d_loss         reference ultralytics/utils/loss.py:928-963
+//                     laplacian_aleatoric_uncertainty_loss_new / compute_heading_loss   loss.py:1112-1136
+//   (one branch; DetectLoss3d, loss.py:741-771, calls it for one2one and, in training, one2many)
+//
+// Head layout [B, nc+35, h, w]: cls(nc) | o2d(2) s2d(2) | o3d(2) s3d(3) hd(24) dep(1) dep_un(1)  (loss.py:825-829).
+// Kernels of a call:
+//   1. dd_stream_kernel : one pass over the head (4*(nc+35)*A bytes per image).  Per anchor: sigmoid scores -> argmax
+//      class -> mean size; 2D box (px); 3D centre / size / heading / depth -> the 8 box corners in camera
+//      coordinates (TaskAlignedAssigner3d.forward tal.py:425-447); sum softplus(logit).  Out: boxes [B,A,4] px and
+//      keypoints [B,A,24] (the assigner's inputs), zeroed claim words.  pd_scores / pd_3d are never materialised.
+//   2. GT keypoints, per-GT top-k, conflict resolution: the assigner core of assign.cu (scores read as logits from the
+//      head).
+//   3. dd_fg_kernel : the seven foreground sums (L1 terms, Laplacian depth, heading CE + L1, BCE correction, sum of
+//      target scores, foreground count) per CTA; 4. dd_finalize_kernel : fixed-order reduction and the loss items.
+#include "assign.cuh"
+
+namespace y3d {
+
+constexpr int kNSum = 10;  // soft+, off2d, size2d, depth, off3d, size3d, hd_ce, hd_l1, x*t, sum t  (+ n_fg kept apart)
+
+struct DDParams {
+    LevelTable t;
+    const float *gts;         // [B,M,17] label bbox4(px) c2d2 s2d2 c3d2 s3d3 depth hbin hres
+    const float *calibs;      // [B,6]
+    const float *mean_sizes;  // [nc,3]
+    float *boxes;             // [B,A,4] px
+    float *pd_kps;            // [B,A,24]
+    unsigned long long *claim;
+    double *part;             // [n_blocks][kNSum + 1]
+    int B, nc, A, M;
+};
+
+// grid (ceil(A/128), B), one thread per anchor
+__global__ void __launch_bounds__(128) dd_stream_kernel(DDParams P, int *work_counter) {
+    __shared__ double red[4];
+    const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0 && work_counter) *work_counter = 0;
+    double soft = 0.0;
+    if (a < P.A) {
+        const LevelTable &t = P.t;
+        const int l = level_of(t, a);
+        const int cell = a - t.start[l];
+        const float st = t.stride[l];
+        const float *x = t.ptr[l] + (long long)b * t.sB[l] + cell;
+        const long long cs = t.sC[l];
+        const int w = t.w[l];
+        const float gx = (float)(cell % w) + 0.5f, gy = (float)(cell / w) + 0.5f;  // make_anchors tal.py:300-312
+        const int nc = P.nc;
+        // classes: first maximum of the sigmoid scores (decode_3d_size tal.py:458-462), sum softplus
+        int cls = 0;
+        float best = -1.0f, acc = 0.f;
+        for (int c = 0; c < nc; ++c) {
+            const float v = x[(long long)c * cs];
+            const float s = 1.0f / (1.0f + expf(-v));
+            if (s > best) { best = s; cls = c; }
+            acc += fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));
+        }
+        soft = (double)acc;
+        const float *r = x + (long long)nc * cs;  // 35 regression channels
+        // 2D box: centres = anchor + offset; xy1 = centres - size/2; xy2 = centres + size/2; * stride (loss.py:812-819)
+        const float cx = dm::add(gx, r[0]), cy = dm::add(gy, r[cs]);
+        const float hw_ = dm::mul(r[2 * cs], 0.5f), hh_ = dm::mul(r[3 * cs], 0.5f);
+        const long long o = (long long)b * P.A + a;
+        *reinterpret_cast<float4 *>(P.boxes + o * 4) =
+            make_float4(dm::mul(dm::sub(cx, hw_), st), dm::mul(dm::sub(cy, hh_), st), dm::mul(dm::add(cx, hw_), st),
+                        dm::mul(dm::add(cy, hh_), st));
+        // 3D: decode_3d_center tal.py:454-456 (anchor px + offset * stride), size = mean + residual, heading argmax
+        const float ax = dm::mul(gx, st), ay = dm::mul(gy, st);
+        const float c3x = dm::add(ax, dm::mul(r[4 * cs], st)), c3y = dm::add(ay, dm::mul(r[5 * cs], st));
+        const float sh_ = dm::add(P.mean_sizes[3 * cls], r[6 * cs]), sw_ = dm::add(P.mean_sizes[3 * cls + 1], r[7 * cs]),
+                    sl_ = dm::add(P.mean_sizes[3 * cls + 2], r[8 * cs]);
+        int hb = 0;
+        float hbv = r[9 * cs];
+        for (int j = 1; j < 12; ++j) {
+            const float v = r[(9 + j) * cs];
+            if (v > hbv) { hbv = v; hb = j; }
+        }
+        float out[24];
+        keypoints24(c3x, c3y, r[33 * cs], sh_, sw_, sl_, hb, r[(9 + 12 + hb) * cs], P.calibs + 6 * b, out);
+        float4 *ok = reinterpret_cast<float4 *>(P.pd_kps + o * 24);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ok[j] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+        if (P.claim) P.claim[o] = 0ull;
+    }
+    soft = warp_sum(soft);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = soft;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *p = P.part + ((long long)b * gridDim.x + blockIdx.x) * (kNSum + 1);
+        p[0] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+}
+
+// grid (ceil(A/128), B): the foreground sums of this CTA's anchors into slots 1..kNSum of its partial row
+__global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
+    __shared__ double red[kNSum][4];
+    const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    double s[kNSum];
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) s[i] = 0.0;
+    if (a < P.A && P.M > 0) {
+        const long long o = (long long)b * P.A + a;
+        const int gi = c.tgi[o];
+        if (gi >= 0) {
+            const LevelTable &t = P.t;
+            const int l = level_of(t, a);
+            const int cell = a - t.start[l];
+            const float st = t.stride[l];
+            const float *x = t.ptr[l] + (long long)b * t.sB[l] + cell;
+            const long long cs = t.sC[l];
+            const int w = t.w[l];
+            const float ax = ((float)(cell % w) + 0.5f) * st, ay = ((float)(cell / w) + 0.5f) * st;
+            const float *g = P.gts + ((long long)b * P.M + gi) * 17;
+            const float *r = x + (long long)P.nc * cs;
+            const float norm = assigned_norm(c, b, gi, c.alignv[o]);  // target score at the assigned label
+            int lab = (int)g[0];
+            lab = lab < 0 ? 0 : lab;
+            // compute_box2d_loss loss.py:913-926 (px): offset vs (center_2d - anchor), size vs size_2d
+            s[1] = (double)fabsf(r[0] * st - (g[5] - ax)) + (double)fabsf(r[cs] * st - (g[6] - ay));
+            s[2] = (double)fabsf(r[2 * cs] * st - g[7]) + (double)fabsf(r[3 * cs] * st - g[8]);
+            // compute_box3d_loss loss.py:928-963
+            const float dep = r[33 * cs], un = r[34 * cs];
+            s[3] = (double)(1.4142f * expf(-0.5f * un) * fabsf(dep - g[14]) + 0.5f * un);  // loss.py:1118
+            s[4] = (double)fabsf(r[4 * cs] * st - (g[9] - ax)) + (double)fabsf(r[5 * cs] * st - (g[10] - ay));
+            s[5] = (double)fabsf(r[6 * cs] - g[11]) + (double)fabsf(r[7 * cs] - g[12]) + (double)fabsf(r[8 * cs] - g[13]);
+            // compute_heading_loss loss.py:1122-1136: CE over the 12 bins + L1 of the residual of the target bin
+            const int tb = (int)g[15];
+            float m = -3.4e38f, hv[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                hv[j] = r[(9 + j) * cs];
+                m = fmaxf(m, hv[j]);
+            }
+            float se = 0.f;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) se += expf(hv[j] - m);
+            s[6] = (double)(m + logf(se) - r[(9 + tb) * cs]);
+            s[7] = (double)fabsf(r[(9 + 12 + tb) * cs] - g[16]);
+            s[8] = (double)x[(long long)lab * cs] * (double)norm;  // BCE(x,t) - BCE(x,0) = -x*t
+            s[9] = (double)norm;
+            s[0] = 1.0;  // foreground count
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) {
+        const double v = warp_sum(s[i]);
+        if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNSum) {
+        double *p = P.part + ((long long)b * gridDim.x + blockIdx.x) * (kNSum + 1);
+        const int i = threadIdx.x;
+        const double v = (red[i][0] + red[i][1]) + (red[i][2] + red[i][3]);
+        if (i == 0) p[kNSum] = v;  // n_fg
+        else p[i] = v;
+    }
+}
+
+// partials float64[kNSum + 1] = soft+, off2d, size2d, depth, off3d, size3d, hd_ce, hd_l1, x*t, sum t, n_fg
+__global__ void __launch_bounds__(256) dd_reduce_kernel(const double *part, int n_rows, double *partials) {
+    __shared__ double red[kNSum + 1][256];
+    double acc[kNSum + 1];
+    for (int i = 0; i <= kNSum; ++i) acc[i] = 0.0;
+    for (int r = threadIdx.x; r < n_rows; r += 256)
+        for (int i = 0; i <= kNSum; ++i) acc[i] += part[(long long)r * (kNSum + 1) + i];
+    for (int i = 0; i <= kNSum; ++i) red[i][threadIdx.x] = acc[i];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int i = 0; i <= kNSum; ++i) red[i][threadIdx.x] += red[i][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x <= kNSum) partials[threadIdx.x] = red[threadIdx.x][0];
+}
+
+// loss.py:879-888: items = loss2d, cls, depth, offset3d, size3d, heading (+ target_scores_sum, n_fg)
+__global__ void dd_finalize_kernel(const double *p, int M, float g2d, float gcls, float gdep, float go3d, float gs3d,
+                                   float ghd, float *items) {
+    if (threadIdx.x != 0) return;
+    if (M == 0) {  // no targets: the reference returns its zero-initialised loss (loss.py:873-876)
+        for (int i = 0; i < 8; ++i) items[i] = 0.f;
+        items[6] = 1.f;
+        return;
+    }
+    const double tss = p[9] > 1.0 ? p[9] : 1.0, nfg = p[10];
+    // F.l1_loss(..., reduction="mean") over [n_fg, 2] elements (NaN when nothing is assigned, like the reference)
+    items[0] = (float)((p[2] / (2.0 * nfg) + p[1] / (2.0 * nfg)) / tss * g2d);
+    items[1] = (float)((p[0] - p[8]) / tss * gcls);
+    items[2] = (float)(p[3] / tss * gdep);
+    items[3] = (float)(p[4] / (2.0 * nfg) / tss * go3d);
+    items[4] = (float)(p[5] / tss * gs3d);
+    items[5] = (float)((p[6] + p[7]) / tss * ghd);
+    items[6] = (float)tss;
+    items[7] = (float)nfg;
+}
+
+struct DDWs {
+    size_t assign, boxes, pd_kps, gt_kps, part, total;
+    int n_rows;
+};
+static DDWs dd_ws_layout(int B, int A, int M) {
+    DDWs w;
+    size_t o = 0;
+    w.assign = o; o += a256(assign_ws_layout(B, A, M).total);
+    w.boxes = o;  o += a256(sizeof(float) * 4 * (size_t)B * A);
+    w.pd_kps = o; o += a256(sizeof(float) * 24 * (size_t)B * A);
+    w.gt_kps = o; o += a256(sizeof(float) * 24 * (size_t)B * (M > 0 ? M : 1));
+    w.n_rows = ((A + 127) / 128) * B;
+    w.part = o;   o += a256(sizeof(double) * (kNSum + 1) * (size_t)w.n_rows);
+    w.total = o;
+    return w;
+}
+size_t dd_loss_workspace_bytes(int B, int A, int M) { return dd_ws_layout(B, A, M).total; }
+
+}  // namespace y3d
+
+using namespace y3d;
+
+extern "C" int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
+                               const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, const float *gts, int M,
+                               const float *calibs, const float *mean_sizes, int topk, float alpha, float beta,
+                               float gamma, int flags, const float *gains, int normalise, float *loss_items,
+                               double *partials, int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes,
+                               void *stream) {
+    if (!lvl_ptr || !lvl_sB || !lvl_sC || !lvl_hw || !lvl_stride || !calibs || !mean_sizes || !gains) return Y3D_EINVAL;
+    if (B < 1 || nc < 1 || M < 0 || (M > 0 && !gts) || !partials || (normalise && !loss_items)) return Y3D_EINVAL;
+    const int use_2d = flags & 1, use_3d = (flags >> 1) & 1, kps_l2 = (flags >> 2) & 1, constrain = (flags >> 3) & 1;
+    if (!use_2d && !use_3d) return Y3D_EINVAL;  // tal.py:486
+    DDParams P{};
+    const int A = make_level_table(P.t, lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl);
+    if (A < 0) return A;
+    for (int l = 0; l < nl; ++l)
+        if (!lvl_ptr[l]) return Y3D_EINVAL;
+    if (topk < 1 || topk > A) return Y3D_EINVAL;
+    if (topk > Y3D_MAX_TOPK) return Y3D_EUNSUPPORTED;
+    const DDWs w = dd_ws_layout(B, A, M);
+    if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
+    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    char *p = (char *)ws;
+    const AssignWs aw = assign_ws_layout(B, A, M);
+    AssignCtx c{};
+    c.t = P.t;
+    assign_bind_ws(c, p + w.assign, aw);
+    P.gts = gts; P.calibs = calibs; P.mean_sizes = mean_sizes;
+    P.boxes = (float *)(p + w.boxes);
+    P.pd_kps = (float *)(p + w.pd_kps);
+    P.claim = nullptr;  // zeroed by the memset below together with the per-GT maxima
+    P.part = (double *)(p + w.part);
+    P.B = B; P.nc = nc; P.A = A; P.M = M;
+    dim3 grid((A + 127) / 128, B);
+    cudaError_t e = cudaMemsetAsync(p + w.assign + aw.off_cnt, 0, aw.zero_bytes, s);
+    if (e != cudaSuccess) return (int)e;
+    dd_stream_kernel<<<grid, 128, 0, s>>>(P, nullptr);
+    Y3D_CHECK_LAUNCH();
+    if (M > 0) {
+        float *gt_kps = (float *)(p + w.gt_kps);
+        int rc = launch_kps_gt(gts, calibs, mean_sizes, B, M, nc, gt_kps, s);
+        if (rc) return rc;
+        c.score_mode = 1; c.cls_ch0 = 0;  // class logits are the first nc channels of the head
+        c.pd_bboxes = P.boxes; c.box_grid_units = 0; c.box_soa = 0;
+        c.use_grid = 1;
+        c.gt_labels = gts; c.gl_stride = 17;
+        c.gt_bboxes = gts + 1; c.gb_stride = 17;
+        c.mask_gt = nullptr;  // valid iff the box sums to > 0 (loss.py:857)
+        c.B = B; c.A = A; c.nc = nc; c.M = M; c.k = topk;
+        c.alpha = alpha; c.beta = beta; c.gamma = gamma; c.eps = 1e-9f;
+        c.use_2d = use_2d; c.use_3d = use_3d; c.kps_l2 = kps_l2; c.constrain = constrain;
+        c.pd_kps = P.pd_kps; c.gt_kps = gt_kps;
+        AssignCtx2 cc{};
+        cc.c[0] = c;
+        cc.work_counter = (int *)(p + w.assign + aw.off_work);
+        rc = assign_run_core(cc, 1, s);
+        if (rc) return rc;
+    }
+    dd_fg_kernel<<<grid, 128, 0, s>>>(c, P);
+    Y3D_CHECK_LAUNCH();
+    dd_reduce_kernel<<<1, 256, 0, s>>>(P.part, w.n_rows, partials);
+    Y3D_CHECK_LAUNCH();
+    if (normalise) {
+        dd_finalize_kernel<<<1, 32, 0, s>>>(partials, M, gains[0], gains[1], gains[2], gains[3], gains[4], gains[5],
+                                            loss_items);
+        Y3D_CHECK_LAUNCH();
+    }
+    if (dbg_target_gt_idx) {  // assigned GT per anchor, -1 = background
+        if (M == 0) e = cudaMemsetAsync(dbg_target_gt_idx, 0xff, sizeof(int32_t) * (size_t)B * A, s);
+        else e = cudaMemcpyAsync(dbg_target_gt_idx, c.tgi, sizeof(int32_t) * (size_t)B * A, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return Y3D_OK;
+}
+
+extern "C" int y3d_dd_loss_finalize(const double *partials, int M, const float *gains, float *loss_items, void *stream) {
+    if (!partials || !gains || !loss_items) return Y3D_EINVAL;
+    dd_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, M, gains[0], gains[1], gains[2], gains[3], gains[4],
+                                                          gains[5], loss_items);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
+}

@@ -1,0 +1,95 @@
+"""``DDDetectionLoss`` / ``DetectLoss3d`` mirrors (reference ultralytics/utils/loss.py:741-900): same constructor
+(``model`` with ``.args`` and the 3D head as ``model.model[-1]``), same ``__call__`` and the same
+``(loss.sum() * batch_size, loss)`` return.  One branch = one call of ``y3d_dd_loss_fwd`` (csrc/loss3d.cu): the head is
+read once, ``pd_scores`` / ``pd_3d`` / the dense targets of the reference are never materialised.
+
+Forward only in this round (the returned loss carries no autograd graph); the fork's distillation and
+foreground-depth-map terms (loss.py:792, 748-751, 890-895) are outside the hot path and raise if enabled."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._util import Levels, ptr, stream_ptr, workspace
+from .loss import pack_targets
+
+
+def dd_loss_forward(feats, strides, nc, gts_packed, calibs, mean_sizes, topk, gains, alpha=0.5, beta=1.0, gamma=1.0,
+                    use_2d=True, use_3d=True, kps_dist_metric="l1", constrain_anchors=True, normalise=True, debug=False):
+    """One branch through ``y3d_dd_loss_fwd``.  ``gts_packed`` [B, M, 17] (DDDetectionLoss.preprocess layout).  Returns
+    (items float32[8] = six loss items, target_scores_sum, n_fg -- or None --, partials float64[11], target_gt_idx
+    int32 [B, A] with -1 = background, or None)."""
+    lv = Levels(feats, strides)
+    if lv.C != nc + 35:
+        raise ValueError(f"expected {nc + 35} channels, got {lv.C}")
+    if not (use_2d or use_3d):
+        raise RuntimeError("Either 2D or 3D assignment or both has to be selected!")  # tal.py:486
+    if kps_dist_metric not in ("l1", "l2"):
+        raise ValueError("kps_dist_metric must be 'l1' or 'l2'")
+    dev = lv.device
+    gts = gts_packed.to(dev, torch.float32).contiguous()
+    M = int(gts.shape[1])
+    cal = calibs.to(dev, torch.float32).contiguous()
+    ms = mean_sizes.to(dev, torch.float32).contiguous()
+    items = torch.empty(8, dtype=torch.float32, device=dev) if normalise else None
+    partials = torch.empty(11, dtype=torch.float64, device=dev)
+    tgi = torch.empty((lv.B, lv.A), dtype=torch.int32, device=dev) if debug else None
+    ws = workspace(_lib.workspace_bytes(_lib.STAGE_DD_LOSS, B=lv.B, A=lv.A, nc=nc, M=M, k=topk), dev)
+    flags = int(use_2d) | int(use_3d) << 1 | int(kps_dist_metric == "l2") << 2 | int(constrain_anchors) << 3
+    g = (C.c_float * 6)(*[float(v) for v in gains])
+    _lib.check(_lib.lib().y3d_dd_loss_fwd(*lv.args(), lv.B, nc, ptr(gts) if M > 0 else None, M, ptr(cal), ptr(ms),
+                                          int(topk), float(alpha), float(beta), float(gamma), flags, g, int(normalise),
+                                          ptr(items), ptr(partials), ptr(tgi), ptr(ws), ws.numel(), stream_ptr(dev)))
+    return items, partials, tgi
+
+
+class DDDetectionLoss:
+    """loss.py:775-900.  ``model.args`` must provide ``loss2d, cls, depth, offset3d, size3d, heading, tal_alpha,
+    tal_beta, tal_gamma, tal_2d, tal_3d, kps_dist_metric, constrain_anchors, distillation``."""
+
+    def __init__(self, model, tal_topk=10):
+        h = model.args
+        m = model.model[-1]
+        self.hyp = h
+        self.stride = m.stride
+        self.nc = m.nc
+        self.no = m.no
+        self.device = next(model.parameters()).device
+        self.topk = tal_topk
+        if getattr(h, "distillation", False):
+            raise _lib.Y3DError("distillation (SupervisionLoss, loss.py:792) is outside the B200 hot path")
+
+    def __call__(self, preds, batch, embeddings=None):
+        feats = preds[1] if isinstance(preds, tuple) else preds  # loss.py:824
+        B = feats[0].shape[0]
+        dev = feats[0].device
+        h, w = feats[0].shape[2] * float(self.stride[0]), feats[0].shape[3] * float(self.stride[0])  # loss.py:844
+        extra = torch.cat([batch[k].view(batch["cls"].numel(), -1).float() for k in
+                           ("center_2d", "size_2d", "center_3d", "size_3d", "depth", "heading_bin", "heading_res")], 1)
+        gts = pack_targets(batch["batch_idx"], batch["cls"], batch["bboxes"], B, (h, w), dev, extra=extra.to(dev))
+        hp = self.hyp
+        items, _, _ = dd_loss_forward(
+            feats, [float(s) for s in self.stride], self.nc, gts, batch["calib"], batch["mean_sizes"], self.topk,
+            (hp.loss2d, hp.cls, hp.depth, hp.offset3d, hp.size3d, hp.heading), alpha=hp.tal_alpha, beta=hp.tal_beta,
+            gamma=hp.tal_gamma, use_2d=hp.tal_2d, use_3d=hp.tal_3d, kps_dist_metric=hp.kps_dist_metric,
+            constrain_anchors=hp.constrain_anchors)
+        loss = items[:6]
+        return loss.sum() * B, loss  # loss.py:897
+
+
+class DetectLoss3d:
+    """loss.py:741-771 without the foreground-depth-map branches."""
+
+    def __init__(self, model):
+        if getattr(model.args, "fgdm_loss", False) or getattr(model.args, "fgdm_supervision", False):
+            raise _lib.Y3DError("fgdm_loss / fgdm_supervision (loss.py:745-748) are outside the B200 hot path")
+        self.one2many = DDDetectionLoss(model, tal_topk=model.args.tal_topk)
+        self.one2one = DDDetectionLoss(model, tal_topk=1)
+        self.model = model
+
+    def __call__(self, preds, batch):
+        loss_one2one = self.one2one(preds["one2one"], batch, embeddings=preds.get("o2o_embs"))
+        if preds.get("one2many", None):
+            loss_one2many = self.one2many(preds["one2many"], batch, embeddings=preds.get("o2m_embs"))
+            return loss_one2many[0] + loss_one2one[0], torch.cat((loss_one2many[1], loss_one2one[1]))
+        return torch.zeros(1), loss_one2one[1]  # loss.py:771

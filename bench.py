@@ -27,6 +27,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: everything else this process or its libraries print (NCCL's version banner,
+# warnings ...) is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout aside for the final line
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "images/sec, v10 head decode + dual TAL assign"
 UNIT = "images/s"
 CFG = dict(B=64, nc=80, img_hw=(640, 640), M=100, gains=(7.5, 0.5, 1.5))
@@ -137,7 +147,7 @@ def main_reference(args):
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
@@ -264,13 +274,13 @@ def main_cuda(args):
                                                  "finish(resolve+fg_loss+reduce)": float(stage_ms[2])}},
             "e2e": {"value": B * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 24, "steps": Ke},
-            "gpu_launches": 3 * K,
+            "gpu_launches": (3 + (1 if world > 1 else 0)) * K,
             "clocks": sampler.summary(),
             "loss_items": [float(v) for v in items.cpu()],
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

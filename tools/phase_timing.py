@@ -41,9 +41,24 @@ gtd = torch.from_numpy(gt).to(dev)
 for _ in range(5):
     y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
 torch.cuda.synchronize()
+h = _lib.lib()
+prof = (ctypes.c_ulonglong * 16)()
+h.y3d_debug_read_topk_prof.argtypes = [ctypes.c_void_p, ctypes.c_int]
+h.y3d_debug_read_topk_prof(prof, 1)
+y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
+torch.cuda.synchronize()
+h.y3d_debug_read_topk_prof(prof, 0)
+pv = np.array(prof, dtype=np.float64)
+names = ["fetch+valid", "gt load+rects", "phase0", "stage1 trips", "stage2 pops", "list updates", "claims"]
+tot = pv[:7].sum()
+print("top-k kernel, warp-cycles by phase (one step):")
+for i, nme in enumerate(names):
+    print(f"  {nme:14s} {pv[i] / 1e6:8.2f} Mcyc  {100 * pv[i] / tot:5.1f}%")
+gts_n = max(pv[8], 1)
+print(f"  valid GT-warps {int(pv[8])}, cells/GT {pv[9] / gts_n:.1f}, trips/GT {pv[10] / gts_n:.2f}, pops/GT {pv[11] / gts_n:.2f}, "
+      f"popped cand/GT {pv[12] / gts_n:.1f}, insertions/GT {pv[13] / gts_n:.1f}, cycles/GT {tot / gts_n:.0f}")
 n = 128 * 8
 buf = (ctypes.c_ulonglong * n)()
-h = _lib.lib()
 h.y3d_debug_read_stamps.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert h.y3d_debug_read_stamps(buf, n) == 0
 t = np.array(buf, dtype=np.uint64).reshape(128, 8).astype(np.int64)

@@ -56,6 +56,34 @@ static __device__ __noinline__ float2 cand_bounds(float x, int score_mode, float
     return make_float2(sb, ub);
 }
 
+#ifdef Y3D_TIMING
+// developer instrumentation (tools/phase_timing.py): cycles and event counts per phase, summed over all warps
+__device__ unsigned long long g_topk_prof[16];
+#define TK_T0() long long tk_t_ = clock64()
+#define TK_ACC(i)                                                                          \
+    do {                                                                                   \
+        const long long n_ = clock64();                                                    \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_topk_prof[i], (unsigned long long)(n_ - tk_t_)); \
+        tk_t_ = n_;                                                                        \
+    } while (0)
+#define TK_CNT(i, v)                                                                       \
+    do {                                                                                   \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_topk_prof[i], (unsigned long long)(v)); \
+    } while (0)
+extern "C" int y3d_debug_read_topk_prof(unsigned long long *host, int reset) {
+    int rc = (int)cudaMemcpyFromSymbol(host, g_topk_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {};
+        cudaMemcpyToSymbol(g_topk_prof, z, sizeof(z));
+    }
+    return rc;
+}
+#else
+#define TK_T0()
+#define TK_ACC(i)
+#define TK_CNT(i, v)
+#endif
+
 struct LvlWalk {  // one level's exact in-GT rectangle (per warp, shared memory)
     int off, ncols, c0, r0;        // first flat index, columns, first column / row
     int w, start, cmid, rmid;      // grid width, first anchor of the level, centre-out pivots
@@ -78,6 +106,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     // Work items = (branch, image, GT).  One warp per GT: persistent warps pull items from a global counter (padded
     // GTs cost one load, big GTs do not stall a whole wave).  Several warps per GT: one item per CTA, static.
     bool static_done = false;
+    TK_T0();
     for (int item = (int)blockIdx.x;;) {
     if (wpg == 1) {
         int it = 0;
@@ -96,6 +125,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         if (wpg == 1) continue;
         break;
     }
+    TK_ACC(0);  // item fetch + validity (incl. padded GTs)
     const GtRec g = load_gt(c, b, m);
     const int k = c.k;
     const bool rect = c.use_grid && c.constrain;
@@ -159,6 +189,9 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         __syncwarp();
     }
 
+    TK_ACC(1);  // GT load + exact rectangles
+    TK_CNT(8, 1);
+    TK_CNT(9, cells);
     unsigned long long tk = 0ull;   // lane-distributed sorted list (descending), lanes >= k unused
     unsigned long long thr = 0ull;  // key of the k-th entry (warp-uniform)
 
@@ -176,6 +209,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
 
     // phase 1: candidates = anchors >= k inside the GT.  One loop body: first entry, then trips while the queue cannot
     // fill a warp, pops otherwise, the remainder at the end.
+    TK_ACC(2);  // phase 0 (first k anchors)
     int qn = 0, qh = 0;  // FIFO ring: candidates are evaluated in walk order (centre first)
     int i0 = wsub * (32 * kTopkU);
     bool done = false;
@@ -253,6 +287,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                 qn += __popc(bal);
             }
             __syncwarp();
+            TK_ACC(3);  // stage 1 trips
+            TK_CNT(10, 1);
             continue;
         } else if (qn > 0) {
             // ---- stage 2: pop full lanes while trips remain, the rest at the end (no loads: pure arithmetic)
@@ -274,6 +310,9 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
             qh += take;
             if (qh >= kTopkQ) qh -= kTopkQ;
             __syncwarp();
+            TK_ACC(4);  // stage 2 pops
+            TK_CNT(11, 1);
+            TK_CNT(12, take);
         } else {
             break;
         }
@@ -289,7 +328,9 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
             else if (lane > pos) tk = up;
             thr = __shfl_sync(0xffffffffu, tk, k - 1);
             if (lane == src) key = 0ull;
+            TK_CNT(13, 1);
         }
+        TK_ACC(5);  // list updates
     }
 
     if (wpg > 1) {  // merge the per-warp lists into the first warp's
@@ -340,6 +381,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         }
     }
     __syncwarp();
+    TK_ACC(6);  // claims + prefetch
     }  // item loop
 }
 

@@ -37,33 +37,6 @@ __device__ __forceinline__ void store_vec(float *p, const VecF<VEC> &r) {
     }
 }
 
-// softmax over R bins followed by the expectation sum_j j*p_j (block.py:59-62), VEC anchors at once.
-// p points at bin 0 of one side; bins are cs elements apart.
-template <int VEC, int R>
-__device__ __forceinline__ VecF<VEC> dfl_expect(const float *p, long long cs) {
-    VecF<VEC> x[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) x[j] = load_vec<VEC>(p + j * cs);
-    VecF<VEC> out;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-        float m = x[0].v[e];
-#pragma unroll
-        for (int j = 1; j < R; ++j) m = fmaxf(m, x[j].v[e]);
-        float s = 0.f, acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-            float ex = expf(x[j].v[e] - m);
-            s += ex;
-            acc += (float)j * ex;
-        }
-        out.v[e] = acc / s;
-    }
-    return out;
-}
-
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
-
 struct QuadMap {  // quads (groups of VEC consecutive cells of one level) per level
     int qstart[Y3D_MAX_LEVELS + 1];
 };
@@ -78,69 +51,78 @@ __device__ __forceinline__ bool locate(const LevelTable &t, const QuadMap &qm, i
     return true;
 }
 
-// grid (ceil(Q/32), B), block (32, 2 + n_cls_roles).  Warp role 0/1: x / y axis of the box (sides l,r / t,b);
-// role >= 2: a chunk of class channels.  One warp instruction touches 32*VEC consecutive anchors of a channel row.
-template <int VEC, int R>
-__global__ void __launch_bounds__(256) decode2d_kernel(LevelTable t, QuadMap qm, int nc, int cls_chunk, int xywh,
-                                                       int A, float *__restrict__ y) {
+// grid (ceil(Q/32), B), block 128 = 32 units of VEC anchors x 4 channel parts (warp = part).  The 64 + nc channel rows
+// are split evenly: parts 0 / 1 own the x / y axis of the box (DFL sides l,r / t,b: 32 rows) plus a few class rows,
+// parts 2 / 3 the remaining class rows.  One warp instruction touches 32*VEC consecutive anchors of a channel row;
+// class rows are loaded 10 at a time before any arithmetic.
+template <int VEC>
+__global__ void __launch_bounds__(128, 4) decode2d_kernel(LevelTable t, QuadMap qm, int nc, int xywh, int A,
+                                                          float *__restrict__ y) {
     const int b = blockIdx.y;
-    const int q = blockIdx.x * 32 + threadIdx.x;
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int q = blockIdx.x * 32 + lane;
     int l, cell;
     if (!locate<VEC>(t, qm, q, l, cell)) return;
-    const int role = threadIdx.y;
     const float *base = t.ptr[l] + (long long)b * t.sB[l] + cell;
     const long long cs = t.sC[l];
     const int a0 = t.start[l] + cell;
     float *yb = y + (long long)b * (4 + nc) * A + a0;
-    if (role < 2) {
-        VecF<VEC> d_lo = dfl_expect<VEC, R>(base + (long long)(role * R) * cs, cs);        // l or t
-        VecF<VEC> d_hi = dfl_expect<VEC, R>(base + (long long)((role + 2) * R) * cs, cs);  // r or b
+    // class rows of this part
+    const int rpp = (64 + nc + 3) >> 2;                   // rows per part
+    const int n01 = max(0, min(nc / 2, rpp - 32));        // class rows of parts 0 and 1 (each)
+    const int rest = nc - 2 * n01, h2 = (rest + 1) >> 1;  // parts 2 and 3 share the rest
+    int c0, c1;
+    if (part < 2) { c0 = part * n01; c1 = c0 + n01; }
+    else if (part == 2) { c0 = 2 * n01; c1 = c0 + h2; }
+    else { c0 = 2 * n01 + h2; c1 = nc; }
+    if (part < 2) {  // box axis `part`
+        VecF<VEC> d_lo, d_hi;
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs) {  // l then r (t then b): 16 rows in flight at a time
+            VecF<VEC> x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = load_vec<VEC>(base + (long long)((part + 2 * hs) * 16 + j) * cs);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                float a[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a[j] = x[j].v[e];
+                (hs ? d_hi : d_lo).v[e] = im::dfl16(a);
+            }
+        }
         const float st = t.stride[l];
         const int w = t.w[l];
+        int cx = cell % w, cy = cell / w;
         VecF<VEC> o0, o1;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            int c = cell + e;
-            float anc = (role == 0 ? (float)(c % w) : (float)(c / w)) + 0.5f;
-            float lo = anc - d_lo.v[e];  // tal.py:319
-            float hi = anc + d_hi.v[e];  // tal.py:320
-            if (xywh) {
-                o0.v[e] = ((lo + hi) / 2.0f) * st;  // tal.py:322 then head.py:76 "* self.strides"
-                o1.v[e] = (hi - lo) * st;           // tal.py:323
-            } else {
-                o0.v[e] = lo * st;
-                o1.v[e] = hi * st;
-            }
+            const float anc = (part == 0 ? (float)cx : (float)cy) + 0.5f;
+            im::box_axis(anc, d_lo.v[e], d_hi.v[e], st, xywh, o0.v[e], o1.v[e]);
+            if (++cx >= w) { cx = 0; ++cy; }
         }
-        store_vec<VEC>(yb + (long long)role * A, o0);
-        store_vec<VEC>(yb + (long long)(role + 2) * A, o1);
-    } else {
-        const int c0 = (role - 2) * cls_chunk;
-        const int c1 = min(nc, c0 + cls_chunk);
-        const float *p = base + (long long)(4 * R + c0) * cs;
-        float *o = yb + (long long)(4 + c0) * A;
-        int c = c0;
-        for (; c + 4 <= c1; c += 4) {  // 4 independent loads in flight
-            VecF<VEC> v[4];
+        store_vec<VEC>(yb + (long long)part * A, o0);
+        store_vec<VEC>(yb + (long long)(part + 2) * A, o1);
+    }
+    const float *p = base + (long long)(64 + c0) * cs;
+    float *o = yb + (long long)(4 + c0) * A;
+    int c = c0;
+    constexpr int CB = 10;
+    for (; c + CB <= c1; c += CB, p += CB * cs, o += (long long)CB * A) {
+        VecF<VEC> v[CB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = load_vec<VEC>(p + (long long)u * cs);
+        for (int u = 0; u < CB; ++u) v[u] = load_vec<VEC>(p + u * cs);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < CB; ++u) {
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) v[u].v[e] = sigmoidf_(v[u].v[e]);  // head.py:78
-                store_vec<VEC>(o + (long long)u * A, v[u]);
-            }
-            p += 4 * cs;
-            o += 4LL * A;
+            for (int e = 0; e < VEC; ++e) v[u].v[e] = im::sigmoid(v[u].v[e]);  // head.py:78
+            store_vec<VEC>(o + (long long)u * A, v[u]);
         }
-        for (; c < c1; ++c) {
-            VecF<VEC> v = load_vec<VEC>(p);
+    }
+    for (; c < c1; ++c, p += cs, o += A) {
+        VecF<VEC> v = load_vec<VEC>(p);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v.v[e] = sigmoidf_(v.v[e]);
-            store_vec<VEC>(o, v);
-            p += cs;
-            o += A;
-        }
+        for (int e = 0; e < VEC; ++e) v.v[e] = im::sigmoid(v.v[e]);
+        store_vec<VEC>(o, v);
     }
 }
 
@@ -275,19 +257,15 @@ extern "C" int y3d_decode2d(const float *const *lvl_ptr, const int64_t *lvl_sB, 
         if (!lvl_ptr[l]) return Y3D_EINVAL;
     if (B == 0) return Y3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    int n_cls_roles = (nc + 15) / 16;
-    if (n_cls_roles > 6) n_cls_roles = 6;
-    int chunk = (nc + n_cls_roles - 1) / n_cls_roles;
-    dim3 block(32, 2 + n_cls_roles);
-    bool v4 = vec4_ok(t) && (((uintptr_t)y) % 16 == 0);
+    bool v4 = vec4_ok(t) && (((uintptr_t)y) % 16 == 0) && A % 4 == 0;
     if (v4) {
         QuadMap qm = make_quads<4>(t);
         dim3 grid((qm.qstart[nl] + 31) / 32, B);
-        decode2d_kernel<4, 16><<<grid, block, 0, s>>>(t, qm, nc, chunk, xywh, A, y);
+        decode2d_kernel<4><<<grid, 128, 0, s>>>(t, qm, nc, xywh, A, y);
     } else {
         QuadMap qm = make_quads<1>(t);
         dim3 grid((qm.qstart[nl] + 31) / 32, B);
-        decode2d_kernel<1, 16><<<grid, block, 0, s>>>(t, qm, nc, chunk, xywh, A, y);
+        decode2d_kernel<1><<<grid, 128, 0, s>>>(t, qm, nc, xywh, A, y);
     }
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;

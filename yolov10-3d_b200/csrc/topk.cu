@@ -37,13 +37,11 @@ struct TopkSrc {
     int xywh;
 };
 
-__device__ __forceinline__ float sigmoid_(float v) { return 1.0f / (1.0f + expf(-v)); }
-
 __device__ __forceinline__ float src_score(const TopkSrc &s, int b, int a, int c) {
     if (s.mode == 0) return s.preds[b * s.sB + a * s.sA + (long long)(s.soff + c) * s.sC];
     int l = level_of(s.t, a);
     const float *p = s.t.ptr[l] + (long long)b * s.t.sB[l] + (a - s.t.start[l]);
-    return sigmoid_(p[(long long)(64 + c) * s.t.sC[l]]);
+    return im::sigmoid(p[(long long)(64 + c) * s.t.sC[l]]);
 }
 
 // decode of one anchor's box from the head (same arithmetic as decode2d_kernel)
@@ -55,33 +53,15 @@ __device__ __forceinline__ void src_box(const TopkSrc &s, int b, int a, float ou
     float d[4];
     for (int side = 0; side < 4; ++side) {
         float x[16];
-        float m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            x[j] = p[(long long)(side * 16 + j) * cs];
-            m = fmaxf(m, x[j]);
-        }
-        float sum = 0.f, acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float e = expf(x[j] - m);
-            sum += e;
-            acc += (float)j * e;
-        }
-        d[side] = acc / sum;
+        for (int j = 0; j < 16; ++j) x[j] = p[(long long)(side * 16 + j) * cs];
+        d[side] = im::dfl16(x);
     }
     const int w = s.t.w[l];
     const float st = s.t.stride[l];
-    float ax = (float)(cell % w) + 0.5f, ay = (float)(cell / w) + 0.5f;
-    float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
-    if (s.xywh) {
-        out[0] = ((x1 + x2) / 2.0f) * st;
-        out[1] = ((y1 + y2) / 2.0f) * st;
-        out[2] = (x2 - x1) * st;
-        out[3] = (y2 - y1) * st;
-    } else {
-        out[0] = x1 * st; out[1] = y1 * st; out[2] = x2 * st; out[3] = y2 * st;
-    }
+    const float ax = (float)(cell % w) + 0.5f, ay = (float)(cell / w) + 0.5f;
+    im::box_axis(ax, d[0], d[2], st, s.xywh, out[0], out[2]);
+    im::box_axis(ay, d[1], d[3], st, s.xywh, out[1], out[3]);
 }
 
 // ------------------------------------------------------------------------------------------ stage 0 kernels
@@ -146,11 +126,11 @@ __global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total
     for (int c = 0; c < nc; ++c) {
         if constexpr (VEC == 4) {
             float4 v = ldg_stream4(p + c * cs);
-            float s0 = sigmoid_(v.x), s1 = sigmoid_(v.y), s2 = sigmoid_(v.z), s3 = sigmoid_(v.w);
+            float s0 = im::sigmoid(v.x), s1 = im::sigmoid(v.y), s2 = im::sigmoid(v.z), s3 = im::sigmoid(v.w);
             nan |= (s0 != s0) | (s1 != s1) | (s2 != s2) | (s3 != s3);
             m[0] = fmaxf(m[0], s0); m[1] = fmaxf(m[1], s1); m[2] = fmaxf(m[2], s2); m[3] = fmaxf(m[3], s3);
         } else {
-            float s0 = sigmoid_(ldg_stream1(p + c * cs));
+            float s0 = im::sigmoid(ldg_stream1(p + c * cs));
             nan |= (s0 != s0);
             m[0] = fmaxf(m[0], s0);
         }

@@ -122,6 +122,46 @@ __device__ __forceinline__ void stg_stream4(float *p, float4 v) {
 // fire-and-forget pull of one line into L2 (latency-bound gathers of a later phase / kernel then hit L2)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// --------------------------------------------------------------------------------------------- im:: math
+// Value-only arithmetic of the inference path (sigmoid of the class logits, DFL softmax expectation): fast SFU
+// intrinsics, relative error ~1e-6, far inside the 1e-5 bar.  decode.cu and topk.cu share these definitions so that the
+// fused decode + top-k path and the unfused one produce identical bits.
+namespace im {
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2a(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid(float v) { return __fdividef(1.0f, 1.0f + ex2a(-v * kLog2e)); }
+// softmax over 16 bins followed by the expectation sum_j j * p_j (DFL.forward block.py:59-62)
+__device__ __forceinline__ float dfl16(const float (&x)[16]) {
+    float m = x[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) m = fmaxf(m, x[j]);
+    const float mo = -m * kLog2e;
+    float s = 0.f, acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float e = ex2a(__fmaf_rn(x[j], kLog2e, mo));
+        s = __fadd_rn(s, e);
+        acc = __fmaf_rn((float)j, e, acc);
+    }
+    return __fdividef(acc, s);
+}
+// dist2bbox (tal.py:315-325) * stride (head.py:76) for one axis: lo = anchor - d_lo, hi = anchor + d_hi
+__device__ __forceinline__ void box_axis(float anc, float d_lo, float d_hi, float st, int xywh, float &o0, float &o1) {
+    const float lo = __fsub_rn(anc, d_lo), hi = __fadd_rn(anc, d_hi);
+    if (xywh) {
+        o0 = __fmul_rn(__fmul_rn(__fadd_rn(lo, hi), 0.5f), st);
+        o1 = __fmul_rn(__fsub_rn(hi, lo), st);
+    } else {
+        o0 = __fmul_rn(lo, st);
+        o1 = __fmul_rn(hi, st);
+    }
+}
+}  // namespace im
+
 // --------------------------------------------------------------------------------------------- dm:: math
 namespace dm {
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }

@@ -147,14 +147,20 @@ struct SelShared {
     unsigned prefix, need, n_gt, n_eq, eq_base, cnt;
 };
 
-// Exact top-D of n keys by (key desc, index asc).  key_at(i) must be pure.  Writes D composites
-// (key << 32 | ~index) into out[0..D) (unordered), out[D..Dpad) = 0, then sorts descending.
+// Exact top-D of n keys by (key desc, index asc).  key_at(i) must be pure.  `out` has room for 2 * Dpad composites
+// (key << 32 | ~index); on return out[0..D) holds the winners sorted descending.
+// MSD radix select, 8 bits per pass, that stops as soon as the boundary bucket is small: everything above the bucket
+// plus the whole bucket (at most 2 * Dpad composites) is sorted directly, which also resolves ties in index order.
+// Only when even the full 32-bit key leaves too many equal keys does the ordered tie pass run.
 template <class KeyAt>
 __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long long *out, SelShared &sh) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { sh.prefix = 0; sh.need = D; }
+    const int cap = 2 * Dpad;
+    if (tid == 0) { sh.prefix = 0; sh.need = D; sh.n_eq = (unsigned)n; }
     unsigned mask = 0;
+    __syncthreads();
     for (int pass = 3; pass >= 0; --pass) {
+        if ((D - (int)sh.need) + (int)sh.n_eq <= cap) break;  // block-uniform: read after a barrier
         const int shift = pass * 8;
         for (int i = tid; i < 256; i += nt) sh.hist[i] = 0;
         __syncthreads();
@@ -201,15 +207,16 @@ __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long l
         __syncthreads();
     }
     const unsigned T = sh.prefix, need_eq = sh.need, n_eq = sh.n_eq, n_gt = D - need_eq;
-    if (tid == 0) { sh.cnt = 0; sh.eq_base = 0; }
-    for (int i = D + tid; i < Dpad; i += nt) out[i] = 0ull;
     __syncthreads();
-    const bool take_all_eq = (n_eq == need_eq);
-    // keys > T (and all == T when no boundary tie): unordered append, warp-aggregated
+    if (tid == 0) { sh.cnt = 0; sh.eq_base = 0; }
+    __syncthreads();
+    const bool fits = (int)(n_gt + n_eq) <= cap;
+    // keys above the boundary bucket, plus the whole bucket when it fits: unordered append, warp-aggregated
     for (int i0 = 0; i0 < n; i0 += nt) {
         int i = i0 + tid;
         unsigned k = i < n ? key_at(i) : 0u;
-        bool sel = i < n && (k > T || (take_all_eq && k == T));
+        const unsigned km = k & mask;
+        bool sel = i < n && (km > T || (fits && km == T));
         unsigned bal = __ballot_sync(0xffffffffu, sel);
         if (bal) {
             unsigned base = 0;
@@ -218,7 +225,7 @@ __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long l
             if (sel) out[base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)k << 32) | (0xFFFFFFFFu - (unsigned)i);
         }
     }
-    if (!take_all_eq) {  // boundary tie: the first need_eq keys == T in index order
+    if (!fits) {  // (only reached with mask == ~0: more than Dpad exact ties) the first need_eq keys == T in index order
         for (int i0 = 0; i0 < n; i0 += nt) {
             __syncthreads();
             if (sh.eq_base >= need_eq) break;
@@ -240,10 +247,15 @@ __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long l
         }
     }
     __syncthreads();
+    const int filled = fits ? (int)(n_gt + n_eq) : D;
+    int L = Dpad;
+    while (L < filled) L <<= 1;  // <= 2 * Dpad
+    for (int i = filled + tid; i < L; i += nt) out[i] = 0ull;
+    __syncthreads();
     // bitonic sort, descending
-    for (int k = 2; k <= Dpad; k <<= 1)
+    for (int k = 2; k <= L; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < Dpad; i += nt) {
+            for (int i = tid; i < L; i += nt) {
                 int p = i ^ j;
                 if (p > i) {
                     unsigned long long x = out[i], y = out[p];
@@ -263,22 +275,82 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
                                                                     int32_t *anchor_idx, int out_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *win1 = (unsigned long long *)smem_raw;
-    unsigned long long *win2 = win1 + Dpad;
-    uint32_t *k2s = (uint32_t *)(win2 + Dpad);
+    unsigned long long *win2 = win1 + 2 * Dpad;
+    uint32_t *k2s = (uint32_t *)(win2 + 2 * Dpad);
     __shared__ SelShared sh;
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const float *kb = keys + (long long)b * A;
     block_topk([&](int i) { return float_key(kb[i]); }, A, D, Dpad, win1, sh);
-    // stage 2: D x nc candidate scores, flattened index j = i*nc + c   (ops.py:858-861)
+    // stage 2: D x nc candidate scores, flattened index j = i*nc + c   (ops.py:858-861).
+    // Every selected anchor contributes its own maximum, so at least D candidates are >= tau, the smallest selected
+    // maximum: the final top-D lives among the candidates with key >= tau.  Those are compacted (typically little more
+    // than D of the D*nc) and sorted directly; the full radix select over D*nc keys is only the overflow fallback.
     const int n2 = D * nc;
     uint32_t *k2 = keys2_smem ? k2s : keys2_ws + (long long)b * n2;
-    for (int j = tid; j < n2; j += nt) {
-        int i = j / nc, c = j - i * nc;
-        int a = (int)(0xFFFFFFFFu - (unsigned)(win1[i] & 0xFFFFFFFFull));
-        k2[j] = float_key(src_score(src, b, a, c));
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(k2);
+    const int cap = (((uintptr_t)cand & 7) == 0) ? min(n2 / 2, 8192) : 0;  // u64 slots available in the key buffer
+    const uint32_t tau = (uint32_t)(win1[D - 1] >> 32);
+    __shared__ unsigned n_cand;
+    if (tid == 0) n_cand = 0;
+    __syncthreads();
+    constexpr int GU = 8;  // gathers in flight per thread: the D*nc score reads are latency-bound sector gathers
+    for (int j0 = 0; j0 < n2; j0 += nt * GU) {
+        uint32_t key[GU];
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const int j = j0 + u * nt + tid;
+            key[u] = 0;
+            if (j < n2) {
+                const int i = j / nc, c = j - i * nc;
+                const int a = (int)(0xFFFFFFFFu - (unsigned)(win1[i] & 0xFFFFFFFFull));
+                key[u] = float_key(src_score(src, b, a, c));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const int j = j0 + u * nt + tid;
+            const bool keep = j < n2 && key[u] >= tau;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (bal) {
+                unsigned base = 0;
+                if ((tid & 31) == 0) base = atomicAdd(&n_cand, (unsigned)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned pos = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+                if (keep && pos < (unsigned)cap) cand[pos] = ((unsigned long long)key[u] << 32) | (0xFFFFFFFFu - (unsigned)j);
+            }
+        }
     }
     __syncthreads();
-    block_topk([&](int j) { return k2[j]; }, n2, D, Dpad, win2, sh);
+    const int nc2 = (int)n_cand;
+    int L = Dpad;
+    while (L < nc2 && L < (1 << 20)) L <<= 1;
+    if (nc2 <= cap && L <= cap) {
+        for (int i = nc2 + tid; i < L; i += nt) cand[i] = 0ull;
+        __syncthreads();
+        for (int k = 2; k <= L; k <<= 1)  // bitonic sort, descending
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int i = tid; i < L; i += nt) {
+                    const int pp = i ^ jj;
+                    if (pp > i) {
+                        const unsigned long long x = cand[i], yv = cand[pp];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (x < yv) : (x > yv)) { cand[i] = yv; cand[pp] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int r = tid; r < D; r += nt) win2[r] = cand[r];
+        __syncthreads();
+    } else {  // overflow (massive ties at tau): exact radix select over all D*nc keys
+        __syncthreads();
+        for (int j = tid; j < n2; j += nt) {
+            int i = j / nc, c = j - i * nc;
+            int a = (int)(0xFFFFFFFFu - (unsigned)(win1[i] & 0xFFFFFFFFull));
+            k2[j] = float_key(src_score(src, b, a, c));
+        }
+        __syncthreads();
+        block_topk([&](int j) { return k2[j]; }, n2, D, Dpad, win2, sh);
+    }
     for (int r = tid; r < D; r += nt) {
         unsigned long long w = win2[r];
         int j = (int)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull));
@@ -328,7 +400,7 @@ static int launch_select(const TopkSrc &src, const float *keys, int B, int A, in
     int Dpad = next_pow2(D);
     int n2 = D * nc;
     int k2smem = n2 <= kKeys2SmemCap;
-    size_t smem = sizeof(unsigned long long) * 2 * (size_t)Dpad + (k2smem ? sizeof(uint32_t) * (size_t)n2 : 0);
+    size_t smem = sizeof(unsigned long long) * 4 * (size_t)Dpad + (k2smem ? sizeof(uint32_t) * (size_t)n2 : 0);
     cudaError_t e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     topk_select_kernel<<<B, kTopkThreads, smem, s>>>(src, keys, A, nc, nreg, D, Dpad, k2smem, keys2_ws, reg, scores,

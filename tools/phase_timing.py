@@ -70,3 +70,17 @@ for i in list(range(0, 6)) + list(range(64, 70)):
     print(i % 64, i // 64, valid[i % 64], round((t[i, 0] - t0) / 1e3, 1), d[i].round(1))
 print("mean phase durations (us):", d.mean(0).round(2), " max:", d.max(0).round(2))
 print("kernel span (us): first start -> last CTA end", (t[:, :5].max() - t0) / 1e3, " final-reduce stamp", (t[:, 5].max() - t0) / 1e3)
+
+# ---- select kernel (fused decode + top-k), CTA 0
+f64 = [f[:64] if f.shape[0] >= 64 else f for f in fo]
+for _ in range(3):
+    y3d.v10detect_export_forward(fo, synth.STRIDES, 80, 300)
+torch.cuda.synchronize()
+st = (ctypes.c_longlong * 16)()
+h.y3d_debug_read_sel_stamps.argtypes = [ctypes.c_void_p]
+h.y3d_debug_read_sel_stamps(st)
+sa = np.array(st, dtype=np.int64)
+print("  (last block_topk call) passes", sa[9] - sa[8], " collect", sa[10] - sa[9], " sort", sa[11] - sa[10], " L", sa[12], " mask", hex(int(sa[13]) & 0xffffffff))
+sv = sa[:5]
+print("select kernel CTA 0 phases (cycles): stage1 top-D", sv[1] - sv[0], " gather+compact", sv[2] - sv[1], " stage2 sort", sv[3] - sv[2],
+      " outputs", sv[4] - sv[3])

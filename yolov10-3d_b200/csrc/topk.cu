@@ -44,71 +44,83 @@ __device__ __forceinline__ float src_score(const TopkSrc &s, int b, int a, int c
     return im::sigmoid(p[(long long)(64 + c) * s.t.sC[l]]);
 }
 
-// decode of one anchor's box from the head (same arithmetic as decode2d_kernel)
-__device__ __forceinline__ void src_box(const TopkSrc &s, int b, int a, float out[4]) {
-    int l = level_of(s.t, a);
-    int cell = a - s.t.start[l];
+// decode of one axis (0: x1/x2 or cx/w, 1: y1/y2 or cy/h) of one anchor's box from the head -- same arithmetic as
+// decode2d_kernel; the 32 bin gathers of the two sides are issued together
+__device__ __forceinline__ void src_box_axis(const TopkSrc &s, int b, int a, int axis, float &o0, float &o1) {
+    const int l = level_of(s.t, a);
+    const int cell = a - s.t.start[l];
     const float *p = s.t.ptr[l] + (long long)b * s.t.sB[l] + cell;
     const long long cs = s.t.sC[l];
-    float d[4];
-    for (int side = 0; side < 4; ++side) {
-        float x[16];
+    float xl[16], xh[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = p[(long long)(side * 16 + j) * cs];
-        d[side] = im::dfl16(x);
+    for (int j = 0; j < 16; ++j) {
+        xl[j] = p[(long long)(axis * 16 + j) * cs];
+        xh[j] = p[(long long)((axis + 2) * 16 + j) * cs];
     }
     const int w = s.t.w[l];
-    const float st = s.t.stride[l];
-    const float ax = (float)(cell % w) + 0.5f, ay = (float)(cell / w) + 0.5f;
-    im::box_axis(ax, d[0], d[2], st, s.xywh, out[0], out[2]);
-    im::box_axis(ay, d[1], d[3], st, s.xywh, out[1], out[3]);
+    const float anc = (float)(axis == 0 ? cell % w : cell / w) + 0.5f;
+    im::box_axis(anc, im::dfl16(xl), im::dfl16(xh), s.t.stride[l], s.xywh, o0, o1);
 }
 
 // ------------------------------------------------------------------------------------------ stage 0 kernels
-// generic strided amax: one warp per anchor, lanes over classes (coalesced when sC == 1)
+// Per anchor: the largest class key (amax of ops.py:855), its class (first maximum) and the second largest key.
+// With the second key the selection kernel knows, without touching the scores again, whether an anchor can contribute
+// more than its best class to the final top-D: only then are its nc scores gathered.
+struct Top2 {
+    uint32_t k1 = 0, k2 = 0;  // keys are order-preserving uint32 images of the floats (0 is below every real key)
+    int arg = 0;
+};
+__device__ __forceinline__ void top2_push(Top2 &t, uint32_t k, int c) {
+    if (k > t.k1) { t.k2 = t.k1; t.k1 = k; t.arg = c; }
+    else if (k > t.k2) t.k2 = k;
+}
+__device__ __forceinline__ void top2_store(const Top2 &t, uint32_t *keys, int2 *aux, long long o) {
+    keys[o] = t.k1;
+    aux[o] = make_int2((int)t.k2, t.arg);
+}
+
+// generic strided layout: one warp per anchor, lanes over classes (coalesced when sC == 1)
 __global__ void amax_warp_kernel(const float *__restrict__ preds, long long sB, long long sA, long long sC, int soff,
-                                 int B, int A, int nc, float *__restrict__ keys) {
+                                 int B, int A, int nc, uint32_t *__restrict__ keys, int2 *__restrict__ aux) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * A) return;
     int b = warp / A, a = warp % A;
     const float *p = preds + b * sB + a * sA + (long long)soff * sC;
-    float m = -INFINITY;
-    bool nan = false;
-    for (int c = lane; c < nc; c += 32) {
-        float v = p[c * sC];
-        nan |= (v != v);
-        m = fmaxf(m, v);
+    Top2 t;
+    for (int c = lane; c < nc; c += 32) top2_push(t, float_key(p[c * sC]), c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // merge: larger k1 wins, lower class on ties; k2 = best of the rest
+        const uint32_t ok1 = __shfl_xor_sync(0xffffffffu, t.k1, o), ok2 = __shfl_xor_sync(0xffffffffu, t.k2, o);
+        const int oarg = __shfl_xor_sync(0xffffffffu, t.arg, o);
+        const bool mine = t.k1 > ok1 || (t.k1 == ok1 && t.arg < oarg);
+        const uint32_t loser = mine ? ok1 : t.k1;
+        const uint32_t second = max(max(t.k2, ok2), loser);
+        if (!mine) { t.k1 = ok1; t.arg = oarg; }
+        t.k2 = second;
     }
-    m = warp_max(m);
-    nan = __any_sync(0xffffffffu, nan);
-    if (lane == 0) keys[warp] = nan ? NAN : m;
+    if (lane == 0) top2_store(t, keys, aux, warp);
 }
-// anchor-contiguous amax (sA == 1, the reference's permuted view of [B, C, A]): one thread per anchor
+// anchor-contiguous layout (sA == 1, the reference's permuted view of [B, C, A]): one thread per anchor
 __global__ void amax_anchor_kernel(const float *__restrict__ preds, long long sB, long long sC, int soff, int B, int A,
-                                   int nc, float *__restrict__ keys) {
+                                   int nc, uint32_t *__restrict__ keys, int2 *__restrict__ aux) {
     int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (a >= A) return;
     const float *p = preds + b * sB + a + (long long)soff * sC;
-    float m = -INFINITY;
-    bool nan = false;
+    Top2 t;
     int c = 0;
     for (; c + 4 <= nc; c += 4) {
         float v0 = ldg_stream1(p + (c + 0) * sC), v1 = ldg_stream1(p + (c + 1) * sC);
         float v2 = ldg_stream1(p + (c + 2) * sC), v3 = ldg_stream1(p + (c + 3) * sC);
-        nan |= (v0 != v0) | (v1 != v1) | (v2 != v2) | (v3 != v3);
-        m = fmaxf(fmaxf(m, fmaxf(v0, v1)), fmaxf(v2, v3));
+        top2_push(t, float_key(v0), c); top2_push(t, float_key(v1), c + 1);
+        top2_push(t, float_key(v2), c + 2); top2_push(t, float_key(v3), c + 3);
     }
-    for (; c < nc; ++c) {
-        float v = ldg_stream1(p + c * sC);
-        nan |= (v != v);
-        m = fmaxf(m, v);
-    }
-    keys[(long long)b * A + a] = nan ? NAN : m;
+    for (; c < nc; ++c) top2_push(t, float_key(ldg_stream1(p + c * sC)), c);
+    top2_store(t, keys, aux, (long long)b * A + a);
 }
-// head levels -> max_c sigmoid(logit): 4 anchors per thread, 128-bit loads; class channels only are read
+// head levels -> sigmoid(logit) keys: 4 anchors per thread, 128-bit loads; class channels only are read
 template <int VEC>
 __global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total, int nc, int A,
-                                                      float *__restrict__ keys) {
+                                                      uint32_t *__restrict__ keys, int2 *__restrict__ aux) {
     // quads are enumerated level by level
     int q = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (q >= nq_total) return;
@@ -119,25 +131,19 @@ __global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total
     int cell = (q - qs) * VEC;
     const float *p = t.ptr[l] + (long long)b * t.sB[l] + cell + 64LL * t.sC[l];
     const long long cs = t.sC[l];
-    float m[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) m[e] = -INFINITY;
-    bool nan = false;
+    Top2 tt[VEC];
     for (int c = 0; c < nc; ++c) {
         if constexpr (VEC == 4) {
             float4 v = ldg_stream4(p + c * cs);
-            float s0 = im::sigmoid(v.x), s1 = im::sigmoid(v.y), s2 = im::sigmoid(v.z), s3 = im::sigmoid(v.w);
-            nan |= (s0 != s0) | (s1 != s1) | (s2 != s2) | (s3 != s3);
-            m[0] = fmaxf(m[0], s0); m[1] = fmaxf(m[1], s1); m[2] = fmaxf(m[2], s2); m[3] = fmaxf(m[3], s3);
+            top2_push(tt[0], float_key(im::sigmoid(v.x)), c); top2_push(tt[1], float_key(im::sigmoid(v.y)), c);
+            top2_push(tt[2], float_key(im::sigmoid(v.z)), c); top2_push(tt[3], float_key(im::sigmoid(v.w)), c);
         } else {
-            float s0 = im::sigmoid(ldg_stream1(p + c * cs));
-            nan |= (s0 != s0);
-            m[0] = fmaxf(m[0], s0);
+            top2_push(tt[0], float_key(im::sigmoid(ldg_stream1(p + c * cs))), c);
         }
     }
-    float *o = keys + (long long)b * A + t.start[l] + cell;
+    const long long o = (long long)b * A + t.start[l] + cell;
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) o[e] = nan ? NAN : m[e];  // (NaN handling is per quad; NaN inputs are unsupported)
+    for (int e = 0; e < VEC; ++e) top2_store(tt[e], keys, aux, o + e);
 }
 
 // ------------------------------------------------------------------------------------------ block select
@@ -146,6 +152,66 @@ struct SelShared {
     unsigned warp_tot[32];
     unsigned prefix, need, n_gt, n_eq, eq_base, cnt;
 };
+
+#ifdef Y3D_TIMING
+__device__ long long g_sel_stamps[16];
+#define SEL_STAMP(i)                                                    \
+    do {                                                                \
+        __syncthreads();                                                \
+        if (threadIdx.x == 0 && blockIdx.x == 0) g_sel_stamps[i] = clock64(); \
+    } while (0)
+extern "C" int y3d_debug_read_sel_stamps(long long *host) {
+    return (int)cudaMemcpyFromSymbol(host, g_sel_stamps, sizeof(long long) * 16);
+}
+#else
+#define SEL_STAMP(i)
+#endif
+
+// Bitonic sort of buf[0..L) (L a power of two), descending.  One element per thread while L <= blockDim.x: partners less
+// than a warp apart are exchanged with shuffles (no barrier), only the strides >= 32 go through shared memory.
+__device__ void block_sort_desc(unsigned long long *buf, int L) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (L <= nt) {
+        // only the L participating threads (whole warps) synchronise, on a named barrier: a full-block barrier per
+        // step costs several hundred cycles with 32 warps
+        __syncthreads();
+        const int nbar = (L + 31) & ~31;
+        if (tid < nbar) {
+            unsigned long long v = tid < L ? buf[tid] : 0ull;
+            for (int k = 2; k <= L; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    unsigned long long o;
+                    if (j >= 32) {
+                        asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");
+                        buf[tid] = v;
+                        asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");
+                        o = buf[tid ^ j];
+                    } else {
+                        o = __shfl_xor_sync(0xffffffffu, v, j);
+                    }
+                    const bool desc = (tid & k) == 0, lower = (tid & j) == 0;
+                    const bool take_max = desc == lower;
+                    v = take_max ? (v > o ? v : o) : (v < o ? v : o);
+                }
+            if (L >= 64) asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");
+            if (tid < L) buf[tid] = v;
+        }
+        __syncthreads();
+        return;
+    }
+    for (int k = 2; k <= L; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < L; i += nt) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long x = buf[i], y = buf[p];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (x < y) : (x > y)) { buf[i] = y; buf[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
 
 // Exact top-D of n keys by (key desc, index asc).  key_at(i) must be pure.  `out` has room for 2 * Dpad composites
 // (key << 32 | ~index); on return out[0..D) holds the winners sorted descending.
@@ -159,6 +225,7 @@ __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long l
     if (tid == 0) { sh.prefix = 0; sh.need = D; sh.n_eq = (unsigned)n; }
     unsigned mask = 0;
     __syncthreads();
+    SEL_STAMP(8);
     for (int pass = 3; pass >= 0; --pass) {
         if ((D - (int)sh.need) + (int)sh.n_eq <= cap) break;  // block-uniform: read after a barrier
         const int shift = pass * 8;
@@ -207,7 +274,7 @@ __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long l
         __syncthreads();
     }
     const unsigned T = sh.prefix, need_eq = sh.need, n_eq = sh.n_eq, n_gt = D - need_eq;
-    __syncthreads();
+    SEL_STAMP(9);
     if (tid == 0) { sh.cnt = 0; sh.eq_base = 0; }
     __syncthreads();
     const bool fits = (int)(n_gt + n_eq) <= cap;
@@ -246,29 +313,22 @@ __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long l
             if (tid == 0) sh.eq_base += total;
         }
     }
-    __syncthreads();
+    SEL_STAMP(10);
     const int filled = fits ? (int)(n_gt + n_eq) : D;
     int L = Dpad;
     while (L < filled) L <<= 1;  // <= 2 * Dpad
     for (int i = filled + tid; i < L; i += nt) out[i] = 0ull;
     __syncthreads();
-    // bitonic sort, descending
-    for (int k = 2; k <= L; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < L; i += nt) {
-                int p = i ^ j;
-                if (p > i) {
-                    unsigned long long x = out[i], y = out[p];
-                    bool desc = (i & k) == 0;
-                    if (desc ? (x < y) : (x > y)) { out[i] = y; out[p] = x; }
-                }
-            }
-            __syncthreads();
-        }
+    block_sort_desc(out, L);
+    SEL_STAMP(11);
+#ifdef Y3D_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) { g_sel_stamps[12] = L; g_sel_stamps[13] = (long long)mask; }
+#endif
 }
 
 // one CTA per image
-__global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, const float *__restrict__ keys, int A,
+__global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, const uint32_t *__restrict__ keys,
+                                                                    const int2 *__restrict__ aux, int A, int keys1_smem,
                                                                     int nc, int nreg, int D, int Dpad, int keys2_smem,
                                                                     uint32_t *__restrict__ keys2_ws, float *reg,
                                                                     float *scores, int64_t *labels,
@@ -279,8 +339,16 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
     uint32_t *k2s = (uint32_t *)(win2 + 2 * Dpad);
     __shared__ SelShared sh;
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const float *kb = keys + (long long)b * A;
-    block_topk([&](int i) { return float_key(kb[i]); }, A, D, Dpad, win1, sh);
+    const uint32_t *kb = keys + (long long)b * A;
+    SEL_STAMP(0);
+    if (keys1_smem) {  // the radix passes re-read the keys: stage them in shared memory once (aliases the stage-2 buffer)
+        for (int i = tid; i < A; i += nt) k2s[i] = kb[i];
+        __syncthreads();
+        block_topk([&](int i) { return k2s[i]; }, A, D, Dpad, win1, sh);
+    } else {
+        block_topk([&](int i) { return kb[i]; }, A, D, Dpad, win1, sh);
+    }
+    SEL_STAMP(1);
     // stage 2: D x nc candidate scores, flattened index j = i*nc + c   (ops.py:858-861).
     // Every selected anchor contributes its own maximum, so at least D candidates are >= tau, the smallest selected
     // maximum: the final top-D lives among the candidates with key >= tau.  Those are compacted (typically little more
@@ -293,52 +361,65 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
     __shared__ unsigned n_cand;
     if (tid == 0) n_cand = 0;
     __syncthreads();
-    constexpr int GU = 8;  // gathers in flight per thread: the D*nc score reads are latency-bound sector gathers
-    for (int j0 = 0; j0 < n2; j0 += nt * GU) {
+    // every selected anchor contributes its best class; only anchors whose SECOND best key also reaches tau can
+    // contribute more, and only their nc scores are gathered
+    __shared__ unsigned n_rich;
+    int *rich = reinterpret_cast<int *>(win2);  // ranks of those anchors (win2 is free until the final copy)
+    if (tid == 0) n_rich = 0;
+    __syncthreads();
+    const int2 *ab = aux + (long long)b * A;
+    for (int i = tid; i < D; i += nt) {
+        const uint32_t k1 = (uint32_t)(win1[i] >> 32);
+        const int a = (int)(0xFFFFFFFFu - (unsigned)(win1[i] & 0xFFFFFFFFull));
+        const int2 ax = ab[a];
+        if ((uint32_t)ax.x >= tau) {
+            rich[atomicAdd(&n_rich, 1u)] = i;
+        } else {
+            const unsigned pos = atomicAdd(&n_cand, 1u);
+            if (pos < (unsigned)cap) cand[pos] = ((unsigned long long)k1 << 32) | (0xFFFFFFFFu - (unsigned)(i * nc + ax.y));
+        }
+    }
+    __syncthreads();
+    const int n2r = (int)n_rich * nc;
+    constexpr int GU = 8;  // gathers in flight per thread: latency-bound sector gathers
+    for (int j0 = 0; j0 < n2r; j0 += nt * GU) {
         uint32_t key[GU];
+        int jj[GU];
 #pragma unroll
         for (int u = 0; u < GU; ++u) {
-            const int j = j0 + u * nt + tid;
+            const int t = j0 + u * nt + tid;
             key[u] = 0;
-            if (j < n2) {
-                const int i = j / nc, c = j - i * nc;
+            jj[u] = -1;
+            if (t < n2r) {
+                const int ri = t / nc, c = t - ri * nc;
+                const int i = rich[ri];
                 const int a = (int)(0xFFFFFFFFu - (unsigned)(win1[i] & 0xFFFFFFFFull));
                 key[u] = float_key(src_score(src, b, a, c));
+                jj[u] = i * nc + c;
             }
         }
 #pragma unroll
         for (int u = 0; u < GU; ++u) {
-            const int j = j0 + u * nt + tid;
-            const bool keep = j < n2 && key[u] >= tau;
+            const bool keep = jj[u] >= 0 && key[u] >= tau;
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (bal) {
                 unsigned base = 0;
                 if ((tid & 31) == 0) base = atomicAdd(&n_cand, (unsigned)__popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 const unsigned pos = base + __popc(bal & ((1u << (tid & 31)) - 1u));
-                if (keep && pos < (unsigned)cap) cand[pos] = ((unsigned long long)key[u] << 32) | (0xFFFFFFFFu - (unsigned)j);
+                if (keep && pos < (unsigned)cap) cand[pos] = ((unsigned long long)key[u] << 32) | (0xFFFFFFFFu - (unsigned)jj[u]);
             }
         }
     }
     __syncthreads();
+    SEL_STAMP(2);
     const int nc2 = (int)n_cand;
     int L = Dpad;
     while (L < nc2 && L < (1 << 20)) L <<= 1;
     if (nc2 <= cap && L <= cap) {
         for (int i = nc2 + tid; i < L; i += nt) cand[i] = 0ull;
         __syncthreads();
-        for (int k = 2; k <= L; k <<= 1)  // bitonic sort, descending
-            for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                for (int i = tid; i < L; i += nt) {
-                    const int pp = i ^ jj;
-                    if (pp > i) {
-                        const unsigned long long x = cand[i], yv = cand[pp];
-                        const bool desc = (i & k) == 0;
-                        if (desc ? (x < yv) : (x > yv)) { cand[i] = yv; cand[pp] = x; }
-                    }
-                }
-                __syncthreads();
-            }
+        block_sort_desc(cand, L);
         for (int r = tid; r < D; r += nt) win2[r] = cand[r];
         __syncthreads();
     } else {  // overflow (massive ties at tau): exact radix select over all D*nc keys
@@ -351,6 +432,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
         __syncthreads();
         block_topk([&](int j) { return k2[j]; }, n2, D, Dpad, win2, sh);
     }
+    SEL_STAMP(3);
     for (int r = tid; r < D; r += nt) {
         unsigned long long w = win2[r];
         int j = (int)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull));
@@ -363,10 +445,18 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
             scores[o] = sc;
             labels[o] = c;
         } else {  // fused export layout [B,D,6] = box, score, label (head.py:531)
-            float bx[4];
-            src_box(src, b, a, bx);
             float *q = reg + o * 6;
-            q[0] = bx[0]; q[1] = bx[1]; q[2] = bx[2]; q[3] = bx[3]; q[4] = sc; q[5] = (float)c;
+            q[4] = sc; q[5] = (float)c;
+        }
+    }
+    if (out_mode != 0) {  // boxes of the winners: one thread per (detection, axis)
+        for (int e = tid; e < 2 * D; e += nt) {
+            const int r = e >> 1, axis = e & 1;
+            const unsigned long long w = win2[r];
+            const int j = (int)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull));
+            const int a = (int)(0xFFFFFFFFu - (unsigned)(win1[j / nc] & 0xFFFFFFFFull));
+            float *q = reg + ((long long)b * D + r) * 6;
+            src_box_axis(src, b, a, axis, q[axis], q[axis + 2]);
         }
     }
     if (out_mode == 0) {
@@ -379,6 +469,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
                 src.preds[b * src.sB + a * src.sA + (long long)(src.roff + rr) * src.sC];
         }
     }
+    SEL_STAMP(4);
 }
 
 static int next_pow2(int v) {
@@ -389,21 +480,25 @@ static int next_pow2(int v) {
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 size_t topk_workspace_bytes(int B, int A, int nc, int D) {
-    size_t keys = align256(sizeof(float) * (size_t)B * A);
+    size_t keys = align256(sizeof(uint32_t) * (size_t)B * A) + align256(sizeof(int2) * (size_t)B * A);
     size_t k2 = (D * nc > kKeys2SmemCap) ? align256(sizeof(uint32_t) * (size_t)B * D * nc) : 0;
     return keys + k2;
 }
 
-static int launch_select(const TopkSrc &src, const float *keys, int B, int A, int nc, int nreg, int D, float *reg,
+static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *aux, int B, int A, int nc, int nreg, int D, float *reg,
                          float *scores, int64_t *labels, int32_t *anchor_idx, int out_mode, uint32_t *keys2_ws,
                          cudaStream_t s) {
     int Dpad = next_pow2(D);
     int n2 = D * nc;
     int k2smem = n2 <= kKeys2SmemCap;
-    size_t smem = sizeof(unsigned long long) * 4 * (size_t)Dpad + (k2smem ? sizeof(uint32_t) * (size_t)n2 : 0);
+    int k1smem = A <= kKeys2SmemCap;
+    size_t nkeys = 0;
+    if (k2smem) nkeys = (size_t)n2;
+    if (k1smem && (size_t)A > nkeys) nkeys = (size_t)A;
+    size_t smem = sizeof(unsigned long long) * 4 * (size_t)Dpad + sizeof(uint32_t) * nkeys;
     cudaError_t e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    topk_select_kernel<<<B, kTopkThreads, smem, s>>>(src, keys, A, nc, nreg, D, Dpad, k2smem, keys2_ws, reg, scores,
+    topk_select_kernel<<<B, kTopkThreads, smem, s>>>(src, keys, aux, A, k1smem, nc, nreg, D, Dpad, k2smem, keys2_ws, reg, scores,
                                                     labels, anchor_idx, out_mode);
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
@@ -424,15 +519,16 @@ extern "C" int y3d_postprocess(const float *preds, int64_t sB, int64_t sA, int64
     if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
     if (B == 0) return Y3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    float *keys = (float *)ws;
-    uint32_t *k2 = (uint32_t *)((char *)ws + align256(sizeof(float) * (size_t)B * A));
+    uint32_t *keys = (uint32_t *)ws;
+    int2 *aux = (int2 *)((char *)ws + align256(sizeof(uint32_t) * (size_t)B * A));
+    uint32_t *k2 = (uint32_t *)((char *)aux + align256(sizeof(int2) * (size_t)B * A));
     const int soff = scores_first ? 0 : nreg, roff = scores_first ? nc : 0;
     if (sA == 1) {
         dim3 grid((A + 255) / 256, B);
-        amax_anchor_kernel<<<grid, 256, 0, s>>>(preds, sB, sC, soff, B, A, nc, keys);
+        amax_anchor_kernel<<<grid, 256, 0, s>>>(preds, sB, sC, soff, B, A, nc, keys, aux);
     } else {
         long long threads = (long long)B * A * 32;
-        amax_warp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(preds, sB, sA, sC, soff, B, A, nc, keys);
+        amax_warp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(preds, sB, sA, sC, soff, B, A, nc, keys, aux);
     }
     Y3D_CHECK_LAUNCH();
     TopkSrc src{};
@@ -440,7 +536,7 @@ extern "C" int y3d_postprocess(const float *preds, int64_t sB, int64_t sA, int64
     src.preds = preds;
     src.sB = sB; src.sA = sA; src.sC = sC;
     src.soff = soff; src.roff = roff;
-    return launch_select(src, keys, B, A, nc, nreg, D, reg, scores, labels, anchor_idx, 0, k2, s);
+    return launch_select(src, keys, aux, B, A, nc, nreg, D, reg, scores, labels, anchor_idx, 0, k2, s);
 }
 
 extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
@@ -461,8 +557,9 @@ extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl
     if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
     if (B == 0) return Y3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    float *keys = (float *)ws;
-    uint32_t *k2 = (uint32_t *)((char *)ws + align256(sizeof(float) * (size_t)B * A));
+    uint32_t *keys = (uint32_t *)ws;
+    int2 *aux = (int2 *)((char *)ws + align256(sizeof(uint32_t) * (size_t)B * A));
+    uint32_t *k2 = (uint32_t *)((char *)aux + align256(sizeof(int2) * (size_t)B * A));
     bool v4 = true;
     for (int l = 0; l < nl; ++l)
         v4 = v4 && (src.t.h[l] * src.t.w[l]) % 4 == 0 && ((uintptr_t)lvl_ptr[l]) % 16 == 0 && lvl_sB[l] % 4 == 0 &&
@@ -470,13 +567,13 @@ extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl
     if (v4) {
         int nq = A / 4;
         dim3 grid((nq + 127) / 128, B);
-        cls_max_kernel<4><<<grid, 128, 0, s>>>(src.t, nq, nc, A, keys);
+        cls_max_kernel<4><<<grid, 128, 0, s>>>(src.t, nq, nc, A, keys, aux);
     } else {
         dim3 grid((A + 127) / 128, B);
-        cls_max_kernel<1><<<grid, 128, 0, s>>>(src.t, A, nc, A, keys);
+        cls_max_kernel<1><<<grid, 128, 0, s>>>(src.t, A, nc, A, keys, aux);
     }
     Y3D_CHECK_LAUNCH();
     src.mode = 1;
     src.xywh = xywh;
-    return launch_select(src, keys, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s);
+    return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s);
 }

@@ -215,6 +215,14 @@ int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const in
                     const float *gains, int normalise, float *loss_items, double *partials,
                     int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes, void *stream);
 int y3d_dd_loss_finalize(const double *partials, int M, const float *gains, float *loss_items, void *stream);
+/* Backward of y3d_dd_loss_fwd (autograd of loss.py:879-888 through compute_box2d_loss, compute_box3d_loss, the
+ * Laplacian depth term and compute_heading_loss): call with the same geometry / gts / M and the untouched workspace of
+ * the forward call.  grad_* index the gradient tensors like the head tensors; every element is written.
+ * loss_items: DEVICE float[8] of the forward pass; grad_items: DEVICE float[6] = d total / d item. */
+int y3d_dd_loss_bwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, float *const *grad_ptr,
+                    const int64_t *grad_sB, const int64_t *grad_sC, const int *lvl_hw, const float *lvl_stride, int nl,
+                    int B, int nc, const float *gts, int M, const float *gains, const float *loss_items,
+                    const float *grad_items, const void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -305,15 +305,20 @@ def case_loss3d(name, B, nc, img_hw, M, topk, seed, **kw):
     model = FakeModel(nc, synth.STRIDES, args)
     model.model[0].no = nc + 35
     crit = ref_loss.DDDetectionLoss(model, tal_topk=topk)
-    feats = [t(f) for f in synth.split_levels(x, lv)]
+    feats = [t(f).requires_grad_(True) for f in synth.split_levels(x, lv)]
     batch = {k: t(v) for k, v in synth.batch_dict3d(gts, img_hw, calibs, ms).items()}
     orig_cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:
         with patched_topk():
             total, items = crit(feats, batch, embeddings=None)
+        total.backward()
     finally:
         torch.Tensor.cuda = orig_cuda
+    gr = torch.cat([f.grad.view(B, nc + 35, -1) for f in feats], 2).numpy()
+    pos = synth.rng(seed + 99).integers(0, gr.size, 4096)
+    nz = np.flatnonzero(gr[0, nc:])[:4096]  # regression rows of image 0: the foreground anchors
+    feats = [f.detach() for f in feats]
     # the packed targets the loss built internally (preprocess loss.py:795-810), for the GT-packing glue test
     imgsz = torch.tensor(feats[0].shape[2:], dtype=torch.float32) * synth.STRIDES[0]
     g_in = torch.cat((batch["batch_idx"].view(-1, 1), batch["cls"].view(-1, 1), batch["bboxes"], batch["center_2d"],
@@ -322,7 +327,9 @@ def case_loss3d(name, B, nc, img_hw, M, topk, seed, **kw):
     packed = crit.preprocess(g_in, B, scale_tensor=imgsz[[1, 0, 1, 0]]).numpy()
     recipe = dict(kind="loss3d", B=B, nc=nc, img_hw=img_hw, M=M, topk=topk, seed=seed, kw=kw, gains=list(gains.values()))
     save(name, recipe, in_crc=np.int64(synth.checksum(gts, x)), calibs=calibs, packed=packed,
-         total=np.float64(total.item()), items=items.detach().numpy().astype(np.float64))
+         total=np.float64(total.item()), items=items.detach().numpy().astype(np.float64), grad_pos=pos,
+         grad=gr.reshape(-1)[pos], grad_abs_sum=np.float64(np.abs(gr).sum(dtype=np.float64)), nz=nz,
+         nz_val=gr[0, nc:].reshape(-1)[nz])
 
 
 if __name__ == "__main__":

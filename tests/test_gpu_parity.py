@@ -404,6 +404,34 @@ def test_dd_loss_golden_and_oracle(y3d, name):
     assert np.array_equal(tgi[tgi >= 0], asg["target_gt_idx"][asg["fg_mask"]])
 
 
+@pytest.mark.parametrize("name", cases.names("loss3d_"))
+def test_dd_loss_backward_vs_reference_autograd(y3d, name):
+    """d total / d head from y3d_dd_loss_bwd against the gradients autograd produced in the REAL DDDetectionLoss."""
+    r, z = cases.load(name)
+    lv, gts, x, calibs, ms = cases.loss3d_inputs(r, z)
+    B, C = r["B"], r["nc"] + 35
+    batch = {k: torch.from_numpy(v) for k, v in synth.batch_dict3d(gts, r["img_hw"], calibs, ms).items()}
+    f = [t.requires_grad_(True) for t in feats_of(x, lv)]
+    total, items = y3d.DDDetectionLoss(FakeModel3d(r["nc"], r, r["topk"]), tal_topk=r["topk"])(f, batch)
+    total.backward()
+    g = torch.cat([t.grad.view(B, C, -1) for t in f], 2).cpu().numpy()
+    ref = z["grad"]
+    np.testing.assert_allclose(g.reshape(-1)[z["grad_pos"]], ref, rtol=2e-4, atol=2e-6 * float(np.abs(ref).max()))
+    np.testing.assert_allclose(np.abs(g).sum(dtype=np.float64), float(z["grad_abs_sum"]), rtol=1e-4)
+    reg = g[0, r["nc"]:].reshape(-1)
+    np.testing.assert_allclose(reg[z["nz"]], z["nz_val"], rtol=1e-3, atol=1e-5 * float(np.abs(z["nz_val"]).max()))
+    A = g.shape[2]
+    mine = set(np.flatnonzero(np.abs(g[0, r["nc"]:]).sum(0)).tolist())
+    refa = set((z["nz"] % A).tolist())
+    assert refa <= mine and (len(z["nz"]) >= 4096 or refa == mine)
+    # no targets: the reference's loss is a constant zero -> zero gradient
+    f0 = [t.requires_grad_(True) for t in feats_of(x, lv)]
+    empty = {k: (v[:0] if k not in ("calib", "mean_sizes") else v) for k, v in batch.items()}
+    t0, _ = y3d.DDDetectionLoss(FakeModel3d(r["nc"], r, r["topk"]), tal_topk=r["topk"])(f0, empty)
+    t0.backward()
+    assert float(t0.detach()) == 0.0 and all(not t.grad.any() for t in f0)
+
+
 def test_dd_loss_no_targets_and_dual(y3d):
     r, z = cases.load("loss3d_k8")
     lv, gts, x, calibs, ms = cases.loss3d_inputs(r, z)

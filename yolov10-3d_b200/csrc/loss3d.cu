@@ -198,6 +198,97 @@ __global__ void dd_finalize_kernel(const double *p, int M, float g2d, float gcls
     items[7] = (float)nfg;
 }
 
+// ------------------------------------------------------------------------------------------------ backward
+struct DDBwdParams {
+    LevelTable t;                    // head tensors (forward inputs)
+    float *g_ptr[Y3D_MAX_LEVELS];    // gradient tensors, same indexing
+    long long g_sB[Y3D_MAX_LEVELS], g_sC[Y3D_MAX_LEVELS];
+    const float *gts;
+    const float *items;              // DEVICE float[8] of the forward pass: [6] = target_scores_sum, [7] = n_fg
+    const float *gitems;             // DEVICE float[6]: d total / d item
+    float gain[6];
+    int B, nc, A, M;
+};
+
+// d (loss items) / d head, reference autograd of loss.py:879-888 with compute_box2d_loss :913-926, compute_box3d_loss
+// :928-963, laplacian_aleatoric_uncertainty_loss_new :1118 and compute_heading_loss :1122-1136.  One thread per
+// anchor writes all nc+35 gradient rows of that anchor (coalesced along the anchor axis): the class rows are dense
+// (sigmoid(x) - t), the regression rows are zero except at foreground anchors.
+__global__ void __launch_bounds__(128) dd_bwd_kernel(AssignCtx c, DDBwdParams P) {
+    const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P.A) return;
+    const LevelTable &t = P.t;
+    const int l = level_of(t, a);
+    const int cell = a - t.start[l];
+    const float st = t.stride[l];
+    const float *x = t.ptr[l] + (long long)b * t.sB[l] + cell;
+    float *g = P.g_ptr[l] + (long long)b * P.g_sB[l] + cell;
+    const long long cs = t.sC[l], gs = P.g_sC[l];
+    const int nc = P.nc;
+    const float tss = P.items[6], nfg = P.items[7];
+    float k[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k[i] = P.M > 0 ? P.gitems[i] * P.gain[i] / tss : 0.0f;  // no targets: constant zero loss
+    const long long o = (long long)b * P.A + a;
+    const int gi = P.M > 0 ? c.tgi[o] : -1;
+    int lab = -1;
+    float norm = 0.f;
+    const float *gt = nullptr;
+    if (gi >= 0) {
+        gt = P.gts + ((long long)b * P.M + gi) * 17;
+        lab = (int)gt[0];
+        lab = lab < 0 ? 0 : lab;
+        norm = assigned_norm(c, b, gi, c.alignv[o]);
+    }
+    for (int cc = 0; cc < nc; ++cc) {  // BCEWithLogits: sigmoid(x) - t
+        const float s = 1.0f / (1.0f + __expf(-x[(long long)cc * cs]));
+        g[(long long)cc * gs] = k[1] * (s - (cc == lab ? norm : 0.f));
+    }
+    const float *r = x + (long long)nc * cs;
+    float *gr = g + (long long)nc * gs;
+    if (gi < 0) {
+#pragma unroll 5
+        for (int j = 0; j < 35; ++j) gr[(long long)j * gs] = 0.f;
+        return;
+    }
+    auto sgn = [](float v) { return v > 0.f ? 1.0f : (v < 0.f ? -1.0f : 0.0f); };
+    const int w = t.w[l];
+    const float ax = ((float)(cell % w) + 0.5f) * st, ay = ((float)(cell / w) + 0.5f) * st;
+    const float m2 = 1.0f / (2.0f * nfg);  // F.l1_loss(reduction="mean") over [n_fg, 2]
+    gr[0] = k[0] * m2 * st * sgn(r[0] * st - (gt[5] - ax));
+    gr[gs] = k[0] * m2 * st * sgn(r[cs] * st - (gt[6] - ay));
+    gr[2 * gs] = k[0] * m2 * st * sgn(r[2 * cs] * st - gt[7]);
+    gr[3 * gs] = k[0] * m2 * st * sgn(r[3 * cs] * st - gt[8]);
+    gr[4 * gs] = k[3] * m2 * st * sgn(r[4 * cs] * st - (gt[9] - ax));
+    gr[5 * gs] = k[3] * m2 * st * sgn(r[5 * cs] * st - (gt[10] - ay));
+    gr[6 * gs] = k[4] * sgn(r[6 * cs] - gt[11]);
+    gr[7 * gs] = k[4] * sgn(r[7 * cs] - gt[12]);
+    gr[8 * gs] = k[4] * sgn(r[8 * cs] - gt[13]);
+    const int tb = (int)gt[15];
+    float hv[12], m = -3.4e38f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        hv[j] = r[(9 + j) * cs];
+        m = fmaxf(m, hv[j]);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        hv[j] = __expf(hv[j] - m);
+        se += hv[j];
+    }
+    const float inv = 1.0f / se;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        gr[(9 + j) * gs] = k[5] * (hv[j] * inv - (j == tb ? 1.0f : 0.0f));
+        gr[(21 + j) * gs] = j == tb ? k[5] * sgn(r[(21 + j) * cs] - gt[16]) : 0.0f;
+    }
+    const float dep = r[33 * cs], un = r[34 * cs];
+    const float e = 1.4142f * __expf(-0.5f * un), d = dep - gt[14];
+    gr[33 * gs] = k[2] * e * sgn(d);
+    gr[34 * gs] = k[2] * (-0.5f * e * fabsf(d) + 0.5f);
+}
+
 struct DDWs {
     size_t assign, boxes, pd_kps, gt_kps, part, total;
     int n_rows;
@@ -291,6 +382,37 @@ extern "C" int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
         else e = cudaMemcpyAsync(dbg_target_gt_idx, c.tgi, sizeof(int32_t) * (size_t)B * A, cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return (int)e;
     }
+    return Y3D_OK;
+}
+
+extern "C" int y3d_dd_loss_bwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
+                               float *const *grad_ptr, const int64_t *grad_sB, const int64_t *grad_sC,
+                               const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, const float *gts, int M,
+                               const float *gains, const float *loss_items, const float *grad_items, const void *ws,
+                               size_t ws_bytes, void *stream) {
+    if (!lvl_ptr || !lvl_sB || !lvl_sC || !grad_ptr || !grad_sB || !grad_sC || !gains || !loss_items || !grad_items)
+        return Y3D_EINVAL;
+    if (B < 1 || nc < 1 || M < 0 || (M > 0 && !gts)) return Y3D_EINVAL;
+    DDBwdParams P{};
+    const int A = make_level_table(P.t, lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl);
+    if (A < 0) return A;
+    for (int l = 0; l < nl; ++l) {
+        if (!lvl_ptr[l] || !grad_ptr[l]) return Y3D_EINVAL;
+        P.g_ptr[l] = grad_ptr[l];
+        P.g_sB[l] = grad_sB[l];
+        P.g_sC[l] = grad_sC[l];
+    }
+    const DDWs w = dd_ws_layout(B, A, M);  // must be the untouched workspace of the forward call
+    if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
+    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    AssignCtx c{};
+    assign_bind_ws(c, (char *)ws + w.assign, assign_ws_layout(B, A, M));
+    c.B = B; c.A = A; c.nc = nc; c.M = M; c.eps = 1e-9f;
+    P.gts = gts; P.items = loss_items; P.gitems = grad_items;
+    for (int i = 0; i < 6; ++i) P.gain[i] = gains[i];
+    P.B = B; P.nc = nc; P.A = A; P.M = M;
+    dd_bwd_kernel<<<dim3((A + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(c, P);
+    Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }
 

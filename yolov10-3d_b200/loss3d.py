@@ -3,8 +3,8 @@
 ``(loss.sum() * batch_size, loss)`` return.  One branch = one call of ``y3d_dd_loss_fwd`` (csrc/loss3d.cu): the head is
 read once, ``pd_scores`` / ``pd_3d`` / the dense targets of the reference are never materialised.
 
-Forward only in this round (the returned loss carries no autograd graph); the fork's distillation and
-foreground-depth-map terms (loss.py:792, 748-751, 890-895) are outside the hot path and raise if enabled."""
+The returned total carries an autograd node whose backward is ``y3d_dd_loss_bwd``.  The fork's distillation and
+foreground-depth-map terms (loss.py:745-751, 792, 890-895) are outside the hot path and raise if enabled."""
 import ctypes as C
 
 import torch
@@ -43,6 +43,43 @@ def dd_loss_forward(feats, strides, nc, gts_packed, calibs, mean_sizes, topk, ga
     return items, partials, tgi
 
 
+class _DDLossFn(torch.autograd.Function):
+    """autograd node of the fused 3D loss: inputs = the per-level head tensors, output = the six loss items."""
+
+    @staticmethod
+    def forward(ctx, cfg, *feats):
+        strides, nc, gts, cal, ms, topk, gains, kw = cfg
+        lv = Levels(feats, strides)
+        dev = lv.device
+        gts = gts.to(dev, torch.float32).contiguous()
+        M = int(gts.shape[1])
+        items = torch.empty(8, dtype=torch.float32, device=dev)
+        partials = torch.empty(11, dtype=torch.float64, device=dev)
+        ws = workspace(_lib.workspace_bytes(_lib.STAGE_DD_LOSS, B=lv.B, A=lv.A, nc=nc, M=M, k=topk), dev)
+        flags = int(kw["use_2d"]) | int(kw["use_3d"]) << 1 | int(kw["kps_dist_metric"] == "l2") << 2 | int(
+            kw["constrain_anchors"]) << 3
+        g = (C.c_float * 6)(*[float(v) for v in gains])
+        _lib.check(_lib.lib().y3d_dd_loss_fwd(*lv.args(), lv.B, nc, ptr(gts) if M > 0 else None, M, ptr(cal), ptr(ms),
+                                              int(topk), float(kw["alpha"]), float(kw["beta"]), float(kw["gamma"]),
+                                              flags, g, 1, ptr(items), ptr(partials), None, ptr(ws), ws.numel(),
+                                              stream_ptr(dev)))
+        ctx.lv, ctx.saved = lv, (gts, M, ws, items, g, nc)
+        ctx.in_dtypes = [f.dtype for f in feats]
+        return items[:6].clone()
+
+    @staticmethod
+    def backward(ctx, grad_items):
+        lv = ctx.lv
+        gts, M, ws, items, g, nc = ctx.saved
+        grads = [torch.empty_like(f) for f in lv.feats]
+        gl = Levels(grads, lv.strides)
+        gi = grad_items.to(lv.device, torch.float32).contiguous()
+        _lib.check(_lib.lib().y3d_dd_loss_bwd(lv.c_ptr, lv.c_sB, lv.c_sC, gl.c_ptr, gl.c_sB, gl.c_sC, lv.c_hw,
+                                              lv.c_stride, lv.nl, lv.B, nc, ptr(gts) if M > 0 else None, M, g,
+                                              ptr(items), ptr(gi), ptr(ws), ws.numel(), stream_ptr(lv.device)))
+        return (None, *[gr.to(dt) for gr, dt in zip(grads, ctx.in_dtypes)])
+
+
 class DDDetectionLoss:
     """loss.py:775-900.  ``model.args`` must provide ``loss2d, cls, depth, offset3d, size3d, heading, tal_alpha,
     tal_beta, tal_gamma, tal_2d, tal_3d, kps_dist_metric, constrain_anchors, distillation``."""
@@ -64,17 +101,21 @@ class DDDetectionLoss:
         B = feats[0].shape[0]
         dev = feats[0].device
         h, w = feats[0].shape[2] * float(self.stride[0]), feats[0].shape[3] * float(self.stride[0])  # loss.py:844
-        extra = torch.cat([batch[k].view(batch["cls"].numel(), -1).float() for k in
-                           ("center_2d", "size_2d", "center_3d", "size_3d", "depth", "heading_bin", "heading_res")], 1)
+        n = batch["cls"].numel()
+        extra = torch.cat([batch[k].reshape(n, wd).float() for k, wd in
+                           (("center_2d", 2), ("size_2d", 2), ("center_3d", 2), ("size_3d", 3), ("depth", 1),
+                            ("heading_bin", 1), ("heading_res", 1))], 1)
         gts = pack_targets(batch["batch_idx"], batch["cls"], batch["bboxes"], B, (h, w), dev, extra=extra.to(dev))
         hp = self.hyp
-        items, _, _ = dd_loss_forward(
-            feats, [float(s) for s in self.stride], self.nc, gts, batch["calib"], batch["mean_sizes"], self.topk,
-            (hp.loss2d, hp.cls, hp.depth, hp.offset3d, hp.size3d, hp.heading), alpha=hp.tal_alpha, beta=hp.tal_beta,
-            gamma=hp.tal_gamma, use_2d=hp.tal_2d, use_3d=hp.tal_3d, kps_dist_metric=hp.kps_dist_metric,
-            constrain_anchors=hp.constrain_anchors)
-        loss = items[:6]
-        return loss.sum() * B, loss  # loss.py:897
+        if not (hp.tal_2d or hp.tal_3d):
+            raise RuntimeError("Either 2D or 3D assignment or both has to be selected!")  # tal.py:486
+        kw = dict(alpha=hp.tal_alpha, beta=hp.tal_beta, gamma=hp.tal_gamma, use_2d=hp.tal_2d, use_3d=hp.tal_3d,
+                  kps_dist_metric=hp.kps_dist_metric, constrain_anchors=hp.constrain_anchors)
+        cal = batch["calib"].to(dev, torch.float32).contiguous()
+        ms = batch["mean_sizes"].to(dev, torch.float32).contiguous()
+        loss = _DDLossFn.apply(([float(s) for s in self.stride], self.nc, gts, cal, ms, self.topk,
+                                (hp.loss2d, hp.cls, hp.depth, hp.offset3d, hp.size3d, hp.heading), kw), *feats)
+        return loss.sum() * B, loss  # loss.py:897 (the reference returns the items attached to the graph as well)
 
 
 class DetectLoss3d:

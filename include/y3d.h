@@ -102,6 +102,17 @@ int y3d_tal_assign(const float *pd_scores, int64_t ss_B, int64_t ss_A, int64_t s
                    float *target_scores, uint8_t *fg_mask, int64_t *target_gt_idx, void *ws, size_t ws_bytes,
                    void *stream);
 
+/* v8DetectionLoss.preprocess (loss.py:180-195, with the xywh2xyxy of ops.py:403-422) and DDDetectionLoss.preprocess
+ * (loss.py:795-810): ragged ground truth -> the padded tensor the loss entry points take.
+ *  batch_idx [N] (image index as float, like the dataloader's), cls [N], bboxes [N,4] xywh normalised to [0,1],
+ *  extra [N, n_extra] (optional columns copied behind the box, e.g. the twelve 3D columns) -- all DEVICE, fp32.
+ *  out [B, M, 5 + n_extra] = cls, xyxy in pixels (img_w, img_h = feature size * stride, loss.py:219), extra; rows of an
+ *  image keep their order of appearance, rows beyond M are dropped, unused rows are zero.  counts [B] int32 (required):
+ *  receives the number of rows of every image (M must be >= its maximum for nothing to be dropped; the Python mirror
+ *  takes it from the host copy of batch_idx the dataloader already has, so no device sync is needed). */
+int y3d_pack_targets(const float *batch_idx, const float *cls, const float *bboxes, const float *extra, int n_extra,
+                     int N, int B, int M, float img_w, float img_h, float *out, int *counts, void *stream);
+
 /* v8DetectionLoss.__call__ forward (ultralytics/utils/loss.py:206-257 with bbox_decode :197, BboxLoss :82-113)
  * for ONE branch, fused: head levels in, three loss items out; pd_scores / target_scores are never materialised.
  *  gt [B,M,5] = cls, xyxy px (the output of v8DetectionLoss.preprocess, loss.py:180-195; zero rows = padding), M >= 0.

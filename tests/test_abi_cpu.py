@@ -59,18 +59,16 @@ def test_empty_gt_early_out_matches_reference_dtypes():
     assert float(out[0][0, 0]) == 4.0 and out[1].shape == (2, 20, 4) and out[2].shape == (2, 20, 4)
 
 
-def test_pack_targets_matches_oracle_preprocess():
-    gt = synth.gt2d(4, 9, 5, (160, 224), seed=3)
-    gt[2] = 0  # an image without objects
-    bd = synth.batch_dict(gt, (160, 224))
-    perm = synth.rng(0).permutation(len(bd["batch_idx"]))  # rows of different images interleaved
-    bd = {k: v[perm] for k, v in bd.items()}
-    want = oracle.preprocess_targets(bd["batch_idx"], bd["cls"], bd["bboxes"], 4, (160, 224))
-    got = y3d.loss.pack_targets(torch.from_numpy(bd["batch_idx"]), torch.from_numpy(bd["cls"]),
-                                torch.from_numpy(bd["bboxes"]), 4, (160, 224), "cpu")
-    np.testing.assert_allclose(got.numpy(), want, rtol=1e-6, atol=1e-4)
+def test_pack_targets_host_side():
+    """Without rows the packed tensor is [B, 0, 5 (+E)] (loss.py:183, 798); with rows the packing is a CUDA kernel
+    (y3d_pack_targets, GPU-tested) and must refuse CPU tensors instead of falling back."""
     empty = y3d.loss.pack_targets(torch.zeros(0), torch.zeros(0, 1), torch.zeros(0, 4), 3, (64, 64), "cpu")
     assert empty.shape == (3, 0, 5)
+    empty3 = y3d.loss.pack_targets(torch.zeros(0), torch.zeros(0, 1), torch.zeros(0, 4), 2, (64, 64), "cpu",
+                                   extra=torch.zeros(0, 12))
+    assert empty3.shape == (2, 0, 17)
+    lib = y3d.lib()
+    assert lib.y3d_pack_targets(None, None, None, None, 0, 4, 2, 3, 64.0, 64.0, None, None, None) == -1
 
 
 def test_make_anchors_matches_oracle():

@@ -239,6 +239,38 @@ def test_v10_loss_golden_and_oracle(y3d, name):
     np.testing.assert_allclose(mine.cpu().numpy(), packed, rtol=1e-6, atol=1e-4)
 
 
+def test_pack_targets_vs_oracle_preprocess(y3d):
+    """y3d_pack_targets == v8DetectionLoss.preprocess / DDDetectionLoss.preprocess (oracle restatement; the oracle is
+    pinned to the reference's packed tensor in tests/test_oracle_vs_golden.py): interleaved images, an empty image,
+    extra columns, more rows than 32 per image, rows beyond M dropped."""
+    lossmod = __import__("yolov10_3d_b200").loss
+    for B, M, hw, E in ((4, 9, (160, 224), 0), (3, 70, (256, 320), 12), (64, 100, (640, 640), 0)):
+        gt = synth.gt2d(B, M, 5, hw, seed=3 + B)
+        gt[min(2, B - 1)] = 0  # an image without objects
+        bd = synth.batch_dict(gt, hw)
+        n = len(bd["batch_idx"])
+        perm = synth.rng(B).permutation(n)  # rows of different images interleaved
+        bd = {k: v[perm] for k, v in bd.items()}
+        extra = synth.rng(1).standard_normal((n, E)).astype(np.float32) if E else None
+        want = oracle.preprocess_targets(bd["batch_idx"], bd["cls"], bd["bboxes"], B, hw, extra=extra)
+        got = lossmod.pack_targets(torch.from_numpy(bd["batch_idx"]), torch.from_numpy(bd["cls"]),
+                                   torch.from_numpy(bd["bboxes"]), B, hw, "cuda",
+                                   extra=torch.from_numpy(extra) if E else None)
+        assert got.shape == want.shape
+        np.testing.assert_array_equal(got.cpu().numpy(), want)  # same fp32 operations in the same order
+    # direct ABI call with M smaller than the fullest image: surplus rows are dropped, counts still exact
+    import ctypes as C
+    bi, cl, bb = (dev(bd[k].reshape(-1) if k != "bboxes" else bd[k]) for k in ("batch_idx", "cls", "bboxes"))
+    out = torch.empty((B, 7, 5), device="cuda")
+    cnt = torch.empty(B, dtype=torch.int32, device="cuda")
+    rc = y3d.lib().y3d_pack_targets(C.c_void_p(bi.data_ptr()), C.c_void_p(cl.data_ptr()), C.c_void_p(bb.data_ptr()), None,
+                                    0, n, B, 7, float(hw[1]), float(hw[0]), C.c_void_p(out.data_ptr()),
+                                    C.c_void_p(cnt.data_ptr()), None)
+    assert rc == 0
+    assert np.array_equal(cnt.cpu().numpy(), np.bincount(bd["batch_idx"].astype(np.int64), minlength=B))
+    np.testing.assert_array_equal(out.cpu().numpy(), want[:, :7])
+
+
 @pytest.mark.parametrize("name", cases.names("loss_"))
 def test_v10_loss_backward_vs_reference_autograd(y3d, name):
     """d total / d head tensors from csrc/loss_bwd.cu against the gradients autograd produced in the REAL reference

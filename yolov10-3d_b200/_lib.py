@@ -19,6 +19,7 @@ SIGNATURES = {
     "y3d_strerror": (C.c_char_p, [_i]),
     "y3d_abi_version": (_i, []),
     "y3d_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "y3d_pack_targets": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
     "y3d_decode2d": (_i, _LEVELS + [_i, _i, _i, _i, _vp, _vp]),
     "y3d_postprocess": (_i, [_vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "y3d_decode_topk2d": (_i, _LEVELS + [_i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -12,35 +12,30 @@ REG_MAX = 16
 
 
 def pack_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device, extra=None):
-    """``v8DetectionLoss.preprocess`` (loss.py:180-195) without the per-image Python loop: ragged [N, ...] rows ->
-    padded [B, Mmax, 5(+extra)] (cls, xyxy px, ...); zero rows are padding.  Row order inside an image is the order of
-    appearance, as in the reference.  The per-image counts are taken on the host when ``batch_idx`` lives there (the
-    dataloader's case), so no device sync is issued."""
-    bi_host = batch_idx.detach().view(-1)
-    n = bi_host.numel()
-    cols = [cls.view(-1, 1), bboxes.view(-1, 4)] + ([extra] if extra is not None else [])
-    rows = torch.cat([c.to(device=device, dtype=torch.float32) for c in cols], 1)
-    W = rows.shape[1]
+    """``v8DetectionLoss.preprocess`` / ``DDDetectionLoss.preprocess`` (loss.py:180-195, 795-810) through
+    ``y3d_pack_targets``: ragged [N, ...] rows -> padded [B, Mmax, 5(+extra)] (cls, xyxy px, ...); zero rows are
+    padding.  Row order inside an image is the order of appearance, as in the reference.  Mmax comes from the host copy
+    of ``batch_idx`` when it lives there (the dataloader's case), so no device sync is issued."""
+    bi = batch_idx.detach().reshape(-1)
+    n = bi.numel()
+    E = 0 if extra is None else int(extra.shape[1])
     if n == 0:
-        return torch.zeros(batch_size, 0, W, device=device)
-    counts = torch.bincount(bi_host.long().cpu(), minlength=batch_size)  # sync only if batch_idx was on the GPU
-    M = int(counts.max())
-    bi = bi_host.to(device).long()
-    order = torch.argsort(bi, stable=True)
-    sbi = bi[order]
-    counts_d = counts.to(device)
-    starts = torch.cumsum(counts_d, 0) - counts_d
-    pos = torch.arange(n, device=device) - starts[sbi]
-    out = torch.zeros(batch_size, M, W, device=device)
-    out[sbi, pos] = rows[order]
-    h, w = imgsz_hw
-    scale = torch.tensor([w, h, w, h], device=device, dtype=torch.float32)  # imgsz[[1, 0, 1, 0]] loss.py:223
-    xywh = out[..., 1:5] * scale
-    dw, dh = xywh[..., 2] / 2, xywh[..., 3] / 2  # xywh2xyxy ops.py:403-422
-    out[..., 1] = xywh[..., 0] - dw
-    out[..., 2] = xywh[..., 1] - dh
-    out[..., 3] = xywh[..., 0] + dw
-    out[..., 4] = xywh[..., 1] + dh
+        return torch.zeros(batch_size, 0, 5 + E, device=device)
+    if bi.is_cuda:
+        M = int(torch.bincount(bi.long(), minlength=batch_size).max())  # one sync, like the reference's counts.max()
+    else:
+        M = int(torch.bincount(bi.long(), minlength=batch_size).max())
+
+    def dev32(t, shape):
+        return t.detach().to(device=device, dtype=torch.float32).reshape(shape).contiguous()
+
+    bi_d, cls_d, box_d = dev32(bi, (n,)), dev32(cls, (n,)), dev32(bboxes, (n, 4))
+    ex_d = dev32(extra, (n, E)) if E else None
+    out = torch.empty((batch_size, M, 5 + E), dtype=torch.float32, device=device)
+    counts = torch.empty(batch_size, dtype=torch.int32, device=device)
+    h, w = imgsz_hw  # scale = imgsz[[1, 0, 1, 0]] (loss.py:223): x by the width, y by the height
+    _lib.check(_lib.lib().y3d_pack_targets(ptr(bi_d), ptr(cls_d), ptr(box_d), ptr(ex_d), E, n, int(batch_size), M,
+                                           float(w), float(h), ptr(out), ptr(counts), stream_ptr(device)))
     return out
 
 

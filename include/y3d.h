@@ -183,6 +183,22 @@ int y3d_v8_loss_finalize(const double *partials, int n_branch, float gain_box, f
 int y3d_decode3d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
                  const float *lvl_stride, int nl, int B, int nc, float *y, void *stream);
 
+/* Sparse evaluation of the 3D head at inference (v10Detect3d.inference_forward_feat, head.py:689-716): the class head
+ * runs densely, every other head only on K = max_det candidate cells per image and level.
+ *  y3d_select_candidates  select_candidates (head.py:681-687) + unravel_index (:652-657): cls = one level's class logits
+ *      [B, nc, H, W] (element strides sB, sC; rows contiguous) -> idx [B, K, 2] int64 = (row, col) of the K cells with
+ *      the largest max_c logit, descending, lowest flat index first among equals.  1 <= K <= min(H*W, Y3D_MAX_DET).
+ *  y3d_extract_patches    extract_patches (head.py:659-679): x [B, C, H, W] -> out [B*K, C, P, P], the zero-padded P x P
+ *      (P odd, the reference uses 5) neighbourhood of every candidate.
+ *  y3d_scatter_candidates head.py:709-714: vals [B*K, Cout] (the 1x1 output of a head evaluated on the patches) ->
+ *      out [B, Cout, H, W], zero except out[b, :, row_k, col_k] = vals[b*K + k, :]. */
+int y3d_select_candidates(const float *cls, int64_t sB, int64_t sC, int B, int nc, int H, int W, int K, int64_t *idx,
+                          void *stream);
+int y3d_extract_patches(const float *x, int64_t sB, int64_t sC, const int64_t *idx, int B, int C, int H, int W, int K,
+                        int P, float *out, void *stream);
+int y3d_scatter_candidates(const float *vals, const int64_t *idx, int B, int Cout, int H, int W, int K, float *out,
+                           void *stream);
+
 /* KITTIDataset.decode_preds (ultralytics/data/datasets/kitti.py:519-576; bin2angle decode_helper.py:12,
  * img_to_rect kitti_utils.py:241, alpha2ry :311, affine_transform :467), undo_augment=True.
  *  dets [B,D,37] fp32 = bbox(4) c3d(2) s3d(3) hd(24) dep un score(logit) label (yolov10_3D/val.py:46-47);

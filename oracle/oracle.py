@@ -341,3 +341,43 @@ def decode_preds(dets, calib, inv_affine, ratio, cls_mean_size, threshold=0.001)
     lib().y3d_o_decode_preds(_p(dets, _f32p), C.c_int(B), C.c_int(D), _p(calib, _f64p), _p(inv_affine, _f64p),
                              _p(ratio, _f64p), _p(cms, _f64p), C.c_double(threshold), _p(rows, _f64p), _p(valid, _u8p))
     return rows, valid.astype(bool)
+
+
+# ------------------------------------------------------------------------------------------------ sparse 3D head glue
+def select_candidates(scores, max_det):
+    """v10Detect3d.select_candidates head.py:681-687 (+ unravel_index :652-657): [B, nc, H, W] -> [B, K, 2] int64
+    (row, col) of the K cells with the largest max-over-classes logit, stable descending order."""
+    s = _f32(scores)
+    B, nc, H, W = s.shape
+    mx = s.max(1).reshape(B, -1)
+    out = np.empty((B, max_det, 2), np.int64)
+    for b in range(B):
+        order = np.argsort(-mx[b], kind="stable")[:max_det]
+        out[b, :, 0], out[b, :, 1] = order // W, order % W
+    return out
+
+
+def extract_patches(x, indices, patch_size=5):
+    """v10Detect3d.extract_patches head.py:659-679: [B, C, H, W], [B, K, 2] -> [B*K, C, P, P], zero padded."""
+    x = _f32(x)
+    B, Cc, H, W = x.shape
+    K = indices.shape[1]
+    pad = patch_size // 2
+    xp = np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    out = np.empty((B * K, Cc, patch_size, patch_size), np.float32)
+    for b in range(B):
+        for k in range(K):
+            r, c = int(indices[b, k, 0]) + pad, int(indices[b, k, 1]) + pad
+            out[b * K + k] = xp[b, :, r - pad:r + pad + 1, c - pad:c + pad + 1]
+    return out
+
+
+def scatter_candidates(values, indices, output_shape):
+    """head.py:709-714: values [B*K, Cout] -> zero-filled [B, Cout, H, W] with out[b, :, row_k, col_k] = values[b*K+k]."""
+    B, Cout, H, W = output_shape
+    K = indices.shape[1]
+    v = _f32(values).reshape(B, K, Cout)
+    out = np.zeros(output_shape, np.float32)
+    for b in range(B):
+        out[b][:, indices[b, :, 0], indices[b, :, 1]] = v[b].T
+    return out

@@ -78,6 +78,19 @@ def loss_inputs(r, z):
     return lv, gt, xm, xo
 
 
+def sparse_head_inputs(r, z):
+    """Same construction as tests/golden/make_golden.py::sparse_head_inputs."""
+    g = synth.rng(r["seed"])
+    B, nc, C, H, W, K, Cout = (r[k] for k in ("B", "nc", "C", "H", "W", "K", "Cout"))
+    scores = (g.standard_normal((B, nc, H, W), dtype=np.float32) * 2 - 4).astype(np.float32)
+    x = g.standard_normal((B, C, H, W), dtype=np.float32)
+    vals = g.standard_normal((B * K, Cout), dtype=np.float32)
+    if r.get("quantise"):
+        scores = (np.round(scores * r["quantise"]) / r["quantise"]).astype(np.float32)
+    assert synth.checksum(scores, x, vals) == int(z["in_crc"]), "regenerated inputs differ"
+    return scores, x, vals
+
+
 def loss3d_inputs(r, z):
     """Same construction as tests/golden/make_golden.py::case_loss3d."""
     B, nc, img_hw, M, seed = r["B"], r["nc"], r["img_hw"], r["M"], r["seed"]

@@ -332,6 +332,37 @@ def case_loss3d(name, B, nc, img_hw, M, topk, seed, **kw):
          nz_val=gr[0, nc:].reshape(-1)[nz])
 
 
+def sparse_head_inputs(B, nc, C, H, W, K, Cout, seed):
+    g = synth.rng(seed)
+    scores = (g.standard_normal((B, nc, H, W), dtype=np.float32) * 2 - 4).astype(np.float32)
+    x = g.standard_normal((B, C, H, W), dtype=np.float32)
+    vals = g.standard_normal((B * K, Cout), dtype=np.float32)
+    return scores, x, vals
+
+
+def case_sparse_head(name, B, nc, C, H, W, K, Cout, seed, quantise=None):
+    """The REAL v10Detect3d.select_candidates / extract_patches (head.py:659-687), called unbound on a stand-in for
+    ``self``, and the scatter-back statements of inference_forward_feat (head.py:709-714)."""
+    scores, x, vals = sparse_head_inputs(B, nc, C, H, W, K, Cout, seed)
+    if quantise:
+        scores = (np.round(scores * quantise) / quantise).astype(np.float32)  # many exact ties
+    self_ = types.SimpleNamespace(max_det=K, patch_size=5)
+    self_.unravel_index = lambda index, shape: v10Detect3d.unravel_index(self_, index, shape)
+    with patched_topk():
+        idx = v10Detect3d.select_candidates(self_, t(scores), B)
+    uidx = v10Detect3d.select_candidates(self_, t(scores), B)
+    patches = v10Detect3d.extract_patches(self_, t(x), idx)
+    output_shape = (B, Cout, H, W)
+    head_output = torch.zeros(output_shape)
+    out = t(vals).view(B * K, Cout, 1, 1)[:, :, 0, 0].view(output_shape[0], K, output_shape[1]).transpose(1, 2)
+    for b in range(B):
+        head_output[b, :, idx[b, :, 0], idx[b, :, 1]] = out[b]
+    recipe = dict(kind="sparse_head", B=B, nc=nc, C=C, H=H, W=W, K=K, Cout=Cout, seed=seed, quantise=quantise)
+    save(name, recipe, in_crc=np.int64(synth.checksum(scores, x, vals)), idx=idx.numpy().astype(np.int16),
+         patches_crc=np.int64(synth.checksum(patches.numpy())), scatter_crc=np.int64(synth.checksum(head_output.numpy())),
+         unpatched_agrees=np.bool_(torch.equal(idx, uidx)))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:] or None
 
@@ -358,6 +389,9 @@ if __name__ == "__main__":
     if want("decode3d") or want("preds3d"):
         dets = case_decode3d("decode3d_small", B=3, nc=3, img_hw=(96, 320), D=50, seed=40)
         case_decode_preds("preds3d_small", dets)
+    if want("sparse_head"):
+        case_sparse_head("sparse_head_kitti", B=3, nc=3, C=16, H=12, W=40, K=50, Cout=24, seed=70)
+        case_sparse_head("sparse_head_ties", B=2, nc=3, C=8, H=24, W=80, K=50, Cout=3, seed=71, quantise=2)
     if want("loss3d"):
         case_loss3d("loss3d_k8", B=2, nc=3, img_hw=(96, 320), M=8, topk=8, seed=60)
         case_loss3d("loss3d_k1", B=2, nc=3, img_hw=(96, 320), M=8, topk=1, seed=61)

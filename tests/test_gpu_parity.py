@@ -484,6 +484,32 @@ def test_dd_loss_no_targets_and_dual(y3d):
     assert float(tot1) == 0.0 and items1.shape == (6,)
 
 
+@pytest.mark.parametrize("name", cases.names("sparse_head_"))
+def test_sparse_head_glue(y3d, name):
+    """select_candidates / extract_patches / scatter_candidates: bit-exact against the reference fixtures and the
+    oracle, plus a KITTI-shape level (48 x 160) against the oracle."""
+    r, z = cases.load(name)
+    scores, x, vals = cases.sparse_head_inputs(r, z)
+    idx = y3d.select_candidates(dev(scores), r["K"])
+    assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), z["idx"].astype(np.int64))
+    patches = y3d.extract_patches(dev(x), idx)
+    assert patches.shape == (r["B"] * r["K"], r["C"], 5, 5)
+    assert synth.checksum(patches.cpu().numpy()) == int(z["patches_crc"])
+    out = y3d.scatter_candidates(dev(vals), idx, (r["B"], r["Cout"], r["H"], r["W"]))
+    assert synth.checksum(out.cpu().numpy()) == int(z["scatter_crc"])
+    # full-size level, K at the compiled limit of the reference (max_det = 50) and larger
+    g = synth.rng(5)
+    s2 = g.standard_normal((4, 3, 48, 160), dtype=np.float32)
+    x2 = g.standard_normal((4, 32, 48, 160), dtype=np.float32)
+    for K in (50, 300):
+        i2 = y3d.select_candidates(dev(s2), K).cpu().numpy()
+        assert np.array_equal(i2, oracle.select_candidates(s2, K))
+        p2 = y3d.extract_patches(dev(x2), torch.from_numpy(i2).cuda(), patch_size=3)
+        assert np.array_equal(p2.cpu().numpy(), oracle.extract_patches(x2, i2, 3))
+    with pytest.raises(RuntimeError):
+        y3d.select_candidates(dev(s2[:, :, :2, :3]), 50)  # K > cells: torch.topk raises too
+
+
 def test_decode_preds(y3d):
     r, z = cases.load("preds3d_small")
     B = z["dets"].shape[0]

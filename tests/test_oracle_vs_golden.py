@@ -116,3 +116,16 @@ def test_dd_loss_oracle_vs_reference(name):
     assert n_fg > 0
     np.testing.assert_allclose(items, z["items"], rtol=2e-5)
     np.testing.assert_allclose(items.sum() * r["B"], float(z["total"]), rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", cases.names("sparse_head_"))
+def test_sparse_head_glue_oracle_vs_reference(name):
+    """oracle.select_candidates / extract_patches / scatter_candidates against the REAL v10Detect3d methods
+    (head.py:659-687) and the scatter-back of inference_forward_feat (head.py:709-714)."""
+    r, z = cases.load(name)
+    scores, x, vals = cases.sparse_head_inputs(r, z)
+    idx = oracle.select_candidates(scores, r["K"])
+    assert np.array_equal(idx, z["idx"].astype(np.int64))
+    assert synth.checksum(oracle.extract_patches(x, idx)) == int(z["patches_crc"])
+    out = oracle.scatter_candidates(vals, idx, (r["B"], r["Cout"], r["H"], r["W"]))
+    assert synth.checksum(out) == int(z["scatter_crc"])

@@ -472,6 +472,68 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
     SEL_STAMP(4);
 }
 
+// ------------------------------------------------------------------------------------------ sparse 3D head glue
+// v10Detect3d.select_candidates (head.py:681-687): per image, top-K cells of one level by max_c(raw class logit), as
+// (row, col) pairs in descending score order (lowest flat index first among equals).  One CTA per image; the per-cell
+// maxima are staged in shared memory (dynamic: H*W uint32 keys + 2 * 2 * Kpad composites).
+__global__ void __launch_bounds__(kTopkThreads) select_candidates_kernel(const float *__restrict__ cls, long long sB,
+                                                                          long long sC, int nc, int HW, int Wd, int K,
+                                                                          int Kpad, int64_t *__restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *win = (unsigned long long *)smem_raw;
+    uint32_t *keys = (uint32_t *)(win + 2 * Kpad);
+    __shared__ SelShared sh;
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const float *p = cls + (long long)b * sB;
+    for (int i = tid; i < HW; i += nt) {
+        uint32_t k = 0;
+        for (int c = 0; c < nc; ++c) k = max(k, float_key(p[(long long)c * sC + i]));  // torch.max(scores, dim=1)[0]
+        keys[i] = k;
+    }
+    __syncthreads();
+    block_topk([&](int i) { return keys[i]; }, HW, K, Kpad, win, sh);
+    for (int r = tid; r < K; r += nt) {
+        const int i = (int)(0xFFFFFFFFu - (unsigned)(win[r] & 0xFFFFFFFFull));
+        idx[((long long)b * K + r) * 2 + 0] = i / Wd;  // unravel_index (head.py:652-657): (row, col)
+        idx[((long long)b * K + r) * 2 + 1] = i % Wd;
+    }
+}
+
+// v10Detect3d.extract_patches (head.py:659-679): zero-padded P x P patch of every channel around each candidate.
+// out [B*K, C, P, P]; one thread per output element
+__global__ void __launch_bounds__(256) extract_patches_kernel(const float *__restrict__ x, long long sB, long long sC,
+                                                              const int64_t *__restrict__ idx, int C, int H, int Wd,
+                                                              int K, int P, long long total, float *__restrict__ out) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    const int dx = (int)(o % P);
+    long long r = o / P;
+    const int dy = (int)(r % P);
+    r /= P;
+    const int c = (int)(r % C);
+    const long long bk = r / C;
+    const int b = (int)(bk / K);
+    const int pad = P / 2;
+    const int row = (int)idx[bk * 2] + dy - pad, col = (int)idx[bk * 2 + 1] + dx - pad;
+    float v = 0.f;
+    if (row >= 0 && row < H && col >= 0 && col < Wd) v = x[b * sB + c * sC + (long long)row * Wd + col];
+    out[o] = v;
+}
+
+// head.py:709-714: head_output[b, :, row_k, col_k] = conv_out[b*K + k, :] into a zero-filled [B, Cout, H, W]
+__global__ void __launch_bounds__(256) scatter_candidates_kernel(const float *__restrict__ vals,
+                                                                 const int64_t *__restrict__ idx, int Cout, int H,
+                                                                 int Wd, int K, long long total, float *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int c = (int)(t % Cout);
+    const long long bk = t / Cout;
+    const int b = (int)(bk / K);
+    const long long row = idx[bk * 2], col = idx[bk * 2 + 1];
+    if (row < 0 || row >= H || col < 0 || col >= Wd) return;
+    out[(((long long)b * Cout + c) * H + row) * Wd + col] = vals[t];
+}
+
 static int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -576,4 +638,48 @@ extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl
     src.mode = 1;
     src.xywh = xywh;
     return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s);
+}
+
+extern "C" int y3d_select_candidates(const float *cls, int64_t sB, int64_t sC, int B, int nc, int H, int W, int K,
+                                     int64_t *idx, void *stream) {
+    if (!cls || !idx || B < 0 || nc < 1 || H < 1 || W < 1) return Y3D_EINVAL;
+    const long long HW = (long long)H * W;
+    if (K < 1 || K > HW) return Y3D_EINVAL;  // torch.topk raises when k exceeds the number of cells
+    if (K > Y3D_MAX_DET) return Y3D_EUNSUPPORTED;
+    if (B == 0) return Y3D_OK;
+    const int Kpad = next_pow2(K);
+    const size_t smem = sizeof(unsigned long long) * 2 * (size_t)Kpad + sizeof(uint32_t) * (size_t)HW;
+    if (smem > 200 * 1024) return Y3D_EUNSUPPORTED;  // level larger than ~48 k cells
+    cudaError_t e = cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    select_candidates_kernel<<<B, kTopkThreads, smem, (cudaStream_t)stream>>>(cls, sB, sC, nc, (int)HW, W, K, Kpad, idx);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
+}
+
+extern "C" int y3d_extract_patches(const float *x, int64_t sB, int64_t sC, const int64_t *idx, int B, int C, int H, int W,
+                                   int K, int P, float *out, void *stream) {
+    if (!x || !idx || !out || B < 0 || C < 1 || H < 1 || W < 1 || K < 0 || P < 1 || !(P & 1)) return Y3D_EINVAL;
+    const long long total = (long long)B * K * C * P * P;
+    if (total == 0) return Y3D_OK;
+    extract_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, sB, sC, idx, C, H, W, K, P,
+                                                                                             total, out);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
+}
+
+extern "C" int y3d_scatter_candidates(const float *vals, const int64_t *idx, int B, int Cout, int H, int W, int K,
+                                      float *out, void *stream) {
+    if (!out || B < 0 || Cout < 1 || H < 1 || W < 1 || K < 0) return Y3D_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = sizeof(float) * (size_t)B * Cout * H * W;
+    if (bytes == 0) return Y3D_OK;
+    cudaError_t e = cudaMemsetAsync(out, 0, bytes, s);  // torch.zeros(output_shape) head.py:709
+    if (e != cudaSuccess) return (int)e;
+    const long long total = (long long)B * K * Cout;
+    if (total == 0) return Y3D_OK;
+    if (!vals || !idx) return Y3D_EINVAL;
+    scatter_candidates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(vals, idx, Cout, H, W, K, total, out);
+    Y3D_CHECK_LAUNCH();
+    return Y3D_OK;
 }

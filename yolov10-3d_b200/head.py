@@ -86,3 +86,59 @@ def detect3d_postprocess(y, max_det=50, nc=3):
     [B, max_det, 37] = reg(35) | score (logit) | label."""
     reg, scores, labels = ops.v10_3Dpostprocess(y.transpose(-1, -2), max_det, nc)
     return torch.cat((reg, scores.unsqueeze(-1), labels.unsqueeze(-1).to(reg.dtype)), dim=-1)
+
+
+# ------------------------------------------------------------------------------------------------ sparse 3D head glue
+def _cuda4d(t, name):
+    if t.dim() != 4:
+        raise ValueError(f"{name} must be [B, C, H, W]")
+    if not t.is_cuda:
+        raise _lib.Y3DError("yolov10-3d_b200 runs on CUDA tensors only (no CPU fallback)")
+    t = t.float() if t.dtype != torch.float32 else t
+    if t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+        t = t.contiguous()
+    return t
+
+
+def select_candidates(scores, max_det):
+    """``v10Detect3d.select_candidates`` (head.py:681-687): class logits of one level [B, nc, H, W] ->
+    ``topk_indices`` [B, max_det, 2] int64 = (row, col), best first.  (The reference keeps this tensor on the CPU and
+    loops over the batch; here it stays on the device.)"""
+    s = _cuda4d(scores, "scores")
+    B, nc, H, W = s.shape
+    if max_det > H * W:
+        raise RuntimeError("selected index k out of range")  # torch.topk
+    idx = torch.empty((B, int(max_det), 2), dtype=torch.int64, device=s.device)
+    _lib.check(_lib.lib().y3d_select_candidates(ptr(s), s.stride(0), s.stride(1), B, nc, H, W, int(max_det), ptr(idx),
+                                                stream_ptr(s.device)))
+    return idx
+
+
+def extract_patches(x, indices, patch_size=5):
+    """``v10Detect3d.extract_patches`` (head.py:659-679): x [B, C, H, W], indices [B, K, 2] ->
+    [B*K, C, patch_size, patch_size] zero-padded neighbourhoods (no Python loop over B x K)."""
+    xx = _cuda4d(x, "x")
+    B, C, H, W = xx.shape
+    idx = indices.to(device=xx.device, dtype=torch.int64).contiguous()
+    K = int(idx.shape[1])
+    out = torch.empty((B * K, C, patch_size, patch_size), dtype=torch.float32, device=xx.device)
+    _lib.check(_lib.lib().y3d_extract_patches(ptr(xx), xx.stride(0), xx.stride(1), ptr(idx), B, C, H, W, K,
+                                              int(patch_size), ptr(out), stream_ptr(xx.device)))
+    return out
+
+
+def scatter_candidates(values, indices, output_shape):
+    """head.py:709-714: ``values`` [B*K, Cout] (or [B*K, Cout, 1, 1]: a head evaluated on the patches) scattered into a
+    zero-filled ``output_shape`` = (B, Cout, H, W) at the candidate cells."""
+    B, Cout, H, W = (int(v) for v in output_shape)
+    v = values.reshape(values.shape[0], -1)
+    if not v.is_cuda:
+        raise _lib.Y3DError("yolov10-3d_b200 runs on CUDA tensors only (no CPU fallback)")
+    v = v.float().contiguous()
+    idx = indices.to(device=v.device, dtype=torch.int64).contiguous()
+    K = int(idx.shape[1])
+    if v.shape != (B * K, Cout):
+        raise ValueError(f"values must be [{B * K}, {Cout}], got {tuple(v.shape)}")
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=v.device)
+    _lib.check(_lib.lib().y3d_scatter_candidates(ptr(v), ptr(idx), B, Cout, H, W, K, ptr(out), stream_ptr(v.device)))
+    return out

@@ -369,6 +369,59 @@ def test_fused_loss_assignment_bit_exact(y3d, topk):
     assert float(partials[3]) > 1.0 and o["fg_mask"].sum() > 0
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(name="cfg2", B=64, M=100, crowd=False),   # BASELINE.json configs[1], full size
+    dict(name="cfg5", B=128, M=500, crowd=True),   # dense-crowd stress, full size
+])
+def test_v10_loss_full_size_properties(y3d, cfg):
+    """Size-independent properties of the fused dual-assignment loss at the BASELINE sizes (the oracle needs minutes
+    there): determinism, additivity of the un-normalised partials over image shards (what the multi-GPU path relies
+    on), in-GT / count invariants of the assignment, and the oracle on a 2-image slice."""
+    lossmod = __import__("yolov10_3d_b200").loss
+    B, M, nc, hw = cfg["B"], cfg["M"], 80, (640, 640)
+    lv = synth.levels(*hw)
+    nb = 8
+    reps = B // nb
+    gt = np.concatenate([synth.gt2d(nb, M, nc, hw, seed=41, crowd=cfg["crowd"], full=cfg["crowd"])] * reps)
+    xm = np.concatenate([synth.train_like_head2d(nb, nc, lv, gt[:nb], seed=42, frac=0.02)] * reps)
+    xo = np.concatenate([synth.train_like_head2d(nb, nc, lv, gt[:nb], seed=43, frac=0.02)] * reps)
+    # make the repeated images differ: shift the class logits of every block a little
+    for r_ in range(reps):
+        xm[r_ * nb:(r_ + 1) * nb, 64:] += np.float32(0.01 * r_)
+        xo[r_ * nb:(r_ + 1) * nb, 64:] -= np.float32(0.01 * r_)
+    fm, fo, gtd = feats_of(xm, lv), feats_of(xo, lv), dev(gt)
+    gains, st = (7.5, 0.5, 1.5), list(synth.STRIDES)
+    items, parts, dbg = lossmod.v10_loss_forward(fm, fo, st, nc, gtd, gains, debug=True)
+    items2, parts2, _ = lossmod.v10_loss_forward(fm, fo, st, nc, gtd, gains)
+    assert torch.equal(items, items2) and torch.equal(parts, parts2)  # bit-deterministic (exact integer / fixed-order sums)
+    # additivity over image shards
+    acc = torch.zeros(8, dtype=torch.float64, device="cuda")
+    for lo in range(0, B, B // 4):
+        hi = lo + B // 4
+        _, p_, _ = lossmod.v10_loss_forward([f[lo:hi] for f in fm], [f[lo:hi] for f in fo], st, nc, gtd[lo:hi], gains,
+                                            normalise=False)
+        acc += p_
+    np.testing.assert_allclose(acc.cpu().numpy(), parts.cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(lossmod.finalize_partials(acc, gains).cpu().numpy(), items.cpu().numpy(), rtol=1e-6)
+    # assignment invariants: every fg anchor lies strictly inside its GT; at most k foreground anchors per valid GT
+    anc, _ = synth.anchors_px(lv)
+    fg, tgi = dbg["fg_mask"].cpu().numpy(), dbg["target_gt_idx"].cpu().numpy()
+    for z, k in ((0, 10), (1, 1)):
+        bi, ai = np.nonzero(fg[z])
+        g = gt[bi, tgi[z][bi, ai]]
+        ax, ay = anc[ai, 0], anc[ai, 1]
+        assert (g[:, 1:5].sum(1) > 0).all()
+        assert ((ax > g[:, 1]) & (ay > g[:, 2]) & (ax < g[:, 3]) & (ay < g[:, 4])).all()
+        # (a GT can end up with more than k anchors: select_highest_overlaps hands a contested anchor to the GT with the
+        # largest overlap even if that GT never selected it, tal.py:252-263 -- but never more than k per GT in total)
+        n_valid = int((gt[..., 1:5].sum(-1) > 0).sum())
+        assert 0 < fg[z].sum() <= n_valid * k
+    # the oracle on the first two images
+    o = oracle.v10_loss(xm[:2], xo[:2], lv, synth.STRIDES, nc, gt[:2], gains=gains)[1]
+    it2, _, _ = lossmod.v10_loss_forward([f[:2] for f in fm], [f[:2] for f in fo], st, nc, gtd[:2], gains)
+    np.testing.assert_allclose(it2.view(2, 4)[:, :3].reshape(6).cpu().numpy(), o, rtol=2e-5)
+
+
 def test_loss_no_targets(y3d):
     lv = synth.levels(160, 160)
     x = synth.head2d(2, 8, lv, seed=1)

@@ -199,6 +199,13 @@ int y3d_extract_patches(const float *x, int64_t sB, int64_t sC, const int64_t *i
 int y3d_scatter_candidates(const float *vals, const int64_t *idx, int B, int Cout, int H, int W, int K, float *out,
                            void *stream);
 
+/* rotate_iou_gpu_eval (ultralytics/data/datasets/kitti_eval.py:309-344; kernel :263-301, device functions :60-260):
+ * overlap of rotated bird's-eye-view boxes for the KITTI evaluator (bev_box_overlap :458, box3d_overlap :503).
+ *  boxes [N,5], query_boxes [K,5] = (cx, cy, dx, dy, angle), DEVICE fp32; iou [N,K] fp32.
+ *  criterion -1: IoU; 0: intersection / area(query); 1: intersection / area(box); 2: intersection area. */
+int y3d_rotate_iou_eval(const float *boxes, int N, const float *query_boxes, int K, int criterion, float *iou,
+                        void *stream);
+
 /* KITTIDataset.decode_preds (ultralytics/data/datasets/kitti.py:519-576; bin2angle decode_helper.py:12,
  * img_to_rect kitti_utils.py:241, alpha2ry :311, affine_transform :467), undo_augment=True.
  *  dets [B,D,37] fp32 = bbox(4) c3d(2) s3d(3) hd(24) dep un score(logit) label (yolov10_3D/val.py:46-47);

@@ -381,3 +381,13 @@ def scatter_candidates(values, indices, output_shape):
     for b in range(B):
         out[b][:, indices[b, :, 0], indices[b, :, 1]] = v[b].T
     return out
+
+
+def rotate_iou_eval(boxes, query_boxes, criterion=-1):
+    """rotate_iou_gpu_eval kitti_eval.py:309-344: boxes [N,5], query_boxes [K,5] = (cx, cy, dx, dy, angle) -> [N,K]."""
+    b, q = _f32(boxes), _f32(query_boxes)
+    N, K = b.shape[0], q.shape[0]
+    out = np.zeros((N, K), np.float32)
+    if N and K:
+        lib().y3d_o_rotate_iou_eval(_p(b, _f32p), C.c_int(N), _p(q, _f32p), C.c_int(K), C.c_int(criterion), _p(out, _f32p))
+    return out

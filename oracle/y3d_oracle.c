@@ -812,3 +812,104 @@ void y3d_o_decode_preds(const float *dets, int B, int D, const double *calib, co
             valid[(long)b * D + j] = (uint8_t)!(score < thr);
         }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* rotate_iou_gpu_eval: ultralytics/data/datasets/kitti_eval.py:60-345 (BEV overlap of the KITTI  */
+/* evaluator).  Boxes are (cx, cy, dx, dy, angle); the overlap polygon of two rotated rectangles  */
+/* is collected as corners-inside + edge intersections, ordered around its centroid and measured */
+/* as a triangle fan.  float32 throughout, like the reference's numba kernel.                     */
+/* ------------------------------------------------------------------------------------------ */
+static void riou_corners(const float *rb, float *c) { /* rbbox_to_corners :149-172 */
+    const float a_cos = cosf(rb[4]), a_sin = sinf(rb[4]);
+    const float xd = rb[2], yd = rb[3];
+    const float cx[4] = {-xd / 2, -xd / 2, xd / 2, xd / 2};
+    const float cy[4] = {-yd / 2, yd / 2, yd / 2, -yd / 2};
+    for (int i = 0; i < 4; ++i) {
+        c[2 * i] = a_cos * cx[i] + a_sin * cy[i] + rb[0];
+        c[2 * i + 1] = -a_sin * cx[i] + a_cos * cy[i] + rb[1];
+    }
+}
+static int riou_point_in_quad(float px, float py, const float *c) { /* :105-122 */
+    const float ab0 = c[2] - c[0], ab1 = c[3] - c[1], ad0 = c[6] - c[0], ad1 = c[7] - c[1];
+    const float ap0 = px - c[0], ap1 = py - c[1];
+    const float abab = ab0 * ab0 + ab1 * ab1, abap = ab0 * ap0 + ab1 * ap1;
+    const float adad = ad0 * ad0 + ad1 * ad1, adap = ad0 * ap0 + ad1 * ap1;
+    const float eps = -1e-6f;
+    return abab - abap >= eps && abap >= eps && adad - adap >= eps && adap >= eps;
+}
+static int riou_seg_intersect(const float *p1, const float *p2, int i, int j, float *t) { /* :60-102 */
+    const float A0 = p1[2 * i], A1 = p1[2 * i + 1], B0 = p1[2 * ((i + 1) % 4)], B1 = p1[2 * ((i + 1) % 4) + 1];
+    const float C0 = p2[2 * j], C1 = p2[2 * j + 1], D0 = p2[2 * ((j + 1) % 4)], D1 = p2[2 * ((j + 1) % 4) + 1];
+    const float BA0 = B0 - A0, BA1 = B1 - A1, DA0 = D0 - A0, CA0 = C0 - A0, DA1 = D1 - A1, CA1 = C1 - A1;
+    const int acd = DA1 * CA0 > CA1 * DA0;
+    const int bcd = (D1 - B1) * (C0 - B0) > (C1 - B1) * (D0 - B0);
+    if (acd != bcd) {
+        const int abc = CA1 * BA0 > BA1 * CA0, abd = DA1 * BA0 > BA1 * DA0;
+        if (abc != abd) {
+            const float DC0 = D0 - C0, DC1 = D1 - C1;
+            const float ABBA = A0 * B1 - B0 * A1, CDDC = C0 * D1 - D0 * C1;
+            const float DH = BA1 * DC0 - BA0 * DC1;
+            t[0] = (ABBA * DC0 - BA0 * CDDC) / DH;
+            t[1] = (ABBA * DC1 - BA1 * CDDC) / DH;
+            return 1;
+        }
+    }
+    return 0;
+}
+static float riou_inter(const float *r1, const float *r2) { /* inter :231-245 */
+    float c1[8], c2[8], ip[16 + 32], t[2];
+    riou_corners(r1, c1);
+    riou_corners(r2, c2);
+    int n = 0;
+    for (int i = 0; i < 4; ++i) { /* quadrilateral_intersection :125-146 */
+        if (riou_point_in_quad(c1[2 * i], c1[2 * i + 1], c2)) { ip[2 * n] = c1[2 * i]; ip[2 * n + 1] = c1[2 * i + 1]; ++n; }
+        if (riou_point_in_quad(c2[2 * i], c2[2 * i + 1], c1)) { ip[2 * n] = c2[2 * i]; ip[2 * n + 1] = c2[2 * i + 1]; ++n; }
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (riou_seg_intersect(c1, c2, i, j, t)) { ip[2 * n] = t[0]; ip[2 * n + 1] = t[1]; ++n; }
+    if (n > 0) { /* sort_vertex_in_convex_polygon :175-212 */
+        float cx = 0.0f, cy = 0.0f, vs[24];
+        for (int i = 0; i < n; ++i) { cx += ip[2 * i]; cy += ip[2 * i + 1]; }
+        cx /= n; cy /= n;
+        for (int i = 0; i < n; ++i) {
+            float v0 = ip[2 * i] - cx, v1 = ip[2 * i + 1] - cy;
+            const float d = sqrtf(v0 * v0 + v1 * v1);
+            v0 = v0 / d; v1 = v1 / d;
+            if (v1 < 0) v0 = -2 - v0;
+            vs[i] = v0;
+        }
+        for (int i = 1; i < n; ++i)
+            if (vs[i - 1] > vs[i]) {
+                const float temp = vs[i], tx = ip[2 * i], ty = ip[2 * i + 1];
+                int j = i;
+                while (j > 0 && vs[j - 1] > temp) {
+                    vs[j] = vs[j - 1]; ip[2 * j] = ip[2 * j - 2]; ip[2 * j + 1] = ip[2 * j - 1];
+                    --j;
+                }
+                vs[j] = temp; ip[2 * j] = tx; ip[2 * j + 1] = ty;
+            }
+    }
+    float area = 0.0f; /* area :221-228, trangle_area :215-218 */
+    for (int i = 0; i < n - 2; ++i) {
+        const float *a = ip, *b = ip + 2 * i + 2, *c = ip + 2 * i + 4;
+        area += fabsf(((a[0] - c[0]) * (b[1] - c[1]) - (a[1] - c[1]) * (b[0] - c[0])) / 2.0f);
+    }
+    return area;
+}
+/* iou [N,K]: iou[n,k] = devRotateIoUEval(query[k], boxes[n], criterion) (:248-260, call site :299-301) */
+void y3d_o_rotate_iou_eval(const float *boxes, int N, const float *query, int K, int criterion, float *iou) {
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            const float *r1 = query + 5 * k, *r2 = boxes + 5 * n;
+            const float a1 = r1[2] * r1[3], a2 = r2[2] * r2[3];
+            const float ai = riou_inter(r1, r2);
+            float v;
+            if (criterion == -1) v = ai / (a1 + a2 - ai);
+            else if (criterion == 0) v = ai / a1;
+            else if (criterion == 1) v = ai / a2;
+            else v = ai;
+            iou[(long)n * K + k] = v;
+        }
+}

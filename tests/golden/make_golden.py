@@ -332,6 +332,21 @@ def case_loss3d(name, B, nc, img_hw, M, topk, seed, **kw):
          nz_val=gr[0, nc:].reshape(-1)[nz])
 
 
+def case_rotate_iou(name, N, K, seed):
+    """The REAL rotate_iou_gpu_eval (data/datasets/kitti_eval.py:309-344), its numba-CUDA kernel executed by numba's
+    CUDA simulator (no GPU in the build container).  The simulator evaluates ``math.cos`` / intermediate products in
+    float64 where the device uses float32, so values agree with a float32 evaluation to ~1e-6, not bit for bit."""
+    from ultralytics.data.datasets.kitti_eval import rotate_iou_gpu_eval
+
+    boxes, query = synth.bev_boxes(N, seed), synth.bev_boxes(K, seed + 1)
+    query[:3] = boxes[:3]  # identical boxes
+    query[3] = boxes[3]
+    query[3, 4] += np.float32(np.pi / 2)  # same box turned by 90 degrees
+    out = {f"iou_c{c if c >= 0 else 'm1'}": rotate_iou_gpu_eval(boxes, query, criterion=c) for c in (-1, 0, 1, 2)}
+    recipe = dict(kind="rotate_iou", N=N, K=K, seed=seed)
+    save(name, recipe, in_crc=np.int64(synth.checksum(boxes, query)), query=query, **out)
+
+
 def sparse_head_inputs(B, nc, C, H, W, K, Cout, seed):
     g = synth.rng(seed)
     scores = (g.standard_normal((B, nc, H, W), dtype=np.float32) * 2 - 4).astype(np.float32)
@@ -389,6 +404,8 @@ if __name__ == "__main__":
     if want("decode3d") or want("preds3d"):
         dets = case_decode3d("decode3d_small", B=3, nc=3, img_hw=(96, 320), D=50, seed=40)
         case_decode_preds("preds3d_small", dets)
+    if want("rotate_iou"):
+        case_rotate_iou("rotate_iou_small", N=40, K=30, seed=80)
     if want("sparse_head"):
         case_sparse_head("sparse_head_kitti", B=3, nc=3, C=16, H=12, W=40, K=50, Cout=24, seed=70)
         case_sparse_head("sparse_head_ties", B=2, nc=3, C=8, H=24, W=80, K=50, Cout=3, seed=71, quantise=2)

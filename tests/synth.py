@@ -248,3 +248,16 @@ def batch_dict3d(gts, img_hw, calibs, mean_sizes):
                 size_2d=c(r[:, 7:9]), center_3d=c(r[:, 9:11]), size_3d=c(r[:, 11:14]), depth=c(r[:, 14]),
                 heading_bin=c(r[:, 15]), heading_res=c(r[:, 16]), calib=np.asarray(calibs, np.float32),
                 mean_sizes=np.asarray(mean_sizes, np.float32))
+
+
+def bev_boxes(n, seed):
+    """Bird's-eye-view boxes [n, 5] = (x, z, l, w, ry) like the KITTI evaluator builds them (kitti_eval.py:458-461):
+    car-sized rectangles scattered densely enough in a 40 m x 40 m patch that many pairs overlap."""
+    g = rng(seed)
+    out = np.empty((n, 5), np.float32)
+    out[:, 0] = g.uniform(-20, 20, n)
+    out[:, 1] = g.uniform(5, 45, n)
+    out[:, 2] = g.uniform(2.5, 6.0, n)
+    out[:, 3] = g.uniform(1.4, 2.6, n)
+    out[:, 4] = g.uniform(-np.pi, np.pi, n)
+    return out

@@ -563,6 +563,24 @@ def test_sparse_head_glue(y3d, name):
         y3d.select_candidates(dev(s2[:, :, :2, :3]), 50)  # K > cells: torch.topk raises too
 
 
+def test_rotate_iou_eval(y3d):
+    """y3d_rotate_iou_eval against the reference fixture (numba kernel under the CUDA simulator) and the oracle; numpy
+    in -> numpy out like the reference, CUDA tensor in -> CUDA tensor out."""
+    r, z = cases.load("rotate_iou_small")
+    boxes = synth.bev_boxes(r["N"], r["seed"])
+    for c, key in ((-1, "iou_cm1"), (0, "iou_c0"), (1, "iou_c1"), (2, "iou_c2")):
+        got = y3d.kitti.rotate_iou_gpu_eval(boxes, z["query"], criterion=c)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == (r["N"], r["K"])
+        np.testing.assert_allclose(got, z[key], rtol=1e-5, atol=2e-6)
+    b2, q2 = synth.bev_boxes(700, 3), synth.bev_boxes(450, 4)
+    q2[:50] = b2[:50]  # identical boxes: the reference's degenerate answer (1/3), reproduced by the same operations
+    got = y3d.kitti.rotate_iou_gpu_eval(dev(b2), dev(q2))
+    want = oracle.rotate_iou_eval(b2, q2)
+    assert got.is_cuda and (want > 0).sum() > 2000
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=2e-5)
+    assert y3d.kitti.rotate_iou_gpu_eval(np.zeros((0, 5), np.float32), q2).shape == (0, 450)
+
+
 def test_decode_preds(y3d):
     r, z = cases.load("preds3d_small")
     B = z["dets"].shape[0]

@@ -129,3 +129,14 @@ def test_sparse_head_glue_oracle_vs_reference(name):
     assert synth.checksum(oracle.extract_patches(x, idx)) == int(z["patches_crc"])
     out = oracle.scatter_candidates(vals, idx, (r["B"], r["Cout"], r["H"], r["W"]))
     assert synth.checksum(out) == int(z["scatter_crc"])
+
+
+def test_rotate_iou_oracle_vs_reference():
+    """oracle.rotate_iou_eval against the REAL rotate_iou_gpu_eval (kitti_eval.py:309-344, numba CUDA simulator)."""
+    r, z = cases.load("rotate_iou_small")
+    boxes = synth.bev_boxes(r["N"], r["seed"])
+    assert synth.checksum(boxes, z["query"]) == int(z["in_crc"])
+    for c, key in ((-1, "iou_cm1"), (0, "iou_c0"), (1, "iou_c1"), (2, "iou_c2")):
+        got = oracle.rotate_iou_eval(boxes, z["query"], c)
+        assert (z[key] > 0).sum() >= 20
+        np.testing.assert_allclose(got, z[key], rtol=1e-5, atol=1e-6)

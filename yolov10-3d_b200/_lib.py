@@ -39,6 +39,7 @@ SIGNATURES = {
     "y3d_select_candidates": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
     "y3d_extract_patches": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "y3d_scatter_candidates": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "y3d_rotate_iou_eval": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "y3d_decode3d": (_i, _LEVELS + [_i, _i, _vp, _vp]),
     "y3d_decode_preds3d": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp]),
     "y3d_tal_assign3d": (_i, [_vp] * 9 + [_i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp, _vp, _i] + [_vp] * 7 +

@@ -46,3 +46,20 @@ def decode_preds(preds, calibs, im_files, ratio_pad, inv_trans, cls_mean_size, t
         r = rows[i][valid[i]]
         out[f] = [[int(x[0])] + x[1:].tolist() for x in r]
     return out
+
+
+def rotate_iou_gpu_eval(boxes, query_boxes, criterion=-1, device_id=0):
+    """``rotate_iou_gpu_eval`` (data/datasets/kitti_eval.py:309-344): numpy (or CUDA tensor) boxes [N,5] / [K,5] =
+    (cx, cy, dx, dy, angle) -> overlap matrix [N,K] in the input's dtype / container.  numpy in -> numpy out, like the
+    reference (whose numba kernel also makes the host round trip); CUDA tensors in -> CUDA tensor out, no round trip."""
+    as_numpy = not torch.is_tensor(boxes)
+    dev = torch.device("cuda", device_id) if as_numpy else boxes.device
+    if not as_numpy and not boxes.is_cuda:
+        raise _lib.Y3DError("yolov10-3d_b200 runs on CUDA tensors only (no CPU fallback)")
+    b = torch.as_tensor(np.asarray(boxes, dtype=np.float32) if as_numpy else boxes, device=dev).float().contiguous()
+    q = torch.as_tensor(np.asarray(query_boxes, dtype=np.float32) if as_numpy else query_boxes, device=dev).float().contiguous()
+    N, K = int(b.shape[0]), int(q.shape[0])
+    iou = torch.zeros((N, K), dtype=torch.float32, device=dev)
+    if N and K:
+        _lib.check(_lib.lib().y3d_rotate_iou_eval(ptr(b), N, ptr(q), K, int(criterion), ptr(iou), stream_ptr(dev)))
+    return iou.cpu().numpy().astype(np.asarray(boxes).dtype) if as_numpy else iou

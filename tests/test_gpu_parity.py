@@ -422,6 +422,59 @@ def test_v10_loss_full_size_properties(y3d, cfg):
     np.testing.assert_allclose(it2.view(2, 4)[:, :3].reshape(6).cpu().numpy(), o, rtol=2e-5)
 
 
+def test_odd_shapes_take_the_scalar_paths(y3d):
+    """Level sizes that are not multiples of 4, nc not a multiple of 4, misaligned (sliced) level tensors: the 128-bit
+    kernels fall back to their scalar variants and the results still match the oracle."""
+    lossmod = __import__("yolov10_3d_b200").loss
+    B, nc, hw, M = 3, 5, (200, 264), 7  # levels 25x33, 12x16, 6x8 -> 825 + 192 + 48 anchors
+    lv = synth.levels(*hw)
+    assert (lv[0][0] * lv[0][1]) % 4 == 1
+    gt = synth.gt2d(B, M, nc, hw, seed=8)
+    xm = synth.train_like_head2d(B, nc, lv, gt, seed=9, frac=0.1)
+    xo = synth.train_like_head2d(B, nc, lv, gt, seed=10, frac=0.1)
+    fm, fo = feats_of(xm, lv), feats_of(xo, lv)
+    # inference: decode + top-k, fused and unfused
+    y, _ = y3d.detect_inference(fo, synth.STRIDES, nc)
+    oy = oracle.decode2d(xo, lv, synth.STRIDES, nc)
+    np.testing.assert_allclose(y.cpu().numpy()[:, 4:], oy[:, 4:], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(y.cpu().numpy()[:, :4], oy[:, :4], rtol=RTOL, atol=1e-3)
+    ye = y3d.detect_inference(fo, synth.STRIDES, nc, export=True)
+    boxes, scores, labels = y3d.v10postprocess(ye.permute(0, 2, 1), 100, nc)
+    ob, osc, ol, _ = oracle.postprocess(ye.cpu().numpy().transpose(0, 2, 1), 100, nc)
+    assert np.array_equal(labels.cpu().numpy(), ol) and np.array_equal(scores.cpu().numpy(), osc)
+    fused = y3d.v10detect_export_forward(fo, synth.STRIDES, nc, 100)
+    assert torch.equal(fused[..., 4], scores) and torch.equal(fused[..., 5], labels.float())
+    assert torch.equal(fused[..., :4], boxes)
+    # training: fused dual loss vs the oracle, and on level tensors that are views with a 4-byte-aligned offset only
+    gains = (7.5, 0.5, 1.5)
+    items, _, _ = lossmod.v10_loss_forward(fm, fo, list(synth.STRIDES), nc, dev(gt), gains)
+    o = oracle.v10_loss(xm, xo, lv, synth.STRIDES, nc, gt, gains=gains)[1]
+    np.testing.assert_allclose(items.view(2, 4)[:, :3].reshape(6).cpu().numpy(), o, rtol=2e-5)
+    lv2 = synth.levels(256, 320)  # sizes are multiples of 4, but the storage is shifted by one float
+    gt2 = synth.gt2d(2, 6, nc, (256, 320), seed=11)
+    x2 = synth.train_like_head2d(2, nc, lv2, gt2, seed=12, frac=0.1)
+
+    def shifted(f):
+        buf = torch.empty(f.numel() + 1, device="cuda")
+        buf[1:] = f.reshape(-1)
+        return buf[1:].view(f.shape)
+
+    f2 = [shifted(f) for f in feats_of(x2, lv2)]
+    assert all(f.data_ptr() % 16 for f in f2)
+    it2, _, _ = lossmod.v8_loss_forward(f2, list(synth.STRIDES), nc, dev(gt2), 10, gains)
+    o2 = oracle.v8_loss(x2, lv2, synth.STRIDES, nc, gt2, 10, gains=gains)[0]
+    np.testing.assert_allclose(it2[:3].cpu().numpy(), o2, rtol=2e-5)
+    # backward on the scalar path == backward on the vector path (same inputs, aligned copy)
+    fa = [f.requires_grad_(True) for f in feats_of(x2, lv2)]
+    fb = [f.detach().requires_grad_(True) for f in f2]
+    batch = {k: torch.from_numpy(v) for k, v in synth.batch_dict(gt2, (256, 320)).items()}
+    model = FakeModel(nc, gains)
+    y3d.v8DetectionLoss(model, tal_topk=10)(fa, batch)[0].backward()
+    y3d.v8DetectionLoss(model, tal_topk=10)(fb, batch)[0].backward()
+    for a_, b_ in zip(fa, fb):
+        np.testing.assert_allclose(a_.grad.cpu().numpy(), b_.grad.cpu().numpy(), rtol=1e-6, atol=1e-9)
+
+
 def test_loss_no_targets(y3d):
     lv = synth.levels(160, 160)
     x = synth.head2d(2, 8, lv, seed=1)

@@ -410,12 +410,25 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
             gi = (int)(cl & 0xffffffffull);
         } else {  // select_highest_overlaps tal.py:252-263: argmax over all GTs, first maximum
             float bv = -1.0f;
-            for (int m = 0; m < c.M; ++m) {
-                const GtRec g = gts[m];
-                float metric = 0.0f, ovl = 0.0f;
-                bool sel = g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box));
-                if (sel) pair_eval(c, b, m, g, a, metric, ovl);
-                if (ovl > bv) { bv = ovl; gi = m; }
+            if (!c.use_3d) {  // the overlap is the CIoU alone: one box load, then pure arithmetic over the GTs
+                const float4 pbox = pair_box(c, pair_load_box(c, b, a), a);
+                for (int m = 0; m < c.M; ++m) {
+                    const GtRec g = gts[m];
+                    float ovl = 0.0f;
+                    if (g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box))) {
+                        ovl = dm::ciou(g.box, pbox, g.at1);
+                        ovl = ovl < 0.0f ? 0.0f : ovl;
+                    }
+                    if (ovl > bv) { bv = ovl; gi = m; }
+                }
+            } else {
+                for (int m = 0; m < c.M; ++m) {
+                    const GtRec g = gts[m];
+                    float metric = 0.0f, ovl = 0.0f;
+                    bool sel = g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box));
+                    if (sel) pair_eval(c, b, m, g, a, metric, ovl);
+                    if (ovl > bv) { bv = ovl; gi = m; }
+                }
             }
         }
         const GtRec g = cnt > 1 ? gts[gi] : load_gt(c, b, gi);

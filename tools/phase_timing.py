@@ -31,8 +31,16 @@ from yolov10_3d_b200 import _lib
 _lib.LIB_PATH = OUT
 import bench
 
-lv, gt, xm, xo = bench.make_inputs(seed=0)
 from tests import synth
+
+if os.environ.get("CROWD"):
+    Bc, Mc = 128, 500
+    lv = synth.levels(640, 640)
+    gt = np.concatenate([synth.gt2d(8, Mc, 80, (640, 640), seed=1, crowd=True, full=True)] * (Bc // 8))
+    xm = np.concatenate([synth.train_like_head2d(8, 80, lv, gt[:8], seed=2, frac=0.02)] * (Bc // 8))
+    xo = np.concatenate([synth.train_like_head2d(8, 80, lv, gt[:8], seed=3, frac=0.02)] * (Bc // 8))
+else:
+    lv, gt, xm, xo = bench.make_inputs(seed=0)
 
 dev = torch.device("cuda", 0)
 fm = [torch.from_numpy(f).to(dev) for f in synth.split_levels(xm, lv)]

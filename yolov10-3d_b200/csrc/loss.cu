@@ -237,12 +237,19 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 constexpr int kConfMax = 1024;  // multiply-claimed anchors resolved cooperatively per image (more: serial fallback)
 constexpr int kFinishWarps = kFinishThreads / 32;
+constexpr int kBucketPx = 32;       // coarse cell of the per-image GT index (pixels)
+constexpr int kBucketCells = 2048;  // at most this many coarse cells (e.g. 1280 x 1280 -> 1600)
+constexpr int kBucketCap = 12288;   // (GT, coarse cell) incidences kept; larger sets fall back to the all-GT scan
 
 struct FinishSmem {  // dynamic shared memory of loss_finish_kernel, followed by GtRec[M], int pos_a[M], int pos_o[M]
     float4 conf_box[kConfMax];            // predicted box (px) of a conflicted anchor
     unsigned long long conf_best[kConfMax];  // (overlap bits << 32) | (0xffffffff - m): atomicMax = first maximum
     float2 conf_xy[kConfMax];             // its anchor point (px)
     int2 queue[kFinishWarps][64];         // per-warp compaction queue of in-GT (conflict, GT) pairs
+    int bucket_start[kBucketCells + 1];   // coarse spatial index of the image's GT boxes: CSR over 32 px cells
+    int bucket_fill[kBucketCells];
+    unsigned short bucket_items[kBucketCap];
+    int bucket_total, bucket_ok;
     long long redl[4][kFinishWarps];
     double redd[kFinishWarps];
     double fin[2][5];
@@ -278,6 +285,65 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
     int *lgi = F.list_gi[z] + (long long)b * c.list_cap;
     float *lal = F.list_al[z] + (long long)b * c.list_cap;
     __syncthreads();
+    // ---- coarse spatial index of the GT boxes (32 px cells): a contested anchor then tests the few GTs registered in
+    //      its cell instead of all M (dense crowds: 500 GTs, thousands of contested anchors per image)
+    const int gw = (int)ceilf(c.t.w[0] * c.t.stride[0] / kBucketPx), gh = (int)ceilf(c.t.h[0] * c.t.stride[0] / kBucketPx);
+    const int ncell = gw * gh;
+    auto cell_range = [&](const float4 &bx, int &x0, int &x1, int &y0, int &y1) {
+        x0 = min(max((int)floorf(bx.x / kBucketPx), 0), gw - 1); x1 = min(max((int)floorf(bx.z / kBucketPx), 0), gw - 1);
+        y0 = min(max((int)floorf(bx.y / kBucketPx), 0), gh - 1); y1 = min(max((int)floorf(bx.w / kBucketPx), 0), gh - 1);
+    };
+    // (worth its construction only when the all-GT scan is long: with M <= 128 the cooperative scan below is faster)
+    if (tid == 0) { S.bucket_total = 0; S.bucket_ok = (ncell <= kBucketCells && M > 128 && M <= 65535 && n > 0) ? 1 : 0; }
+    __syncthreads();
+    if (S.bucket_ok) {
+        for (int i = tid; i < ncell; i += kFinishThreads) { S.bucket_start[i] = 0; S.bucket_fill[i] = 0; }
+        __syncthreads();
+        for (int m = tid; m < M; m += kFinishThreads)
+            if (gts[m].valid) {
+                int x0, x1, y0, y1;
+                cell_range(gts[m].box, x0, x1, y0, y1);
+                atomicAdd(&S.bucket_total, (x1 - x0 + 1) * (y1 - y0 + 1));
+                for (int y = y0; y <= y1; ++y)
+                    for (int x = x0; x <= x1; ++x) atomicAdd(&S.bucket_start[y * gw + x], 1);
+            }
+        __syncthreads();
+        if (S.bucket_total > kBucketCap) {
+            if (tid == 0) S.bucket_ok = 0;
+        } else if (wid == 0) {  // exclusive prefix over the cells (one warp, lane-strided chunks)
+            const int per = (ncell + 31) / 32;
+            const int lo = min(lane * per, ncell), hi = min(lo + per, ncell);
+            int s_ = 0;
+            for (int i = lo; i < hi; ++i) s_ += S.bucket_start[i];
+            int inc = s_;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            int run = inc - s_;
+            for (int i = lo; i < hi; ++i) {
+                const int cnt_i = S.bucket_start[i];
+                S.bucket_start[i] = run;
+                run += cnt_i;
+            }
+            if (lane == 31) S.bucket_start[ncell] = run;
+        }
+        __syncthreads();
+        if (S.bucket_ok)
+            for (int m = tid; m < M; m += kFinishThreads)
+                if (gts[m].valid) {
+                    int x0, x1, y0, y1;
+                    cell_range(gts[m].box, x0, x1, y0, y1);
+                    for (int y = y0; y <= y1; ++y)
+                        for (int x = x0; x <= x1; ++x) {
+                            const int cell = y * gw + x;
+                            S.bucket_items[S.bucket_start[cell] + atomicAdd(&S.bucket_fill[cell], 1)] = (unsigned short)m;
+                        }
+                }
+        __syncthreads();
+    }
+    const bool use_buckets = S.bucket_ok != 0;
     Y3D_STAMP(1);
     // ---- resolve, step 1: singly-claimed anchors are final; multiply-claimed ones (select_highest_overlaps
     //      tal.py:237-264: argmax over ALL GTs of the overlap, first maximum) are parked for the cooperative step
@@ -299,7 +365,24 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         anchor_px(c, a, ax, ay, st);
         int gi = (int)(cl & 0xffffffffull);
         const PairRaw raw = pair_load_box(c, b, a);
-        if (cnt > 1) {
+        if (cnt > 1 && use_buckets) {  // only the GTs registered in the anchor's coarse cell can contain it
+            const float4 pbox = pair_box(c, raw, a);
+            const int cell = min(max((int)floorf(ay / kBucketPx), 0), gh - 1) * gw + min(max((int)floorf(ax / kBucketPx), 0), gw - 1);
+            unsigned long long best = 0xffffffffull;  // overlap 0 at GT 0
+            for (int i = S.bucket_start[cell]; i < S.bucket_start[cell + 1]; ++i) {
+                const int m = S.bucket_items[i];
+                const GtRec g = gts[m];
+                if (dm::in_gt(ax, ay, g.box)) {
+                    const float ovl = dm::ciou(g.box, pbox, g.at1);
+                    if (ovl > 0.0f) {
+                        const unsigned long long key =
+                            ((unsigned long long)__float_as_uint(ovl) << 32) | (unsigned long long)(0xffffffffu - (unsigned)m);
+                        best = key > best ? key : best;
+                    }
+                }
+            }
+            gi = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+        } else if (cnt > 1) {
             const float4 pbox = pair_box(c, raw, a);
             const int ci = atomicAdd(&S.n_conf, 1);
             if (ci < kConfMax) {

@@ -4,10 +4,11 @@
 // ever materialising the reference's dense [B, M, A] tensors:
 //
 //   tal_topk_kernel    one warp per (image, GT) -- or kTopkWarps warps per GT when every anchor is a candidate
-//                      (no grid promised / constrain_anchors off): walks the cells of the GT's rectangle 64 at a time
-//                      (loads of both halves issued before any arithmetic), evaluates score^alpha * CIoU^beta
-//                      (* sim^gamma) for the in-GT anchors, keeps the per-GT top-k as a lane-distributed sorted list
-//                      (value desc, index asc) and claims the winners with one 64-bit atomic per (GT, anchor).
+//                      (no grid promised / constrain_anchors off).  Exact in-GT rectangle per level, flat centre-out
+//                      walk, score / fast-IoU upper bounds before the exactly rounded CIoU, survivors compacted and
+//                      evaluated on full lanes; the per-GT top-k is a lane-distributed sorted list of 64-bit keys
+//                      (value desc, index asc); winners are claimed with one 64-bit atomic per (GT, anchor).  Details
+//                      in assign.cu.
 //                      Zero-metric ties are exact: anchors 0..k-1 always enter the list (they are what a dense
 //                      stable top-k would pick among zeros), zero-metric anchors >= k can never be selected.
 //   tal_resolve_kernel one thread per (image, anchor): 0 claims -> background; 1 claim -> that GT; >1 claims ->
@@ -208,10 +209,6 @@ __device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, cons
 __device__ __forceinline__ void pair_eval(const AssignCtx &c, int b, int m, const GtRec &g, int a, float &metric,
                                           float &ovl) {
     pair_eval(c, b, m, g, a, pair_load(c, b, a, g.label), metric, ovl);
-}
-
-__device__ __forceinline__ bool better(float am, int ai, float bm, int bi) {
-    return am > bm || (am == bm && ai < bi);
 }
 
 // norm_align_metric of an assigned anchor (tal.py:89-92)

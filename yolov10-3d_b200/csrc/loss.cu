@@ -258,7 +258,7 @@ struct FinishSmem {  // dynamic shared memory of loss_finish_kernel, followed by
 };
 size_t finish_smem_bytes(int M) { return sizeof(FinishSmem) + (sizeof(GtRec) + 2 * sizeof(int)) * (size_t)M; }
 
-// grid (B, n_branch), block 1024; one CTA per (image, branch) over the image's claimed anchors only
+// grid (B, n_branch), block kFinishThreads; one CTA per (image, branch) over the image's claimed anchors only
 __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 cc, FinishParams F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FinishSmem &S = *reinterpret_cast<FinishSmem *>(smem_raw);

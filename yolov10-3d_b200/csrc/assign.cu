@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     __shared__ LvlWalk walk[kTopkWarps][Y3D_MAX_LEVELS];
     __shared__ unsigned long long mrg[kTopkWarps][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // let a programmatically dependent kernel (the fused loss' finishing kernel) be scheduled as this grid drains; it
+    // waits for this grid's completion itself before touching anything written here
+    asm volatile("griddepcontrol.launch_dependents;");
     const int per_branch = cc.c[0].B * cc.c[0].M;  // host checks n_branch * B * M < 2^31
     const int total = per_branch * n_branch;
     const int wsub = wpg == 1 ? 0 : wid;  // this warp's share of the GT's chunks

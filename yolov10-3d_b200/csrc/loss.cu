@@ -280,6 +280,9 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
             F.dbg_fg[z][(long long)b * A + a] = 0;
             F.dbg_gi[z][(long long)b * A + a] = 0;
         }
+    // Everything above reads only the caller's inputs; what follows reads what the top-k kernel wrote.  With
+    // programmatic dependent launch this CTA may have started while that kernel was still draining: wait here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int n = M > 0 ? min(__ldcg(c.list_count + b), c.list_cap) : 0;
     const int *la = c.list_a + (long long)b * c.list_cap;
     int *lgi = F.list_gi[z] + (long long)b * c.list_cap;
@@ -707,7 +710,20 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         cudaError_t e = cudaFuncSetAttribute(loss_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
         if (e != cudaSuccess) return (int)e;
     }
-    loss_finish_kernel<<<dim3(B, nb), kFinishThreads, fin_smem, s>>>(cc, F);
+    {   // programmatic dependent launch: the prologue (GT records, shared-memory setup) overlaps the top-k kernel's tail
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(B, nb);
+        cfg.blockDim = dim3(kFinishThreads);
+        cfg.dynamicSmemBytes = fin_smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, loss_finish_kernel, cc, F);
+        if (le != cudaSuccess) return (int)le;
+    }
     Y3D_CHECK_LAUNCH();
     mark(3);
     return Y3D_OK;

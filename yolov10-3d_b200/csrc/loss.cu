@@ -211,6 +211,25 @@ struct FinishParams {
     float gain_box, gain_cls, gain_dfl;
 };
 
+// bbox_iou(box1, box2, xywh=False, CIoU=True) (metrics.py:96-131) with fast division: for VALUES (loss terms, alignment
+// weights), never for anything that decides an index -- those go through the exactly rounded dm::ciou.
+__device__ __forceinline__ float ciou_fast(float4 b1, float4 b2) {
+    const float eps = 1e-7f;
+    const float w1 = b1.z - b1.x, h1 = b1.w - b1.y + eps, w2 = b2.z - b2.x, h2 = b2.w - b2.y + eps;
+    const float iw = fmaxf(fminf(b1.z, b2.z) - fmaxf(b1.x, b2.x), 0.f), ih = fmaxf(fminf(b1.w, b2.w) - fmaxf(b1.y, b2.y), 0.f);
+    const float inter = iw * ih;
+    const float uni = w1 * h1 + w2 * h2 - inter + eps;
+    const float iou = __fdividef(inter, uni);
+    const float cw = fmaxf(b1.z, b2.z) - fminf(b1.x, b2.x), ch = fmaxf(b1.w, b2.w) - fminf(b1.y, b2.y);
+    const float c2 = cw * cw + ch * ch + eps;
+    const float dx = b2.x + b2.z - b1.x - b1.z, dy = b2.y + b2.w - b1.y - b1.w;
+    const float rho2 = (dx * dx + dy * dy) * 0.25f;
+    const float da = atanf(__fdividef(w2, h2)) - atanf(__fdividef(w1, h1));
+    const float v = 0.4052847345693511f * da * da;
+    const float alpha = __fdividef(v, v - iou + (1.0f + eps));
+    return iou - (__fdividef(rho2, c2) + v * alpha);
+}
+
 constexpr double kFix = 4294967296.0;  // 2^32: loss terms are summed as 64-bit fixed point (exact, order-independent)
 __device__ __forceinline__ long long to_fix(float v) { return __double2ll_rn((double)v * kFix); }
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
@@ -495,7 +514,7 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         }
         const float xlab = hp[(long long)(4 * kR + lab) * cs];
         const float4 pb = make_float4(pbv[0], pbv[1], pbv[2], pbv[3]);
-        const float iou = dm::ciou(pb, tb, dm::box1_atan(pb));  // BboxLoss.forward loss.py:85 (box1 = pred)
+        const float iou = ciou_fast(pb, tb);  // BboxLoss.forward loss.py:85 (box1 = pred)
         float dfl = 0.f;
 #pragma unroll
         for (int side = 0; side < 4; ++side)  // _df_loss loss.py:99-113

@@ -167,6 +167,10 @@ def main_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     y3d.lib()
+    reducer = None
+    if world > 1 and os.environ.get("Y3D_NCCL_REDUCE") != "1":
+        reducer = y3d.dist.PeerLossReducer(dev)
+    peer = reducer is not None and reducer.available
     B, nc, gains = CFG["B"], CFG["nc"], CFG["gains"]
     lv, gt, xm, xo = make_inputs(seed=100 * rank)
     A = synth.num_anchors(lv)
@@ -202,10 +206,12 @@ def main_cuda(args):
 
     def step(i=None):
         pe = ev_c[i] if i is not None else None
-        return y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=pe)
+        return y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=pe,
+                                         reducer=reducer)
 
     for i in range(W):
-        y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=evw_c[i])
+        y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=evw_c[i],
+                                  reducer=reducer)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -282,7 +288,10 @@ def main_cuda(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "sharding": f"by image, {B}/GPU",
                        "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed",
-                       "collective": "all_reduce of 8 float64 loss partials per step" if world > 1 else "none"},
+                       "collective": ("none" if world == 1 else
+                                      "8 float64 loss partials per step: one fused all-reduce + normalise kernel over NVLink "
+                                      "peer memory (csrc/xrank.cu)" if peer else
+                                      "NCCL all_reduce of 8 float64 loss partials per step + finalize kernel")},
             "roofline": {"bound": "hbm", "kernel": "head_stream_kernel<4>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(stage_ms[0]),
@@ -291,7 +300,7 @@ def main_cuda(args):
                                                  "finish: resolve+fg_loss+reduce (warm-up steps)": float(stage_ms[2])}},
             "e2e": {"value": B * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 24, "steps": Ke},
-            "gpu_launches": (3 + (1 if world > 1 else 0)) * K,
+            "gpu_launches": (3 + (1 if world > 1 else 0)) * K,  # + the NCCL kernel when the peer path is unavailable
             "clocks": sampler.summary(),
             "loss_items": [float(v) for v in items.cpu()],
         }

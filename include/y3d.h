@@ -167,6 +167,19 @@ int y3d_v10_loss_bwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const i
                      int M, int topk_o2m, int topk_o2o, float gain_box, float gain_cls, float gain_dfl,
                      const float *loss_items, const float *grad_items, const void *ws, size_t ws_bytes, void *stream);
 
+/* The one cross-rank step of the image-sharded loss as a single kernel over NVLink peer memory:
+ * all-reduce(sum) of the per-rank partials + the normalisation of y3d_v8_loss_finalize.
+ *  peer_bufs: HOST array of `world` DEVICE pointers, peer_bufs[r] = rank r's exchange buffer of
+ *  y3d_xrank_buffer_bytes(world) bytes, zero-initialised once, addressable from this device (symmetric / peer memory,
+ *  e.g. torch.distributed._symmetric_memory); seq: call counter, 1, 2, 3, ... identical on all ranks; every rank must
+ *  make the same sequence of calls.  partials: this rank's DEVICE double[4 * n_branch]; loss_items: DEVICE
+ *  float[4 * n_branch] (identical on every rank afterwards); global_partials (optional): the summed partials;
+ *  status (optional DEVICE int): 0, or 1 when a peer did not arrive within ~8 s (items are NaN then). */
+size_t y3d_xrank_buffer_bytes(int world);
+int y3d_loss_allreduce_finalize(const double *partials, int n_branch, int rank, int world, void *const *peer_bufs,
+                                unsigned long long seq, float gain_box, float gain_cls, float gain_dfl,
+                                float *loss_items, double *global_partials, int *status, void *stream);
+
 /* v8DetectionLoss.bbox_decode (loss.py:197-204) + the permute/sigmoid of loss.py:214,232: head levels ->
  * pd_bboxes [B,A,4] xyxy in GRID units (caller multiplies by stride, loss.py:233) and, optionally (may be NULL),
  * pd_scores [B,A,nc] = sigmoid(class logits).  Same device arithmetic as the fused loss uses internally. */

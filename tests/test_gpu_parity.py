@@ -708,3 +708,21 @@ def test_tal_assign3d_kitti_shape_vs_oracle(y3d):
         assert np.array_equal(targets[1].cpu().numpy(), o["target_scores"])
         assert np.array_equal(pk.cpu().numpy(), o["pd_keypoints"])
         assert o["fg_mask"].sum() > 0
+
+
+@pytest.mark.gpu
+def test_peer_memory_loss_reduction_multi_gpu():
+    """csrc/xrank.cu (fused all-reduce + normalise over NVLink peer memory) against NCCL all_reduce + finalize, one
+    process per GPU.  Needs at least two GPUs on the box; skipped otherwise (the single-GPU tier)."""
+    import subprocess
+    import sys
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", "tools/check_peer_reduce.py"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "peer reduce == nccl reduce: True" in r.stdout

@@ -6,10 +6,15 @@
   normalisation -- this reproduces the single-process reference on the full batch.
 No other collective is issued: assignment and decode are independent per image.
 """
+import ctypes as C
+import sys
+
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from . import loss as _loss
+from ._util import ptr, stream_ptr
 
 
 def shard_range(batch, rank, world):
@@ -45,16 +50,61 @@ def reduce_partials(partials, group=None):
     return partials
 
 
-def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_batch, group=None, prof_events=None):
+class PeerLossReducer:
+    """The loss path's one exchange as ONE kernel over NVLink peer memory (csrc/xrank.cu): every rank stores its 8
+    partial sums straight into every peer's exchange buffer, waits for the peers' sequence flags, sums in rank order
+    and normalises -- instead of an NCCL all-reduce of 64 bytes followed by a finalize kernel.
+
+    The exchange buffers come from ``torch.distributed._symmetric_memory`` (peer-mapped allocations of one process per
+    GPU).  Construction is collective; ``available`` is False when symmetric memory cannot be set up on this system,
+    and callers then use the NCCL path."""
+
+    def __init__(self, device, group=None):
+        self.available = False
+        self.seq = 0
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            pg = group if group is not None else dist.group.WORLD
+            self.world, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+            nbytes = int(_lib.lib().y3d_xrank_buffer_bytes(self.world))
+            self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.handle = symm_mem.rendezvous(self.buf, pg.group_name if hasattr(pg, "group_name") else pg)
+            self.ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+            self.status = torch.zeros(1, dtype=torch.int32, device=device)
+            torch.cuda.synchronize(device)
+            dist.barrier(group=pg)  # every buffer is zeroed before anyone's first store can land
+            self.available = True
+        except Exception as e:  # no peer access / symmetric memory unsupported: NCCL path
+            print(f"[yolov10-3d_b200] peer-memory loss reduction unavailable ({type(e).__name__}: {e}); using NCCL",
+                  file=sys.stderr)
+
+    def __call__(self, partials, gains):
+        """partials float64[4n] of this rank -> items float32[4n] of the global batch (same on every rank)."""
+        self.seq += 1
+        n = partials.numel() // 4
+        items = torch.empty(4 * n, dtype=torch.float32, device=partials.device)
+        _lib.check(_lib.lib().y3d_loss_allreduce_finalize(
+            ptr(partials), n, self.rank, self.world, self.ptrs, C.c_uint64(self.seq), float(gains[0]), float(gains[1]),
+            float(gains[2]), ptr(items), None, ptr(self.status), stream_ptr(partials.device)))
+        return items
+
+
+def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_batch, group=None, prof_events=None,
+                     reducer=None):
     """``v10DetectLoss`` (loss.py:727-737) on this rank's image shard, normalised over the GLOBAL batch.
 
     Returns ``(total, items[6])`` identical on every rank and equal to the single-process result on the full batch.
-    One rank: the kernels normalise directly.  Several ranks: un-normalised partials -> one all_reduce of 8 doubles
-    -> ``y3d_v8_loss_finalize``."""
+    One rank: the kernels normalise directly.  Several ranks: un-normalised partials -> ``reducer`` (a
+    :class:`PeerLossReducer`: one kernel over NVLink peer memory) or, without one, an NCCL all_reduce of 8 doubles ->
+    ``y3d_v8_loss_finalize``."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     items, parts, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains, normalise=not multi,
                                              prof_events=prof_events)
-    if multi:
+    if multi and reducer is not None and reducer.available:
+        items = reducer(parts, gains)  # one kernel over peer memory: all-reduce + normalisation
+    elif multi:
         items = _loss.finalize_partials(reduce_partials(parts, group), gains)
     items = items.view(2, 4)[:, :3].reshape(6)
     return items.sum() * global_batch, items

@@ -215,9 +215,11 @@ def main_cuda(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)  # clocks / throttle reasons while the GPU is under load: timed region + e2e region
     sampler.start()
-    time.sleep(0.25)
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 3.0:  # nvidia-smi needs a moment to print its first line
+        time.sleep(0.02)
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
@@ -228,7 +230,6 @@ def main_cuda(args):
     if world > 1:
         dist.barrier()
     ms_total = t_start.elapsed_time(t_stop)
-    sampler.stop()
     stage_ms = np.zeros(3)
     for row in ev:
         stage_ms[0] += row[0].elapsed_time(row[1])
@@ -262,6 +263,7 @@ def main_cuda(args):
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
+    sampler.stop()
 
     times = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -301,7 +303,7 @@ def main_cuda(args):
             "e2e": {"value": B * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 24, "steps": Ke},
             "gpu_launches": (3 + (1 if world > 1 else 0)) * K,  # + the NCCL kernel when the peer path is unavailable
-            "clocks": sampler.summary(),
+            "clocks": dict(sampler.summary(), window="timed region + e2e region (nvidia-smi every 100 ms)"),
             "loss_items": [float(v) for v in items.cpu()],
         }
         if cpu is not None:

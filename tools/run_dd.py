@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Developer tool: a few calls of the fused 3D loss at cfg3 shape (for ncu launch lists)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import yolov10_3d_b200 as y3d  # noqa: E402
+from tests import synth  # noqa: E402
+
+hw, nc, B, M = (384, 1280), 3, 32, 50
+lv = synth.levels(*hw)
+gts = synth.gt3d(B, M, nc, hw, seed=1)
+x3 = synth.train_like_head3d(B, nc, lv, gts, seed=0, frac=0.03)
+f3 = [torch.from_numpy(v).cuda() for v in synth.split_levels(x3, lv)]
+cal = torch.from_numpy(np.tile(np.array(synth.KITTI_CALIB, np.float32), (B, 1))).cuda()
+ms = torch.tensor(synth.KITTI_MEAN_SIZES, dtype=torch.float32).cuda()
+g = torch.from_numpy(gts).cuda()
+for k in (8, 1, 8, 1):
+    y3d.loss3d.dd_loss_forward(f3, list(synth.STRIDES), nc, g, cal, ms, k, (1, 1, 1, 1, 1, 1))
+torch.cuda.synchronize()

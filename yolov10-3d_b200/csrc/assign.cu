@@ -448,8 +448,11 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
 
 int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s) {
     const AssignCtx &c = cc.c[0];
-    const int wpg = (c.use_grid && c.constrain && cc.work_counter) ? 1 : kTopkWarps;
     const long long items = (long long)c.B * c.M * n;
+    // one persistent warp per GT fills the machine only when there are many GTs; with few (e.g. KITTI: 32 x 50) the
+    // kernel's duration is one GT's latency, so each GT is split over kTopkWarps warps instead
+    const bool few = items < 16LL * kNumSMs;
+    const int wpg = (c.use_grid && c.constrain && cc.work_counter && !few) ? 1 : kTopkWarps;
     if (items >= 0x7fffffffLL) return Y3D_EUNSUPPORTED;
     long long blocks = wpg == 1 ? (items + kTopkWarps - 1) / kTopkWarps : items;
     if (wpg == 1) {  // persistent: no more CTAs than fit at once

@@ -161,20 +161,32 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
 }
 
 // partials float64[kNSum + 1] = soft+, off2d, size2d, depth, off3d, size3d, hd_ce, hd_l1, x*t, sum t, n_fg
-__global__ void __launch_bounds__(256) dd_reduce_kernel(const double *part, int n_rows, double *partials) {
-    __shared__ double red[kNSum + 1][256];
-    double acc[kNSum + 1];
-    for (int i = 0; i <= kNSum; ++i) acc[i] = 0.0;
-    for (int r = threadIdx.x; r < n_rows; r += 256)
-        for (int i = 0; i <= kNSum; ++i) acc[i] += part[(long long)r * (kNSum + 1) + i];
-    for (int i = 0; i <= kNSum; ++i) red[i][threadIdx.x] = acc[i];
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s)
-            for (int i = 0; i <= kNSum; ++i) red[i][threadIdx.x] += red[i][threadIdx.x + s];
-        __syncthreads();
+__global__ void __launch_bounds__(1024) dd_reduce_kernel(const double *part, int n_rows, double *partials) {
+    __shared__ double red[kNSum + 1][32];
+    // thread = (row group, column): consecutive threads read consecutive doubles of a row (coalesced); fixed order
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int W = kNSum + 1;
+    const long long total = (long long)n_rows * W;
+    double acc = 0.0;
+    int col = -1;
+    // each thread owns the elements e = tid, tid + 1024 * W', ... of one column: stride a multiple of W keeps the column
+    const int stride = 1024 / W * W;  // 1023 for W = 11
+    if (tid < stride) {
+        col = tid % W;
+        for (long long e = tid; e < total; e += stride) acc += part[e];
     }
-    if (threadIdx.x <= kNSum) partials[threadIdx.x] = red[threadIdx.x][0];
+    // reduce per column in a fixed order: shared memory slots [col][slot], slot = tid / W (< 93 -> folded into 32)
+    for (int c = 0; c < W; ++c) {
+        double v = (col == c) ? acc : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) red[c][wid] = v;
+    }
+    __syncthreads();
+    if (tid < W) {
+        double s = 0.0;
+        for (int w = 0; w < 32; ++w) s += red[tid][w];
+        partials[tid] = s;
+    }
 }
 
 // loss.py:879-888: items = loss2d, cls, depth, offset3d, size3d, heading (+ target_scores_sum, n_fg)
@@ -370,7 +382,7 @@ extern "C" int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
     }
     dd_fg_kernel<<<grid, 128, 0, s>>>(c, P);
     Y3D_CHECK_LAUNCH();
-    dd_reduce_kernel<<<1, 256, 0, s>>>(P.part, w.n_rows, partials);
+    dd_reduce_kernel<<<1, 1024, 0, s>>>(P.part, w.n_rows, partials);
     Y3D_CHECK_LAUNCH();
     if (normalise) {
         dd_finalize_kernel<<<1, 32, 0, s>>>(partials, M, gains[0], gains[1], gains[2], gains[3], gains[4], gains[5],

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     const bool iou_bound = prune && c.use_2d &&
                            (c.beta == 1.0f || c.beta == 2.0f || c.beta == 3.0f || c.beta == 4.0f || c.beta == 6.0f);
     const float g_area = (g.box.z - g.box.x) * (g.box.w - g.box.y);
+    const bool fast_sq = iou_bound && c.score_mode == 1 && c.alpha == 0.5f && c.beta == 6.0f;
 
     int cells = c.A;  // candidates in the flat index space
     int off1 = 0x7fffffff, off2 = 0x7fffffff, off3 = 0x7fffffff;
@@ -267,23 +268,45 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
             }
             i0 += wpg * (32 * kTopkU);
             const unsigned tm = prune ? (unsigned)(thr >> 32) : 0u;
+            const float thr_m = __uint_as_float(tm);
+            const float tq = thr_m * thr_m * 0.999f;  // threshold of the squared-domain bound (conservative)
 #pragma unroll
             for (int u = 0; u < kTopkU; ++u) {
-                float sb = 0.f, ub = 0.f;  // score^alpha and the upper bound of the metric
-                if (__any_sync(0xffffffffu, h[u])) {
-                    const float2 r2 = cand_bounds(x[u], c.score_mode, c.alpha, bx[u],
-                                                  c.box_grid_units ? sv[u] : 1.0f, g.box, g_area,
-                                                  iou_bound ? c.beta : -1.0f);
-                    sb = h[u] ? r2.x : 0.f;
-                    ub = r2.y;
+                float payload = 0.f, ub = 0.f;
+                bool pass = false;
+                if (fast_sq) {
+                    // the common configuration (logits in, alpha = 0.5, beta = 6): bound metric^2 = sigmoid(x) * CIoU^12
+                    // from above with SFU approximations and safety factors -- no division, no square root; the exact
+                    // score^alpha is computed in stage 2, for the survivors only
+                    const float e = im::ex2a(-x[u] * im::kLog2e);
+                    const float s_ub = __fdividef(1.0002f, __fmaf_rn(0.9998f, e, 1.0f));
+                    const float stv = c.box_grid_units ? sv[u] : 1.0f;
+                    const float px1 = bx[u].x * stv, py1 = bx[u].y * stv, px2 = bx[u].z * stv, py2 = bx[u].w * stv;
+                    const float iw = fmaxf(fminf(g.box.z, px2) - fmaxf(g.box.x, px1), 0.f);
+                    const float ih = fmaxf(fminf(g.box.w, py2) - fmaxf(g.box.y, py1), 0.f);
+                    const float inter = iw * ih;
+                    const float uni = g_area + (px2 - px1) * (py2 - py1) - inter;
+                    const float iou = fminf(__fdividef(inter, fmaxf(uni, 1e-30f)) * 1.0001f, 1.0f);  // CIoU <= IoU
+                    const float i2 = iou * iou, i4 = i2 * i2;
+                    ub = s_ub * (i4 * i4 * i4) * 1.0001f;
+                    payload = x[u];
+                    pass = h[u] && ub >= tq;
+                } else {
+                    if (__any_sync(0xffffffffu, h[u])) {
+                        const float2 r2 = cand_bounds(x[u], c.score_mode, c.alpha, bx[u],
+                                                      c.box_grid_units ? sv[u] : 1.0f, g.box, g_area,
+                                                      iou_bound ? c.beta : -1.0f);
+                        payload = h[u] ? r2.x : 0.f;  // score^alpha
+                        ub = r2.y;
+                    }
+                    pass = h[u] && payload > 0.0f && __float_as_uint(ub) >= tm;
                 }
-                const bool pass = h[u] && sb > 0.0f && __float_as_uint(ub) >= tm;
                 const unsigned bal = __ballot_sync(0xffffffffu, pass);
                 if (pass) {
                     int pos = qh + qn + __popc(bal & lt_mask);
                     if (pos >= kTopkQ) pos -= kTopkQ;
                     q_a[wid][pos] = a[u];
-                    q_s[wid][pos] = sb;
+                    q_s[wid][pos] = payload;
                     q_u[wid][pos] = ub;
                     q_b[wid][pos] = bx[u];
                 }
@@ -300,12 +323,16 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
             if (qi >= kTopkQ) qi -= kTopkQ;
             if (lane < take) {
                 const int a2 = q_a[wid][qi];
-                if (!prune || __float_as_uint(q_u[wid][qi]) >= (unsigned)(thr >> 32)) {
+                const float thr_now = __uint_as_float((unsigned)(thr >> 32));
+                const bool alive = !prune || (fast_sq ? q_u[wid][qi] >= thr_now * thr_now * 0.999f
+                                                      : __float_as_uint(q_u[wid][qi]) >= (unsigned)(thr >> 32));
+                if (alive) {
                     PairRaw raw;
                     raw.box = q_b[wid][qi];
                     raw.s = 0.0f;
                     float ovl;
-                    const float metric = pair_metric(c, b, m, g, a2, raw, q_s[wid][qi], ovl);
+                    const float sb = fast_sq ? dm::pow_(pair_score(c, q_s[wid][qi]), c.alpha) : q_s[wid][qi];
+                    const float metric = pair_metric(c, b, m, g, a2, raw, sb, ovl);
                     if (metric > 0.0f) key = tk_key(metric, a2, 1);
                 }
             }

@@ -216,12 +216,15 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     TK_ACC(2);  // phase 0 (first k anchors)
     int qn = 0, qh = 0;  // FIFO ring: candidates are evaluated in walk order (centre first)
     int i0 = wsub * (32 * kTopkU);
+    // the first round trip of a one-warp walk takes only the 32 most central cells: their metrics set the k-th
+    // threshold before the bulk of the rectangle is tested against it
+    bool seed_trip = wpg == 1 && rect, flush_seed = false;
     bool done = false;
     for (bool first = true;; first = false) {
         unsigned long long key = 0ull;
         if (first) {
             key = key0;
-        } else if (qn < 32 && !done) {
+        } else if (qn < 32 && !done && !(flush_seed && qn > 0)) {
             if (i0 >= cells) { done = true; continue; }
             // ---- stage 1: locate, one round trip for the gathers of up to kTopkU candidates per lane, bounds
             bool h[kTopkU];
@@ -231,12 +234,13 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
 #pragma unroll
             for (int u = 0; u < kTopkU; ++u) {
                 const int j = i0 + u * 32 + lane;
+                const bool live = !seed_trip || u == 0;
                 h[u] = false;
                 a[u] = 0;
                 x[u] = 0.f;
                 sv[u] = 1.0f;
                 bx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < cells) {
+                if (live && j < cells) {
                     if (rect) {
                         const int l = (j >= off1 ? 1 : 0) + (j >= off2 ? 1 : 0) + (j >= off3 ? 1 : 0);
                         const LvlWalk &L = walk[wid][l];
@@ -266,7 +270,9 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                     if (h[u]) bx[u] = pair_load_box(c, b, a[u]).box;
                 }
             }
-            i0 += wpg * (32 * kTopkU);
+            i0 += seed_trip ? 32 : wpg * (32 * kTopkU);
+            flush_seed = seed_trip;  // evaluate the seed candidates before walking on
+            seed_trip = false;
             const unsigned tm = prune ? (unsigned)(thr >> 32) : 0u;
             const float thr_m = __uint_as_float(tm);
             const float tq = thr_m * thr_m * 0.999f;  // threshold of the squared-domain bound (conservative)
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
             continue;
         } else if (qn > 0) {
             // ---- stage 2: pop full lanes while trips remain, the rest at the end (no loads: pure arithmetic)
+            flush_seed = false;
             const int take = qn < 32 ? qn : 32;
             int qi = qh + lane;
             if (qi >= kTopkQ) qi -= kTopkQ;

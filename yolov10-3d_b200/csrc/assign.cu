@@ -142,39 +142,49 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     int off1 = 0x7fffffff, off2 = 0x7fffffff, off3 = 0x7fffffff;
     if (rect) {
         // exact in-GT rectangle of every level: in_gt(ax, ay) = min(ax-x1, ay-y1, x2-ax, y2-ay) > 1e-9 splits into four
-        // monotone edge tests; each edge is located with the very comparison the dense test uses, starting one cell
-        // outside the real-valued estimate (all lanes do the same scalar work)
+        // monotone edge tests; each edge is located with the very comparison the dense test uses
+        // The 4 edges x nl levels are independent: lane 4*l + e finds edge e (x lo, x hi, y lo, y hi) of level l.
+        // lo edge: first index i with (i + 0.5) * st - lo > 1e-9; hi edge: last index with hi - (i + 0.5) * st > 1e-9.
+        // The real-valued estimate is off by at most one cell, so a window of four cells around it brackets the flip
+        // of the (monotone) comparison; anything else falls back to a linear search.
+        int my_edge = 0;
+        if (lane < 4 * c.t.nl) {
+            const int lv = lane >> 2, e = lane & 3;
+            const float st = c.t.stride[lv];
+            const int n = e < 2 ? c.t.w[lv] : c.t.h[lv];
+            const float v = e == 0 ? g.box.x : e == 1 ? g.box.z : e == 2 ? g.box.y : g.box.w;
+            const bool hi = e & 1;
+            auto ok = [&](int i) {
+                const float p = dm::mul((float)i + 0.5f, st);
+                return hi ? dm::sub(v, p) > 1e-9f : dm::sub(p, v) > 1e-9f;
+            };
+            const float r = v / st - 0.5f;
+            if (!hi) {
+                const int f = (int)floorf(r);
+                int ed = f - 1 + (ok(f - 1) ? 0 : 1) + (ok(f) ? 0 : 1) + (ok(f + 1) ? 0 : 1) + (ok(f + 2) ? 0 : 1);
+                if (ok(f - 1) || !ok(f + 2)) {  // flip not inside the window
+                    ed = f - 1;
+                    while (ed > 0 && ok(ed - 1)) --ed;
+                    while (ed < n && !ok(ed)) ++ed;
+                }
+                my_edge = max(ed, 0);
+            } else {
+                const int f = (int)ceilf(r);
+                int ed = f + 1 - (ok(f + 1) ? 0 : 1) - (ok(f) ? 0 : 1) - (ok(f - 1) ? 0 : 1) - (ok(f - 2) ? 0 : 1);
+                if (ok(f + 1) || !ok(f - 2)) {
+                    ed = f + 1;
+                    while (ed < n - 1 && ok(ed + 1)) ++ed;
+                    while (ed >= 0 && !ok(ed)) --ed;
+                }
+                my_edge = min(ed, n - 1);
+            }
+        }
         cells = 0;
         for (int l = 0; l < c.t.nl; ++l) {
             const float st = c.t.stride[l];
-            const int w = c.t.w[l], h = c.t.h[l];
-            // lo edge: first index i with (i + 0.5) * st - lo > 1e-9; hi edge: last index with hi - (i + 0.5) * st > 1e-9.
-            // The real-valued estimate is off by at most one cell, so a window of four cells around it brackets the
-            // flip of the (monotone) comparison; anything else falls back to a linear search.
-            auto lo_edge = [&](float lo, int n) {
-                const int f = (int)floorf(lo / st - 0.5f);
-                auto ok = [&](int i) { return dm::sub(dm::mul((float)i + 0.5f, st), lo) > 1e-9f; };
-                int e = f - 1 + (ok(f - 1) ? 0 : 1) + (ok(f) ? 0 : 1) + (ok(f + 1) ? 0 : 1) + (ok(f + 2) ? 0 : 1);
-                if (ok(f - 1) || !ok(f + 2)) {  // flip not inside the window
-                    e = f - 1;
-                    while (e > 0 && ok(e - 1)) --e;
-                    while (e < n && !ok(e)) ++e;
-                }
-                return max(e, 0);
-            };
-            auto hi_edge = [&](float hi, int n) {
-                const int f = (int)ceilf(hi / st - 0.5f);
-                auto ok = [&](int i) { return dm::sub(hi, dm::mul((float)i + 0.5f, st)) > 1e-9f; };
-                int e = f + 1 - (ok(f + 1) ? 0 : 1) - (ok(f) ? 0 : 1) - (ok(f - 1) ? 0 : 1) - (ok(f - 2) ? 0 : 1);
-                if (ok(f + 1) || !ok(f - 2)) {
-                    e = f + 1;
-                    while (e < n - 1 && ok(e + 1)) ++e;
-                    while (e >= 0 && !ok(e)) --e;
-                }
-                return min(e, n - 1);
-            };
-            const int cA = lo_edge(g.box.x, w), cB = hi_edge(g.box.z, w);
-            const int rA = lo_edge(g.box.y, h), rB = hi_edge(g.box.w, h);
+            const int w = c.t.w[l];
+            const int cA = __shfl_sync(0xffffffffu, my_edge, 4 * l), cB = __shfl_sync(0xffffffffu, my_edge, 4 * l + 1);
+            const int rA = __shfl_sync(0xffffffffu, my_edge, 4 * l + 2), rB = __shfl_sync(0xffffffffu, my_edge, 4 * l + 3);
             const int ncols = cB >= cA ? cB - cA + 1 : 0, nrows = rB >= rA ? rB - rA + 1 : 0;
             if (lane == 0) {
                 LvlWalk &L = walk[wid][l];

@@ -487,7 +487,9 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         const float alv = lal[e];
         const float pa = __int_as_float(pos_a[gi]), po = __int_as_float(pos_o[gi]);
         const float wgt = dm::div(dm::mul(alv, po), dm::add(pa, c.eps));  // = target_scores.sum(-1), tal.py:89-92
-        F.list_w[z][(long long)b * c.list_cap + e] = wgt;  // kept for the backward pass
+        // kept for the backward pass: the claim word of a foreground anchor becomes (1 << 63 | GT index << 32 | weight)
+        c.claim[(long long)b * A + a] =
+            0x8000000000000000ull | ((unsigned long long)(unsigned)gi << 32) | (unsigned long long)__float_as_uint(wgt);
         const int l = level_of(c.t, a);
         const int cell = a - c.t.start[l];
         const float st = c.t.stride[l];

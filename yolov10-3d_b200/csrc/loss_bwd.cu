@@ -8,13 +8,17 @@
 //   * class rows (dense):  g_cls * gain_cls / tss * (sigmoid(x) - t),  t = alignment weight at the assigned label
 //   * box rows: zero except at foreground anchors, where the CIoU term flows through dist2bbox and the softmax
 //     expectation of the 16 DFL bins, plus the DFL cross-entropy term.
-// Two kernels: a dense streaming pass (reads the class logits, writes every row: 4*nc*A read + 4*(4R+nc)*A written per
-// image and branch) and a sparse pass over the claimed-anchor lists the forward pass left in the workspace.
+// One streaming kernel (reads the class logits, writes every row: 4*nc*A read + 4*(4R+nc)*A written per image and
+// branch).  The forward pass left, in the claim word of every foreground anchor, its GT index and alignment weight
+// (loss.cu, loss_finish_kernel): the thread that owns an anchor's rows looks the word up and patches the few
+// foreground values itself, right after its own full-width stores, so that no second pass has to read-modify-write
+// 4-byte pieces of sectors that have already left the L2.
 #include "loss.cuh"
 
 namespace y3d {
 
 constexpr int kBwdThreads = 128;
+constexpr int kBwdRows = 10;     // class rows in flight per thread (as in the forward streaming kernel)
 
 struct BwdParams {
     LevelTable t[2];                       // head tensors (inputs of the forward pass)
@@ -26,51 +30,13 @@ struct BwdParams {
     int n_branch, B, nc, A, M, cap;
     const float *gt5;                      // [B,M,5]
     const float *boxes[2];                 // forward workspace: [B,4,A] xyxy grid units
-    const int *list_count[2], *list_a[2], *list_gi[2];
-    const float *list_w[2];
+    const unsigned long long *claim[2];    // forward workspace: [B,A]; bit 63 = foreground, GT index << 32 | weight bits
 };
 
 template <int V>
 __device__ __forceinline__ void st_zero(float *p) {
     if constexpr (V == 4) *reinterpret_cast<float4 *>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
     else p[0] = 0.f;
-}
-
-// grid (ceil(A/V/32), B, n_branch), block 128 = 32 units of V anchors x 4 channel parts (same decomposition as the
-// forward streaming kernel)
-template <int V>
-__global__ void __launch_bounds__(kBwdThreads) loss_bwd_dense_kernel(BwdParams P) {
-    const int z = blockIdx.z, b = blockIdx.y;
-    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
-    const int q = blockIdx.x * 32 + lane;
-    if (q * V >= P.A) return;
-    const LevelTable &t = P.t[z];
-    const int a0 = q * V;
-    const int l = level_of(t, a0);
-    const int cell = a0 - t.start[l];
-    const float *x = t.ptr[l] + (long long)b * t.sB[l] + cell;
-    float *g = P.g_ptr[z][l] + (long long)b * P.g_sB[z][l] + cell;
-    const long long cs = t.sC[l], gs = P.g_sC[z][l];
-    const float coef = P.gitems[3 * z + 1] * P.gain_cls / P.items[4 * z + 3];
-#pragma unroll
-    for (int j = 0; j < kR; ++j) st_zero<V>(g + (long long)(part * kR + j) * gs);
-    const int cpp = (P.nc + 3) >> 2;
-    const int c_lo = part * cpp, c_hi = min(P.nc, c_lo + cpp);
-    for (int c = c_lo; c < c_hi; ++c) {
-        const float *px = x + (long long)(4 * kR + c) * cs;
-        float *pg = g + (long long)(4 * kR + c) * gs;
-        if constexpr (V == 4) {
-            const float4 v = ldg_stream4(px);
-            float4 o;
-            o.x = coef * __fdividef(1.0f, 1.0f + __expf(-v.x));
-            o.y = coef * __fdividef(1.0f, 1.0f + __expf(-v.y));
-            o.z = coef * __fdividef(1.0f, 1.0f + __expf(-v.z));
-            o.w = coef * __fdividef(1.0f, 1.0f + __expf(-v.w));
-            *reinterpret_cast<float4 *>(pg) = o;
-        } else {
-            pg[0] = coef * __fdividef(1.0f, 1.0f + __expf(-ldg_stream1(px)));
-        }
-    }
 }
 
 // d CIoU(box1 = pred, box2 = target) / d pred, alpha constant (metrics.py:96-131).  min/max ties split the gradient
@@ -116,20 +82,18 @@ __device__ __forceinline__ void ciou_grad(float4 p, float4 t, float (&d)[4]) {
     }
 }
 
-// grid (ceil(4*cap/128), B, n_branch): thread = (claimed anchor, side)
-__global__ void __launch_bounds__(kBwdThreads) loss_bwd_fg_kernel(BwdParams P) {
-    const int z = blockIdx.z, b = blockIdx.y;
-    const int tix = blockIdx.x * kBwdThreads + threadIdx.x;
-    const int e = tix >> 2, side = tix & 3;
-    const int n = P.M > 0 ? min(P.list_count[z][b], P.cap) : 0;
-    if (e >= n) return;
+// Gradient of the rows of foreground anchor `a` that belong to `side`: the 16 DFL bins of that side and, for side 0,
+// the class row of the assigned label.
+__device__ __noinline__ void bwd_fg_patch(const BwdParams &P, int z, int b, int a, int side, unsigned long long cl) {
     const LevelTable &t = P.t[z];
-    const int A = P.A;
-    const long long le = (long long)b * P.cap + e;
-    const int a = P.list_a[z][le], gi = P.list_gi[z][le];
-    const float wgt = P.list_w[z][le];
     const int l = level_of(t, a);
     const int cell = a - t.start[l];
+    const long long cs = t.sC[l], gs = P.g_sC[z][l];
+    const float *x = t.ptr[l] + (long long)b * t.sB[l] + cell;
+    float *g = P.g_ptr[z][l] + (long long)b * P.g_sB[z][l] + cell;
+    const int A = P.A;
+    const int gi = (int)((cl >> 32) & 0x7fffffffull);
+    const float wgt = __uint_as_float((unsigned)(cl & 0xffffffffull));
     const float st = t.stride[l];
     const float ax = (float)(cell % t.w[l]) + 0.5f, ay = (float)(cell / t.w[l]) + 0.5f;
     const float *g5 = P.gt5 + ((long long)b * P.M + gi) * 5;
@@ -143,12 +107,12 @@ __global__ void __launch_bounds__(kBwdThreads) loss_bwd_fg_kernel(BwdParams P) {
     const float c_cls = P.gitems[3 * z + 1] * P.gain_cls / tss;
     const float c_dfl = P.gitems[3 * z + 2] * P.gain_dfl / tss;
     // this side's 16 bins: softmax, expectation
-    const float *x = t.ptr[l] + (long long)b * t.sB[l] + cell + (long long)(side * kR) * t.sC[l];
+    const float *xs = x + (long long)(side * kR) * cs;
     float v[kR];
     float m = -3.4e38f;
 #pragma unroll
     for (int j = 0; j < kR; ++j) {
-        v[j] = x[(long long)j * t.sC[l]];
+        v[j] = xs[(long long)j * cs];
         m = fmaxf(m, v[j]);
     }
     float s = 0.f, ex = 0.f;
@@ -163,26 +127,110 @@ __global__ void __launch_bounds__(kBwdThreads) loss_bwd_fg_kernel(BwdParams P) {
     // d loss / d dist_side through (1 - CIoU) * w: x1 = ax - d0, y1 = ay - d1, x2 = ax + d2, y2 = ay + d3
     float dc[4];
     ciou_grad(pb, tb, dc);
-    const float gd = -wgt * c_box * dc[side] * (side < 2 ? -1.0f : 1.0f);
+    const float dcs = side == 0 ? dc[0] : side == 1 ? dc[1] : side == 2 ? dc[2] : dc[3];
+    const float gd = -wgt * c_box * dcs * (side < 2 ? -1.0f : 1.0f);
     // DFL target of this side (bbox2dist tal.py:328-331, _df_loss loss.py:99-113)
     const float ltrb = side == 0 ? ax - tb.x : side == 1 ? ay - tb.y : side == 2 ? tb.z - ax : tb.w - ay;
     const float tt = fminf(fmaxf(ltrb, 0.0f), (float)(kR - 1) - 0.01f);
     const int tl = (int)tt;
     const float wl = (float)(tl + 1) - tt, wr = 1.0f - wl;
     const float cd = c_dfl * wgt * 0.25f;
-    float *g = P.g_ptr[z][l] + (long long)b * P.g_sB[z][l] + cell + (long long)(side * kR) * P.g_sC[z][l];
+    float *gp = g + (long long)(side * kR) * gs;
 #pragma unroll
     for (int j = 0; j < kR; ++j) {
         const float p = v[j] * inv;
         float gx = gd * p * ((float)j - ex) + cd * p;
         if (j == tl) gx -= cd * wl;
         if (j == tl + 1) gx -= cd * wr;
-        g[(long long)j * P.g_sC[z][l]] = gx;
+        gp[(long long)j * gs] = gx;
     }
     if (side == 0) {  // BCE target: t = w at the assigned label
-        float *gc = P.g_ptr[z][l] + (long long)b * P.g_sB[z][l] + cell + (long long)(4 * kR + lab) * P.g_sC[z][l];
-        *gc -= c_cls * wgt;
+        const float xv = x[(long long)(4 * kR + lab) * cs];
+        g[(long long)(4 * kR + lab) * gs] = c_cls * __fdividef(1.0f, 1.0f + __expf(-xv)) - c_cls * wgt;
     }
+}
+
+// grid (ceil(A/V/32), B, n_branch), block 128 = 32 units of V anchors x 4 channel parts (same decomposition as the
+// forward streaming kernel): part p writes the 16 DFL rows of side p (zeros) and a quarter of the class rows.  The CTA's
+// foreground anchors are collected in shared memory and patched after a barrier, one (anchor, side) pair per thread, so
+// that the rare path runs on full warps.  (Several tiles per CTA, or persistent CTAs striding over the tiles, measured
+// 10-30 % slower: consecutive CTAs on consecutive 512-byte pieces of each row is what keeps the DRAM pages open.)
+template <int V>
+__global__ void __launch_bounds__(kBwdThreads) loss_bwd_kernel(const __grid_constant__ BwdParams P) {
+    __shared__ int s_n;
+    __shared__ int s_a[32 * V];
+    __shared__ unsigned long long s_cl[32 * V];
+    const int z = blockIdx.z, b = blockIdx.y;
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int q = blockIdx.x * 32 + lane;
+    if (q * V < P.A) {
+        const LevelTable &t = P.t[z];
+        const int a0 = q * V;
+        const int l = level_of(t, a0);
+        const int cell = a0 - t.start[l];
+        const float *x = t.ptr[l] + (long long)b * t.sB[l] + cell;
+        float *g = P.g_ptr[z][l] + (long long)b * P.g_sB[z][l] + cell;
+        const long long cs = t.sC[l], gs = P.g_sC[z][l];
+        const float coef = P.gitems[3 * z + 1] * P.gain_cls / P.items[4 * z + 3];
+        if (part == 0 && P.claim[z]) {
+            const unsigned long long *cp = P.claim[z] + (long long)b * P.A + a0;
+            unsigned long long cl[V];
+            if constexpr (V == 4) {
+                const ulonglong2 c01 = __ldg(reinterpret_cast<const ulonglong2 *>(cp));
+                const ulonglong2 c23 = __ldg(reinterpret_cast<const ulonglong2 *>(cp) + 1);
+                cl[0] = c01.x; cl[1] = c01.y; cl[2] = c23.x; cl[3] = c23.y;
+            } else {
+                cl[0] = __ldg(cp);
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (cl[i] >> 63) {
+                    const int k = atomicAdd(&s_n, 1);
+                    s_a[k] = a0 + i;
+                    s_cl[k] = cl[i];
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < kR; ++j) st_zero<V>(g + (long long)(part * kR + j) * gs);
+        const int cpp = (P.nc + 3) >> 2;
+        const int c_lo = part * cpp, c_hi = min(P.nc, c_lo + cpp);
+        constexpr int CB = kBwdRows;  // class rows in flight per thread
+        for (int c0 = c_lo; c0 < c_hi; c0 += CB) {
+            const float *px = x + (long long)(4 * kR + c0) * cs;
+            float *pg = g + (long long)(4 * kR + c0) * gs;
+            const int n = min(CB, c_hi - c0);
+            if constexpr (V == 4) {
+                float4 v[CB];
+                if (n == CB) {
+#pragma unroll
+                    for (int j = 0; j < CB; ++j) v[j] = ldg_stream4(px + (long long)j * cs);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CB; ++j)
+                        if (j < n) v[j] = ldg_stream4(px + (long long)j * cs);
+                }
+#pragma unroll
+                for (int j = 0; j < CB; ++j) {
+                    if (j < n) {
+                        float4 o;
+                        o.x = coef * __fdividef(1.0f, 1.0f + __expf(-v[j].x));
+                        o.y = coef * __fdividef(1.0f, 1.0f + __expf(-v[j].y));
+                        o.z = coef * __fdividef(1.0f, 1.0f + __expf(-v[j].z));
+                        o.w = coef * __fdividef(1.0f, 1.0f + __expf(-v[j].w));
+                        *reinterpret_cast<float4 *>(pg + (long long)j * gs) = o;
+                    }
+                }
+            } else {
+                for (int j = 0; j < n; ++j)
+                    pg[(long long)j * gs] = coef * __fdividef(1.0f, 1.0f + __expf(-ldg_stream1(px + (long long)j * cs)));
+            }
+        }
+    }
+    __syncthreads();  // orders the patches below after every thread's full-width stores above
+    const int n_items = 4 * s_n;
+    for (int it = threadIdx.x; it < n_items; it += kBwdThreads) bwd_fg_patch(P, z, b, s_a[it >> 2], it & 3, s_cl[it >> 2]);
 }
 
 static bool vec4_ok_bwd(const BwdParams &P, int z) {
@@ -231,10 +279,7 @@ static int loss_bwd_run(int nb, const BranchBwd *br, const int *lvl_hw, const fl
     for (int z = 0; z < nb; ++z) {
         const char *q = p + z * w.per_branch;
         P.boxes[z] = (const float *)(q + w.boxes);
-        P.list_count[z] = (const int *)(q + w.list_count);
-        P.list_a[z] = (const int *)(q + w.list_a);
-        P.list_gi[z] = (const int *)(q + w.list_gi);
-        P.list_w[z] = (const float *)(q + w.list_w);
+        P.claim[z] = M > 0 ? (const unsigned long long *)(q + w.claim) : nullptr;
     }
     P.items = loss_items; P.gitems = grad_items;
     P.gain_box = gain_box; P.gain_cls = gain_cls; P.gain_dfl = gain_dfl;
@@ -243,14 +288,9 @@ static int loss_bwd_run(int nb, const BranchBwd *br, const int *lvl_hw, const fl
     const bool v4 = vec4_ok_bwd(P, 0) && (nb < 2 || vec4_ok_bwd(P, 1));
     const int units = v4 ? A / 4 : A;
     dim3 grid((units + 31) / 32, B, nb);
-    if (v4) loss_bwd_dense_kernel<4><<<grid, kBwdThreads, 0, s>>>(P);
-    else loss_bwd_dense_kernel<1><<<grid, kBwdThreads, 0, s>>>(P);
+    if (v4) loss_bwd_kernel<4><<<grid, kBwdThreads, 0, s>>>(P);
+    else loss_bwd_kernel<1><<<grid, kBwdThreads, 0, s>>>(P);
     Y3D_CHECK_LAUNCH();
-    if (M > 0) {
-        dim3 fgrid((4 * w.cap + kBwdThreads - 1) / kBwdThreads, B, nb);
-        loss_bwd_fg_kernel<<<fgrid, kBwdThreads, 0, s>>>(P);
-        Y3D_CHECK_LAUNCH();
-    }
     return Y3D_OK;
 }
 

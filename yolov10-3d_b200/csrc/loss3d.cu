@@ -14,8 +14,9 @@
 //      keypoints [B,A,24] (the assigner's inputs), zeroed claim words.  pd_scores / pd_3d are never materialised.
 //   2. GT keypoints, per-GT top-k, conflict resolution: the assigner core of assign.cu (scores read as logits from the
 //      head).
-//   3. dd_fg_kernel : the seven foreground sums (L1 terms, Laplacian depth, heading CE + L1, BCE correction, sum of
-//      target scores, foreground count) per CTA; 4. dd_finalize_kernel : fixed-order reduction and the loss items.
+//   3. dd_fg_kernel : the foreground sums (L1 terms, Laplacian depth, heading CE + L1, BCE correction, sum of target
+//      scores, foreground count) per CTA; the last CTA of an image reduces the image's rows, the last image reduces
+//      the images and writes the partials and the loss items (fixed orders: deterministic whichever CTA is last).
 #include "assign.cuh"
 
 namespace y3d {
@@ -31,6 +32,11 @@ struct DDParams {
     float *pd_kps;            // [B,A,24]
     unsigned long long *claim;
     double *part;             // [n_blocks][kNSum + 1]
+    double *part_img;         // [B][kNSum + 1]
+    unsigned *tickets;        // [B + 1], zeroed by the streaming kernel
+    double *partials;         // out: float64[kNSum + 1]
+    float *items;             // out (optional): float[8]
+    float gain[6];
     int B, nc, A, M;
 };
 
@@ -39,6 +45,10 @@ __global__ void __launch_bounds__(128) dd_stream_kernel(DDParams P, int *work_co
     __shared__ double red[4];
     const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0 && work_counter) *work_counter = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.tickets[b] = 0u;
+        if (b == 0) P.tickets[P.B] = 0u;
+    }
     double soft = 0.0;
     if (a < P.A) {
         const LevelTable &t = P.t;
@@ -93,6 +103,25 @@ __global__ void __launch_bounds__(128) dd_stream_kernel(DDParams P, int *work_co
         double *p = P.part + ((long long)b * gridDim.x + blockIdx.x) * (kNSum + 1);
         p[0] = (red[0] + red[1]) + (red[2] + red[3]);
     }
+}
+
+// loss.py:879-888: items = loss2d, cls, depth, offset3d, size3d, heading (+ target_scores_sum, n_fg) from the partials
+__device__ __forceinline__ void dd_items(const double *p, int M, const float *g, float *items) {
+    if (M == 0) {  // no targets: the reference returns its zero-initialised loss (loss.py:873-876)
+        for (int i = 0; i < 8; ++i) items[i] = 0.f;
+        items[6] = 1.f;
+        return;
+    }
+    const double tss = p[9] > 1.0 ? p[9] : 1.0, nfg = p[10];
+    // F.l1_loss(..., reduction="mean") over [n_fg, 2] elements (NaN when nothing is assigned, like the reference)
+    items[0] = (float)((p[2] / (2.0 * nfg) + p[1] / (2.0 * nfg)) / tss * g[0]);
+    items[1] = (float)((p[0] - p[8]) / tss * g[1]);
+    items[2] = (float)(p[3] / tss * g[2]);
+    items[3] = (float)(p[4] / (2.0 * nfg) / tss * g[3]);
+    items[4] = (float)(p[5] / tss * g[4]);
+    items[5] = (float)((p[6] + p[7]) / tss * g[5]);
+    items[6] = (float)tss;
+    items[7] = (float)nfg;
 }
 
 // grid (ceil(A/128), B): the foreground sums of this CTA's anchors into slots 1..kNSum of its partial row
@@ -158,56 +187,46 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
         if (i == 0) p[kNSum] = v;  // n_fg
         else p[i] = v;
     }
+    // ---- last CTA of the image: the image's rows -> part_img[b]; last image: part_img -> partials (+ items)
+    __shared__ unsigned s_ticket;
+    __shared__ double s_fin[kNSum + 1];
+    constexpr int W = kNSum + 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(P.tickets + b, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    for (int col = wid; col < W; col += 4) {  // warp per column, lanes stride the rows, fixed shuffle tree
+        double acc = 0.0;
+        for (int r = lane; r < (int)gridDim.x; r += 32) acc += __ldcg(P.part + ((long long)b * gridDim.x + r) * W + col);
+        acc = warp_sum(acc);
+        if (lane == 0) P.part_img[(long long)b * W + col] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(P.tickets + P.B, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.y - 1) return;
+    __threadfence();
+    for (int col = wid; col < W; col += 4) {
+        double acc = 0.0;
+        for (int r = lane; r < P.B; r += 32) acc += __ldcg(P.part_img + (long long)r * W + col);
+        acc = warp_sum(acc);
+        if (lane == 0) { s_fin[col] = acc; P.partials[col] = acc; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && P.items) dd_items(s_fin, P.M, P.gain, P.items);
 }
 
 // partials float64[kNSum + 1] = soft+, off2d, size2d, depth, off3d, size3d, hd_ce, hd_l1, x*t, sum t, n_fg
-__global__ void __launch_bounds__(1024) dd_reduce_kernel(const double *part, int n_rows, double *partials) {
-    __shared__ double red[kNSum + 1][32];
-    // thread = (row group, column): consecutive threads read consecutive doubles of a row (coalesced); fixed order
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int W = kNSum + 1;
-    const long long total = (long long)n_rows * W;
-    double acc = 0.0;
-    int col = -1;
-    // each thread owns the elements e = tid, tid + 1024 * W', ... of one column: stride a multiple of W keeps the column
-    const int stride = 1024 / W * W;  // 1023 for W = 11
-    if (tid < stride) {
-        col = tid % W;
-        for (long long e = tid; e < total; e += stride) acc += part[e];
-    }
-    // reduce per column in a fixed order: shared memory slots [col][slot], slot = tid / W (< 93 -> folded into 32)
-    for (int c = 0; c < W; ++c) {
-        double v = (col == c) ? acc : 0.0;
-        v = warp_sum(v);
-        if (lane == 0) red[c][wid] = v;
-    }
-    __syncthreads();
-    if (tid < W) {
-        double s = 0.0;
-        for (int w = 0; w < 32; ++w) s += red[tid][w];
-        partials[tid] = s;
-    }
-}
-
 // loss.py:879-888: items = loss2d, cls, depth, offset3d, size3d, heading (+ target_scores_sum, n_fg)
 __global__ void dd_finalize_kernel(const double *p, int M, float g2d, float gcls, float gdep, float go3d, float gs3d,
                                    float ghd, float *items) {
     if (threadIdx.x != 0) return;
-    if (M == 0) {  // no targets: the reference returns its zero-initialised loss (loss.py:873-876)
-        for (int i = 0; i < 8; ++i) items[i] = 0.f;
-        items[6] = 1.f;
-        return;
-    }
-    const double tss = p[9] > 1.0 ? p[9] : 1.0, nfg = p[10];
-    // F.l1_loss(..., reduction="mean") over [n_fg, 2] elements (NaN when nothing is assigned, like the reference)
-    items[0] = (float)((p[2] / (2.0 * nfg) + p[1] / (2.0 * nfg)) / tss * g2d);
-    items[1] = (float)((p[0] - p[8]) / tss * gcls);
-    items[2] = (float)(p[3] / tss * gdep);
-    items[3] = (float)(p[4] / (2.0 * nfg) / tss * go3d);
-    items[4] = (float)(p[5] / tss * gs3d);
-    items[5] = (float)((p[6] + p[7]) / tss * ghd);
-    items[6] = (float)tss;
-    items[7] = (float)nfg;
+    const float g[6] = {g2d, gcls, gdep, go3d, gs3d, ghd};
+    dd_items(p, M, g, items);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(128) dd_bwd_kernel(AssignCtx c, DDBwdParams P)
 }
 
 struct DDWs {
-    size_t assign, boxes, pd_kps, gt_kps, part, total;
+    size_t assign, boxes, pd_kps, gt_kps, part, part_img, tickets, total;
     int n_rows;
 };
 static DDWs dd_ws_layout(int B, int A, int M) {
@@ -314,6 +333,8 @@ static DDWs dd_ws_layout(int B, int A, int M) {
     w.gt_kps = o; o += a256(sizeof(float) * 24 * (size_t)B * (M > 0 ? M : 1));
     w.n_rows = ((A + 127) / 128) * B;
     w.part = o;   o += a256(sizeof(double) * (kNSum + 1) * (size_t)w.n_rows);
+    w.part_img = o; o += a256(sizeof(double) * (kNSum + 1) * (size_t)B);
+    w.tickets = o;  o += a256(sizeof(unsigned) * ((size_t)B + 1));
     w.total = o;
     return w;
 }
@@ -354,6 +375,11 @@ extern "C" int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
     P.pd_kps = (float *)(p + w.pd_kps);
     P.claim = nullptr;  // zeroed by the memset below together with the per-GT maxima
     P.part = (double *)(p + w.part);
+    P.part_img = (double *)(p + w.part_img);
+    P.tickets = (unsigned *)(p + w.tickets);
+    P.partials = partials;
+    P.items = normalise ? loss_items : nullptr;
+    for (int i = 0; i < 6; ++i) P.gain[i] = gains[i];
     P.B = B; P.nc = nc; P.A = A; P.M = M;
     dim3 grid((A + 127) / 128, B);
     cudaError_t e = cudaMemsetAsync(p + w.assign + aw.off_cnt, 0, aw.zero_bytes, s);
@@ -382,13 +408,6 @@ extern "C" int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
     }
     dd_fg_kernel<<<grid, 128, 0, s>>>(c, P);
     Y3D_CHECK_LAUNCH();
-    dd_reduce_kernel<<<1, 1024, 0, s>>>(P.part, w.n_rows, partials);
-    Y3D_CHECK_LAUNCH();
-    if (normalise) {
-        dd_finalize_kernel<<<1, 32, 0, s>>>(partials, M, gains[0], gains[1], gains[2], gains[3], gains[4], gains[5],
-                                            loss_items);
-        Y3D_CHECK_LAUNCH();
-    }
     if (dbg_target_gt_idx) {  // assigned GT per anchor, -1 = background
         if (M == 0) e = cudaMemsetAsync(dbg_target_gt_idx, 0xff, sizeof(int32_t) * (size_t)B * A, s);
         else e = cudaMemcpyAsync(dbg_target_gt_idx, c.tgi, sizeof(int32_t) * (size_t)B * A, cudaMemcpyDeviceToDevice, s);

@@ -447,37 +447,53 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
         for (int m = threadIdx.x; m < c.M; m += blockDim.x) gts[m] = load_gt(c, b, m);
         __syncthreads();
     }
+    // multiply-claimed anchors (select_highest_overlaps tal.py:252-263: argmax over all GTs of the overlap, first
+    // maximum): the warp takes them one at a time, lanes over the GTs; only the overlap itself is evaluated (the CIoU
+    // for the 2D assigner, the keypoint similarity when use_3d)
+    int gi = cnt == 1 ? (int)(cl & 0xffffffffull) : -1;
+    {
+        const int lane = threadIdx.x & 31;
+        const int kflags = c.kps_l2 ? 4 : 0;
+        unsigned cm = __ballot_sync(0xffffffffu, cnt > 1);
+        while (cm) {
+            const int src = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int a_s = __shfl_sync(0xffffffffu, a, src);
+            float ax, ay, st;
+            anchor_px(c, a_s, ax, ay, st);
+            float4 pbox = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 *pk = nullptr;
+            if (c.use_3d) pk = reinterpret_cast<const float4 *>(c.pd_kps + ((long long)b * c.A + a_s) * 24);
+            else pbox = pair_box(c, pair_load_box(c, b, a_s), a_s);
+            unsigned long long best = 0xffffffffull;  // overlap 0 at GT 0: what the reference's argmax of zeros gives
+            for (int m = lane; m < c.M; m += 32) {
+                const GtRec g = gts[m];
+                if (g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box))) {
+                    float ovl;
+                    if (c.use_3d) {
+                        ovl = kps_sim(pk, reinterpret_cast<const float4 *>(c.gt_kps + ((long long)b * c.M + m) * 24), kflags);
+                    } else {
+                        ovl = dm::ciou(g.box, pbox, g.at1);
+                        ovl = ovl < 0.0f ? 0.0f : ovl;
+                    }
+                    const unsigned long long key =
+                        ((unsigned long long)__float_as_uint(ovl) << 32) | (unsigned long long)(0xffffffffu - (unsigned)m);
+                    best = key > best ? key : best;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, best, off);
+                best = o2 > best ? o2 : best;
+            }
+            if (lane == src) gi = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+        }
+    }
     if (a >= c.A) return;
-    int gi = -1;
     float alignv = 0.0f;
     if (cnt > 0) {
         float ax, ay, st;
         anchor_px(c, a, ax, ay, st);
-        if (cnt == 1) {
-            gi = (int)(cl & 0xffffffffull);
-        } else {  // select_highest_overlaps tal.py:252-263: argmax over all GTs, first maximum
-            float bv = -1.0f;
-            if (!c.use_3d) {  // the overlap is the CIoU alone: one box load, then pure arithmetic over the GTs
-                const float4 pbox = pair_box(c, pair_load_box(c, b, a), a);
-                for (int m = 0; m < c.M; ++m) {
-                    const GtRec g = gts[m];
-                    float ovl = 0.0f;
-                    if (g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box))) {
-                        ovl = dm::ciou(g.box, pbox, g.at1);
-                        ovl = ovl < 0.0f ? 0.0f : ovl;
-                    }
-                    if (ovl > bv) { bv = ovl; gi = m; }
-                }
-            } else {
-                for (int m = 0; m < c.M; ++m) {
-                    const GtRec g = gts[m];
-                    float metric = 0.0f, ovl = 0.0f;
-                    bool sel = g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box));
-                    if (sel) pair_eval(c, b, m, g, a, metric, ovl);
-                    if (ovl > bv) { bv = ovl; gi = m; }
-                }
-            }
-        }
         const GtRec g = cnt > 1 ? gts[gi] : load_gt(c, b, gi);
         float metric = 0.0f, ovl = 0.0f;
         bool sel = g.valid && (!c.constrain || dm::in_gt(ax, ay, g.box));

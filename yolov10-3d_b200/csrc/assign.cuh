@@ -150,6 +150,26 @@ __device__ __forceinline__ float4 pair_box(const AssignCtx &c, const PairRaw &r,
     return p;
 }
 
+// keypoint similarity of one (prediction, GT) pair: keypoint_distance_3d tal.py:464-470, 1 / exp(mean distance)
+// (flags bit2: squared distances, halved).  pk: the anchor's 24 keypoint coordinates, gk: the GT's.
+__device__ __forceinline__ float kps_sim(const float4 *pk, const float4 *gk, int flags) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        float4 p = pk[j], q = __ldg(gk + j);
+        float d0 = dm::sub(p.x, q.x), d1 = dm::sub(p.y, q.y), d2 = dm::sub(p.z, q.z), d3 = dm::sub(p.w, q.w);
+        if (flags & 4) {
+            acc = dm::add(acc, dm::mul(d0, d0)); acc = dm::add(acc, dm::mul(d1, d1));
+            acc = dm::add(acc, dm::mul(d2, d2)); acc = dm::add(acc, dm::mul(d3, d3));
+        } else {
+            acc = dm::add(acc, fabsf(d0)); acc = dm::add(acc, fabsf(d1));
+            acc = dm::add(acc, fabsf(d2)); acc = dm::add(acc, fabsf(d3));
+        }
+    }
+    const float dist = dm::div(acc, 24.0f);
+    return dm::div(1.0f, dm::exp_((flags & 4) ? dm::mul(0.5f, dist) : dist));
+}
+
 // get_box_metrics (tal.py:108-127) / get_box_kp_metrics / get_keypoint_metrics (tal.py:553-603) for one in-mask pair,
 // given sb = score^alpha.  ovl is what the reference calls `overlaps` downstream: CIoU for the 2D assigner, the 3D
 // similarity when use_3d.
@@ -167,22 +187,8 @@ static __device__ __noinline__ float pair_metric_core(float4 gbox, float gat1, f
         metric = dm::mul(metric, dm::pow_(o, beta));
         ovl = o;
     }
-    if (flags & 2) {  // keypoint_distance_3d tal.py:464-470
-        float acc = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            float4 p = pk[j], q = __ldg(gk + j);
-            float d0 = dm::sub(p.x, q.x), d1 = dm::sub(p.y, q.y), d2 = dm::sub(p.z, q.z), d3 = dm::sub(p.w, q.w);
-            if (flags & 4) {
-                acc = dm::add(acc, dm::mul(d0, d0)); acc = dm::add(acc, dm::mul(d1, d1));
-                acc = dm::add(acc, dm::mul(d2, d2)); acc = dm::add(acc, dm::mul(d3, d3));
-            } else {
-                acc = dm::add(acc, fabsf(d0)); acc = dm::add(acc, fabsf(d1));
-                acc = dm::add(acc, fabsf(d2)); acc = dm::add(acc, fabsf(d3));
-            }
-        }
-        float dist = dm::div(acc, 24.0f);
-        float sim = dm::div(1.0f, dm::exp_((flags & 4) ? dm::mul(0.5f, dist) : dist));
+    if (flags & 2) {
+        const float sim = kps_sim(pk, gk, flags);
         metric = dm::mul(metric, dm::pow_(sim, gamma));
         ovl = sim;  // tal.py:602-603
     }

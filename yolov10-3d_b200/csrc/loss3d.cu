@@ -124,16 +124,26 @@ __device__ __forceinline__ void dd_items(const double *p, int M, const float *g,
     items[7] = (float)nfg;
 }
 
-// grid (ceil(A/128), B): the foreground sums of this CTA's anchors into slots 1..kNSum of its partial row
-__global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
+// grid (ceil(ceil(A/128) / kFgRows), B): a CTA covers the anchors of kFgRows CTAs of the streaming kernel and puts
+// their foreground sums into slots 1..kNSum of the first of those partial rows (n_rows = the streaming kernel's grid.x)
+constexpr int kFgRows = 1;  // (4 measured slower: the few foreground anchors of a thread then run back to back, and the kernel is one latency chain)
+__global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P, int n_rows) {
     __shared__ double red[kNSum][4];
-    const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
     double s[kNSum];
 #pragma unroll
     for (int i = 0; i < kNSum; ++i) s[i] = 0.0;
-    if (a < P.A && P.M > 0) {
+    int gis[kFgRows];
+#pragma unroll
+    for (int i = 0; i < kFgRows; ++i) {
+        const int a = (blockIdx.x * kFgRows + i) * 128 + threadIdx.x;
+        gis[i] = (a < P.A && P.M > 0) ? c.tgi[(long long)b * P.A + a] : -1;
+    }
+#pragma unroll 1
+    for (int i = 0; i < kFgRows; ++i) {
+        const int a = (blockIdx.x * kFgRows + i) * 128 + threadIdx.x;
         const long long o = (long long)b * P.A + a;
-        const int gi = c.tgi[o];
+        const int gi = gis[i];
         if (gi >= 0) {
             const LevelTable &t = P.t;
             const int l = level_of(t, a);
@@ -149,13 +159,13 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
             int lab = (int)g[0];
             lab = lab < 0 ? 0 : lab;
             // compute_box2d_loss loss.py:913-926 (px): offset vs (center_2d - anchor), size vs size_2d
-            s[1] = (double)fabsf(r[0] * st - (g[5] - ax)) + (double)fabsf(r[cs] * st - (g[6] - ay));
-            s[2] = (double)fabsf(r[2 * cs] * st - g[7]) + (double)fabsf(r[3 * cs] * st - g[8]);
+            s[1] += (double)fabsf(r[0] * st - (g[5] - ax)) + (double)fabsf(r[cs] * st - (g[6] - ay));
+            s[2] += (double)fabsf(r[2 * cs] * st - g[7]) + (double)fabsf(r[3 * cs] * st - g[8]);
             // compute_box3d_loss loss.py:928-963
             const float dep = r[33 * cs], un = r[34 * cs];
-            s[3] = (double)(1.4142f * expf(-0.5f * un) * fabsf(dep - g[14]) + 0.5f * un);  // loss.py:1118
-            s[4] = (double)fabsf(r[4 * cs] * st - (g[9] - ax)) + (double)fabsf(r[5 * cs] * st - (g[10] - ay));
-            s[5] = (double)fabsf(r[6 * cs] - g[11]) + (double)fabsf(r[7 * cs] - g[12]) + (double)fabsf(r[8 * cs] - g[13]);
+            s[3] += (double)(1.4142f * expf(-0.5f * un) * fabsf(dep - g[14]) + 0.5f * un);  // loss.py:1118
+            s[4] += (double)fabsf(r[4 * cs] * st - (g[9] - ax)) + (double)fabsf(r[5 * cs] * st - (g[10] - ay));
+            s[5] += (double)fabsf(r[6 * cs] - g[11]) + (double)fabsf(r[7 * cs] - g[12]) + (double)fabsf(r[8 * cs] - g[13]);
             // compute_heading_loss loss.py:1122-1136: CE over the 12 bins + L1 of the residual of the target bin
             const int tb = (int)g[15];
             float m = -3.4e38f, hv[12];
@@ -167,21 +177,26 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
             float se = 0.f;
 #pragma unroll
             for (int j = 0; j < 12; ++j) se += expf(hv[j] - m);
-            s[6] = (double)(m + logf(se) - r[(9 + tb) * cs]);
-            s[7] = (double)fabsf(r[(9 + 12 + tb) * cs] - g[16]);
-            s[8] = (double)x[(long long)lab * cs] * (double)norm;  // BCE(x,t) - BCE(x,0) = -x*t
-            s[9] = (double)norm;
-            s[0] = 1.0;  // foreground count
+            s[6] += (double)(m + logf(se) - r[(9 + tb) * cs]);
+            s[7] += (double)fabsf(r[(9 + 12 + tb) * cs] - g[16]);
+            s[8] += (double)x[(long long)lab * cs] * (double)norm;  // BCE(x,t) - BCE(x,0) = -x*t
+            s[9] += (double)norm;
+            s[0] += 1.0;  // foreground count
         }
     }
+    if (__syncthreads_or(s[0] != 0.0)) {
 #pragma unroll
-    for (int i = 0; i < kNSum; ++i) {
-        const double v = warp_sum(s[i]);
-        if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v;
+        for (int i = 0; i < kNSum; ++i) {
+            const double v = warp_sum(s[i]);
+            if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v;
+        }
+        __syncthreads();
+    } else if (threadIdx.x < 4 * kNSum) {  // most CTAs hold no foreground anchor: their row is zero
+        red[threadIdx.x >> 2][threadIdx.x & 3] = 0.0;
     }
     __syncthreads();
     if (threadIdx.x < kNSum) {
-        double *p = P.part + ((long long)b * gridDim.x + blockIdx.x) * (kNSum + 1);
+        double *p = P.part + ((long long)b * n_rows + blockIdx.x * kFgRows) * (kNSum + 1);
         const int i = threadIdx.x;
         const double v = (red[i][0] + red[i][1]) + (red[i][2] + red[i][3]);
         if (i == 0) p[kNSum] = v;  // n_fg
@@ -198,11 +213,21 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
-    for (int col = wid; col < W; col += 4) {  // warp per column, lanes stride the rows, fixed shuffle tree
-        double acc = 0.0;
-        for (int r = lane; r < (int)gridDim.x; r += 32) acc += __ldcg(P.part + ((long long)b * gridDim.x + r) * W + col);
-        acc = warp_sum(acc);
-        if (lane == 0) P.part_img[(long long)b * W + col] = acc;
+    {  // warp w takes columns w, w + 4, w + 8; lanes stride the rows; fixed shuffle tree
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int r = lane; r < n_rows; r += 32) {  // column 0 (soft+) lives in every row, the others in every kFgRows-th
+            const double *row = P.part + ((long long)b * n_rows + r) * W;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int col = wid + 4 * j;
+                if (col < W && (col == 0 || r % kFgRows == 0)) acc[j] += __ldcg(row + col);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double v = warp_sum(acc[j]);
+            if (lane == 0 && wid + 4 * j < W) P.part_img[(long long)b * W + wid + 4 * j] = v;
+        }
     }
     __threadfence();
     __syncthreads();
@@ -210,11 +235,19 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P) {
     __syncthreads();
     if (s_ticket != gridDim.y - 1) return;
     __threadfence();
-    for (int col = wid; col < W; col += 4) {
-        double acc = 0.0;
-        for (int r = lane; r < P.B; r += 32) acc += __ldcg(P.part_img + (long long)r * W + col);
-        acc = warp_sum(acc);
-        if (lane == 0) { s_fin[col] = acc; P.partials[col] = acc; }
+    {
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int r = lane; r < P.B; r += 32) {
+            const double *row = P.part_img + (long long)r * W;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (wid + 4 * j < W) acc[j] += __ldcg(row + wid + 4 * j);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double v = warp_sum(acc[j]);
+            if (lane == 0 && wid + 4 * j < W) { s_fin[wid + 4 * j] = v; P.partials[wid + 4 * j] = v; }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0 && P.items) dd_items(s_fin, P.M, P.gain, P.items);
@@ -406,7 +439,7 @@ extern "C" int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_s
         rc = assign_run_core(cc, 1, s);
         if (rc) return rc;
     }
-    dd_fg_kernel<<<grid, 128, 0, s>>>(c, P);
+    dd_fg_kernel<<<dim3((grid.x + kFgRows - 1) / kFgRows, B), 128, 0, s>>>(c, P, (int)grid.x);
     Y3D_CHECK_LAUNCH();
     if (dbg_target_gt_idx) {  // assigned GT per anchor, -1 = background
         if (M == 0) e = cudaMemsetAsync(dbg_target_gt_idx, 0xff, sizeof(int32_t) * (size_t)B * A, s);

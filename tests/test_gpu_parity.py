@@ -416,6 +416,15 @@ def test_v10_loss_full_size_properties(y3d, cfg):
         # largest overlap even if that GT never selected it, tal.py:252-263 -- but never more than k per GT in total)
         n_valid = int((gt[..., 1:5].sum(-1) > 0).sum())
         assert 0 < fg[z].sum() <= n_valid * k
+    # the full batch runs the top-k kernel with persistent warps pulling GTs from a queue (cfg2: in longest-first order
+    # from the size-class lists the streaming kernel builds); a few images at a time run it with one CTA per GT.  Both
+    # must assign identically, bit for bit
+    cs = max(1, (16 * 148 - 1) // (2 * M))
+    for lo in (0, cs, B // 2, B - cs):
+        _, _, d_ = lossmod.v10_loss_forward([f[lo:lo + cs] for f in fm], [f[lo:lo + cs] for f in fo], st, nc,
+                                            gtd[lo:lo + cs], gains, debug=True)
+        assert torch.equal(d_["fg_mask"], dbg["fg_mask"][:, lo:lo + cs])
+        assert torch.equal(d_["target_gt_idx"], dbg["target_gt_idx"][:, lo:lo + cs])
     # the oracle on the first two images
     o = oracle.v10_loss(xm[:2], xo[:2], lv, synth.STRIDES, nc, gt[:2], gains=gains)[1]
     it2, _, _ = lossmod.v10_loss_forward([f[:2] for f in fm], [f[:2] for f in fo], st, nc, gtd[:2], gains)

@@ -83,6 +83,18 @@ extern "C" int y3d_debug_read_topk_prof(unsigned long long *host, int reset) {
 #define TK_ACC(i)
 #define TK_CNT(i, v)
 #endif
+#ifdef Y3D_TAILTIME
+// developer instrumentation (tools/tail_timing.py): start / exit time and item counts of every persistent warp
+__device__ unsigned long long g_topk_tail[4096 * 4];
+__device__ __forceinline__ unsigned long long tk_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+extern "C" int y3d_debug_read_topk_tail(unsigned long long *host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_topk_tail, sizeof(unsigned long long) * n);
+}
+#endif
 
 struct LvlWalk {  // one level's exact in-GT rectangle (per warp, shared memory)
     int off, ncols, c0, r0;        // first flat index, columns, first column / row
@@ -110,6 +122,44 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     // GTs cost one load, big GTs do not stall a whole wave).  Several warps per GT: one item per CTA, static.
     bool static_done = false;
     TK_T0();
+#ifdef Y3D_TAILTIME
+    const unsigned long long tail_t0 = tk_now();
+    unsigned tail_items = 0, tail_valid = 0;
+#endif
+    // Longest-first order (fused loss): the streaming kernel has sorted every image's valid GTs into size classes.
+    // Segment s = (class, branch, image) holds ord_cnt[image][class] items; s_pref = exclusive prefix over the segments.
+    // (Handing the very biggest GTs to whole CTAs, merged as in the static mode, was measured too: the four warps of
+    // such an item cost more warp-time than the shorter tail gives back.)
+    __shared__ int s_pref[kOrdMaxSeg + 1];
+    const bool ordered = wpg == 1 && cc.ord_cnt != nullptr;
+    const int n_img = cc.c[0].B;
+    const int n_seg = kOrdClasses * n_branch * n_img;
+    if (ordered) {
+        for (int s = threadIdx.x; s < n_seg; s += blockDim.x)
+            s_pref[s] = __ldg(cc.ord_cnt + (s % n_img) * 4 + s / (n_branch * n_img));
+        __syncthreads();
+        if (wid == 0) {  // in-place exclusive scan: lane-contiguous chunks, warp scan of the chunk sums
+            const int chunk = (n_seg + 31) / 32;
+            const int lo = min(lane * chunk, n_seg), hi = min(lo + chunk, n_seg);
+            int sum = 0;
+            for (int s = lo; s < hi; ++s) sum += s_pref[s];
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            int run = inc - sum;
+            for (int s = lo; s < hi; ++s) {
+                const int v = s_pref[s];
+                s_pref[s] = run;
+                run += v;
+            }
+            if (lane == 31) s_pref[n_seg] = inc;
+        }
+        __syncthreads();
+    }
+    const int seg_stride = (n_seg + 32) / 32;  // 32 * seg_stride >= n_seg + 1; <= 64
     for (int item = (int)blockIdx.x;;) {
     if (wpg == 1) {
         int it = 0;
@@ -119,17 +169,58 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         if (static_done) break;  // static mapping: a single pass
         static_done = true;
     }
-    if (item >= total) break;
-    const int z = item >= per_branch ? 1 : 0;
-    const int gt_id = item - z * per_branch;
+    int z, b, m;
+    GtRec og;
+    if (ordered) {
+        if (item >= s_pref[n_seg]) break;
+        // last segment whose prefix is <= item: a 32-way step, then up to 64 entries
+        const int i1 = min(lane * seg_stride, n_seg);
+        const unsigned m1 = __ballot_sync(0xffffffffu, s_pref[i1] <= item);
+        const int base = (31 - __clz(m1)) * seg_stride;
+        const int i2 = base + lane;
+        const unsigned m2 = __ballot_sync(0xffffffffu, lane < seg_stride && i2 < n_seg && s_pref[i2] <= item);
+        const unsigned m3 = __ballot_sync(0xffffffffu, lane + 32 < seg_stride && i2 + 32 < n_seg && s_pref[min(i2 + 32, n_seg)] <= item);
+        const int seg = base + (m3 ? 63 - __clz(m3) : 31 - __clz(m2));
+        const int cls = seg / (n_branch * n_img);
+        z = (seg / n_img) % n_branch;
+        b = seg % n_img;
+        int off = item - s_pref[seg];  // position in the image's class-sorted list
+        for (int c2 = 0; c2 < cls; ++c2) {
+            const int s2 = (c2 * n_branch + z) * n_img + b;
+            off += s_pref[s2 + 1] - s_pref[s2];
+        }
+        // the sorted list carries the GT record itself (index, label, box): one load, no second round trip
+        const int4 *rec = reinterpret_cast<const int4 *>(cc.ord_list) + ((long long)b * cc.c[0].M + off) * 2;
+        const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+        m = r0.x;
+        og.label = r0.y;
+        og.box = make_float4(__int_as_float(r0.z), __int_as_float(r0.w), __int_as_float(r1.x), __int_as_float(r1.y));
+    } else {
+        if (item >= total) break;
+        z = item >= per_branch ? 1 : 0;
+        const int gt_id = item - z * per_branch;
+        b = gt_id / cc.c[0].M;
+        m = gt_id - b * cc.c[0].M;
+    }
+#ifdef Y3D_TAILTIME
+    ++tail_items;
+#endif
     const AssignCtx &c = cc.c[z];
-    const int b = gt_id / c.M, m = gt_id - b * c.M;
-    if (!gt_valid(c, b, m)) {  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104)
+    if (!ordered && !gt_valid(c, b, m)) {  // padded GT: top-k indices forced to 0 and masked out (tal.py:155,104)
         if (wpg == 1) continue;
         break;
     }
     TK_ACC(0);  // item fetch + validity (incl. padded GTs)
-    const GtRec g = load_gt(c, b, m);
+#ifdef Y3D_TAILTIME
+    ++tail_valid;
+#endif
+    if (ordered) {
+        og.valid = true;
+        og.at1 = dm::box1_atan(og.box);
+    } else {
+        og = load_gt(c, b, m);
+    }
+    const GtRec g = og;
     const int k = c.k;
     const bool rect = c.use_grid && c.constrain;
     const bool prune = c.beta >= 0.0f && c.gamma >= 0.0f;  // the upper bounds need non-negative exponents
@@ -383,7 +474,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     if (wpg > 1) {  // merge the per-warp lists into the first warp's
         mrg[wid][lane] = lane < k ? tk : 0ull;
         __syncthreads();
-        if (wid != 0) return;
+        if (wid != 0) break;
         for (int w2 = 1; w2 < wpg; ++w2) {
             unsigned long long km = mrg[w2][lane];
             for (;;) {
@@ -430,6 +521,12 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     __syncwarp();
     TK_ACC(6);  // claims + prefetch
     }  // item loop
+#ifdef Y3D_TAILTIME
+    if (lane == 0 && blockIdx.x * kTopkWarps + wid < 4096) {
+        unsigned long long *o = g_topk_tail + (blockIdx.x * kTopkWarps + wid) * 4;
+        o[0] = tail_t0; o[1] = tk_now(); o[2] = tail_items; o[3] = tail_valid;
+    }
+#endif
 }
 
 // grid (ceil(A/256), B, n_branch); dynamic smem: M GtRec

@@ -261,7 +261,13 @@ __device__ __forceinline__ void keypoints24(float c3x, float c3y, float dep, flo
 struct AssignCtx2 {
     AssignCtx c[2];
     int *work_counter;  // zero-initialised: dynamic (branch, image, GT) work distribution of tal_topk_kernel
+    // optional (fused loss): the valid GTs of every image sorted into kOrdClasses size classes, biggest first --
+    // ord_cnt [B][4] = GTs per class, ord_list [B][M] = 32-byte records (GT index, label, box).  The dynamic distribution then hands out the
+    // expensive GTs first (longest processing time first) and never sees a padded row.
+    const int *ord_cnt, *ord_list;
 };
+constexpr int kOrdClasses = 4;
+constexpr int kOrdMaxSeg = 2047;  // segments = classes x branches x images the top-k kernel's prefix table holds
 
 // host helpers --------------------------------------------------------------------------------------------------
 struct AssignWs {

@@ -72,12 +72,48 @@ struct StreamParams {
     int *list_count[2];    // optional [B], zeroed here
     unsigned *counter;     // optional ticket of the finishing kernel (+1: work counter of the top-k kernel), zeroed here
     double *part_bce;      // [n_branch][gridDim.x * B] or nullptr
+    const float *gt5;      // optional [B,M,5] (with ord_cnt / ord_list)
+    int *ord_cnt, *ord_list;  // optional [B][4], [B][M] x 32-byte records: see AssignCtx2
+    float ord_cells_per_px2;  // sum over the levels of 1 / stride^2: candidate cells of a GT per px^2 of its area
+    int M;
     int n_branch, B, nc, A, box_aos;
 };
 
+// One warp sorts the valid GTs of image b into kOrdClasses classes by their number of candidate cells (stable within a
+// class, so the result does not depend on timing).  Out of line: the streaming kernel's register budget is not touched.
+static __device__ __noinline__ void gt_order_image(const float *gt5, int M, int b, float cells_per_px2, int *ord_cnt,
+                                                   int *ord_list, int lane) {
+    const float *g = gt5 + (long long)b * M * 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int base = 0;
+    for (int c = 0; c < kOrdClasses; ++c) {
+        int cnt = 0;
+        for (int m0 = 0; m0 < M; m0 += 32) {
+            const int m = m0 + lane;
+            int cls = -1;
+            if (m < M) {
+                const float x1 = g[m * 5 + 1], y1 = g[m * 5 + 2], x2 = g[m * 5 + 3], y2 = g[m * 5 + 4];
+                if (dm::add(dm::add(dm::add(x1, y1), x2), y2) > 0.0f) {  // gt_valid (assign.cuh)
+                    const float cells = (x2 - x1) * (y2 - y1) * cells_per_px2;
+                    cls = cells >= 650.0f ? 0 : cells >= 450.0f ? 1 : cells >= 180.0f ? 2 : 3;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, cls == c);
+            if (cls == c) {  // the record the top-k kernel loads: GT index, label, box (32 bytes)
+                int4 *rec = reinterpret_cast<int4 *>(ord_list) + ((long long)b * M + base + cnt + __popc(bal & lt_mask)) * 2;
+                rec[0] = make_int4(m, (int)g[m * 5], __float_as_int(g[m * 5 + 1]), __float_as_int(g[m * 5 + 2]));
+                rec[1] = make_int4(__float_as_int(g[m * 5 + 3]), __float_as_int(g[m * 5 + 4]), 0, 0);
+            }
+            cnt += __popc(bal);
+        }
+        if (lane == 0) ord_cnt[b * 4 + c] = cnt;
+        base += cnt;
+    }
+}
+
 // grid (ceil(A/V/32), B, n_branch), block 128 = 32 units of V anchors x 4 channel parts (warp = part)
 template <int V, bool PS>
-__global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamParams P) {
+__global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __grid_constant__ StreamParams P) {
     __shared__ double red[4];
     const int z = blockIdx.z, b = blockIdx.y;
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
@@ -191,6 +227,9 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(StreamPa
         if (threadIdx.x == 0)
             P.part_bce[((long long)z * gridDim.y + b) * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
     }
+    // one warp per image: the processing order of the image's GTs for the top-k kernel
+    if (P.ord_cnt && blockIdx.x == 0 && z == 0 && part == 0)
+        gt_order_image(P.gt5, P.M, b, P.ord_cells_per_px2, P.ord_cnt, P.ord_list, lane);
 }
 
 // ---------------------------------------------------------------------------------------------- finishing kernel
@@ -708,6 +747,18 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         F.list_w[z] = (float *)(q + w.list_w);
         F.dbg_fg[z] = dbg_fg_mask ? dbg_fg_mask + (size_t)z * B * A : nullptr;
         F.dbg_gi[z] = dbg_target_gt_idx ? dbg_target_gt_idx + (size_t)z * B * A : nullptr;
+    }
+    // Longest-first work order for the top-k kernel: pays when a persistent warp gets only a few GTs (cfg2: 1.7 valid
+    // GTs per warp -- the kernel's tail was one or two big GTs picked up late); with dozens of GTs per warp (crowds) the
+    // dynamic distribution balances by itself and the per-item table lookup would only cost (measured: +6 % at cfg5).
+    if (M > 0 && kOrdClasses * nb * B <= kOrdMaxSeg && (long long)nb * B * M <= 8LL * 6 * kTopkWarps * kNumSMs) {
+        P.gt5 = gt; P.M = M;
+        P.ord_cnt = (int *)(p + w.off_ord_cnt);
+        P.ord_list = (int *)(p + w.off_ord_list);
+        P.ord_cells_per_px2 = 0.0f;
+        for (int l = 0; l < nl; ++l) P.ord_cells_per_px2 += 1.0f / (lvl_stride[l] * lvl_stride[l]);
+        cc.ord_cnt = P.ord_cnt;
+        cc.ord_list = P.ord_list;
     }
     int n_bce = 0;
     int rc = launch_stream(P, &n_bce, s);

@@ -1,6 +1,6 @@
 // loss.cuh -- declarations shared by loss.cu (fused forward) and loss_bwd.cu (backward): constants and the
 // workspace layout.  The backward pass reads what the forward pass left in the caller-owned workspace (claimed-anchor
-// lists with their assigned GT and alignment weight), so both sides must agree on the layout.
+// lists, and the claim words carrying the assigned GT and alignment weight), so both sides must agree on the layout.
 #pragma once
 #include "assign.cuh"
 
@@ -10,7 +10,7 @@ constexpr int kR = 16;  // reg_max (head.py:37)
 
 struct LossWs {  // all offsets 256-byte aligned; per-branch blocks are contiguous
     size_t claim, boxes, lse, list_a, list_gi, list_al, list_w, list_count, per_branch;
-    size_t off_counter, off_pfg, off_pbce, total;
+    size_t off_counter, off_pfg, off_pbce, off_ord_cnt, off_ord_list, total;
     int cap, n_bce;
 };
 inline int stream_blocks_x(int A) { return (A + 31) / 32; }  // upper bound (the scalar path)
@@ -32,7 +32,9 @@ inline LossWs loss_ws_layout(int nb, int B, int A, int M, int k) {
     w.off_pfg = w.off_counter + 256;
     w.off_pbce = w.off_pfg + a256(sizeof(double) * 5 * (size_t)nb * B);
     w.n_bce = stream_blocks_x(A) * B;
-    w.total = w.off_pbce + a256(sizeof(double) * (size_t)nb * w.n_bce);
+    w.off_ord_cnt = w.off_pbce + a256(sizeof(double) * (size_t)nb * w.n_bce);  // [B][4]: valid GTs per size class
+    w.off_ord_list = w.off_ord_cnt + a256(sizeof(int) * 4 * (size_t)B);  // [B][M] x 32 B: GT records, big first
+    w.total = w.off_ord_list + a256(32 * (size_t)B * (M > 0 ? M : 1));
     return w;
 }
 

@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     __shared__ LvlWalk walk[kTopkWarps][Y3D_MAX_LEVELS];
     __shared__ unsigned long long mrg[kTopkWarps][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // let a programmatically dependent kernel (the fused loss' finishing kernel) be scheduled as this grid drains; it
-    // waits for this grid's completion itself before touching anything written here
+    // programmatic dependent launch, both ways: in the fused loss this grid is scheduled while the streaming kernel
+    // drains and must wait for its completion before reading anything (a no-op after an ordinary launch); then it lets
+    // its own dependent (the finishing kernel) be scheduled as this grid drains -- that one waits for this grid itself
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
     const int per_branch = cc.c[0].B * cc.c[0].M;  // host checks n_branch * B * M < 2^31
     const int total = per_branch * n_branch;
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
     c.alignv[o] = alignv;
 }
 
-int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s) {
+int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl) {
     const AssignCtx &c = cc.c[0];
     const long long items = (long long)c.B * c.M * n;
     // one persistent warp per GT fills the machine only when there are many GTs; with few (e.g. KITTI: 32 x 50) the
@@ -618,7 +620,21 @@ int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (blocks > 6LL * sms) blocks = 6LL * sms;
     }
-    tal_topk_kernel<<<(unsigned)blocks, kTopkWarps * 32, 0, s>>>(cc, wpg, n);
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)blocks);
+        cfg.blockDim = dim3(kTopkWarps * 32);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, tal_topk_kernel, cc, wpg, n);
+        if (le != cudaSuccess) return (int)le;
+    } else {
+        tal_topk_kernel<<<(unsigned)blocks, kTopkWarps * 32, 0, s>>>(cc, wpg, n);
+    }
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }

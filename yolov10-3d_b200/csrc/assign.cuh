@@ -305,6 +305,6 @@ int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t aft
 int launch_kps_gt(const float *gts, const float *calibs, const float *mean_sizes, int B, int M, int nc, float *gt_kps,
                   cudaStream_t s);
 // top-k + claims only (the fused loss path finishes with its own kernel)
-int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s);
+int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl = false);
 
 }  // namespace y3d

@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __
     const LevelTable &t = P.t[z];
     const int A = P.A;
     const unsigned long long pol = l2_evict_first_policy();
+    // lets a programmatically dependent launch (the fused loss' top-k kernel) be scheduled as this grid drains
+    asm volatile("griddepcontrol.launch_dependents;");
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (P.list_count[z]) P.list_count[z][b] = 0;
         if (b == 0 && z == 0 && P.counter) { P.counter[0] = 0u; P.counter[1] = 0u; }
@@ -766,7 +768,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     mark(1);
     cc.work_counter = (int *)(P.counter + 1);
     if (M > 0) {
-        rc = assign_run_topk(cc, nb, s);
+        rc = assign_run_topk(cc, nb, s, /*pdl=*/true);  // scheduled while the streaming kernel drains
         if (rc) return rc;
     }
     mark(2);

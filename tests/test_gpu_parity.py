@@ -431,6 +431,44 @@ def test_v10_loss_full_size_properties(y3d, cfg):
     np.testing.assert_allclose(it2.view(2, 4)[:, :3].reshape(6).cpu().numpy(), o, rtol=2e-5)
 
 
+def test_ordered_queue_many_images_bit_exact(y3d):
+    """Many small images: the top-k kernel's longest-first queue has more (class, branch, image) segments than one
+    32 x 32 lookup covers (second lookup step over up to 64 entries), GT sizes span all four size classes, some images
+    have no GT at all.  Assignment and loss must equal what a few images at a time give (one CTA per GT, no queue), and
+    the oracle on a slice."""
+    lossmod = __import__("yolov10_3d_b200").loss
+    B, M, nc, hw = 200, 16, 8, (320, 320)
+    lv = synth.levels(*hw)
+    gt = synth.gt2d(B, M, nc, hw, seed=71)
+    g = synth.rng(72)
+    for b in range(B):  # sizes from a few cells to most of the image, so that every size class is populated
+        n = int((gt[b, :, 1:5].sum(-1) > 0).sum())
+        w, h = g.uniform(8, 300, n), g.uniform(8, 300, n)
+        cx, cy = g.uniform(0.2, 0.8, n) * hw[1], g.uniform(0.2, 0.8, n) * hw[0]
+        gt[b, :n, 1:5] = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    gt[5] = 0
+    gt[B - 1] = 0
+    xm = synth.train_like_head2d(B, nc, lv, gt, seed=73, frac=0.05)
+    xo = synth.train_like_head2d(B, nc, lv, gt, seed=74, frac=0.05)
+    fm, fo, gtd = feats_of(xm, lv), feats_of(xo, lv), dev(gt)
+    gains, st = (7.5, 0.5, 1.5), list(synth.STRIDES)
+    assert 2 * B * M >= 16 * 148 and 4 * 2 * B > 1023  # queue mode, more than 1023 segments
+    items, parts, dbg = lossmod.v10_loss_forward(fm, fo, st, nc, gtd, gains, debug=True)
+    cs = 50  # 2 * 50 * 16 = 1600 items: one CTA per GT
+    acc = torch.zeros(8, dtype=torch.float64, device="cuda")
+    for lo in range(0, B, cs):
+        _, p_, d_ = lossmod.v10_loss_forward([f[lo:lo + cs] for f in fm], [f[lo:lo + cs] for f in fo], st, nc,
+                                             gtd[lo:lo + cs], gains, normalise=False, debug=True)
+        assert torch.equal(d_["fg_mask"], dbg["fg_mask"][:, lo:lo + cs])
+        assert torch.equal(d_["target_gt_idx"], dbg["target_gt_idx"][:, lo:lo + cs])
+        acc += p_
+    np.testing.assert_allclose(acc.cpu().numpy(), parts.cpu().numpy(), rtol=1e-12)
+    assert dbg["fg_mask"].any() and not dbg["fg_mask"][:, 5].any() and not dbg["fg_mask"][:, B - 1].any()
+    o = oracle.v10_loss(xm[:6], xo[:6], lv, synth.STRIDES, nc, gt[:6], gains=gains)[1]
+    it6, _, _ = lossmod.v10_loss_forward([f[:6] for f in fm], [f[:6] for f in fo], st, nc, gtd[:6], gains)
+    np.testing.assert_allclose(it6.view(2, 4)[:, :3].reshape(6).cpu().numpy(), o, rtol=2e-5)
+
+
 def test_odd_shapes_take_the_scalar_paths(y3d):
     """Level sizes that are not multiples of 4, nc not a multiple of 4, misaligned (sliced) level tensors: the 128-bit
     kernels fall back to their scalar variants and the results still match the oracle."""

@@ -145,6 +145,24 @@ int y3d_v10_loss_fwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const i
                      float *loss_items, double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx,
                      void *const *prof_events, void *ws, size_t ws_bytes, void *stream);
 
+/* y3d_v10_loss_fwd on this rank's image shard of a batch that is spread over `world` GPUs of one node (SURVEY.md
+ * section 8e), with the one cross-rank step fused into the last kernel: the CTA that finishes last pushes the rank's
+ * 8 partial sums straight into every peer's exchange buffer over NVLink (peer memory), waits for the peers' flags,
+ * sums in rank order and normalises by the batch-global target_scores_sum (loss.py:240) -- no separate collective
+ * launch.  loss_items (required): DEVICE float[8], identical on every rank and equal to what one process computes on
+ * the whole batch; partials (optional): DEVICE double[8], the sums over all ranks.
+ *  peer_bufs_dev: DEVICE array of `world` pointers, entry r = rank r's exchange buffer (y3d_xrank_buffer_bytes(world)
+ *  bytes, zero-initialised once, mapped into every peer: e.g. torch.distributed._symmetric_memory); seq: call counter,
+ *  1, 2, 3, ... -- the same on every rank; status (optional): DEVICE int, 1 when a peer did not arrive within ~8 s
+ *  (the items are NaN then).  world == 1 degenerates to y3d_v10_loss_fwd.  Every rank must make the call. */
+int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC,
+                             const float *const *o2o_ptr, const int64_t *o2o_sB, const int64_t *o2o_sC,
+                             const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
+                             const float *gt, int M, int topk_o2m, int topk_o2o, float gain_box, float gain_cls,
+                             float gain_dfl, float *loss_items, double *partials, int rank, int world,
+                             void *const *peer_bufs_dev, unsigned long long seq, int *status, void *const *prof_events,
+                             void *ws, size_t ws_bytes, void *stream);
+
 /* Backward of y3d_v8_loss_fwd / y3d_v10_loss_fwd: what autograd produces in the reference for loss.py:206-257
  * (BCEWithLogits :240, BboxLoss.forward :82-96, _df_loss :99-113, bbox_decode :197-204; CIoU metrics.py:78-134 with
  * alpha under no_grad :128-129; the assigner, tal.py:44, is @torch.no_grad and therefore a constant).

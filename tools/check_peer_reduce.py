@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Multi-GPU check of the fused peer-memory all-reduce + finalize kernel (csrc/xrank.cu) against the NCCL path.
+"""Multi-GPU check of the peer-memory all-reduce + finalize kernel (csrc/xrank.cu) and of the same exchange fused into
+the loss' last kernel (y3d_v10_loss_fwd_sharded) against the NCCL path.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
         tools/check_peer_reduce.py
@@ -36,6 +37,35 @@ for it in range(200):
         print(rank, it, items, want)
         break
 assert int(red.status.item()) == 0
+# the exchange fused into the loss' last kernel (y3d_v10_loss_fwd_sharded) against the NCCL route, on a small shard
+import numpy as np  # noqa: E402
+
+from tests import synth  # noqa: E402
+
+nc, hw, Bl, M = 8, (320, 320), 4, 20
+lv = synth.levels(*hw)
+gt = synth.gt2d(Bl, M, nc, hw, seed=100 + rank)
+if rank == world - 1:
+    gt[1:] = 0  # a rank with almost no targets
+fm = [torch.from_numpy(f).to(dev) for f in synth.split_levels(synth.train_like_head2d(Bl, nc, lv, gt, seed=200 + rank, frac=0.05), lv)]
+fo = [torch.from_numpy(f).to(dev) for f in synth.split_levels(synth.train_like_head2d(Bl, nc, lv, gt, seed=300 + rank, frac=0.05), lv)]
+gtd = torch.from_numpy(gt).to(dev)
+for it in range(20):
+    tot_f, it_f = y3d.dist.v10_loss_sharded(fm, fo, list(synth.STRIDES), nc, gtd, gains, Bl * world, reducer=red)
+    tot_n, it_n = y3d.dist.v10_loss_sharded(fm, fo, list(synth.STRIDES), nc, gtd, gains, Bl * world, reducer=None)
+    if not (torch.allclose(it_f, it_n, rtol=1e-6, atol=0) and torch.isfinite(it_f).all()):
+        ok = False
+        print("fused sharded loss != nccl route", rank, it, it_f, it_n)
+        break
+    chk = it_f.clone()
+    dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+    if not torch.equal(chk, it_f):  # identical on every rank, bit for bit
+        ok = False
+        print("ranks disagree", rank, it_f, chk)
+        break
+assert int(red.status.item()) == 0
+if rank == 0:
+    print("fused sharded loss == nccl route:", ok, it_f.tolist())
 # timing: back-to-back calls
 torch.cuda.synchronize()
 dist.barrier()

@@ -23,6 +23,7 @@
 //        (fixed-point, order-independent) block sums; the last CTA reduces all partials in a fixed order and
 //        writes the loss items.
 #include "loss.cuh"
+#include "xrank.cuh"
 
 namespace y3d {
 
@@ -250,6 +251,12 @@ struct FinishParams {
     int32_t *dbg_gi[2];
     int n_bce_x, n_branch, normalise;  // n_bce_x: BCE partials per image (= gridDim.x of the stream kernel)
     float gain_box, gain_cls, gain_dfl;
+    // image-sharded loss over several GPUs (optional, x_world > 1): the last CTA exchanges the partial sums with the
+    // peer ranks over NVLink peer memory (xrank.cuh) before it normalises -- compute and collective in one kernel
+    XSlot *const *x_bufs;      // DEVICE table of x_world exchange buffers
+    int x_rank, x_world;
+    unsigned long long x_seq;
+    int *x_status;             // optional: 1 when a peer never arrived
 };
 
 // bbox_iou(box1, box2, xywh=False, CIoU=True) (metrics.py:96-131) with fast division: for VALUES (loss terms, alignment
@@ -313,6 +320,8 @@ struct FinishSmem {  // dynamic shared memory of loss_finish_kernel, followed by
     long long redl[4][kFinishWarps];
     double redd[kFinishWarps];
     double fin[2][5];
+    double xv[kXMaxVals], xs[kXMaxVals];  // this rank's partial sums, the sums over the ranks
+    int xfail;
     int n_conf;
     unsigned ticket;
 };
@@ -610,21 +619,25 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         if (lane == 0) S.fin[zz][k] = acc;
     }
     __syncthreads();
-    if (tid < F.n_branch) {
+    if (tid < 4 * F.n_branch) {  // partials of a branch: iou, bce, dfl, target_scores_sum
+        const int zz = tid >> 2, j = tid & 3;
+        S.xv[tid] = j == 0 ? S.fin[zz][0] : j == 1 ? S.fin[zz][4] - S.fin[zz][3] : j == 2 ? S.fin[zz][1] : S.fin[zz][2];
+    }
+    __syncthreads();
+    const double *tot = S.xv;
+    if (F.x_world > 1) {  // sum over the ranks: stores into every peer's buffer, flag, wait, rank-ordered sum
+        xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, S.xv, 4 * F.n_branch, S.xs, &S.xfail);
+        tot = S.xs;
+        if (tid == 0 && F.x_status) *F.x_status = S.xfail;
+    }
+    if (tid < 4 * F.n_branch && F.partials) F.partials[tid] = tot[tid];
+    if (tid < F.n_branch && F.normalise && F.loss_items) {
         const int zz = tid;
-        const double s_i = S.fin[zz][0], s_d = S.fin[zz][1], s_t = S.fin[zz][2];
-        const double bce_t = S.fin[zz][4] - S.fin[zz][3];
-        if (F.partials) {
-            F.partials[4 * zz + 0] = s_i; F.partials[4 * zz + 1] = bce_t;
-            F.partials[4 * zz + 2] = s_d; F.partials[4 * zz + 3] = s_t;
-        }
-        if (F.normalise && F.loss_items) {
-            const double tss = s_t > 1.0 ? s_t : 1.0;  // max(target_scores.sum(), 1) loss.py:240
-            F.loss_items[4 * zz + 0] = (float)(s_i / tss * F.gain_box);
-            F.loss_items[4 * zz + 1] = (float)(bce_t / tss * F.gain_cls);
-            F.loss_items[4 * zz + 2] = (float)(s_d / tss * F.gain_dfl);
-            F.loss_items[4 * zz + 3] = (float)tss;
-        }
+        const double tss = tot[4 * zz + 3] > 1.0 ? tot[4 * zz + 3] : 1.0;  // max(target_scores.sum(), 1) loss.py:240
+        F.loss_items[4 * zz + 0] = (float)(tot[4 * zz + 0] / tss * F.gain_box);
+        F.loss_items[4 * zz + 1] = (float)(tot[4 * zz + 1] / tss * F.gain_cls);
+        F.loss_items[4 * zz + 2] = (float)(tot[4 * zz + 2] / tss * F.gain_dfl);
+        F.loss_items[4 * zz + 3] = (float)tss;
     }
     Y3D_STAMP(5);
 }
@@ -682,12 +695,21 @@ struct BranchIn {
     const int64_t *sB, *sC;
     int topk;
 };
+struct XRankIn {  // cross-rank exchange of the fused loss (world <= 1: none)
+    void *const *bufs_dev;
+    int rank, world;
+    unsigned long long seq;
+    int *status;
+};
 
 static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc,
                     int reg_max, const float *gt, int M, float gain_box, float gain_cls, float gain_dfl, int normalise,
                     float *loss_items, double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx,
-                    void *const *prof_events, void *ws, size_t ws_bytes, void *stream) {
+                    void *const *prof_events, void *ws, size_t ws_bytes, void *stream, const XRankIn *xr = nullptr) {
     if (!lvl_hw || !lvl_stride || B < 1 || nc < 1 || M < 0 || (M > 0 && !gt)) return Y3D_EINVAL;
+    if (xr && xr->world > 1 &&
+        (!xr->bufs_dev || xr->world > kXMaxWorld || xr->rank < 0 || xr->rank >= xr->world || xr->seq == 0))
+        return Y3D_EINVAL;
     if (!loss_items && !partials) return Y3D_EINVAL;
     if ((dbg_fg_mask == nullptr) != (dbg_target_gt_idx == nullptr)) return Y3D_EINVAL;
     if (reg_max != kR) return Y3D_EUNSUPPORTED;
@@ -780,6 +802,10 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     F.loss_items = loss_items;
     F.n_bce_x = n_bce / B; F.n_branch = nb; F.normalise = normalise;
     F.gain_box = gain_box; F.gain_cls = gain_cls; F.gain_dfl = gain_dfl;
+    if (xr && xr->world > 1) {
+        F.x_bufs = (XSlot *const *)xr->bufs_dev;
+        F.x_rank = xr->rank; F.x_world = xr->world; F.x_seq = xr->seq; F.x_status = xr->status;
+    }
     {
         cudaError_t e = cudaFuncSetAttribute(loss_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
         if (e != cudaSuccess) return (int)e;
@@ -847,6 +873,21 @@ extern "C" int y3d_v10_loss_fwd(const float *const *o2m_ptr, const int64_t *o2m_
     BranchIn br[2] = {{o2m_ptr, o2m_sB, o2m_sC, topk_o2m}, {o2o_ptr, o2o_sB, o2o_sC, topk_o2o}};
     return loss_run(2, br, lvl_hw, lvl_stride, nl, B, nc, reg_max, gt, M, gain_box, gain_cls, gain_dfl, normalise,
                     loss_items, partials, dbg_fg_mask, dbg_target_gt_idx, prof_events, ws, ws_bytes, stream);
+}
+
+extern "C" int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC,
+                                        const float *const *o2o_ptr, const int64_t *o2o_sB, const int64_t *o2o_sC,
+                                        const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
+                                        const float *gt, int M, int topk_o2m, int topk_o2o, float gain_box,
+                                        float gain_cls, float gain_dfl, float *loss_items, double *partials,
+                                        int rank, int world, void *const *peer_bufs_dev, unsigned long long seq,
+                                        int *status, void *const *prof_events, void *ws, size_t ws_bytes,
+                                        void *stream) {
+    if (!loss_items) return Y3D_EINVAL;
+    BranchIn br[2] = {{o2m_ptr, o2m_sB, o2m_sC, topk_o2m}, {o2o_ptr, o2o_sB, o2o_sC, topk_o2o}};
+    XRankIn xr = {peer_bufs_dev, rank, world, seq, status};
+    return loss_run(2, br, lvl_hw, lvl_stride, nl, B, nc, reg_max, gt, M, gain_box, gain_cls, gain_dfl, 1, loss_items,
+                    partials, nullptr, nullptr, prof_events, ws, ws_bytes, stream, &xr);
 }
 
 extern "C" int y3d_v8_loss_finalize(const double *partials, int n_branch, float gain_box, float gain_cls,

@@ -8,29 +8,13 @@
 // ~2 NVLink latencies, instead of an NCCL all-reduce of 64 bytes (launch + protocol ~25 us) followed by a finalize
 // kernel.  Slots are double-buffered by the parity of the sequence number: a peer can only be one call ahead, because it
 // needs this rank's next flag to finish that call.
-#include "y3d_common.cuh"
+#include "xrank.cuh"
 
 namespace y3d {
 
-constexpr int kXMaxWorld = 64;
-constexpr int kXMaxVals = 16;  // doubles per rank and call
-struct XSlot {
-    double v[kXMaxVals];
-    unsigned long long seq;
-    unsigned long long pad;
-};
 struct XPeers {
     XSlot *buf[kXMaxWorld];  // buf[r] = rank r's exchange buffer: XSlot[2][world]
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // one CTA of 64 threads; thread r talks to rank r
 __global__ void __launch_bounds__(64) loss_allreduce_finalize_kernel(XPeers peers, const double *__restrict__ partials,
@@ -43,32 +27,8 @@ __global__ void __launch_bounds__(64) loss_allreduce_finalize_kernel(XPeers peer
     __shared__ double sum[kXMaxVals];
     __shared__ int failed;
     const int tid = threadIdx.x;
-    const int par = (int)(seq & 1ull);
-    if (tid == 0) failed = 0;
-    __syncthreads();
-    if (tid < world) {
-        XSlot *dst = peers.buf[tid] + (size_t)par * world + rank;  // my slot in rank `tid`'s buffer
-        for (int j = 0; j < n_vals; ++j) dst->v[j] = partials[j];
-        __threadfence_system();
-        st_release_sys(&dst->seq, seq);
-        const XSlot *src = peers.buf[rank] + (size_t)par * world + tid;  // rank `tid`'s slot in my buffer
-        const long long t0 = clock64();
-        while (ld_acquire_sys(&src->seq) != seq) {
-            if (clock64() - t0 > (1ll << 34)) {  // ~8 s: a peer never arrived; fail loudly instead of hanging the GPU
-                failed = 1;
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    if (tid < n_vals) {
-        double s = 0.0;
-        const XSlot *mine = peers.buf[rank] + (size_t)par * world;
-        for (int r = 0; r < world; ++r) s += mine[r].v[tid];  // rank order: the same sum on every rank
-        sum[tid] = failed ? __longlong_as_double(0x7ff8000000000000ll) : s;
-        if (global_partials) global_partials[tid] = sum[tid];
-    }
-    __syncthreads();
+    xrank_allreduce(peers.buf, rank, world, seq, partials, n_vals, sum, &failed);
+    if (tid < n_vals && global_partials) global_partials[tid] = sum[tid];
     if (tid < n_branch) {
         const double tss = sum[4 * tid + 3] > 1.0 ? sum[4 * tid + 3] : 1.0;  // max(target_scores.sum(), 1) loss.py:240
         loss_items[4 * tid + 0] = (float)(sum[4 * tid + 0] / tss * gain_box);

@@ -72,6 +72,8 @@ class PeerLossReducer:
             self.buf.zero_()
             self.handle = symm_mem.rendezvous(self.buf, pg.group_name if hasattr(pg, "group_name") else pg)
             self.ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+            # the same table on the device, for the exchange fused into the loss' last kernel
+            self.ptrs_dev = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
             self.status = torch.zeros(1, dtype=torch.int32, device=device)
             torch.cuda.synchronize(device)
             dist.barrier(group=pg)  # every buffer is zeroed before anyone's first store can land
@@ -79,6 +81,12 @@ class PeerLossReducer:
         except Exception as e:  # no peer access / symmetric memory unsupported: NCCL path
             print(f"[yolov10-3d_b200] peer-memory loss reduction unavailable ({type(e).__name__}: {e}); using NCCL",
                   file=sys.stderr)
+
+    def next_call(self):
+        """Arguments (rank, world, peer_bufs_dev, seq, status) of ``y3d_v10_loss_fwd_sharded`` for the next collective
+        call; every rank must make that call."""
+        self.seq += 1
+        return self.rank, self.world, ptr(self.ptrs_dev), C.c_uint64(self.seq), ptr(self.status)
 
     def __call__(self, partials, gains):
         """partials float64[4n] of this rank -> items float32[4n] of the global batch (same on every rank)."""
@@ -91,20 +99,31 @@ class PeerLossReducer:
         return items
 
 
+def fused_off():
+    """Y3D_XRANK_SEPARATE=1: keep the peer-memory reduction as its own kernel (measurement of the fusion's effect)."""
+    import os
+    return os.environ.get("Y3D_XRANK_SEPARATE") == "1"
+
+
 def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_batch, group=None, prof_events=None,
                      reducer=None):
     """``v10DetectLoss`` (loss.py:727-737) on this rank's image shard, normalised over the GLOBAL batch.
 
     Returns ``(total, items[6])`` identical on every rank and equal to the single-process result on the full batch.
-    One rank: the kernels normalise directly.  Several ranks: un-normalised partials -> ``reducer`` (a
-    :class:`PeerLossReducer`: one kernel over NVLink peer memory) or, without one, an NCCL all_reduce of 8 doubles ->
-    ``y3d_v8_loss_finalize``."""
+    One rank: the kernels normalise directly.  Several ranks with a ``reducer`` (:class:`PeerLossReducer`): the
+    loss' last kernel exchanges the partial sums over NVLink peer memory itself (``y3d_v10_loss_fwd_sharded``);
+    without one: un-normalised partials -> NCCL all_reduce of 8 doubles -> ``y3d_v8_loss_finalize``."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    items, parts, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains, normalise=not multi,
-                                             prof_events=prof_events)
-    if multi and reducer is not None and reducer.available:
-        items = reducer(parts, gains)  # one kernel over peer memory: all-reduce + normalisation
-    elif multi:
-        items = _loss.finalize_partials(reduce_partials(parts, group), gains)
+    if multi and reducer is not None and reducer.available and not fused_off():
+        # the exchange rides in the loss' last kernel: no collective launch at all
+        items, _, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains, prof_events=prof_events,
+                                             xrank=reducer)
+    else:
+        items, parts, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains,
+                                                 normalise=not multi, prof_events=prof_events)
+        if multi and reducer is not None and reducer.available:
+            items = reducer(parts, gains)  # one extra kernel over peer memory: all-reduce + normalisation
+        elif multi:
+            items = _loss.finalize_partials(reduce_partials(parts, group), gains)
     items = items.view(2, 4)[:, :3].reshape(6)
     return items.sum() * global_batch, items

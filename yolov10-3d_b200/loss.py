@@ -39,7 +39,7 @@ def pack_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device, extra=Non
     return out
 
 
-def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_events):
+def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_events, xrank=None):
     """Shared body of the one- and two-branch forward calls.  ``levels``: list of 1 or 2 ``Levels``.  Returns a dict with
     ``items`` (float32[4n] or None), ``partials`` (float64[4n]), ``dbg``, and what the backward pass needs (``ws``,
     ``gt``, ``M``)."""
@@ -64,7 +64,15 @@ def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_e
     tail = (ptr(gt) if M > 0 else None, M, *[int(k) for k in topk], float(gains[0]), float(gains[1]), float(gains[2]),
             int(normalise), ptr(items), ptr(partials), ptr(dbg["fg_mask"]) if debug else None,
             ptr(dbg["target_gt_idx"]) if debug else None, prof_events, ptr(ws), ws.numel(), stream_ptr(dev))
-    if n == 1:
+    if xrank is not None:  # two branches, cross-rank exchange fused into the last kernel (dist.PeerLossReducer)
+        if n != 2 or debug or not normalise:
+            raise ValueError("the sharded entry point takes both branches, normalises, and has no debug outputs")
+        l1 = levels[1]
+        _lib.check(_lib.lib().y3d_v10_loss_fwd_sharded(
+            l0.c_ptr, l0.c_sB, l0.c_sC, l1.c_ptr, l1.c_sB, l1.c_sC, l0.c_hw, l0.c_stride, l0.nl, l0.B, nc, REG_MAX,
+            ptr(gt) if M > 0 else None, M, int(topk[0]), int(topk[1]), float(gains[0]), float(gains[1]), float(gains[2]),
+            ptr(items), ptr(partials), *xrank.next_call(), prof_events, ptr(ws), ws.numel(), stream_ptr(dev)))
+    elif n == 1:
         _lib.check(_lib.lib().y3d_v8_loss_fwd(*l0.args(), l0.B, nc, REG_MAX, *tail))
     else:
         l1 = levels[1]
@@ -82,13 +90,16 @@ def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, 
 
 
 def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(10, 1), normalise=True, debug=False,
-                     prof_events=None):
+                     prof_events=None, xrank=None):
     """Both branches of ``v10DetectLoss`` through ONE call of ``y3d_v10_loss_fwd`` (same launches for both).
 
     Returns (items float32[8] = (box, cls, dfl, target_scores_sum) x (one2many, one2one) or ``None`` when not
-    normalising, partials float64[8], debug dict or None).  Nothing synchronises."""
+    normalising, partials float64[8], debug dict or None).  Nothing synchronises.
+    ``xrank``: a ``dist.PeerLossReducer`` -- this rank's images are a shard of a batch spread over several GPUs; the
+    last kernel then sums the partials over the ranks through NVLink peer memory before normalising
+    (``y3d_v10_loss_fwd_sharded``), and items / partials are those of the whole batch."""
     r = _branch_forward([Levels(feats_o2m, strides), Levels(feats_o2o, strides)], nc, gt_packed, topk, gains,
-                        normalise, debug, prof_events)
+                        normalise, debug, prof_events, xrank)
     return r["items"], r["partials"], r["dbg"]
 
 

@@ -297,8 +297,11 @@ def main_cuda(args):
             "config": {"workload": WORKLOAD, "global_batch": B * world, "sharding": f"by image, {B}/GPU",
                        "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed",
                        "collective": ("none" if world == 1 else
-                                      "8 float64 loss partials per step: one fused all-reduce + normalise kernel over NVLink "
-                                      "peer memory (csrc/xrank.cu)" if peer else
+                                      ("8 float64 loss partials per step, exchanged over NVLink peer memory by the loss' "
+                                       "own last kernel (y3d_v10_loss_fwd_sharded, csrc/xrank.cuh): no collective launch"
+                                       if not y3d.dist.fused_off() else
+                                       "8 float64 loss partials per step: one all-reduce + normalise kernel over NVLink "
+                                       "peer memory (csrc/xrank.cu)") if peer else
                                       "NCCL all_reduce of 8 float64 loss partials per step + finalize kernel")},
             "roofline": {"bound": "hbm", "kernel": "head_stream_kernel<4>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -310,7 +313,9 @@ def main_cuda(args):
                                                  "finish: resolve+fg_loss+reduce (warm-up steps)": float(stage_ms[2])}},
             "e2e": {"value": B * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 24, "steps": Ke},
-            "gpu_launches": (3 + (1 if world > 1 else 0)) * K,  # + the NCCL kernel when the peer path is unavailable
+            # stream, top-k, finish per step (+ the stand-alone exchange kernel when it is not fused; the NCCL route
+            # adds NCCL's own kernel on top of our finalize kernel)
+            "gpu_launches": (3 + (1 if world > 1 and (not peer or y3d.dist.fused_off()) else 0)) * K,
             "clocks": dict(sampler.summary(), window="timed region + e2e region (nvidia-smi every 100 ms)"),
             "loss_items": [float(v) for v in items.cpu()],
         }

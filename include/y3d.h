@@ -167,7 +167,7 @@ int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64_t *o2m_sB,
  * (BCEWithLogits :240, BboxLoss.forward :82-96, _df_loss :99-113, bbox_decode :197-204; CIoU metrics.py:78-134 with
  * alpha under no_grad :128-129; the assigner, tal.py:44, is @torch.no_grad and therefore a constant).
  *  Call right after the forward call with the SAME geometry, gt, M, topk and the SAME, untouched workspace (the
- *  forward leaves the claimed-anchor lists with assigned GT and alignment weight in it).
+ *  forward leaves, in the claim word of every foreground anchor, its assigned GT and alignment weight).
  *  grad_ptr / grad_sB / grad_sC: one gradient tensor per level, indexed like the head tensors; every element is
  *  written (box rows of background anchors are zero).  loss_items: DEVICE float[4 * n_branch] of the forward pass
  *  (after y3d_v8_loss_finalize in the multi-GPU case: the batch-global target_scores_sum must be in [4z+3]).

@@ -15,13 +15,17 @@
 //        (xyxy, grid units) and the per-side log-sum-exp as [B,4,A] planes (coalesced 128-bit stores; 32 B/anchor,
 //        the only dense writes), zeroed claim words, and sum softplus(logit) = sum BCE(logit, 0) per CTA.
 //        pd_scores and the dense target_scores of the reference are never materialised:
-//        sum BCE(x,t) = sum BCE(x,0) - sum_fg x[label]*t.
-//   2. tal_topk_kernel (assign.cu) : per-GT candidate walk + top-k + claims; first claimers append the anchor to
-//        the image's list.  Scores are read as logits straight from the head.
+//        sum BCE(x,t) = sum BCE(x,0) - sum_fg x[label]*t.  One warp per image also sorts the image's valid GTs into
+//        size classes: the work order of the next kernel.
+//   2. tal_topk_kernel (assign.cu) : per-GT candidate walk + top-k + claims, biggest GTs first; first claimers append
+//        the anchor to the image's list.  Scores are read as logits straight from the head.  Launched
+//        programmatically dependent on 1, as 3 is on 2.
 //   3. loss_finish_kernel : one CTA per (image, branch) over the claimed anchors only: conflict resolution
 //        (select_highest_overlaps), per-GT maxima in shared memory, CIoU / DFL-CE / BCE-correction terms, exact
 //        (fixed-point, order-independent) block sums; the last CTA reduces all partials in a fixed order and
-//        writes the loss items.
+//        writes the loss items -- after summing them over the ranks through NVLink peer memory when the batch is
+//        sharded over several GPUs (y3d_v10_loss_fwd_sharded).  The claim word of a foreground anchor ends up as
+//        (GT index, alignment weight): what the backward pass reads.
 #include "loss.cuh"
 #include "xrank.cuh"
 
@@ -241,7 +245,6 @@ struct FinishParams {
     const float *lse[2];       // [B,4,A]
     int *list_gi[2];           // [B,cap] scratch
     float *list_al[2];         // [B,cap] scratch
-    float *list_w[2];          // [B,cap] out: normalised alignment weight of each entry (read by the backward pass)
     const double *part_bce;    // [n_branch][n_bce]
     double *part_fg;           // [n_branch][B][5]: iou, dfl, target_scores, x*t, softplus
     unsigned *counter;         // zeroed by the stream kernel
@@ -768,7 +771,6 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         F.lse[z] = P.lse[z];
         F.list_gi[z] = (int *)(q + w.list_gi);
         F.list_al[z] = (float *)(q + w.list_al);
-        F.list_w[z] = (float *)(q + w.list_w);
         F.dbg_fg[z] = dbg_fg_mask ? dbg_fg_mask + (size_t)z * B * A : nullptr;
         F.dbg_gi[z] = dbg_target_gt_idx ? dbg_target_gt_idx + (size_t)z * B * A : nullptr;
     }

@@ -9,7 +9,7 @@ namespace y3d {
 constexpr int kR = 16;  // reg_max (head.py:37)
 
 struct LossWs {  // all offsets 256-byte aligned; per-branch blocks are contiguous
-    size_t claim, boxes, lse, list_a, list_gi, list_al, list_w, list_count, per_branch;
+    size_t claim, boxes, lse, list_a, list_gi, list_al, list_count, per_branch;
     size_t off_counter, off_pfg, off_pbce, off_ord_cnt, off_ord_list, total;
     int cap, n_bce;
 };
@@ -25,7 +25,6 @@ inline LossWs loss_ws_layout(int nb, int B, int A, int M, int k) {
     w.list_a = o;     o += a256(sizeof(int) * (size_t)B * w.cap);
     w.list_gi = o;    o += a256(sizeof(int) * (size_t)B * w.cap);
     w.list_al = o;    o += a256(sizeof(float) * (size_t)B * w.cap);
-    w.list_w = o;     o += a256(sizeof(float) * (size_t)B * w.cap);
     w.list_count = o; o += a256(sizeof(int) * (size_t)B);
     w.per_branch = o;
     w.off_counter = (size_t)nb * w.per_branch;

@@ -35,6 +35,7 @@ __device__ __forceinline__ int tk_anchor(unsigned long long key) { return 0x7fff
 //  * stage 2 pops 32 at a time (full lanes, no loads): exact CIoU / keypoint similarity and the sorted-list update.
 constexpr int kTopkU = 4;             // cells per lane and round trip
 constexpr int kTopkQ = 32 * kTopkU + 32;  // queue slots per warp
+constexpr int kTopkSortMerge = 6;  // keys above the threshold from which the sorted list is merged, not inserted into
 
 // score^alpha of a candidate and an upper bound of its metric: sb * IoU^beta with a fast IoU (CIoU <= IoU; the factor
 // 1.0001 covers the fast arithmetic and the eps terms of the exact expression).  beta < 0: no IoU bound.  Out of line:
@@ -456,7 +457,32 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         } else {
             break;
         }
-        // ---- sorted-list update with this lane's candidate key (0 = none)
+        // ---- sorted-list update with this lane's candidate key (0 = none).  Many keys at once (a GT's first pops,
+        //      when the list is still short): sort the keys across the lanes (bitonic network), reverse them against
+        //      the sorted list -- the lane-wise maximum holds the 32 largest of both and is bitonic -- and sort that
+        //      with five more exchanges.  A few keys: insert them one by one.
+        if (__popc(__ballot_sync(0xffffffffu, key > thr)) >= kTopkSortMerge) {
+            unsigned long long v = key > thr ? key : 0ull;
+#pragma unroll
+            for (int ksz = 2; ksz <= 32; ksz <<= 1) {
+#pragma unroll
+                for (int j = ksz >> 1; j > 0; j >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+                    const bool keep_max = ((lane & ksz) == 0) == ((lane & j) == 0);  // descending: lane 0 ends largest
+                    v = (o > v) == keep_max ? o : v;
+                }
+            }
+            const unsigned long long vr = __shfl_sync(0xffffffffu, v, 31 - lane);
+            tk = vr > tk ? vr : tk;
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, tk, j);
+                tk = (o > tk) == ((lane & j) == 0) ? o : tk;
+            }
+            thr = __shfl_sync(0xffffffffu, tk, k - 1);
+            key = 0ull;
+            TK_CNT(13, 1);
+        }
         for (;;) {
             const unsigned mk = __ballot_sync(0xffffffffu, key > thr);
             if (!mk) break;

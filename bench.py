@@ -136,7 +136,9 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    S = 16  # bounded sample: 16 images of the cfg2 workload per step
+    # bounded sample: up to 16 images of the cfg2 workload per step, fewer when many steps are asked for, so that the
+    # whole run stays around two minutes at the ~30 images/s the host cores manage
+    S = max(1, min(16, 3600 // max(1, args.steps + max(args.warmup, 1))))
     ips, ms, cores = cpu_reference_run(args.steps, max(args.warmup, 1), S)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -214,17 +216,18 @@ def main_cuda(args):
         return y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=pe,
                                          reducer=reducer)
 
+    sampler = ClockSampler(local)  # clocks / throttle reasons while the GPU is under load: timed region + e2e region
+    sampler.start()
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 3.0:  # nvidia-smi needs a moment to print its first line
+        time.sleep(0.02)
+    # warm-up right before the timed region (the wait above leaves the GPU idle: clocks and caches would be cold)
     for i in range(W):
         y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=evw_c[i],
                                   reducer=reducer)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)  # clocks / throttle reasons while the GPU is under load: timed region + e2e region
-    sampler.start()
-    t_wait = time.time()
-    while not sampler.rows and time.time() - t_wait < 3.0:  # nvidia-smi needs a moment to print its first line
-        time.sleep(0.02)
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
@@ -344,8 +347,8 @@ def _fake_model(torch, nc, gains, dev):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

@@ -734,7 +734,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
     if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
     const size_t fin_smem = finish_smem_bytes(M);
-    if (fin_smem > 220 * 1024) return Y3D_EUNSUPPORTED;
+    if (fin_smem > 212 * 1024) return Y3D_EUNSUPPORTED;  // + 8 KB static (exchange scratch) <= 227 KB
     cudaStream_t s = (cudaStream_t)stream;
     char *p = (char *)ws;
     auto mark = [&](int i) {

@@ -1,13 +1,8 @@
 // xrank.cu -- the one cross-rank step of the image-sharded loss, as a single kernel over NVLink peer memory (sm_100a).
 //   y3d_loss_allreduce_finalize : sum of the per-rank un-normalised loss partials (8 doubles for v10DetectLoss) over
 //       all ranks + the target_scores_sum normalisation of reference ultralytics/utils/loss.py:240-256.
-// Every rank owns one exchange buffer that all peers can address (symmetric memory: the host passes the `world` device
-// pointers).  A call pushes this rank's partials straight into every peer's buffer (P2P stores through NVSwitch),
-// publishes a sequence number with a system-scope release, waits until the sequence numbers of all peers have arrived
-// in its own buffer, sums the slots in rank order (deterministic, identical on every rank) and normalises.  One launch,
-// ~2 NVLink latencies, instead of an NCCL all-reduce of 64 bytes (launch + protocol ~25 us) followed by a finalize
-// kernel.  Slots are double-buffered by the parity of the sequence number: a peer can only be one call ahead, because it
-// needs this rank's next flag to finish that call.
+// The exchange protocol (flag-in-data words over peer memory, no fence, no separate flag) is in xrank.cuh; the fused
+// loss runs the same exchange inside its finishing kernel (y3d_v10_loss_fwd_sharded, loss.cu).
 #include "xrank.cuh"
 
 namespace y3d {

@@ -69,6 +69,8 @@ def loss_inputs(r, z):
     B, nc, img_hw, M, seed = r["B"], r["nc"], r["img_hw"], r["M"], r["seed"]
     lv = synth.levels(*img_hw)
     gt = synth.gt2d(B, M, nc, img_hw, seed=seed + 1, crowd=r["crowd"])
+    if r.get("ragged"):
+        synth.make_ragged(gt, img_hw)
     if r["inputs"] == "random":
         xm, xo = synth.head2d(B, nc, lv, seed=seed), synth.head2d(B, nc, lv, seed=seed + 7)
     else:

@@ -149,9 +149,11 @@ class FakeModel(torch.nn.Module):
         self.model = [head]
 
 
-def case_loss(name, kind, B, nc, img_hw, M, seed, crowd=False):
+def case_loss(name, kind, B, nc, img_hw, M, seed, crowd=False, ragged=False):
     lv = synth.levels(*img_hw)
     gt = synth.gt2d(B, M, nc, img_hw, seed=seed + 1, crowd=crowd)
+    if ragged:
+        synth.make_ragged(gt, img_hw)
     if kind == "random":
         xm, xo = synth.head2d(B, nc, lv, seed=seed), synth.head2d(B, nc, lv, seed=seed + 7)
     else:
@@ -172,7 +174,7 @@ def case_loss(name, kind, B, nc, img_hw, M, seed, crowd=False):
     # plus every position with a non-zero box-channel gradient of image 0 (fg anchors), capped
     nzm = np.flatnonzero(gm[0, :64])[:4096]
     nzo = np.flatnonzero(go[0, :64])[:4096]
-    recipe = dict(kind="loss", inputs=kind, B=B, nc=nc, img_hw=img_hw, M=M, seed=seed, crowd=crowd,
+    recipe = dict(kind="loss", inputs=kind, B=B, nc=nc, img_hw=img_hw, M=M, seed=seed, crowd=crowd, ragged=ragged,
                   gains=[7.5, 0.5, 1.5])
     save(name, recipe, in_crc=np.int64(synth.checksum(gt, xm, xo)), total=np.float64(total.item()),
          items=items.detach().numpy().astype(np.float64), grad_pos=pos, grad_m=gm.reshape(-1)[pos],
@@ -401,6 +403,7 @@ if __name__ == "__main__":
         case_loss("loss_random", "random", B=3, nc=8, img_hw=(160, 160), M=10, seed=30)
         case_loss("loss_trained", "trained", B=3, nc=8, img_hw=(256, 320), M=12, seed=31)
         case_loss("loss_crowd", "trained", B=2, nc=8, img_hw=(256, 320), M=60, seed=32, crowd=True)
+        case_loss("loss_ragged", "trained", B=3, nc=8, img_hw=(256, 320), M=12, seed=33, ragged=True)
     if want("decode3d") or want("preds3d"):
         dets = case_decode3d("decode3d_small", B=3, nc=3, img_hw=(96, 320), D=50, seed=40)
         case_decode_preds("preds3d_small", dets)

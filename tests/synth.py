@@ -90,6 +90,20 @@ def gt2d(B, M, nc, img_hw, seed=1, crowd=False, full=False):
     return out
 
 
+def make_ragged(gt, img_hw):
+    """Edge cases of the ragged ground truth, in place on a packed [B>=3, M>=3, 5]: image 1 without any box, image 2
+    with a single one; in image 0 a box smaller than a stride-8 cell that contains no anchor centre (no candidate at
+    all), a box covering most of the image, and a zero-area box (a valid row -- its coordinates sum to > 0 -- that no
+    anchor can lie inside)."""
+    H, W = img_hw
+    gt[1] = 0
+    gt[2, 1:] = 0
+    gt[0, 0, 1:5] = (17.0, 17.0, 19.5, 19.5)           # between the centres 12 and 20
+    gt[0, 1, 1:5] = (0.05 * W, 0.05 * H, 0.95 * W, 0.95 * H)
+    gt[0, 2, 1:5] = (0.5 * W, 0.25 * H, 0.5 * W, 0.75 * H)  # zero width
+    return gt
+
+
 def batch_dict(gt_packed, img_hw):
     """Packed GT -> the raw dataloader form v8DetectionLoss consumes (loss.py:222): batch_idx [N], cls [N,1],
     bboxes [N,4] normalised xywh."""

@@ -181,10 +181,11 @@ def preprocess_targets(batch_idx, cls, bboxes, batch_size, img_hw, extra=None):
     return out
 
 
-def v8_loss(xcat, lvl_hw, lvl_stride, nc, gt_packed, topk, gains=(7.5, 0.5, 1.5), reg_max=16):
+def v8_loss(xcat, lvl_hw, lvl_stride, nc, gt_packed, topk, gains=(7.5, 0.5, 1.5), reg_max=16, debug=False):
     """v8DetectionLoss.__call__ loss.py:206-257 for one branch.  ``gt_packed`` [B,M,5] (cls, xyxy px) is the
     output of :func:`preprocess_targets`.  Returns (loss_items float64[3] = box, cls, dfl after gains,
-    target_scores_sum, n_fg).  total = loss_items.sum() * B."""
+    target_scores_sum, n_fg); with ``debug`` also the assignment it was computed from: fg_mask bool [B,A] and
+    target_gt_idx int64 [B,A].  total = loss_items.sum() * B."""
     xcat = _f32(xcat)
     B, Cc, A = xcat.shape
     anc, s = make_anchors(lvl_hw, lvl_stride)
@@ -193,10 +194,17 @@ def v8_loss(xcat, lvl_hw, lvl_stride, nc, gt_packed, topk, gains=(7.5, 0.5, 1.5)
     loss = np.zeros(3, np.float64)
     tss = C.c_double(0)
     nfg = C.c_int64(0)
-    rc = lib().y3d_o_v8_loss(_p(xcat, _f32p), C.c_int(B), C.c_int(nc), C.c_int(reg_max), C.c_int(A), _p(anc, _f32p),
-                             _p(s, _f32p), _p(gt, _f32p), C.c_int(M), C.c_int(topk), C.c_float(gains[0]),
-                             C.c_float(gains[1]), C.c_float(gains[2]), _p(loss, _f64p), C.byref(tss), C.byref(nfg))
+    fg = np.zeros((B, A), np.uint8) if debug else None
+    tgi = np.zeros((B, A), np.int64) if debug else None
+    fn = lib().y3d_o_v8_loss_dbg
+    fn.restype = C.c_int
+    rc = fn(_p(xcat, _f32p), C.c_int(B), C.c_int(nc), C.c_int(reg_max), C.c_int(A), _p(anc, _f32p), _p(s, _f32p),
+            _p(gt, _f32p), C.c_int(M), C.c_int(topk), C.c_float(gains[0]), C.c_float(gains[1]), C.c_float(gains[2]),
+            _p(loss, _f64p), C.byref(tss), C.byref(nfg),
+            fg.ctypes.data_as(C.c_void_p) if debug else None, tgi.ctypes.data_as(C.c_void_p) if debug else None)
     assert rc == 0
+    if debug:
+        return loss, tss.value, nfg.value, fg.astype(bool), tgi
     return loss, tss.value, nfg.value
 
 

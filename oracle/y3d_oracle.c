@@ -524,9 +524,11 @@ static double bce_logits(double x, double t) { /* BCEWithLogits, reduction none 
     return (x > 0 ? x : 0) - x * t + log1p(exp(-ax));
 }
 
-int y3d_o_v8_loss(const float *xcat, int B, int nc, int R, int A, const float *anc, const float *stride,
-                  const float *gt /* [B,M,5] cls,xyxy px */, int M, int k, float gain_box, float gain_cls,
-                  float gain_dfl, double *loss3, double *tss_out, int64_t *nfg_out) {
+/* fg_out [B,A] u8 / tgi_out [B,A] i64 (optional): the assignment the loss was computed from */
+int y3d_o_v8_loss_dbg(const float *xcat, int B, int nc, int R, int A, const float *anc, const float *stride,
+                      const float *gt /* [B,M,5] cls,xyxy px */, int M, int k, float gain_box, float gain_cls,
+                      float gain_dfl, double *loss3, double *tss_out, int64_t *nfg_out, uint8_t *fg_out,
+                      int64_t *tgi_out) {
     int C = 4 * R + nc;
     long BA = (long)B * A;
     float *pd_scores = (float *)malloc(sizeof(float) * (size_t)BA * nc);
@@ -572,7 +574,12 @@ int y3d_o_v8_loss(const float *xcat, int B, int nc, int R, int A, const float *a
         int64_t *t_gi = (int64_t *)malloc(sizeof(int64_t) * (size_t)BA);
         y3d_o_tal_assign(pd_scores, pbox_px, anc_px, gl, gbx, mg, B, A, nc, M, k, 0.5f, 6.0f, 1e-9f, NULL, t_box, t_sc,
                          fg, t_gi, NULL, NULL, NULL);
+        if (fg_out) memcpy(fg_out, fg, (size_t)BA);
+        if (tgi_out) memcpy(tgi_out, t_gi, sizeof(int64_t) * (size_t)BA);
         free(gl); free(gbx); free(mg); free(t_gi);
+    } else {
+        if (fg_out) memset(fg_out, 0, (size_t)BA);
+        if (tgi_out) memset(tgi_out, 0, sizeof(int64_t) * (size_t)BA);
     }
     for (long i = 0; i < BA; ++i) {
         for (int c = 0; c < nc; ++c) {
@@ -622,6 +629,13 @@ int y3d_o_v8_loss(const float *xcat, int B, int nc, int R, int A, const float *a
     free(pd_scores); free(pd_dist); free(logit); free(pbox); free(pbox_px); free(anc_px);
     free(t_sc); free(t_box); free(fg);
     return 0;
+}
+
+int y3d_o_v8_loss(const float *xcat, int B, int nc, int R, int A, const float *anc, const float *stride,
+                  const float *gt, int M, int k, float gain_box, float gain_cls, float gain_dfl, double *loss3,
+                  double *tss_out, int64_t *nfg_out) {
+    return y3d_o_v8_loss_dbg(xcat, B, nc, R, A, anc, stride, gt, M, k, gain_box, gain_cls, gain_dfl, loss3, tss_out,
+                             nfg_out, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------ */

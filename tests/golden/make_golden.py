@@ -183,6 +183,45 @@ def case_loss(name, kind, B, nc, img_hw, M, seed, crowd=False, ragged=False):
          nz_o=nzo, nz_o_val=go[0, :64].reshape(-1)[nzo])
 
 
+
+def case_loss_assign(name, B, nc, img_hw, M, seed, crowd=False, frac=0.02):
+    """v10DetectLoss at a BASELINE shape with the assignment captured INSIDE the real loss: fg_mask / target_gt_idx of
+    both branches as TaskAlignedAssigner.forward returned them to v8DetectionLoss.__call__ (loss.py:231)."""
+    lv = synth.levels(*img_hw)
+    gt = synth.gt2d(B, M, nc, img_hw, seed=seed + 1, crowd=crowd, full=crowd)
+    xm = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 2, frac=frac)
+    xo = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 3, frac=frac)
+    batch = {k: t(v) for k, v in synth.batch_dict(gt, img_hw).items()}
+    fm = [t(f) for f in synth.split_levels(xm, lv)]
+    fo = [t(f) for f in synth.split_levels(xo, lv)]
+    model = FakeModel(nc, synth.STRIDES, types.SimpleNamespace(box=7.5, cls=0.5, dfl=1.5))
+    crit = ref_loss.v10DetectLoss(model)
+    captured = {}
+
+    def capture(branch, asg):
+        inner = asg.forward
+
+        def fwd(*a, **k):
+            out = inner(*a, **k)
+            captured[branch] = (out[3].numpy().copy(), out[4].numpy().copy())
+            return out
+
+        asg.forward = fwd
+
+    capture(0, crit.one2many.assigner)
+    capture(1, crit.one2one.assigner)
+    with patched_topk(), torch.no_grad():
+        total, items = crit({"one2many": fm, "one2one": fo}, batch)
+    arrays = {}
+    for z in (0, 1):
+        fg, tgi = captured[z]
+        arrays[f"fg{z}"] = np.packbits(fg)
+        arrays[f"tgi{z}"] = tgi[fg].astype(np.int16)  # row-major over (image, anchor) at the foreground positions
+    recipe = dict(kind="loss_assign", B=B, nc=nc, img_hw=img_hw, M=M, seed=seed, crowd=crowd, frac=frac,
+                  gains=[7.5, 0.5, 1.5])
+    save(name, recipe, in_crc=np.int64(synth.checksum(gt, xm, xo)), total=np.float64(total.item()),
+         items=items.detach().numpy().astype(np.float64), **arrays)
+
 # ---------------------------------------------------------------------------------------------- 3D
 def head3d_ns(nc, strides):
     ns = types.SimpleNamespace(nc=nc, no=nc + 35, dynamic=False, shape=None, export=False, format=None,
@@ -404,6 +443,9 @@ if __name__ == "__main__":
         case_loss("loss_trained", "trained", B=3, nc=8, img_hw=(256, 320), M=12, seed=31)
         case_loss("loss_crowd", "trained", B=2, nc=8, img_hw=(256, 320), M=60, seed=32, crowd=True)
         case_loss("loss_ragged", "trained", B=3, nc=8, img_hw=(256, 320), M=12, seed=33, ragged=True)
+    if want("lossasg"):  # BASELINE shapes (cfg2 / cfg5: nc 80, 640 x 640, 100 / 500 GT per image)
+        case_loss_assign("lossasg_cfg2", B=4, nc=80, img_hw=(640, 640), M=100, seed=90)
+        case_loss_assign("lossasg_cfg5", B=2, nc=80, img_hw=(640, 640), M=500, seed=91, crowd=True)
     if want("decode3d") or want("preds3d"):
         dets = case_decode3d("decode3d_small", B=3, nc=3, img_hw=(96, 320), D=50, seed=40)
         case_decode_preds("preds3d_small", dets)

@@ -520,7 +520,52 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         }
     }
     // claims: mask_pos = mask_topk * mask_in_gts * mask_gt (tal.py:104)
-    if (lane < k && tk != 0ull && (tk & 1ull)) {
+    if (c.rec) {
+        // record path: the claim atomic, the slot allocation and the gathers of the pair's loss inputs are all in flight
+        // together (one round trip), then the record is written
+        const bool claiming = lane < k && tk != 0ull && (tk & 1ull);
+        const unsigned cmask = __ballot_sync(0xffffffffu, claiming);
+        if (cmask) {
+            int a = 0;
+            unsigned long long old = 0ull;
+            float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f), r2 = r1, r3 = r1, r4 = r1;
+            float xlab = 0.f;
+            if (claiming) {
+                a = tk_anchor(tk);
+                const int lv = level_of(c.t, a);
+                const int cell = a - c.t.start[lv];
+                const float gx = (float)(cell % c.t.w[lv]) + 0.5f, gy = (float)(cell / c.t.w[lv]) + 0.5f;
+                float4 tb;
+                float tt[4];
+                dfl_target(g.box, c.t.stride[lv], gx, gy, tb, tt);
+                const float *hp = c.t.ptr[lv] + (long long)b * c.t.sB[lv] + cell;
+                const long long cs = c.t.sC[lv];
+                const int t0 = (int)tt[0], t1 = (int)tt[1], t2 = (int)tt[2], t3 = (int)tt[3];
+                r3 = make_float4(hp[(long long)t0 * cs], hp[(long long)(16 + t1) * cs], hp[(long long)(32 + t2) * cs],
+                                 hp[(long long)(48 + t3) * cs]);
+                r4 = make_float4(hp[(long long)(t0 + 1) * cs], hp[(long long)(17 + t1) * cs], hp[(long long)(33 + t2) * cs],
+                                 hp[(long long)(49 + t3) * cs]);
+                xlab = hp[(long long)(c.cls_ch0 + (g.label < 0 ? 0 : g.label)) * cs];
+                const float *bp = c.pd_bboxes + (long long)b * 4 * c.A + a;
+                r1 = make_float4(bp[0], bp[c.A], bp[2 * (long long)c.A], bp[3 * (long long)c.A]);
+                const float *lp = c.lse + (long long)b * 4 * c.A + a;
+                r2 = make_float4(lp[0], lp[c.A], lp[2 * (long long)c.A], lp[3 * (long long)c.A]);
+                old = atomicAdd(c.claim + (long long)b * c.A + a, (1ull << 32) | (unsigned long long)m);
+            }
+            const int leader = __ffs(cmask) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(c.list_count + b, __popc(cmask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            const int slot = base + __popc(cmask & lt_mask);
+            if (claiming && slot < c.rec_cap) {
+                float4 *r = c.rec + ((long long)b * c.rec_cap + slot) * 5;
+                const int first = (old >> 32) == 0 ? (int)0x80000000 : 0;  // the first claimer owns the anchor downstream
+                r[0] = make_float4(__int_as_float(a | first), __int_as_float(m),
+                                   __uint_as_float((unsigned)(tk >> 32)), xlab);
+                r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4;
+            }
+        }
+    } else if (lane < k && tk != 0ull && (tk & 1ull)) {
         const int a = tk_anchor(tk);
         const unsigned long long old = atomicAdd(c.claim + (long long)b * c.A + a, (1ull << 32) | (unsigned long long)m);
         if (c.list_a) {

@@ -58,7 +58,26 @@ struct AssignCtx {
     int *list_count;
     int *list_a;
     int list_cap;
+    // optional (fused loss, anchor-parallel finish): instead of the list, EVERY claim leaves a record of 5 float4 at
+    // rec[b * rec_cap + slot] (slot from list_count[b]) with everything the finishing kernel needs for this
+    // (anchor, GT) pair, gathered here -- spread over this kernel's run time instead of one burst of scattered DRAM
+    // reads at the end of the step:
+    //   [0] anchor | first-claimer bit << 31, GT index, alignment metric bits, logit of the GT's label
+    //   [1] predicted box xyxy (grid units)   [2] log-sum-exp of the 4 DFL sides
+    //   [3] logit of the lower DFL target bin of every side   [4] logit of the upper one
+    float4 *rec;
+    int rec_cap;
+    const float *lse;  // [B,4,A] planes written by the streaming kernel
 };
+
+// bbox2dist (tal.py:328-331) of anchor (gx, gy) in grid units against GT box gbox (px) at stride st, clamped like
+// BboxLoss.forward (loss.py:93): the DFL target distance of every side; lower bin = (int)tt, its weight (lower + 1) - tt
+__device__ __forceinline__ void dfl_target(float4 gbox, float st, float gx, float gy, float4 &tb, float (&tt)[4]) {
+    tb = make_float4(dm::div(gbox.x, st), dm::div(gbox.y, st), dm::div(gbox.z, st), dm::div(gbox.w, st));  // loss.py:248
+    const float ltrb[4] = {gx - tb.x, gy - tb.y, tb.z - gx, tb.w - gy};
+#pragma unroll
+    for (int side = 0; side < 4; ++side) tt[side] = fminf(fmaxf(ltrb[side], 0.0f), 15.0f - 0.01f);
+}
 
 struct GtRec {
     float4 box;

@@ -75,6 +75,8 @@ struct StreamParams {
     float *pd_scores[2];   // optional [B,A,nc] sigmoid (y3d_train_decode only)
     unsigned long long *claim[2];  // optional [B,A], zeroed here
     int *list_count[2];    // optional [B], zeroed here
+    int *img_cnt[2];       // optional [B], zeroed here: finished chunks of the image (anchor-parallel finishing kernel)
+    int *pos[2];           // optional [B,M,2], zeroed here: per-GT maxima of alignment metric and overlap
     unsigned *counter;     // optional ticket of the finishing kernel (+1: work counter of the top-k kernel), zeroed here
     double *part_bce;      // [n_branch][gridDim.x * B] or nullptr
     const float *gt5;      // optional [B,M,5] (with ord_cnt / ord_list)
@@ -116,6 +118,10 @@ static __device__ __noinline__ void gt_order_image(const float *gt5, int M, int 
     }
 }
 
+static __device__ __noinline__ void zero_ints(int *p, int n, int lane) {
+    for (int i = lane; i < n; i += 32) p[i] = 0;
+}
+
 // grid (ceil(A/V/32), B, n_branch), block 128 = 32 units of V anchors x 4 channel parts (warp = part)
 template <int V, bool PS>
 __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __grid_constant__ StreamParams P) {
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __
     asm volatile("griddepcontrol.launch_dependents;");
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (P.list_count[z]) P.list_count[z][b] = 0;
+        if (P.img_cnt[z]) P.img_cnt[z][b] = 0;
         if (b == 0 && z == 0 && P.counter) { P.counter[0] = 0u; P.counter[1] = 0u; }
     }
     float bce = 0.f;
@@ -237,14 +244,18 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __
     // one warp per image: the processing order of the image's GTs for the top-k kernel
     if (P.ord_cnt && blockIdx.x == 0 && z == 0 && part == 0)
         gt_order_image(P.gt5, P.M, b, P.ord_cells_per_px2, P.ord_cnt, P.ord_list, lane);
+    // one warp per image and branch: zero the per-GT maxima the finishing kernel folds its atomicMax into
+    if (P.pos[z] && blockIdx.x == 0 && part == 1) zero_ints(P.pos[z] + (long long)b * P.M * 2, 2 * P.M, lane);
 }
 
 // ---------------------------------------------------------------------------------------------- finishing kernel
 struct FinishParams {
     const float *gt5;          // [B,M,5]
     const float *lse[2];       // [B,4,A]
-    int *list_gi[2];           // [B,cap] scratch
-    float *list_al[2];         // [B,cap] scratch
+    int *list_gi[2];           // [B,cap] scratch (per-image kernel)
+    float *list_al[2];         // [B,cap] scratch (per-image kernel)
+    int *img_cnt[2];           // [B] zeroed by the stream kernel: chunks of the image that have finished
+    int *pos[2];               // [B,M,2] zeroed by the stream kernel: per-GT max alignment metric / max overlap (float bits)
     const double *part_bce;    // [n_branch][n_bce]
     double *part_fg;           // [n_branch][B][5]: iou, dfl, target_scores, x*t, softplus
     unsigned *counter;         // zeroed by the stream kernel
@@ -290,7 +301,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 }
 
 #ifdef Y3D_TIMING
-__device__ unsigned long long g_y3d_stamps[2 * 1024 * 8];
+__device__ unsigned long long g_y3d_stamps[2048 * 8];
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -650,6 +661,287 @@ extern "C" int y3d_debug_read_stamps(unsigned long long *host, int n) {
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------- anchor-parallel finish
+// The per-image kernel above keeps a whole image on one SM: its ~10 scattered gathers per claimed anchor (two DFL bins
+// per side, box, log-sum-exp, label logit) queue up behind one SM's load pipe (16 us for an image with 1000 claimed
+// anchors, the critical path of the step).  For M <= kFinishApMaxM the claimed anchors of an image are therefore
+// spread over the machine: CTA (chunk, image, branch) takes kFinApThreads consecutive list entries, one per thread.
+//   phase R (every chunk): conflict resolution (select_highest_overlaps), the pair's exact alignment metric / overlap
+//       folded into the image's per-GT maxima (global atomicMax), and everything of the loss terms that does not need
+//       those maxima: 1 - CIoU, the DFL cross-entropy and the label logit -> one 20-byte record per anchor.
+//   phase S (the chunk that finishes last for its image, found with a counter -- nobody ever waits): weight =
+//       align * max overlap / (max align + eps) per record (tal.py:89-92), exact fixed-point sums, the claim word the
+//       backward pass reads, the image's BCE partials; the globally last image then reduces all images in a fixed order,
+//       exchanges with the peer ranks (sharded batch) and normalises.
+constexpr int kFinApThreads = 128;
+constexpr int kFinApWarps = kFinApThreads / 32;
+constexpr int kFinApPairs = 1024;
+#ifdef Y3D_TIMING
+#define Y3D_APSTAMP(i)                                                                                              \
+    do {                                                                                                            \
+        if (threadIdx.x == 0)                                                                                       \
+            g_y3d_stamps[(((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 2047) * 8 + (i)] = gtimer(); \
+    } while (0)
+#else
+#define Y3D_APSTAMP(i)
+#endif
+
+__global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx2 cc, FinishParams F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GtRec *gts = reinterpret_cast<GtRec *>(smem_raw);
+    __shared__ float2 s_cxy[kFinApThreads];                // contested anchors of the chunk: anchor point (px)
+    __shared__ float4 s_cbox[kFinApThreads];               // predicted box (px)
+    __shared__ unsigned long long s_cbest[kFinApThreads];  // (overlap bits << 32) | (0xffffffff - m): atomicMax = first maximum
+    __shared__ int2 s_pairs[kFinApPairs];                  // (contested anchor, GT) with the anchor inside the GT
+    __shared__ int s_ncf, s_np;
+    __shared__ long long s_redl[4][kFinApWarps];
+    __shared__ double s_redd[kFinApWarps];
+    __shared__ double s_fin[2][5];
+    __shared__ double s_xv[kXMaxVals], s_xs[kXMaxVals];
+    __shared__ int s_xfail, s_flag;
+    const int z = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const AssignCtx &c = cc.c[z];
+    const int M = c.M, A = c.A;
+    Y3D_APSTAMP(0);
+    if (tid == 0) { s_ncf = 0; s_np = 0; }
+    for (int m = tid; m < M; m += kFinApThreads) gts[m] = load_gt(c, b, m);
+    // Everything above reads only the caller's inputs; what follows reads what the top-k kernel wrote.  With
+    // programmatic dependent launch this CTA may have started while that kernel was still draining: wait here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int n = M > 0 ? min(__ldcg(c.list_count + b), c.rec_cap) : 0;
+    const int n_chunks = max(1, (n + kFinApThreads - 1) / kFinApThreads);
+    Y3D_APSTAMP(1);
+    if (chunk >= n_chunks) return;
+    __syncthreads();
+    float4 *rec = c.rec + (long long)b * c.rec_cap * kRecF4;
+    int *pos = F.pos[z] + (long long)b * M * 2;
+    // ---- phase R: one claim record per thread; only the first claimer of an anchor carries it on
+    {
+        const int e = chunk * kFinApThreads + tid;
+        bool active = e < n;
+        int a = 0, cnt = 0, gi = 0, m0 = 0;
+        float ax = 0.f, ay = 0.f, st = 1.f, metric = 0.f, xlab = 0.f;
+        PairRaw raw;
+        raw.box = make_float4(0.f, 0.f, 0.f, 0.f);
+        raw.s = 0.f;
+        float4 ls4 = raw.box, xl4 = raw.box, xr4 = raw.box;
+        if (active) {
+            const float4 r0 = __ldcg(rec + (long long)e * kRecF4);
+            const int aw = __float_as_int(r0.x);
+            active = aw < 0;  // first-claimer bit
+            a = aw & 0x7fffffff;
+            m0 = __float_as_int(r0.y);
+            metric = r0.z;
+            xlab = r0.w;
+        }
+        if (active) {
+            raw.box = __ldcg(rec + (long long)e * kRecF4 + 1);
+            ls4 = __ldcg(rec + (long long)e * kRecF4 + 2);
+            xl4 = __ldcg(rec + (long long)e * kRecF4 + 3);
+            xr4 = __ldcg(rec + (long long)e * kRecF4 + 4);
+            const unsigned long long cl = __ldcg(c.claim + (long long)b * A + a);
+            cnt = (int)(cl >> 32);
+            gi = m0;
+            anchor_px(c, a, ax, ay, st);
+        }
+        const float4 pbox = pair_box(c, raw, a);
+        // multiply-claimed anchors (select_highest_overlaps tal.py:237-264: argmax over ALL GTs of the overlap, first
+        // maximum), resolved by the whole CTA: thread m tests GT m against every contested anchor of the chunk, the
+        // (anchor, GT) pairs with the anchor inside the GT are collected, and their CIoU is evaluated one pair per thread
+        const bool contested = active && cnt > 1;
+        int my_ci = -1;
+        if (contested) {
+            my_ci = atomicAdd(&s_ncf, 1);
+            s_cxy[my_ci] = make_float2(ax, ay);
+            s_cbox[my_ci] = pbox;
+            s_cbest[my_ci] = 0xffffffffull;  // overlap 0 at GT 0: what the reference's argmax of zeros gives
+        }
+        __syncthreads();
+        const int ncf = s_ncf;
+        if (ncf > 0) {
+            auto eval_pair = [&](int ci, int m) {
+                const GtRec g = gts[m];
+                const float ovl = dm::ciou(g.box, s_cbox[ci], g.at1);
+                if (ovl > 0.0f)
+                    atomicMax(&s_cbest[ci],
+                              ((unsigned long long)__float_as_uint(ovl) << 32) | (unsigned long long)(0xffffffffu - (unsigned)m));
+            };
+            for (int m = tid; m < M; m += kFinApThreads) {
+                const GtRec g = gts[m];
+                if (!g.valid) continue;
+                for (int ci = 0; ci < ncf; ++ci) {
+                    const float2 xy = s_cxy[ci];
+                    if (dm::in_gt(xy.x, xy.y, g.box)) {
+                        const int q = atomicAdd(&s_np, 1);
+                        if (q < kFinApPairs) s_pairs[q] = make_int2(ci, m);
+                        else eval_pair(ci, m);  // pair buffer full (every GT contains every contested anchor): in place
+                    }
+                }
+            }
+            __syncthreads();
+            const int np = min(s_np, kFinApPairs);
+            for (int q = tid; q < np; q += kFinApThreads) eval_pair(s_pairs[q].x, s_pairs[q].y);
+            __syncthreads();
+            if (contested) gi = (int)(0xffffffffu - (unsigned)(s_cbest[my_ci] & 0xffffffffull));
+        }
+        if (active) {
+            const GtRec g = gts[gi];
+            const int l = level_of(c.t, a);
+            const int cell = a - c.t.start[l];
+            const float gx = (float)(cell % c.t.w[l]) + 0.5f, gy = (float)(cell / c.t.w[l]) + 0.5f;
+            float4 tb;
+            float tt[4];
+            dfl_target(g.box, st, gx, gy, tb, tt);
+            float ovl = 0.0f;
+            if (gi != m0) {
+                // the anchor went to a GT other than its first claimer (possibly one that never selected it): this
+                // pair's inputs were not gathered by the top-k kernel
+                const float *hp = c.t.ptr[l] + (long long)b * c.t.sB[l] + cell;
+                const long long cs = c.t.sC[l];
+                const int t0 = (int)tt[0], t1 = (int)tt[1], t2 = (int)tt[2], t3 = (int)tt[3];
+                xl4 = make_float4(hp[(long long)t0 * cs], hp[(long long)(kR + t1) * cs], hp[(long long)(2 * kR + t2) * cs],
+                                  hp[(long long)(3 * kR + t3) * cs]);
+                xr4 = make_float4(hp[(long long)(t0 + 1) * cs], hp[(long long)(kR + 1 + t1) * cs],
+                                  hp[(long long)(2 * kR + 1 + t2) * cs], hp[(long long)(3 * kR + 1 + t3) * cs]);
+                xlab = hp[(long long)(4 * kR + (g.label < 0 ? 0 : g.label)) * cs];
+                const float xs = g.label < 0 ? pair_load_score(c, b, a, g.label) : xlab;  // the score the assigner saw
+                metric = 0.0f;
+                if (g.valid && dm::in_gt(ax, ay, g.box))
+                    metric = pair_metric(c, b, gi, g, a, raw, dm::pow_(pair_score(c, xs), c.alpha), ovl);
+            } else {  // metric: the very value the top-k kernel ranked; overlap = clamp(CIoU, 0) as in get_box_metrics
+                ovl = dm::ciou(g.box, pbox, g.at1);
+                ovl = ovl < 0.0f ? 0.0f : ovl;
+            }
+            atomicMax(pos + 2 * gi, __float_as_int(metric));  // values >= 0: int order == float order
+            atomicMax(pos + 2 * gi + 1, __float_as_int(ovl));
+            const float iou = ciou_fast(raw.box, tb);  // BboxLoss.forward loss.py:85 (box1 = pred, grid units)
+            const float xl[4] = {xl4.x, xl4.y, xl4.z, xl4.w}, xr[4] = {xr4.x, xr4.y, xr4.z, xr4.w};
+            const float ls[4] = {ls4.x, ls4.y, ls4.z, ls4.w};
+            float dfl = 0.f;
+#pragma unroll
+            for (int side = 0; side < 4; ++side) {  // _df_loss loss.py:99-113
+                const float wl = (float)((int)tt[side] + 1) - tt[side];
+                dfl += (ls[side] - xl[side]) * wl + (ls[side] - xr[side]) * (1.0f - wl);
+            }
+            // phase S reads words 0 and 1 of the record
+            __stcg(rec + (long long)e * kRecF4, make_float4(__int_as_float(a | (int)0x80000000), __int_as_float(gi), metric, xlab));
+            __stcg(rec + (long long)e * kRecF4 + 1, make_float4(1.0f - iou, dfl * 0.25f, 0.f, 0.f));
+        }
+    }
+    // ---- which chunk of the image finishes last?
+    __syncthreads();
+    Y3D_APSTAMP(2);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag = atomicAdd(F.img_cnt[z] + b, 1) == n_chunks - 1;
+    __syncthreads();
+    Y3D_APSTAMP(3);
+    if (!s_flag) return;
+    __threadfence();
+    // ---- phase S: weights and sums of the whole image
+    long long s_iou = 0, s_dfl = 0, s_ts = 0, s_xt = 0;
+    constexpr int SU = 8;  // records in flight per thread: the loop is two dependent round trips per batch
+    for (int e0 = tid; e0 < n; e0 += kFinApThreads * SU) {
+        float4 r0[SU], r1[SU];
+        int2 pp[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int e = e0 + u * kFinApThreads;
+            r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            r1[u] = r0[u];
+            if (e < n) {
+                r0[u] = __ldcg(rec + (long long)e * kRecF4);
+                r1[u] = __ldcg(rec + (long long)e * kRecF4 + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            pp[u] = make_int2(0, 0);
+            if (__float_as_int(r0[u].x) < 0) pp[u] = __ldcg(reinterpret_cast<const int2 *>(pos) + __float_as_int(r0[u].y));
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int aw = __float_as_int(r0[u].x);
+            if (aw >= 0) continue;  // past the end, or not the anchor's first claimer
+            const int a = aw & 0x7fffffff;
+            const int gi = __float_as_int(r0[u].y);
+            const float alv = r0[u].z, xlab = r0[u].w;
+            const float pa = __int_as_float(pp[u].x), po = __int_as_float(pp[u].y);
+            const float wgt = dm::div(dm::mul(alv, po), dm::add(pa, c.eps));  // = target_scores.sum(-1), tal.py:89-92
+            // kept for the backward pass: the claim word of a foreground anchor becomes (1 << 63 | GT index << 32 | weight)
+            c.claim[(long long)b * A + a] =
+                0x8000000000000000ull | ((unsigned long long)(unsigned)gi << 32) | (unsigned long long)__float_as_uint(wgt);
+            s_iou += to_fix(r1[u].x * wgt);
+            s_dfl += to_fix(r1[u].y * wgt);  // .mean(-1) over the 4 sides is in the record
+            s_ts += to_fix(wgt);
+            s_xt += to_fix(xlab * wgt);  // BCE(x,t) - BCE(x,0) = -x*t
+            if (F.dbg_fg[z]) {
+                F.dbg_fg[z][(long long)b * A + a] = 1;
+                F.dbg_gi[z][(long long)b * A + a] = gi;
+            }
+        }
+    }
+    s_iou = warp_sum_ll(s_iou); s_dfl = warp_sum_ll(s_dfl); s_ts = warp_sum_ll(s_ts); s_xt = warp_sum_ll(s_xt);
+    double bce = 0.0;
+    for (int i = tid; i < F.n_bce_x; i += kFinApThreads)
+        bce += __ldcg(F.part_bce + ((long long)z * gridDim.y + b) * F.n_bce_x + i);
+    bce = warp_sum(bce);
+    if (lane == 0) {
+        s_redl[0][wid] = s_iou; s_redl[1][wid] = s_dfl; s_redl[2][wid] = s_ts; s_redl[3][wid] = s_xt;
+        s_redd[wid] = bce;
+    }
+    __syncthreads();
+    const int B = gridDim.y;
+    double *pimg = F.part_fg + ((long long)z * B + b) * 5;
+    if (tid < 4) {
+        long long s = 0;
+        for (int i = 0; i < kFinApWarps; ++i) s += s_redl[tid][i];
+        pimg[tid] = (double)s / kFix;
+    } else if (tid == 4) {
+        double s = 0.0;
+        for (int i = 0; i < kFinApWarps; ++i) s += s_redd[i];
+        pimg[4] = s;
+    }
+    // last image done: fixed-order reduction of the per-image partials (deterministic whichever CTA it is)
+    Y3D_APSTAMP(4);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag = atomicAdd(F.counter, 1u) == (unsigned)(B * gridDim.z) - 1u;
+    __syncthreads();
+    Y3D_APSTAMP(5);
+    if (!s_flag) return;
+    __threadfence();
+    for (int w = wid; w < 5 * F.n_branch; w += kFinApWarps) {  // warp job (zz, k): lane-strided, then a fixed shuffle tree
+        const int zz = w / 5, k = w % 5;
+        double acc = 0.0;
+        for (int i = lane; i < B; i += 32) acc += __ldcg(F.part_fg + ((long long)zz * B + i) * 5 + k);
+        acc = warp_sum(acc);
+        if (lane == 0) s_fin[zz][k] = acc;
+    }
+    __syncthreads();
+    if (tid < 4 * F.n_branch) {  // partials of a branch: iou, bce, dfl, target_scores_sum
+        const int zz = tid >> 2, j = tid & 3;
+        s_xv[tid] = j == 0 ? s_fin[zz][0] : j == 1 ? s_fin[zz][4] - s_fin[zz][3] : j == 2 ? s_fin[zz][1] : s_fin[zz][2];
+    }
+    __syncthreads();
+    const double *tot = s_xv;
+    if (F.x_world > 1) {  // sum over the ranks: stores into every peer's buffer, wait, rank-ordered sum
+        xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, s_xv, 4 * F.n_branch, s_xs, &s_xfail);
+        tot = s_xs;
+        if (tid == 0 && F.x_status) *F.x_status = s_xfail;
+    }
+    if (tid < 4 * F.n_branch && F.partials) F.partials[tid] = tot[tid];
+    if (tid < F.n_branch && F.normalise && F.loss_items) {
+        const int zz = tid;
+        const double tss = tot[4 * zz + 3] > 1.0 ? tot[4 * zz + 3] : 1.0;  // max(target_scores.sum(), 1) loss.py:240
+        F.loss_items[4 * zz + 0] = (float)(tot[4 * zz + 0] / tss * F.gain_box);
+        F.loss_items[4 * zz + 1] = (float)(tot[4 * zz + 1] / tss * F.gain_cls);
+        F.loss_items[4 * zz + 2] = (float)(tot[4 * zz + 2] / tss * F.gain_dfl);
+        F.loss_items[4 * zz + 3] = (float)tss;
+    }
+}
+
 __global__ void loss_finalize_partials_kernel(const double *__restrict__ partials, int n_branch, float gain_box,
                                               float gain_cls, float gain_dfl, float *__restrict__ loss_items) {
     const int z = threadIdx.x;
@@ -733,9 +1025,16 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     const LossWs w = loss_ws_layout(nb, B, A, M, kmax);
     if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
     if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    const size_t A0 = (size_t)A;
+    const bool use_ap = M <= kFinishApMaxM;
     const size_t fin_smem = finish_smem_bytes(M);
-    if (fin_smem > 212 * 1024) return Y3D_EUNSUPPORTED;  // + 8 KB static (exchange scratch) <= 227 KB
+    if (!use_ap && fin_smem > 212 * 1024) return Y3D_EUNSUPPORTED;  // + 8 KB static (exchange scratch) <= 227 KB
     cudaStream_t s = (cudaStream_t)stream;
+    if (use_ap && dbg_fg_mask) {  // the anchor-parallel kernel writes the foreground entries only
+        cudaError_t e1 = cudaMemsetAsync(dbg_fg_mask, 0, (size_t)nb * B * A0, s);
+        cudaError_t e2 = cudaMemsetAsync(dbg_target_gt_idx, 0, sizeof(int32_t) * (size_t)nb * B * A0, s);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
+    }
     char *p = (char *)ws;
     auto mark = [&](int i) {
         if (prof_events && prof_events[i]) cudaEventRecord((cudaEvent_t)prof_events[i], s);
@@ -752,12 +1051,20 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         c.list_count = (int *)(q + w.list_count);
         c.list_a = (int *)(q + w.list_a);
         c.list_cap = w.cap;
+        if (M <= kFinishApMaxM) {  // anchor-parallel finish: claim records instead of the list
+            c.list_a = nullptr;
+            c.rec = (float4 *)(q + w.rec);
+            c.rec_cap = w.rcap;
+            c.lse = (const float *)(q + w.lse);
+        }
         float *boxes = (float *)(q + w.boxes);
         P.boxes[z] = boxes;
         P.lse[z] = (float *)(q + w.lse);
         P.pd_scores[z] = nullptr;
         P.claim[z] = M > 0 ? c.claim : nullptr;
         P.list_count[z] = c.list_count;
+        P.img_cnt[z] = (int *)(q + w.img_cnt);
+        P.pos[z] = M > 0 ? (int *)(q + w.pos) : nullptr;
         c.score_mode = 1;
         c.cls_ch0 = 4 * kR;
         c.pd_bboxes = boxes; c.box_grid_units = 1; c.box_soa = 1;
@@ -771,6 +1078,8 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         F.lse[z] = P.lse[z];
         F.list_gi[z] = (int *)(q + w.list_gi);
         F.list_al[z] = (float *)(q + w.list_al);
+        F.img_cnt[z] = P.img_cnt[z];
+        F.pos[z] = (int *)(q + w.pos);
         F.dbg_fg[z] = dbg_fg_mask ? dbg_fg_mask + (size_t)z * B * A : nullptr;
         F.dbg_gi[z] = dbg_target_gt_idx ? dbg_target_gt_idx + (size_t)z * B * A : nullptr;
     }
@@ -808,21 +1117,32 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         F.x_bufs = (XSlot *const *)xr->bufs_dev;
         F.x_rank = xr->rank; F.x_world = xr->world; F.x_seq = xr->seq; F.x_status = xr->status;
     }
-    {
-        cudaError_t e = cudaFuncSetAttribute(loss_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    {   // programmatic dependent launch: the prologue (GT records, shared-memory setup) overlaps the top-k kernel's tail
-        cudaLaunchConfig_t cfg = {};
+    // programmatic dependent launch: the prologue (GT records) overlaps the top-k kernel's tail
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (use_ap) {  // claimed anchors spread over the machine, kFinApThreads per CTA
+        cfg.gridDim = dim3((unsigned)((w.rcap + kFinApThreads - 1) / kFinApThreads), B, nb);
+        cfg.blockDim = dim3(kFinApThreads);
+        cfg.dynamicSmemBytes = sizeof(GtRec) * (size_t)M;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, loss_finish_ap_kernel, cc, F);
+        if (le != cudaSuccess) return (int)le;
+    } else {  // dense crowds: one CTA per (image, branch) with a spatial index of the GT boxes
+        static bool attr_set = false;  // the limit only ever grows to the largest value asked for
+        static size_t attr_bytes = 0;
+        if (!attr_set || fin_smem > attr_bytes) {
+            cudaError_t e = cudaFuncSetAttribute(loss_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+            attr_bytes = 212 * 1024;
+        }
         cfg.gridDim = dim3(B, nb);
         cfg.blockDim = dim3(kFinishThreads);
         cfg.dynamicSmemBytes = fin_smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
         cudaError_t le = cudaLaunchKernelEx(&cfg, loss_finish_kernel, cc, F);
         if (le != cudaSuccess) return (int)le;
     }

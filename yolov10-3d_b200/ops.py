@@ -43,12 +43,14 @@ def v10_3Dpostprocess(preds, max_det, nc=3):
 
 
 def xywh2xyxy(x):
-    """ops.py:403-422 (tiny elementwise glue used by the validators right after v10postprocess)."""
-    assert x.shape[-1] == 4, f"input shape last dimension expected 4 but input shape is {x.shape}"
-    y = torch.empty_like(x)
-    dw, dh = x[..., 2] / 2, x[..., 3] / 2
-    y[..., 0] = x[..., 0] - dw
-    y[..., 1] = x[..., 1] - dh
-    y[..., 2] = x[..., 0] + dw
-    y[..., 3] = x[..., 1] + dh
-    return y
+    """(cx, cy, w, h) -> (x1, y1, x2, y2) on the last axis, torch tensor or numpy array (the contract of ops.py:403-422;
+    the validators call it right after ``v10postprocess``).  Halving is exact in binary floating point, so the result
+    equals the reference's ``x - w / 2`` bit for bit."""
+    if x.shape[-1] != 4:
+        raise AssertionError(f"input shape last dimension expected 4 but input shape is {x.shape}")
+    centre, half = x[..., :2], x[..., 2:] * 0.5
+    if torch.is_tensor(x):
+        return torch.cat((centre - half, centre + half), dim=-1)
+    import numpy as np
+
+    return np.concatenate((centre - half, centre + half), axis=-1)

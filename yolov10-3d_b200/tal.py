@@ -9,18 +9,18 @@ from ._util import f32c, geometry, ptr, stream_ptr, workspace
 
 
 def make_anchors(feats, strides, grid_cell_offset=0.5):
-    """tal.py:300-312 (kept as a torch helper for callers that want the tensors; the kernels never read them)."""
-    anchor_points, stride_tensor = [], []
-    assert feats is not None
+    """Anchor centres and stride column with the semantics of the reference helper (tal.py:300-312): level by level,
+    row-major inside a level, ``(x, y) = (col, row) + grid_cell_offset`` in grid units.  Convenience for callers that want
+    the tensors -- the kernels derive both from the cell index and never read them."""
     dtype, device = feats[0].dtype, feats[0].device
-    for i, stride in enumerate(strides):
-        _, _, h, w = feats[i].shape
-        sx = torch.arange(end=w, device=device, dtype=dtype) + grid_cell_offset
-        sy = torch.arange(end=h, device=device, dtype=dtype) + grid_cell_offset
-        sy, sx = torch.meshgrid(sy, sx, indexing="ij")
-        anchor_points.append(torch.stack((sx, sy), -1).view(-1, 2))
-        stride_tensor.append(torch.full((h * w, 1), float(stride), dtype=dtype, device=device))
-    return torch.cat(anchor_points), torch.cat(stride_tensor)
+    points, stride_col = [], []
+    for f, s in zip(feats, strides):
+        h, w = int(f.shape[-2]), int(f.shape[-1])
+        cell = torch.arange(h * w, device=device)
+        xy = torch.stack((cell % w, cell // w), dim=1).to(dtype) + grid_cell_offset
+        points.append(xy)
+        stride_col.append(xy.new_full((h * w, 1), float(s)))
+    return torch.cat(points), torch.cat(stride_col)
 
 
 def _require_cuda(t):

@@ -9,15 +9,6 @@
 
 namespace y3d {
 
-// ----------------------------------------------------------------------------------------------------------------
-// Top-k entries are 64-bit keys: metric bits (>= 0, so integer order == float order) | 0x7fffffff - anchor | in-GT bit.
-// A larger key is a better entry (value desc, index asc); 0 is the empty slot.
-__device__ __forceinline__ unsigned long long tk_key(float metric, int a, int in) {
-    return ((unsigned long long)__float_as_uint(metric) << 32) | ((unsigned long long)(0x7fffffff - a) << 1) |
-           (unsigned long long)(in & 1);
-}
-__device__ __forceinline__ int tk_anchor(unsigned long long key) { return 0x7fffffff - (int)((key & 0xffffffffull) >> 1); }
-
 // grid: persistent CTAs (rectangle walk) or one CTA per (branch, image, GT) (all-anchor scan); block kTopkWarps*32.
 // wpg = warps per GT: 1 (rectangle walk) or kTopkWarps (all-anchor scan; the warps' lists are merged through shared
 // memory).
@@ -546,10 +537,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                 r4 = make_float4(hp[(long long)(t0 + 1) * cs], hp[(long long)(17 + t1) * cs], hp[(long long)(33 + t2) * cs],
                                  hp[(long long)(49 + t3) * cs]);
                 xlab = hp[(long long)(c.cls_ch0 + (g.label < 0 ? 0 : g.label)) * cs];
-                const float *bp = c.pd_bboxes + (long long)b * 4 * c.A + a;
-                r1 = make_float4(bp[0], bp[c.A], bp[2 * (long long)c.A], bp[3 * (long long)c.A]);
-                const float *lp = c.lse + (long long)b * 4 * c.A + a;
-                r2 = make_float4(lp[0], lp[c.A], lp[2 * (long long)c.A], lp[3 * (long long)c.A]);
+                r1 = reinterpret_cast<const float4 *>(c.pd_bboxes)[(long long)b * c.A + a];
+                r2 = reinterpret_cast<const float4 *>(c.lse)[(long long)b * c.A + a];
                 old = atomicAdd(c.claim + (long long)b * c.A + a, (1ull << 32) | (unsigned long long)m);
             }
             const int leader = __ffs(cmask) - 1;
@@ -565,6 +554,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
                 r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4;
             }
         }
+        __syncwarp();
+        if (lane == 0 && c.topk_done) red_release_add1(c.topk_done + b);  // this GT is through (see assign.cuh)
     } else if (lane < k && tk != 0ull && (tk & 1ull)) {
         const int a = tk_anchor(tk);
         const unsigned long long old = atomicAdd(c.claim + (long long)b * c.A + a, (1ull << 32) | (unsigned long long)m);

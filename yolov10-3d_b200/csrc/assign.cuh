@@ -67,7 +67,10 @@ struct AssignCtx {
     //   [3] logit of the lower DFL target bin of every side   [4] logit of the upper one
     float4 *rec;
     int rec_cap;
-    const float *lse;  // [B,4,A] planes written by the streaming kernel
+    const float *lse;  // [B,A,4] written by the streaming kernel
+    // optional, with rec: [B] zero-initialised; +1 (release) after a valid GT's records are written, so that the
+    // finishing kernel can take an image as soon as all its GTs are through instead of waiting for the whole grid
+    unsigned *topk_done;
 };
 
 // bbox2dist (tal.py:328-331) of anchor (gx, gy) in grid units against GT box gbox (px) at stride st, clamped like
@@ -288,6 +291,24 @@ struct AssignCtx2 {
 constexpr int kOrdClasses = 4;
 constexpr int kOrdMaxSeg = 2047;  // segments = classes x branches x images the top-k kernel's prefix table holds
 
+// ----------------------------------------------------------------------------------------------------------------
+// Top-k entries are 64-bit keys: metric bits (>= 0, so integer order == float order) | 0x7fffffff - anchor | in-GT bit.
+// A larger key is a better entry (value desc, index asc); 0 is the empty slot.
+__device__ __forceinline__ unsigned long long tk_key(float metric, int a, int in) {
+    return ((unsigned long long)__float_as_uint(metric) << 32) | ((unsigned long long)(0x7fffffff - a) << 1) |
+           (unsigned long long)(in & 1);
+}
+__device__ __forceinline__ int tk_anchor(unsigned long long key) { return 0x7fffffff - (int)((key & 0xffffffffull) >> 1); }
+
+__device__ __forceinline__ void red_release_add1(unsigned *p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // host helpers --------------------------------------------------------------------------------------------------
 struct AssignWs {
     size_t off_cnt, off_pa, off_po, off_work, off_tgi, off_align, off_norm, off_lab, total, zero_bytes;
@@ -325,5 +346,9 @@ int launch_kps_gt(const float *gts, const float *calibs, const float *mean_sizes
                   cudaStream_t s);
 // top-k + claims only (the fused loss path finishes with its own kernel)
 int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl = false);
+// the same for the fused loss' configuration (logits from the head, alpha 0.5, beta 6, in-GT constraint, grid, [B,A,4]
+// boxes in grid units): specialised kernel in topk_fused.cu.  Returns Y3D_EUNSUPPORTED when the context does not match.
+int assign_run_topk_fused(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl);
+int device_sm_count();
 
 }  // namespace y3d

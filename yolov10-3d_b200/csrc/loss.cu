@@ -67,15 +67,47 @@ __device__ __forceinline__ void stv(float *p, const float (&o)[V]) {
     }
 }
 
+#ifdef Y3D_TIMING
+// step timeline (developer builds): [0] ~first stream CTA start [1] last stream CTA end [2] ~first finish CTA start
+// [3] ~first finish CTA past its image wait [4] last phase-R end [5] final reduction end   (~t under atomicMax = minimum)
+__device__ unsigned long long g_y3d_tl[8];
+#define Y3D_TL_MIN(i) do { if (threadIdx.x == 0) atomicMax(&g_y3d_tl[i], ~gtimer()); } while (0)
+#define Y3D_TL_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_y3d_tl[i], gtimer()); } while (0)
+extern "C" int y3d_debug_read_timeline(unsigned long long *host, int reset) {
+    int rc = (int)cudaMemcpyFromSymbol(host, g_y3d_tl, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {};
+        cudaMemcpyToSymbol(g_y3d_tl, z, sizeof(z));
+    }
+    return rc;
+}
+__device__ unsigned long long g_y3d_stamps[2048 * 8];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define Y3D_STAMP(i)                                                                                  \
+    do {                                                                                              \
+        __syncthreads();                                                                              \
+        if (threadIdx.x == 0) g_y3d_stamps[((blockIdx.y * gridDim.x + blockIdx.x) & 2047) * 8 + (i)] = gtimer(); \
+    } while (0)
+#else
+#define Y3D_STAMP(i)
+#define Y3D_TL_MIN(i)
+#define Y3D_TL_MAX(i)
+#endif
+
 // ---------------------------------------------------------------------------------------------- stream kernel
 struct StreamParams {
     LevelTable t[2];
-    float *boxes[2];       // [B,4,A] planes (box_aos == 0) or [B,A,4] (box_aos == 1); xyxy grid units
-    float *lse[2];         // optional [B,4,A]: log-sum-exp of the 16 DFL bins of every side
+    float *boxes[2];       // [B,A,4] xyxy grid units (the layout of the reference's pred_bboxes, loss.py:233)
+    float *lse[2];         // optional [B,A,4]: log-sum-exp of the 16 DFL bins of every side
     float *pd_scores[2];   // optional [B,A,nc] sigmoid (y3d_train_decode only)
     unsigned long long *claim[2];  // optional [B,A], zeroed here
     int *list_count[2];    // optional [B], zeroed here
     int *img_cnt[2];       // optional [B], zeroed here: finished chunks of the image (anchor-parallel finishing kernel)
+    unsigned *topk_done[2];  // optional [B], zeroed here: GTs of the image the top-k kernel has finished
     int *pos[2];           // optional [B,M,2], zeroed here: per-GT maxima of alignment metric and overlap
     unsigned *counter;     // optional ticket of the finishing kernel (+1: work counter of the top-k kernel), zeroed here
     double *part_bce;      // [n_branch][gridDim.x * B] or nullptr
@@ -83,7 +115,7 @@ struct StreamParams {
     int *ord_cnt, *ord_list;  // optional [B][4], [B][M] x 32-byte records: see AssignCtx2
     float ord_cells_per_px2;  // sum over the levels of 1 / stride^2: candidate cells of a GT per px^2 of its area
     int M;
-    int n_branch, B, nc, A, box_aos;
+    int n_branch, B, nc, A;
 };
 
 // One warp sorts the valid GTs of image b into kOrdClasses classes by their number of candidate cells (stable within a
@@ -126,17 +158,25 @@ static __device__ __noinline__ void zero_ints(int *p, int n, int lane) {
 template <int V, bool PS>
 __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __grid_constant__ StreamParams P) {
     __shared__ double red[4];
+    // the four warps of a CTA each decode one side of the same 32 * V anchors: the sides meet here so that boxes and
+    // log-sum-exps leave as one 16-byte record per anchor (what every later gather wants), in coalesced stores
+    __shared__ __align__(16) float s_box[4][32 * V];
+    __shared__ __align__(16) float s_lse[4][32 * V];
     const int z = blockIdx.z, b = blockIdx.y;
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
     const int q = blockIdx.x * 32 + lane;
     const LevelTable &t = P.t[z];
     const int A = P.A;
     const unsigned long long pol = l2_evict_first_policy();
-    // lets a programmatically dependent launch (the fused loss' top-k kernel) be scheduled as this grid drains
+    // programmatic dependent launch, both ways: wait for the previous kernel in the stream (a no-op after an ordinary
+    // launch), then let the dependent of this grid (the fused loss' top-k kernel) be scheduled as this grid drains
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
+    Y3D_TL_MIN(0);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (P.list_count[z]) P.list_count[z][b] = 0;
         if (P.img_cnt[z]) P.img_cnt[z][b] = 0;
+        if (P.topk_done[z]) P.topk_done[z][b] = 0u;
         if (b == 0 && z == 0 && P.counter) { P.counter[0] = 0u; P.counter[1] = 0u; }
     }
     float bce = 0.f;
@@ -174,13 +214,8 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __
                 ob[i] = part < 2 ? __fsub_rn(anc, d) : __fadd_rn(anc, d);  // dist2bbox xyxy tal.py:319-325
                 if (++cx >= w) { cx = 0; ++cy; }
             }
-            if (P.box_aos) {
-#pragma unroll
-                for (int i = 0; i < V; ++i) P.boxes[z][((long long)b * A + a0 + i) * 4 + part] = ob[i];
-            } else {
-                stv<V>(P.boxes[z] + ((long long)b * 4 + part) * A + a0, ob);
-            }
-            if (P.lse[z]) stv<V>(P.lse[z] + ((long long)b * 4 + part) * A + a0, ol);
+            stv<V>(&s_box[part][lane * V], ob);
+            stv<V>(&s_lse[part][lane * V], ol);
         }
         if (part == 0 && P.claim[z]) {
             unsigned long long *cl = P.claim[z] + (long long)b * A + a0;
@@ -234,18 +269,30 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __
 #pragma unroll
         for (int i = 0; i < V; ++i) bce += tot[i];
     }
-    if (P.part_bce) {  // fixed-order block reduction -> one partial per CTA
+    {  // fixed-order block reduction -> one partial per CTA
         const double w = warp_sum((double)bce);
         if (lane == 0) red[part] = w;
         __syncthreads();
-        if (threadIdx.x == 0)
+        if (P.part_bce && threadIdx.x == 0)
             P.part_bce[((long long)z * gridDim.y + b) * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+    {  // anchor t of this CTA's 32 * V: its four sides as one float4
+        const int t = threadIdx.x;
+        const int a = blockIdx.x * 32 * V + t;
+        if (t < 32 * V && a < A) {
+            reinterpret_cast<float4 *>(P.boxes[z])[(long long)b * A + a] =
+                make_float4(s_box[0][t], s_box[1][t], s_box[2][t], s_box[3][t]);
+            if (P.lse[z])
+                reinterpret_cast<float4 *>(P.lse[z])[(long long)b * A + a] =
+                    make_float4(s_lse[0][t], s_lse[1][t], s_lse[2][t], s_lse[3][t]);
+        }
     }
     // one warp per image: the processing order of the image's GTs for the top-k kernel
     if (P.ord_cnt && blockIdx.x == 0 && z == 0 && part == 0)
         gt_order_image(P.gt5, P.M, b, P.ord_cells_per_px2, P.ord_cnt, P.ord_list, lane);
     // one warp per image and branch: zero the per-GT maxima the finishing kernel folds its atomicMax into
     if (P.pos[z] && blockIdx.x == 0 && part == 1) zero_ints(P.pos[z] + (long long)b * P.M * 2, 2 * P.M, lane);
+    Y3D_TL_MAX(1);
 }
 
 // ---------------------------------------------------------------------------------------------- finishing kernel
@@ -300,21 +347,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
     return v;
 }
 
-#ifdef Y3D_TIMING
-__device__ unsigned long long g_y3d_stamps[2048 * 8];
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define Y3D_STAMP(i)                                                                                  \
-    do {                                                                                              \
-        __syncthreads();                                                                              \
-        if (threadIdx.x == 0) g_y3d_stamps[((blockIdx.y * gridDim.x + blockIdx.x) & 2047) * 8 + (i)] = gtimer(); \
-    } while (0)
-#else
-#define Y3D_STAMP(i)
-#endif
+
 
 constexpr int kConfMax = 1024;  // multiply-claimed anchors resolved cooperatively per image (more: serial fallback)
 constexpr int kFinishWarps = kFinishThreads / 32;
@@ -348,6 +381,7 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
     const int z = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AssignCtx &c = cc.c[z];
     const int M = c.M, A = c.A;
+    asm volatile("griddepcontrol.launch_dependents;");  // the next kernel in the stream may become resident (it waits)
     Y3D_STAMP(0);
     GtRec *gts = reinterpret_cast<GtRec *>(smem_raw + sizeof(FinishSmem));
     int *pos_a = reinterpret_cast<int *>(gts + M);
@@ -565,9 +599,10 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         // target_bboxes /= stride_tensor (loss.py:248)
         const float4 tb = make_float4(dm::div(g.box.x, st), dm::div(g.box.y, st), dm::div(g.box.z, st), dm::div(g.box.w, st));
         const float ltrb[4] = {ax - tb.x, ay - tb.y, tb.z - ax, tb.w - ay};  // bbox2dist tal.py:328-331
-        const float *bp = c.pd_bboxes + (long long)b * 4 * A + a;
-        const float *lp = F.lse[z] + (long long)b * 4 * A + a;
-        float xl[4], xr[4], ls[4], wl[4], pbv[4];
+        const float4 pb4 = __ldcg(reinterpret_cast<const float4 *>(c.pd_bboxes) + (long long)b * A + a);
+        const float4 ls4 = __ldcg(reinterpret_cast<const float4 *>(F.lse[z]) + (long long)b * A + a);
+        const float ls[4] = {ls4.x, ls4.y, ls4.z, ls4.w};
+        float xl[4], xr[4], wl[4];
 #pragma unroll
         for (int side = 0; side < 4; ++side) {  // all gathers first
             const float tt = fminf(fmaxf(ltrb[side], 0.0f), (float)(kR - 1) - 0.01f);
@@ -575,11 +610,9 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
             wl[side] = (float)(tl + 1) - tt;
             xl[side] = hp[(long long)(side * kR + tl) * cs];
             xr[side] = hp[(long long)(side * kR + tl + 1) * cs];
-            ls[side] = __ldcg(lp + (long long)side * A);
-            pbv[side] = __ldcg(bp + (long long)side * A);
         }
         const float xlab = hp[(long long)(4 * kR + lab) * cs];
-        const float4 pb = make_float4(pbv[0], pbv[1], pbv[2], pbv[3]);
+        const float4 pb = pb4;
         const float iou = ciou_fast(pb, tb);  // BboxLoss.forward loss.py:85 (box1 = pred)
         float dfl = 0.f;
 #pragma unroll
@@ -703,15 +736,29 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AssignCtx &c = cc.c[z];
     const int M = c.M, A = c.A;
+    asm volatile("griddepcontrol.launch_dependents;");  // the next kernel in the stream may become resident (it waits)
     Y3D_APSTAMP(0);
+    Y3D_TL_MIN(2);
     if (tid == 0) { s_ncf = 0; s_np = 0; }
-    for (int m = tid; m < M; m += kFinApThreads) gts[m] = load_gt(c, b, m);
-    // Everything above reads only the caller's inputs; what follows reads what the top-k kernel wrote.  With
-    // programmatic dependent launch this CTA may have started while that kernel was still draining: wait here.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    bool my_valid = false;
+    for (int m = tid; m < M; m += kFinApThreads) {
+        gts[m] = load_gt(c, b, m);
+        my_valid = gts[m].valid;  // M <= kFinishApMaxM == blockDim.x: one GT per thread
+    }
+    const int n_valid = __syncthreads_count(my_valid);
+    if (chunk > 0 && chunk * kFinApThreads >= n_valid * c.k) return;  // more records than this image can have
+    // Everything above reads only the caller's inputs.  This grid is launched programmatically dependent on the top-k
+    // kernel and becomes resident as that kernel's CTAs retire; it does not wait for the whole grid but for its own
+    // image: the top-k kernel counts the GTs it has finished per image (release), all of them = the records are there.
+    if (tid == 0 && n_valid > 0) {
+        const unsigned *done = c.topk_done + b;
+        while (ld_acquire_u32(done) < (unsigned)n_valid) __nanosleep(200);
+    }
+    __syncthreads();
     const int n = M > 0 ? min(__ldcg(c.list_count + b), c.rec_cap) : 0;
     const int n_chunks = max(1, (n + kFinApThreads - 1) / kFinApThreads);
     Y3D_APSTAMP(1);
+    Y3D_TL_MIN(3);
     if (chunk >= n_chunks) return;
     __syncthreads();
     float4 *rec = c.rec + (long long)b * c.rec_cap * kRecF4;
@@ -832,6 +879,7 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     // ---- which chunk of the image finishes last?
     __syncthreads();
     Y3D_APSTAMP(2);
+    Y3D_TL_MAX(4);
     __threadfence();
     __syncthreads();
     if (tid == 0) s_flag = atomicAdd(F.img_cnt[z] + b, 1) == n_chunks - 1;
@@ -911,6 +959,10 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     __syncthreads();
     Y3D_APSTAMP(5);
     if (!s_flag) return;
+    // every image is through, so the top-k kernel has no work left -- but its last warps may still be on their way out,
+    // and the next kernel in the stream (which waits for THIS grid) resets the counters they read: do not complete
+    // before the primary grid has
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __threadfence();
     for (int w = wid; w < 5 * F.n_branch; w += kFinApWarps) {  // warp job (zz, k): lane-strided, then a fixed shuffle tree
         const int zz = w / 5, k = w % 5;
@@ -973,14 +1025,27 @@ static int launch_stream(const StreamParams &P, int *n_bce, cudaStream_t s) {
     dim3 grid((units + 31) / 32, P.B, P.n_branch);
     *n_bce = (int)(grid.x * grid.y);
     const bool ps = P.pd_scores[0] != nullptr;
+    // programmatic dependent launch: when the previous kernel in the stream lets its dependents start early (the
+    // finishing kernel of the previous step does), this grid is resident and waiting when that kernel ends
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kStreamThreads);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le;
     if (v4 && !ps)
-        head_stream_kernel<4, false><<<grid, kStreamThreads, 0, s>>>(P);
+        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<4, false>, P);
     else if (v4)
-        head_stream_kernel<4, true><<<grid, kStreamThreads, 0, s>>>(P);
+        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<4, true>, P);
     else if (!ps)
-        head_stream_kernel<1, false><<<grid, kStreamThreads, 0, s>>>(P);
+        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<1, false>, P);
     else
-        head_stream_kernel<1, true><<<grid, kStreamThreads, 0, s>>>(P);
+        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<1, true>, P);
+    if (le != cudaSuccess) return (int)le;
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }
@@ -1040,7 +1105,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         if (prof_events && prof_events[i]) cudaEventRecord((cudaEvent_t)prof_events[i], s);
     };
     mark(0);
-    P.n_branch = nb; P.B = B; P.nc = nc; P.A = A; P.box_aos = 0;
+    P.n_branch = nb; P.B = B; P.nc = nc; P.A = A;
     P.part_bce = (double *)(p + w.off_pbce);
     P.counter = (unsigned *)(p + w.off_counter);
     FinishParams F{};
@@ -1056,6 +1121,8 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
             c.rec = (float4 *)(q + w.rec);
             c.rec_cap = w.rcap;
             c.lse = (const float *)(q + w.lse);
+            c.topk_done = (unsigned *)(q + w.topk_done);
+            P.topk_done[z] = c.topk_done;
         }
         float *boxes = (float *)(q + w.boxes);
         P.boxes[z] = boxes;
@@ -1067,7 +1134,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         P.pos[z] = M > 0 ? (int *)(q + w.pos) : nullptr;
         c.score_mode = 1;
         c.cls_ch0 = 4 * kR;
-        c.pd_bboxes = boxes; c.box_grid_units = 1; c.box_soa = 1;
+        c.pd_bboxes = boxes; c.box_grid_units = 1; c.box_soa = 0;
         c.use_grid = 1;
         c.gt_labels = gt; c.gl_stride = 5;
         c.gt_bboxes = gt ? gt + 1 : nullptr; c.gb_stride = 5;
@@ -1101,7 +1168,8 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     mark(1);
     cc.work_counter = (int *)(P.counter + 1);
     if (M > 0) {
-        rc = assign_run_topk(cc, nb, s, /*pdl=*/true);  // scheduled while the streaming kernel drains
+        rc = assign_run_topk_fused(cc, nb, s, /*pdl=*/true);  // scheduled while the streaming kernel drains
+        if (rc == Y3D_EUNSUPPORTED) rc = assign_run_topk(cc, nb, s, /*pdl=*/true);  // few GTs: several warps per GT
         if (rc) return rc;
     }
     mark(2);
@@ -1160,6 +1228,7 @@ extern "C" int y3d_train_decode(const float *const *lvl_ptr, const int64_t *lvl_
                                 float *pd_bboxes, float *pd_scores, void *stream) {
     if (!lvl_ptr || !lvl_sB || !lvl_sC || !pd_bboxes || B < 0 || nc < 1) return Y3D_EINVAL;
     if (reg_max != kR) return Y3D_EUNSUPPORTED;
+    if (((uintptr_t)pd_bboxes) % 16) return Y3D_EALIGN;  // one 16-byte store per anchor
     StreamParams P{};
     int A = make_level_table(P.t[0], lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl);
     if (A < 0) return A;
@@ -1168,7 +1237,7 @@ extern "C" int y3d_train_decode(const float *const *lvl_ptr, const int64_t *lvl_
     if (B == 0) return Y3D_OK;
     P.t[1] = P.t[0];
     P.n_branch = 1; P.B = B; P.nc = nc; P.A = A;
-    P.boxes[0] = pd_bboxes; P.box_aos = 1;  // the reference layout [B,A,4]
+    P.boxes[0] = pd_bboxes;  // the reference layout [B,A,4]
     P.pd_scores[0] = pd_scores;
     int n_bce;
     return launch_stream(P, &n_bce, (cudaStream_t)stream);

@@ -11,7 +11,7 @@ constexpr int kFinishApMaxM = 128;  // GTs per image up to which the anchor-para
 constexpr int kRecF4 = 5;           // float4 words of a claim record (assign.cuh)
 
 struct LossWs {  // all offsets 256-byte aligned; per-branch blocks are contiguous
-    size_t claim, boxes, lse, list_a, list_gi, list_al, rec, list_count, img_cnt, pos, per_branch;
+    size_t claim, boxes, lse, list_a, list_gi, list_al, rec, list_count, img_cnt, topk_done, pos, per_branch;
     size_t off_counter, off_pfg, off_pbce, off_ord_cnt, off_ord_list, total;
     int cap, rcap, n_bce;
 };
@@ -35,6 +35,7 @@ inline LossWs loss_ws_layout(int nb, int B, int A, int M, int k) {
     w.rec = o;        o += a256(16 * (size_t)kRecF4 * B * w.rcap);
     w.list_count = o; o += a256(sizeof(int) * (size_t)B);
     w.img_cnt = o;    o += a256(sizeof(int) * (size_t)B);
+    w.topk_done = o;  o += a256(sizeof(int) * (size_t)B);
     w.pos = o;        o += a256(sizeof(int) * 2 * (size_t)B * (M > 0 ? M : 1));  // per GT: max alignment, max overlap
     w.per_branch = o;
     w.off_counter = (size_t)nb * w.per_branch;

@@ -29,7 +29,7 @@ struct BwdParams {
     float gain_box, gain_cls, gain_dfl;
     int n_branch, B, nc, A, M, cap;
     const float *gt5;                      // [B,M,5]
-    const float *boxes[2];                 // forward workspace: [B,4,A] xyxy grid units
+    const float *boxes[2];                 // forward workspace: [B,A,4] xyxy grid units
     const unsigned long long *claim[2];    // forward workspace: [B,A]; bit 63 = foreground, GT index << 32 | weight bits
 };
 
@@ -100,8 +100,7 @@ __device__ __noinline__ void bwd_fg_patch(const BwdParams &P, int z, int b, int 
     int lab = (int)g5[0];
     lab = lab < 0 ? 0 : lab;
     const float4 tb = make_float4(g5[1] / st, g5[2] / st, g5[3] / st, g5[4] / st);
-    const float *bp = P.boxes[z] + (long long)b * 4 * A + a;
-    const float4 pb = make_float4(bp[0], bp[A], bp[2 * (long long)A], bp[3 * (long long)A]);
+    const float4 pb = reinterpret_cast<const float4 *>(P.boxes[z])[(long long)b * A + a];
     const float tss = P.items[4 * z + 3];
     const float c_box = P.gitems[3 * z + 0] * P.gain_box / tss;
     const float c_cls = P.gitems[3 * z + 1] * P.gain_cls / tss;

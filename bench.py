@@ -208,8 +208,9 @@ def main_cuda(args):
 
     # The bracket around the dominant kernel is recorded on every EV_EVERY-th timed step only: an event record between
     # two launches costs ~2 us and keeps the top-k kernel from being scheduled while the streaming kernel drains
-    # (programmatic dependent launch), so bracketing every step would slow down what it measures.
-    EV_EVERY = max(1, int(os.environ.get("Y3D_BENCH_EVENT_EVERY", "4")))
+    # (programmatic dependent launch), so bracketing every step would slow down what it measures (a bracketed step is
+    # ~5 us longer than a plain one).
+    EV_EVERY = max(1, int(os.environ.get("Y3D_BENCH_EVENT_EVERY", "8")))
 
     def step(i=None):
         pe = ev_c[i] if (i is not None and i % EV_EVERY == 0) else None
@@ -307,7 +308,10 @@ def main_cuda(args):
                                        "peer memory (csrc/xrank.cu)") if peer else
                                       "NCCL all_reduce of 8 float64 loss partials per step + finalize kernel")},
             "roofline": {"bound": "hbm", "kernel": "head_stream_kernel<4>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         # the whole step against the same roof: algorithmic bytes / ms_per_step / peak (north star: >= 0.6)
+                         "step_frac": alg_bytes * world / ((ms_total / K) * 1e-3) / 1e9 / peak / world,
+                         "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(stage_ms[0]),
                          "kernel_ms_source": f"CUDA events around the kernel on every {EV_EVERY}th step of the timed region "
                                              f"({len(bracketed)} launches)",

@@ -120,6 +120,9 @@ int y3d_pack_targets(const float *batch_idx, const float *cls, const float *bbox
  *  target_scores_sum (max(sum,1), loss.py:240).  partials (optional DEVICE double[4]): un-normalised
  *  sum (1-ciou)*w, sum bce, sum dfl*w, sum target_scores -- what a multi-GPU caller all-reduces before
  *  normalising; when `normalise` is 0 loss_items is left untouched.
+ *  loss_total (optional DEVICE float[1], written when normalising): total_scale * (box + cls + dfl), summed over the
+ *  branches -- with total_scale = batch size the reference's `loss.sum() * batch_size` (loss.py:257, 736), so that a
+ *  forward-only caller needs no further kernel.
  *  v10DetectLoss (loss.py:727-737) = this with topk=10 on one2many + topk=1 on one2one.
  *  dbg_fg_mask [B,A] u8 / dbg_target_gt_idx [B,A] i32 (optional, NULL in production): the assignment the fused
  *  path used, for parity tests.
@@ -130,8 +133,8 @@ int y3d_pack_targets(const float *batch_idx, const float *cls, const float *bbox
 int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
                     const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt, int M, int topk,
                     float gain_box, float gain_cls, float gain_dfl, int normalise, float *loss_items,
-                    double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx, void *const *prof_events,
-                    void *ws, size_t ws_bytes, void *stream);
+                    double *partials, float total_scale, float *loss_total, uint8_t *dbg_fg_mask,
+                    int32_t *dbg_target_gt_idx, void *const *prof_events, void *ws, size_t ws_bytes, void *stream);
 
 /* v10DetectLoss.__call__ forward (loss.py:727-737): BOTH branches of the consistent dual assignment in the same
  * launches -- one2many (top-k topk_o2m = 10) and one2one (top-k topk_o2o = 1) share the level geometry, the GT set
@@ -142,8 +145,8 @@ int y3d_v10_loss_fwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const i
                      const float *const *o2o_ptr, const int64_t *o2o_sB, const int64_t *o2o_sC, const int *lvl_hw,
                      const float *lvl_stride, int nl, int B, int nc, int reg_max, const float *gt, int M,
                      int topk_o2m, int topk_o2o, float gain_box, float gain_cls, float gain_dfl, int normalise,
-                     float *loss_items, double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx,
-                     void *const *prof_events, void *ws, size_t ws_bytes, void *stream);
+                     float *loss_items, double *partials, float total_scale, float *loss_total, uint8_t *dbg_fg_mask,
+                     int32_t *dbg_target_gt_idx, void *const *prof_events, void *ws, size_t ws_bytes, void *stream);
 
 /* y3d_v10_loss_fwd on this rank's image shard of a batch that is spread over `world` GPUs of one node (SURVEY.md
  * section 8e), with the one cross-rank step fused into the last kernel: the CTA that finishes last pushes the rank's
@@ -159,9 +162,10 @@ int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64_t *o2m_sB,
                              const float *const *o2o_ptr, const int64_t *o2o_sB, const int64_t *o2o_sC,
                              const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
                              const float *gt, int M, int topk_o2m, int topk_o2o, float gain_box, float gain_cls,
-                             float gain_dfl, float *loss_items, double *partials, int rank, int world,
-                             void *const *peer_bufs_dev, unsigned long long seq, int *status, void *const *prof_events,
-                             void *ws, size_t ws_bytes, void *stream);
+                             float gain_dfl, float *loss_items, double *partials, float total_scale,
+                             float *loss_total, int rank, int world, void *const *peer_bufs_dev,
+                             unsigned long long seq, int *status, void *const *prof_events, void *ws, size_t ws_bytes,
+                             void *stream);
 
 /* Backward of y3d_v8_loss_fwd / y3d_v10_loss_fwd: what autograd produces in the reference for loss.py:206-257
  * (BCEWithLogits :240, BboxLoss.forward :82-96, _df_loss :99-113, bbox_decode :197-204; CIoU metrics.py:78-134 with

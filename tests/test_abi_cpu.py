@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/y3d.h but not exported"
     assert set(names) == set(y3d._lib.SIGNATURES), "ctypes binding out of sync with include/y3d.h"
-    assert y3d.lib().y3d_abi_version() == 1
+    assert y3d.lib().y3d_abi_version() == 2
     assert b"workspace" in y3d.lib().y3d_strerror(-4)
     assert y3d._lib.workspace_bytes(y3d._lib.STAGE_TAL_ASSIGN, B=2, A=100, nc=4, M=3, k=10) > 0
 
@@ -47,8 +47,8 @@ def test_sharded_loss_entry_and_peer_exchange_host_side():
     lib = y3d.lib()
     assert lib.y3d_xrank_buffer_bytes(8) == 2 * 8 * 32 * 8 and lib.y3d_xrank_buffer_bytes(0) == 2 * 32 * 8
     null = [None] * 8
-    assert lib.y3d_v10_loss_fwd_sharded(*null, 3, 2, 8, 16, None, 0, 10, 1, 7.5, 0.5, 1.5, None, None, 0, 2, None,
-                                        ctypes.c_uint64(1), None, None, None, 0, None) == -1
+    assert lib.y3d_v10_loss_fwd_sharded(*null, 3, 2, 8, 16, None, 0, 10, 1, 7.5, 0.5, 1.5, None, None, 2.0, None, 0, 2,
+                                        None, ctypes.c_uint64(1), None, None, None, 0, None) == -1
     assert lib.y3d_loss_allreduce_finalize(None, 2, 0, 2, None, ctypes.c_uint64(1), 7.5, 0.5, 1.5, None, None, None,
                                            None) == -1
     red = y3d.dist.PeerLossReducer(torch.device("cpu"))

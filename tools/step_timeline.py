@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer tool: timeline of one fused-loss step inside a back-to-back sequence (library built with -DY3D_TIMING by
+"""Developer tool: timeline of the fused-loss steps inside a back-to-back train (library built with -DY3D_TIMING by
 tools/phase_timing.py build): when do the three kernels start / end relative to each other?  Run on the GPU box."""
 import ctypes
 import os
@@ -23,29 +23,35 @@ fm = [torch.from_numpy(f).to(dev) for f in synth.split_levels(xm, lv)]
 fo = [torch.from_numpy(f).to(dev) for f in synth.split_levels(xo, lv)]
 gtd = torch.from_numpy(gt).to(dev)
 h = _lib.lib()
-a = (ctypes.c_ulonglong * 8)()
-t = (ctypes.c_ulonglong * 4)()
+a = (ctypes.c_ulonglong * 128)()
+t = (ctypes.c_ulonglong * 64)()
 h.y3d_debug_read_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
 h.y3d_debug_read_topk_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
 NOT = (1 << 64) - 1
-for rep in range(3):
-    for _ in range(10):
-        y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
-    torch.cuda.synchronize()
-    h.y3d_debug_read_timeline(a, 1)
-    h.y3d_debug_read_topk_timeline(t, 1)
-    # one step in the middle of a sequence: reset, run 3, the stamps keep min-of-first ... so run exactly ONE step between
-    # two unstamped neighbours is not possible; instead run one step after a sync and one inside a train of 3
+for _ in range(20):
     y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
-    torch.cuda.synchronize()
-    h.y3d_debug_read_timeline(a, 1)
-    h.y3d_debug_read_topk_timeline(t, 1)
-    s0 = NOT - a[0]
-    ev = {"stream first start": 0.0, "stream last end": (a[1] - s0) / 1e3,
-          "topk first past wait": (NOT - t[0] - s0) / 1e3, "topk prologue done (last)": (t[3] - s0) / 1e3,
-          "topk first warp exit": (NOT - t[2] - s0) / 1e3, "topk last warp exit": (t[1] - s0) / 1e3,
-          "finish first CTA start": (NOT - a[2] - s0) / 1e3, "finish first past image wait": (NOT - a[3] - s0) / 1e3,
-          "finish last R end": (a[4] - s0) / 1e3, "finish final end": (a[5] - s0) / 1e3}
-    print(f"--- isolated step (us from the first stream CTA), rep {rep}")
-    for k, v in ev.items():
-        print(f"   {k:32s} {v:8.1f}")
+torch.cuda.synchronize()
+h.y3d_debug_read_timeline(a, 1)
+h.y3d_debug_read_topk_timeline(t, 1)
+N = 12
+for _ in range(N):
+    y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
+torch.cuda.synchronize()
+h.y3d_debug_read_timeline(a, 0)
+h.y3d_debug_read_topk_timeline(t, 0)
+A = np.array(a, dtype=np.uint64).reshape(16, 8)
+T = np.array(t, dtype=np.uint64).reshape(16, 4)
+inv = lambda v: (NOT - int(v))
+base = inv(A[0, 0])
+names = ["stream first start", "stream last end", "topk first past wait", "topk prologue done (last)", "topk first warp exit",
+         "topk last warp exit", "finish first CTA start", "finish first past image wait", "finish last R end", "finish final end"]
+print("step |", " | ".join(n[:14] for n in names), "| period")
+prev = None
+for sidx in range(N):
+    v = [inv(A[sidx, 0]), int(A[sidx, 1]), inv(T[sidx, 0]), int(T[sidx, 3]), inv(T[sidx, 2]), int(T[sidx, 1]), inv(A[sidx, 2]),
+         inv(A[sidx, 3]), int(A[sidx, 4]), int(A[sidx, 5])]
+    s0 = v[0]
+    rel = [(x - s0) / 1e3 for x in v]
+    per = (s0 - prev) / 1e3 if prev else float("nan")
+    prev = s0
+    print(f"{sidx:4d} |", " | ".join(f"{r:14.1f}" for r in rel), f"| {per:6.1f}")

@@ -21,7 +21,7 @@ extern "C" const char *y3d_strerror(int rc) {
     return "y3d: unknown error";
 }
 
-extern "C" int y3d_abi_version(void) { return 1; }
+extern "C" int y3d_abi_version(void) { return 2; }
 
 extern "C" size_t y3d_workspace_bytes(int stage, int B, int A, int nc, int M, int k, int D) {
     switch (stage) {

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
     const int n_seg = kOrdClasses * n_branch * n_img;
     if (ordered) {
         for (int s = threadIdx.x; s < n_seg; s += blockDim.x)
-            s_pref[s] = __ldg(cc.ord_cnt + (s % n_img) * 4 + s / (n_branch * n_img));
+            s_pref[s] = __ldcg(cc.ord_cnt + (s % n_img) * 4 + s / (n_branch * n_img));  // written by the primary grid: not .nc
         __syncthreads();
         if (wid == 0) {  // in-place exclusive scan: lane-contiguous chunks, warp scan of the chunk sums
             const int chunk = (n_seg + 31) / 32;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 6) tal_topk_kernel(AssignCtx2
         }
         // the sorted list carries the GT record itself (index, label, box): one load, no second round trip
         const int4 *rec = reinterpret_cast<const int4 *>(cc.ord_list) + ((long long)b * cc.c[0].M + off) * 2;
-        const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+        const int4 r0 = __ldcg(rec), r1 = __ldcg(rec + 1);
         m = r0.x;
         og.label = r0.y;
         og.box = make_float4(__int_as_float(r0.z), __int_as_float(r0.w), __int_as_float(r1.x), __int_as_float(r1.y));
@@ -672,16 +672,12 @@ int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl) {
     const long long items = (long long)c.B * c.M * n;
     // one persistent warp per GT fills the machine only when there are many GTs; with few (e.g. KITTI: 32 x 50) the
     // kernel's duration is one GT's latency, so each GT is split over kTopkWarps warps instead
-    const bool few = items < 16LL * kNumSMs;
+    const int sms = device_sm_count();
+    const bool few = items < 16LL * sms;
     const int wpg = (c.use_grid && c.constrain && cc.work_counter && !few) ? 1 : kTopkWarps;
     if (items >= 0x7fffffffLL) return Y3D_EUNSUPPORTED;
     long long blocks = wpg == 1 ? (items + kTopkWarps - 1) / kTopkWarps : items;
-    if (wpg == 1) {  // persistent: no more CTAs than fit at once
-        int dev = 0, sms = kNumSMs;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (blocks > 6LL * sms) blocks = 6LL * sms;
-    }
+    if (wpg == 1 && blocks > 6LL * sms) blocks = 6LL * sms;  // persistent: no more CTAs than fit at once
     if (pdl) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)blocks);
@@ -707,9 +703,11 @@ int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t aft
     if (rc0) return rc0;
     if (after_topk) cudaEventRecord(after_topk, s);
     size_t smem = sizeof(GtRec) * (size_t)c.M;
-    if (smem > 48 * 1024) {
+    static size_t smem_limit = 48 * 1024;  // raised once per process to the largest size asked for
+    if (smem > smem_limit) {
         cudaError_t e = cudaFuncSetAttribute(tal_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+        smem_limit = smem;
     }
     dim3 grid((c.A + 255) / 256, c.B, n);
     tal_resolve_kernel<<<grid, 256, smem, s>>>(cc);

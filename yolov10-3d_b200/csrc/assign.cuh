@@ -349,6 +349,5 @@ int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl = fals
 // the same for the fused loss' configuration (logits from the head, alpha 0.5, beta 6, in-GT constraint, grid, [B,A,4]
 // boxes in grid units): specialised kernel in topk_fused.cu.  Returns Y3D_EUNSUPPORTED when the context does not match.
 int assign_run_topk_fused(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl);
-int device_sm_count();
 
 }  // namespace y3d

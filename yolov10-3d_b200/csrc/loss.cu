@@ -70,14 +70,24 @@ __device__ __forceinline__ void stv(float *p, const float (&o)[V]) {
 #ifdef Y3D_TIMING
 // step timeline (developer builds): [0] ~first stream CTA start [1] last stream CTA end [2] ~first finish CTA start
 // [3] ~first finish CTA past its image wait [4] last phase-R end [5] final reduction end   (~t under atomicMax = minimum)
-__device__ unsigned long long g_y3d_tl[8];
-#define Y3D_TL_MIN(i) do { if (threadIdx.x == 0) atomicMax(&g_y3d_tl[i], ~gtimer()); } while (0)
-#define Y3D_TL_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_y3d_tl[i], gtimer()); } while (0)
+// one row of 8 per step, 16 steps kept (g_y3d_step counts the steps: bumped by the finishing kernel's very last CTA)
+__device__ unsigned long long g_y3d_tl[16 * 8];
+__device__ unsigned g_y3d_step;
+__device__ __forceinline__ unsigned long long gtimer0() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define Y3D_TL_MIN(i) do { if (threadIdx.x == 0) atomicMax(&g_y3d_tl[(*(volatile unsigned *)&g_y3d_step & 15) * 8 + (i)], ~gtimer0()); } while (0)
+#define Y3D_TL_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_y3d_tl[(*(volatile unsigned *)&g_y3d_step & 15) * 8 + (i)], gtimer0()); } while (0)
+#define Y3D_TL_STEP() do { if (threadIdx.x == 0) { __threadfence(); atomicAdd(&g_y3d_step, 1u); } } while (0)
 extern "C" int y3d_debug_read_timeline(unsigned long long *host, int reset) {
-    int rc = (int)cudaMemcpyFromSymbol(host, g_y3d_tl, sizeof(unsigned long long) * 8);
+    int rc = (int)cudaMemcpyFromSymbol(host, g_y3d_tl, sizeof(unsigned long long) * 16 * 8);
     if (reset) {
-        unsigned long long z[8] = {};
+        unsigned long long z[16 * 8] = {};
         cudaMemcpyToSymbol(g_y3d_tl, z, sizeof(z));
+        unsigned zero = 0;
+        cudaMemcpyToSymbol(g_y3d_step, &zero, sizeof(zero));
     }
     return rc;
 }
@@ -96,6 +106,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define Y3D_STAMP(i)
 #define Y3D_TL_MIN(i)
 #define Y3D_TL_MAX(i)
+#define Y3D_TL_STEP()
 #endif
 
 // ---------------------------------------------------------------------------------------------- stream kernel
@@ -168,9 +179,9 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __
     const LevelTable &t = P.t[z];
     const int A = P.A;
     const unsigned long long pol = l2_evict_first_policy();
-    // programmatic dependent launch, both ways: wait for the previous kernel in the stream (a no-op after an ordinary
-    // launch), then let the dependent of this grid (the fused loss' top-k kernel) be scheduled as this grid drains
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // lets a programmatically dependent launch (the fused loss' top-k kernel) be scheduled as this grid drains.  (This
+    // grid itself is launched the ordinary way: parked behind the previous step's last kernel, its first wave starts in
+    // lockstep and the whole pass ran 20 % slower -- measured.)
     asm volatile("griddepcontrol.launch_dependents;");
     Y3D_TL_MIN(0);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -308,6 +319,8 @@ struct FinishParams {
     unsigned *counter;         // zeroed by the stream kernel
     double *partials;          // optional out [n_branch][4]
     float *loss_items;         // optional out [n_branch][4]
+    float *loss_total;         // optional out [1]: total_scale * sum over the branches of (box + cls + dfl)
+    float total_scale;
     uint8_t *dbg_fg[2];
     int32_t *dbg_gi[2];
     int n_bce_x, n_branch, normalise;  // n_bce_x: BCE partials per image (= gridDim.x of the stream kernel)
@@ -317,6 +330,7 @@ struct FinishParams {
     XSlot *const *x_bufs;      // DEVICE table of x_world exchange buffers
     int x_rank, x_world;
     unsigned long long x_seq;
+    long long x_timeout;       // clock cycles (xrank_timeout_cycles)
     int *x_status;             // optional: 1 when a peer never arrived
 };
 
@@ -381,7 +395,6 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
     const int z = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AssignCtx &c = cc.c[z];
     const int M = c.M, A = c.A;
-    asm volatile("griddepcontrol.launch_dependents;");  // the next kernel in the stream may become resident (it waits)
     Y3D_STAMP(0);
     GtRec *gts = reinterpret_cast<GtRec *>(smem_raw + sizeof(FinishSmem));
     int *pos_a = reinterpret_cast<int *>(gts + M);
@@ -673,7 +686,7 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
     __syncthreads();
     const double *tot = S.xv;
     if (F.x_world > 1) {  // sum over the ranks: stores into every peer's buffer, flag, wait, rank-ordered sum
-        xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, S.xv, 4 * F.n_branch, S.xs, &S.xfail);
+        xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, S.xv, 4 * F.n_branch, S.xs, &S.xfail, F.x_timeout);
         tot = S.xs;
         if (tid == 0 && F.x_status) *F.x_status = S.xfail;
     }
@@ -685,6 +698,16 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
         F.loss_items[4 * zz + 1] = (float)(tot[4 * zz + 1] / tss * F.gain_cls);
         F.loss_items[4 * zz + 2] = (float)(tot[4 * zz + 2] / tss * F.gain_dfl);
         F.loss_items[4 * zz + 3] = (float)tss;
+    }
+    if (tid == 0 && F.normalise && F.loss_total) {  // loss.sum() * batch_size per branch, added up (loss.py:257, 736)
+        float total = 0.f;
+        for (int zz = 0; zz < F.n_branch; ++zz) {
+            const double tss = tot[4 * zz + 3] > 1.0 ? tot[4 * zz + 3] : 1.0;
+            const float i0 = (float)(tot[4 * zz + 0] / tss * F.gain_box), i1 = (float)(tot[4 * zz + 1] / tss * F.gain_cls),
+                        i2 = (float)(tot[4 * zz + 2] / tss * F.gain_dfl);
+            total += ((i0 + i1) + i2) * F.total_scale;
+        }
+        *F.loss_total = total;
     }
     Y3D_STAMP(5);
 }
@@ -736,7 +759,6 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AssignCtx &c = cc.c[z];
     const int M = c.M, A = c.A;
-    asm volatile("griddepcontrol.launch_dependents;");  // the next kernel in the stream may become resident (it waits)
     Y3D_APSTAMP(0);
     Y3D_TL_MIN(2);
     if (tid == 0) { s_ncf = 0; s_np = 0; }
@@ -979,7 +1001,7 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     __syncthreads();
     const double *tot = s_xv;
     if (F.x_world > 1) {  // sum over the ranks: stores into every peer's buffer, wait, rank-ordered sum
-        xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, s_xv, 4 * F.n_branch, s_xs, &s_xfail);
+        xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, s_xv, 4 * F.n_branch, s_xs, &s_xfail, F.x_timeout);
         tot = s_xs;
         if (tid == 0 && F.x_status) *F.x_status = s_xfail;
     }
@@ -992,6 +1014,19 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
         F.loss_items[4 * zz + 2] = (float)(tot[4 * zz + 2] / tss * F.gain_dfl);
         F.loss_items[4 * zz + 3] = (float)tss;
     }
+    if (tid == 0 && F.normalise && F.loss_total) {  // loss.sum() * batch_size per branch, added up (loss.py:257, 736)
+        float total = 0.f;
+        for (int zz = 0; zz < F.n_branch; ++zz) {
+            const double tss = tot[4 * zz + 3] > 1.0 ? tot[4 * zz + 3] : 1.0;
+            const float i0 = (float)(tot[4 * zz + 0] / tss * F.gain_box), i1 = (float)(tot[4 * zz + 1] / tss * F.gain_cls),
+                        i2 = (float)(tot[4 * zz + 2] / tss * F.gain_dfl);
+            total += ((i0 + i1) + i2) * F.total_scale;
+        }
+        *F.loss_total = total;
+    }
+    Y3D_APSTAMP(6);
+    Y3D_TL_MAX(5);
+    Y3D_TL_STEP();
 }
 
 __global__ void loss_finalize_partials_kernel(const double *__restrict__ partials, int n_branch, float gain_box,
@@ -1025,27 +1060,14 @@ static int launch_stream(const StreamParams &P, int *n_bce, cudaStream_t s) {
     dim3 grid((units + 31) / 32, P.B, P.n_branch);
     *n_bce = (int)(grid.x * grid.y);
     const bool ps = P.pd_scores[0] != nullptr;
-    // programmatic dependent launch: when the previous kernel in the stream lets its dependents start early (the
-    // finishing kernel of the previous step does), this grid is resident and waiting when that kernel ends
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kStreamThreads);
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t le;
     if (v4 && !ps)
-        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<4, false>, P);
+        head_stream_kernel<4, false><<<grid, kStreamThreads, 0, s>>>(P);
     else if (v4)
-        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<4, true>, P);
+        head_stream_kernel<4, true><<<grid, kStreamThreads, 0, s>>>(P);
     else if (!ps)
-        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<1, false>, P);
+        head_stream_kernel<1, false><<<grid, kStreamThreads, 0, s>>>(P);
     else
-        le = cudaLaunchKernelEx(&cfg, head_stream_kernel<1, true>, P);
-    if (le != cudaSuccess) return (int)le;
+        head_stream_kernel<1, true><<<grid, kStreamThreads, 0, s>>>(P);
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }
@@ -1065,7 +1087,8 @@ struct XRankIn {  // cross-rank exchange of the fused loss (world <= 1: none)
 static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc,
                     int reg_max, const float *gt, int M, float gain_box, float gain_cls, float gain_dfl, int normalise,
                     float *loss_items, double *partials, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx,
-                    void *const *prof_events, void *ws, size_t ws_bytes, void *stream, const XRankIn *xr = nullptr) {
+                    void *const *prof_events, void *ws, size_t ws_bytes, void *stream, const XRankIn *xr = nullptr,
+                    float total_scale = 0.f, float *loss_total = nullptr) {
     if (!lvl_hw || !lvl_stride || B < 1 || nc < 1 || M < 0 || (M > 0 && !gt)) return Y3D_EINVAL;
     if (xr && xr->world > 1 &&
         (!xr->bufs_dev || xr->world > kXMaxWorld || xr->rank < 0 || xr->rank >= xr->world || xr->seq == 0))
@@ -1153,7 +1176,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     // Longest-first work order for the top-k kernel: pays when a persistent warp gets only a few GTs (cfg2: 1.7 valid
     // GTs per warp -- the kernel's tail was one or two big GTs picked up late); with dozens of GTs per warp (crowds) the
     // dynamic distribution balances by itself and the per-item table lookup would only cost (measured: +6 % at cfg5).
-    if (M > 0 && kOrdClasses * nb * B <= kOrdMaxSeg && (long long)nb * B * M <= 8LL * 6 * kTopkWarps * kNumSMs) {
+    if (M > 0 && kOrdClasses * nb * B <= kOrdMaxSeg && (long long)nb * B * M <= 8LL * 6 * kTopkWarps * device_sm_count()) {
         P.gt5 = gt; P.M = M;
         P.ord_cnt = (int *)(p + w.off_ord_cnt);
         P.ord_list = (int *)(p + w.off_ord_list);
@@ -1179,11 +1202,14 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     F.counter = P.counter;
     F.partials = partials;
     F.loss_items = loss_items;
+    F.loss_total = loss_total;
+    F.total_scale = total_scale;
     F.n_bce_x = n_bce / B; F.n_branch = nb; F.normalise = normalise;
     F.gain_box = gain_box; F.gain_cls = gain_cls; F.gain_dfl = gain_dfl;
     if (xr && xr->world > 1) {
         F.x_bufs = (XSlot *const *)xr->bufs_dev;
         F.x_rank = xr->rank; F.x_world = xr->world; F.x_seq = xr->seq; F.x_status = xr->status;
+        F.x_timeout = xrank_timeout_cycles();
     }
     // programmatic dependent launch: the prologue (GT records) overlaps the top-k kernel's tail
     cudaLaunchConfig_t cfg = {};
@@ -1200,13 +1226,11 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         cudaError_t le = cudaLaunchKernelEx(&cfg, loss_finish_ap_kernel, cc, F);
         if (le != cudaSuccess) return (int)le;
     } else {  // dense crowds: one CTA per (image, branch) with a spatial index of the GT boxes
-        static bool attr_set = false;  // the limit only ever grows to the largest value asked for
-        static size_t attr_bytes = 0;
-        if (!attr_set || fin_smem > attr_bytes) {
+        static bool attr_set = false;  // once per process: the largest size the kernel is ever launched with
+        if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(loss_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
-            attr_bytes = 212 * 1024;
         }
         cfg.gridDim = dim3(B, nb);
         cfg.blockDim = dim3(kFinishThreads);
@@ -1246,12 +1270,13 @@ extern "C" int y3d_train_decode(const float *const *lvl_ptr, const int64_t *lvl_
 extern "C" int y3d_v8_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
                                const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
                                const float *gt, int M, int topk, float gain_box, float gain_cls, float gain_dfl,
-                               int normalise, float *loss_items, double *partials, uint8_t *dbg_fg_mask,
-                               int32_t *dbg_target_gt_idx, void *const *prof_events, void *ws, size_t ws_bytes,
-                               void *stream) {
+                               int normalise, float *loss_items, double *partials, float total_scale,
+                               float *loss_total, uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx,
+                               void *const *prof_events, void *ws, size_t ws_bytes, void *stream) {
     BranchIn br[1] = {{lvl_ptr, lvl_sB, lvl_sC, topk}};
     return loss_run(1, br, lvl_hw, lvl_stride, nl, B, nc, reg_max, gt, M, gain_box, gain_cls, gain_dfl, normalise,
-                    loss_items, partials, dbg_fg_mask, dbg_target_gt_idx, prof_events, ws, ws_bytes, stream);
+                    loss_items, partials, dbg_fg_mask, dbg_target_gt_idx, prof_events, ws, ws_bytes, stream, nullptr,
+                    total_scale, loss_total);
 }
 
 extern "C" int y3d_v10_loss_fwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC,
@@ -1259,11 +1284,13 @@ extern "C" int y3d_v10_loss_fwd(const float *const *o2m_ptr, const int64_t *o2m_
                                 const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
                                 const float *gt, int M, int topk_o2m, int topk_o2o, float gain_box, float gain_cls,
                                 float gain_dfl, int normalise, float *loss_items, double *partials,
-                                uint8_t *dbg_fg_mask, int32_t *dbg_target_gt_idx, void *const *prof_events, void *ws,
-                                size_t ws_bytes, void *stream) {
+                                float total_scale, float *loss_total, uint8_t *dbg_fg_mask,
+                                int32_t *dbg_target_gt_idx, void *const *prof_events, void *ws, size_t ws_bytes,
+                                void *stream) {
     BranchIn br[2] = {{o2m_ptr, o2m_sB, o2m_sC, topk_o2m}, {o2o_ptr, o2o_sB, o2o_sC, topk_o2o}};
     return loss_run(2, br, lvl_hw, lvl_stride, nl, B, nc, reg_max, gt, M, gain_box, gain_cls, gain_dfl, normalise,
-                    loss_items, partials, dbg_fg_mask, dbg_target_gt_idx, prof_events, ws, ws_bytes, stream);
+                    loss_items, partials, dbg_fg_mask, dbg_target_gt_idx, prof_events, ws, ws_bytes, stream, nullptr,
+                    total_scale, loss_total);
 }
 
 extern "C" int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC,
@@ -1271,14 +1298,15 @@ extern "C" int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64
                                         const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
                                         const float *gt, int M, int topk_o2m, int topk_o2o, float gain_box,
                                         float gain_cls, float gain_dfl, float *loss_items, double *partials,
-                                        int rank, int world, void *const *peer_bufs_dev, unsigned long long seq,
+                                        float total_scale, float *loss_total, int rank, int world,
+                                        void *const *peer_bufs_dev, unsigned long long seq,
                                         int *status, void *const *prof_events, void *ws, size_t ws_bytes,
                                         void *stream) {
     if (!loss_items) return Y3D_EINVAL;
     BranchIn br[2] = {{o2m_ptr, o2m_sB, o2m_sC, topk_o2m}, {o2o_ptr, o2o_sB, o2o_sC, topk_o2o}};
     XRankIn xr = {peer_bufs_dev, rank, world, seq, status};
     return loss_run(2, br, lvl_hw, lvl_stride, nl, B, nc, reg_max, gt, M, gain_box, gain_cls, gain_dfl, 1, loss_items,
-                    partials, nullptr, nullptr, prof_events, ws, ws_bytes, stream, &xr);
+                    partials, nullptr, nullptr, prof_events, ws, ws_bytes, stream, &xr, total_scale, loss_total);
 }
 
 extern "C" int y3d_v8_loss_finalize(const double *partials, int n_branch, float gain_box, float gain_cls,

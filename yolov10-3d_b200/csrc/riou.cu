@@ -93,9 +93,11 @@ __device__ float riou_inter(const float *r1, const float *r2) {  // inter :231-2
     return area;
 }
 
-// grid (ceil(K/64), ceil(N/64)), block (64): thread = one box row of the tile, loops over the tile's 64 queries
-// (the reference's decomposition; writes of a warp go to 32 different rows, so each thread keeps its row in registers
-// and the tile is transposed through shared memory for coalesced stores)
+// grid (ceil(K/64), ceil(N/64)), block 256: a CTA owns a 64 x 64 tile of the overlap matrix (box rows x queries), both
+// box sets of the tile staged in shared memory; four threads share a box row, thread (tid & 3) takes the queries
+// (tid & 3) + 4 j, j = 0..15, so the four stores of a row group are adjacent.  Work per pair: two 4 x 4 edge-intersection
+// tests, 8 point-in-quadrilateral tests, a <= 24-point convex polygon sort and area (about 1.5 k fp32 operations); the
+// kernel is ALU-bound, its memory traffic (20 (N + K) + 4 N K bytes) is negligible.
 __global__ void __launch_bounds__(256) rotate_iou_kernel(const float *__restrict__ boxes, int N,
                                                          const float *__restrict__ query, int K, int criterion,
                                                          float *__restrict__ iou) {
@@ -108,7 +110,6 @@ __global__ void __launch_bounds__(256) rotate_iou_kernel(const float *__restrict
         sq[i] = (k0 + r < K) ? query[(long long)k0 * 5 + i] : 0.f;
     }
     __syncthreads();
-    // 256 threads: thread -> (row = tid / 4 ... ) each thread handles 16 pairs: row r = tid >> 2, columns (tid & 3) + 4*j
     const int r = tid >> 2;
     if (n0 + r >= N) return;
     const float *r2 = sb + 5 * r;

@@ -558,8 +558,12 @@ static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *a
     if (k2smem) nkeys = (size_t)n2;
     if (k1smem && (size_t)A > nkeys) nkeys = (size_t)A;
     size_t smem = sizeof(unsigned long long) * 4 * (size_t)Dpad + sizeof(uint32_t) * nkeys;
-    cudaError_t e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t smem_limit = 48 * 1024;  // raised once per process to the largest size asked for
+    if (smem > smem_limit) {
+        cudaError_t e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        smem_limit = smem;
+    }
     topk_select_kernel<<<B, kTopkThreads, smem, s>>>(src, keys, aux, A, k1smem, nc, nreg, D, Dpad, k2smem, keys2_ws, reg, scores,
                                                     labels, anchor_idx, out_mode);
     Y3D_CHECK_LAUNCH();
@@ -650,8 +654,12 @@ extern "C" int y3d_select_candidates(const float *cls, int64_t sB, int64_t sC, i
     const int Kpad = next_pow2(K);
     const size_t smem = sizeof(unsigned long long) * 2 * (size_t)Kpad + sizeof(uint32_t) * (size_t)HW;
     if (smem > 200 * 1024) return Y3D_EUNSUPPORTED;  // level larger than ~48 k cells
-    cudaError_t e = cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t smem_limit = 48 * 1024;  // raised once per process to the largest size asked for
+    if (smem > smem_limit) {
+        cudaError_t e = cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        smem_limit = smem;
+    }
     select_candidates_kernel<<<B, kTopkThreads, smem, (cudaStream_t)stream>>>(cls, sB, sC, nc, (int)HW, W, K, Kpad, idx);
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;

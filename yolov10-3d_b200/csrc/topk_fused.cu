@@ -48,25 +48,32 @@ __device__ __forceinline__ float fused_metric(float4 gbox, float gat1, float4 pb
 
 #ifdef Y3D_TIMING
 // developer builds: [0] ~first warp past the dependency wait [1] last warp exit [2] ~first warp exit [3] last prologue end
-__device__ unsigned long long g_tkf_tl[4];
+__device__ unsigned long long g_tkf_tl[16 * 4];
+__device__ unsigned g_tkf_step;  // bumped by the warp that draws the first ticket past the end
 __device__ __forceinline__ unsigned long long tkf_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
 extern "C" int y3d_debug_read_topk_timeline(unsigned long long *host, int reset) {
-    int rc = (int)cudaMemcpyFromSymbol(host, g_tkf_tl, sizeof(unsigned long long) * 4);
+    int rc = (int)cudaMemcpyFromSymbol(host, g_tkf_tl, sizeof(unsigned long long) * 16 * 4);
     if (reset) {
-        unsigned long long z[4] = {};
+        unsigned long long z[16 * 4] = {};
         cudaMemcpyToSymbol(g_tkf_tl, z, sizeof(z));
+        unsigned zero = 0;
+        cudaMemcpyToSymbol(g_tkf_step, &zero, sizeof(zero));
     }
     return rc;
 }
-#define TKF_MIN(i) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_tkf_tl[i], ~tkf_now()); } while (0)
-#define TKF_MAX(i) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_tkf_tl[i], tkf_now()); } while (0)
+#define TKF_STEP0() const unsigned tkf_step = *(volatile unsigned *)&g_tkf_step
+#define TKF_MIN(i) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_tkf_tl[(tkf_step & 15) * 4 + (i)], ~tkf_now()); } while (0)
+#define TKF_MAX(i) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_tkf_tl[(tkf_step & 15) * 4 + (i)], tkf_now()); } while (0)
+#define TKF_BUMP(cond) do { if ((cond) && (threadIdx.x & 31) == 0) atomicAdd(&g_tkf_step, 1u); } while (0)
 #else
+#define TKF_STEP0()
 #define TKF_MIN(i)
 #define TKF_MAX(i)
+#define TKF_BUMP(cond)
 #endif
 
 // grid: persistent CTAs of kTopkWarps warps; a warp pulls (branch, image, GT) items from cc.work_counter.
@@ -81,6 +88,7 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
     // programmatic dependent launch, both ways (see tal_topk_kernel)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
+    TKF_STEP0();
     TKF_MIN(0);
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_img = cc.c[0].B, M = cc.c[0].M, A = cc.c[0].A;
@@ -135,6 +143,7 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
         int z, b, m;
         GtRec g;
         if (ORDERED) {
+            TKF_BUMP(item == s_pref[n_seg]);
             if (item >= s_pref[n_seg]) break;
             // last segment whose prefix is <= item: a 32-way step, then up to 64 entries
             const int i1 = min(lane * seg_stride, n_seg);

@@ -18,11 +18,11 @@ __global__ void __launch_bounds__(64) loss_allreduce_finalize_kernel(XPeers peer
                                                                      float gain_cls, float gain_dfl,
                                                                      float *__restrict__ loss_items,
                                                                      double *__restrict__ global_partials,
-                                                                     int *__restrict__ status) {
+                                                                     int *__restrict__ status, long long timeout_cycles) {
     __shared__ double sum[kXMaxVals];
     __shared__ int failed;
     const int tid = threadIdx.x;
-    xrank_allreduce(peers.buf, rank, world, seq, partials, n_vals, sum, &failed);
+    xrank_allreduce(peers.buf, rank, world, seq, partials, n_vals, sum, &failed, timeout_cycles);
     if (tid < n_vals && global_partials) global_partials[tid] = sum[tid];
     if (tid < n_branch) {
         const double tss = sum[4 * tid + 3] > 1.0 ? sum[4 * tid + 3] : 1.0;  // max(target_scores.sum(), 1) loss.py:240
@@ -53,7 +53,7 @@ extern "C" int y3d_loss_allreduce_finalize(const double *partials, int n_branch,
     }
     loss_allreduce_finalize_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(P, partials, 4 * n_branch, n_branch, rank, world, seq,
                                                                       gain_box, gain_cls, gain_dfl, loss_items,
-                                                                      global_partials, status);
+                                                                      global_partials, status, xrank_timeout_cycles());
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }

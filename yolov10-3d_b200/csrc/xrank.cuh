@@ -10,6 +10,8 @@
 // the sequence number: a peer can be at most one call ahead, because it needs this rank's next words to finish that
 // call.
 #pragma once
+#include <cstdlib>
+
 #include "y3d_common.cuh"
 
 namespace y3d {
@@ -29,12 +31,29 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     return v;
 }
 
+// How long a rank waits for its peers before it gives up (sums = NaN, *failed = 1).  Like an NCCL collective the call
+// is meant to wait: ranks legitimately arrive far apart (rank 0 validates and checkpoints while the others are already
+// in the next step's loss), so the default is ten minutes; Y3D_XRANK_TIMEOUT_S overrides it (seconds, host side).
+inline long long xrank_timeout_cycles() {
+    static long long cycles = 0;
+    if (cycles == 0) {
+        double sec = 600.0;
+        if (const char *e = getenv("Y3D_XRANK_TIMEOUT_S")) {
+            const double v = atof(e);
+            if (v > 0.0) sec = v;
+        }
+        cycles = (long long)(sec * 2.0e9);  // clock64 ticks at the SM clock (< 2 GHz)
+    }
+    return cycles;
+}
+
 // Called by ALL threads of one CTA (at least max(world, n_vals) of them; contains barriers).  bufs[r] = rank r's
 // exchange buffer.  vals: this rank's n_vals doubles (shared or global memory, written before the call and made
 // visible by a barrier); sum: shared double[n_vals] receiving the rank-ordered sums (NaN when a peer never arrived);
 // *failed: shared int.
 __device__ __forceinline__ void xrank_allreduce(XSlot *const *bufs, int rank, int world, unsigned long long seq,
-                                                const double *vals, int n_vals, double *sum, int *failed) {
+                                                const double *vals, int n_vals, double *sum, int *failed,
+                                                long long timeout_cycles) {
     __shared__ double recv[kXMaxWorld][kXMaxVals];
     const int tid = threadIdx.x;
     const int par = (int)(seq & 1ull);
@@ -55,7 +74,7 @@ __device__ __forceinline__ void xrank_allreduce(XSlot *const *bufs, int rank, in
             unsigned long long hi, lo;
             while (((hi = ld_relaxed_sys(&src->w[2 * j])) & 0xffffffffull) != flag ||
                    ((lo = ld_relaxed_sys(&src->w[2 * j + 1])) & 0xffffffffull) != flag) {
-                if (clock64() - t0 > (1ll << 34)) {  // ~8 s: a peer never arrived; fail loudly instead of hanging the GPU
+                if (clock64() - t0 > timeout_cycles) {  // a peer never arrived (default: ten minutes, xrank_timeout_cycles)
                     dead = true;
                     break;
                 }

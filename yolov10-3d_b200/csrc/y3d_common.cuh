@@ -21,7 +21,8 @@
 
 namespace y3d {
 
-constexpr int kNumSMs = 148;  // B200
+// number of SMs of the current device (148 on B200), queried once per process: one process per GPU (topk_fused.cu)
+int device_sm_count();
 
 struct LevelTable {
     const float *ptr[Y3D_MAX_LEVELS];

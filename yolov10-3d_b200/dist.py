@@ -24,17 +24,28 @@ def shard_range(batch, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def all_gather_detections(dets_local, group=None):
-    """[b_local, D, K] on every rank -> [sum b_local, D, K] on every rank (equal shards: one all_gather_into_tensor;
-    ragged shards: padded to the largest)."""
+def all_gather_detections(dets_local, group=None, equal_shards=None):
+    """[b_local, D, K] on every rank -> [sum b_local, D, K] on every rank.
+
+    ``equal_shards=True`` (what ``shard_range`` gives when the batch divides by the world size -- the caller knows):
+    ONE ``all_gather_into_tensor``, nothing else, no host synchronisation.  ``None`` / ``False``: the shard sizes are
+    exchanged first (one small all_gather and a host read), equal sizes then take the single-call route and ragged
+    ones are padded to the largest."""
     world = dist.get_world_size(group)
     if world == 1:
         return dets_local
+    dets_local = dets_local.contiguous()
+    if equal_shards:
+        out = dets_local.new_empty((world * dets_local.shape[0],) + tuple(dets_local.shape[1:]))
+        dist.all_gather_into_tensor(out, dets_local, group=group)
+        return out
     n = torch.tensor([dets_local.shape[0]], device=dets_local.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
     sizes = [int(s) for s in sizes]
     mx = max(sizes)
+    if min(sizes) == mx:
+        return all_gather_detections(dets_local, group, equal_shards=True)
     pad = dets_local
     if dets_local.shape[0] < mx:
         pad = torch.cat([dets_local, dets_local.new_zeros((mx - dets_local.shape[0],) + tuple(dets_local.shape[1:]))])
@@ -57,7 +68,12 @@ class PeerLossReducer:
 
     The exchange buffers come from ``torch.distributed._symmetric_memory`` (peer-mapped allocations of one process per
     GPU).  Construction is collective; ``available`` is False when symmetric memory cannot be set up on this system,
-    and callers then use the NCCL path."""
+    and callers then use the NCCL path.
+
+    Like any collective, EVERY rank must make every call, in the same order; a rank that waits longer than
+    ``Y3D_XRANK_TIMEOUT_S`` seconds (default 600) for a peer gives up, gets NaN sums and :meth:`check` raises.  The
+    sequence number travels as a kernel argument, so calls must not be captured into a CUDA graph and replayed (a replay
+    would see the previous replay's flags as its own)."""
 
     def __init__(self, device, group=None):
         self.available = False
@@ -75,12 +91,41 @@ class PeerLossReducer:
             # the same table on the device, for the exchange fused into the loss' last kernel
             self.ptrs_dev = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
             self.status = torch.zeros(1, dtype=torch.int32, device=device)
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._calls, self.check_every, self._pg = 0, 16, pg
             torch.cuda.synchronize(device)
             dist.barrier(group=pg)  # every buffer is zeroed before anyone's first store can land
             self.available = True
         except Exception as e:  # no peer access / symmetric memory unsupported: NCCL path
             print(f"[yolov10-3d_b200] peer-memory loss reduction unavailable ({type(e).__name__}: {e}); using NCCL",
                   file=sys.stderr)
+
+    def check(self):
+        """Raises if an earlier exchange timed out (a peer never made the call; its sums came back as NaN).  Does not
+        synchronise: every ``check_every`` calls the device-side status word is copied to pinned host memory
+        asynchronously and this looks at the last copy that has landed, so a failure surfaces a few calls late instead
+        of silently.  After a failure the ranks' sequence numbers are out of step: call :meth:`reset` on every rank."""
+        if not self.available:
+            return
+        if int(self._status_host[0]) != 0:
+            raise _lib.Y3DError("peer-memory loss exchange timed out: a rank did not reach the call within "
+                                "Y3D_XRANK_TIMEOUT_S (default 600 s); every rank must call the sharded loss, then reset()")
+        self._calls += 1
+        if self._calls % self.check_every == 0:
+            self._status_host.copy_(self.status, non_blocking=True)
+
+    def reset(self):
+        """Collective: brings the exchange back to its initial state (after a failure, or to re-synchronise)."""
+        if not self.available:
+            return
+        torch.cuda.synchronize(self.buf.device)
+        dist.barrier(group=self._pg)
+        self.buf.zero_()
+        self.status.zero_()
+        self._status_host.zero_()
+        self.seq = 0
+        torch.cuda.synchronize(self.buf.device)
+        dist.barrier(group=self._pg)
 
     def next_call(self):
         """Arguments (rank, world, peer_bufs_dev, seq, status) of ``y3d_v10_loss_fwd_sharded`` for the next collective
@@ -96,6 +141,7 @@ class PeerLossReducer:
         _lib.check(_lib.lib().y3d_loss_allreduce_finalize(
             ptr(partials), n, self.rank, self.world, self.ptrs, C.c_uint64(self.seq), float(gains[0]), float(gains[1]),
             float(gains[2]), ptr(items), None, ptr(self.status), stream_ptr(partials.device)))
+        self.check()
         return items
 
 
@@ -114,16 +160,20 @@ def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_
     loss' last kernel exchanges the partial sums over NVLink peer memory itself (``y3d_v10_loss_fwd_sharded``);
     without one: un-normalised partials -> NCCL all_reduce of 8 doubles -> ``y3d_v8_loss_finalize``."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    if multi and reducer is not None and reducer.available and not fused_off():
-        # the exchange rides in the loss' last kernel: no collective launch at all
-        items, _, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains, prof_events=prof_events,
-                                             xrank=reducer)
+    if (multi and reducer is not None and reducer.available and not fused_off()) or not multi:
+        # one rank, or the exchange rides in the loss' last kernel: no collective launch at all, and the same kernel
+        # writes the total (global_batch * sum of the items)
+        items, _, _, total = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains,
+                                                    prof_events=prof_events, xrank=reducer if multi else None,
+                                                    total_scale=global_batch, return_total=True)
+        if multi:
+            reducer.check()
+        return total[0], items.view(2, 4)[:, :3].reshape(6)
+    items, parts, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains, normalise=False,
+                                             prof_events=prof_events)
+    if reducer is not None and reducer.available:
+        items = reducer(parts, gains)  # one extra kernel over peer memory: all-reduce + normalisation
     else:
-        items, parts, _ = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains,
-                                                 normalise=not multi, prof_events=prof_events)
-        if multi and reducer is not None and reducer.available:
-            items = reducer(parts, gains)  # one extra kernel over peer memory: all-reduce + normalisation
-        elif multi:
-            items = _loss.finalize_partials(reduce_partials(parts, group), gains)
+        items = _loss.finalize_partials(reduce_partials(parts, group), gains)
     items = items.view(2, 4)[:, :3].reshape(6)
     return items.sum() * global_batch, items

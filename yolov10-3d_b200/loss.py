@@ -39,10 +39,10 @@ def pack_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device, extra=Non
     return out
 
 
-def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_events, xrank=None):
+def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_events, xrank=None, total_scale=None):
     """Shared body of the one- and two-branch forward calls.  ``levels``: list of 1 or 2 ``Levels``.  Returns a dict with
-    ``items`` (float32[4n] or None), ``partials`` (float64[4n]), ``dbg``, and what the backward pass needs (``ws``,
-    ``gt``, ``M``)."""
+    ``items`` (float32[4n] or None), ``partials`` (float64[4n]), ``dbg``, ``total`` (float32[1] = ``total_scale`` * sum
+    of the loss items, written by the last kernel, or None) and what the backward pass needs (``ws``, ``gt``, ``M``)."""
     n = len(levels)
     l0 = levels[0]
     for lv in levels:
@@ -55,6 +55,8 @@ def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_e
     M = int(gt.shape[1])
     items = torch.empty(4 * n, dtype=torch.float32, device=dev) if normalise else None
     partials = torch.empty(4 * n, dtype=torch.float64, device=dev)
+    total = torch.empty(1, dtype=torch.float32, device=dev) if (normalise and total_scale is not None) else None
+    tsc = float(total_scale) if total is not None else 0.0
     dbg = None
     if debug:
         shape = (l0.B, l0.A) if n == 1 else (n, l0.B, l0.A)
@@ -62,7 +64,7 @@ def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_e
                    target_gt_idx=torch.empty(shape, dtype=torch.int32, device=dev))
     ws = workspace(_lib.workspace_bytes(_lib.STAGE_V8_LOSS, B=l0.B, A=l0.A, nc=nc, M=M, k=max(topk)), dev)
     tail = (ptr(gt) if M > 0 else None, M, *[int(k) for k in topk], float(gains[0]), float(gains[1]), float(gains[2]),
-            int(normalise), ptr(items), ptr(partials), ptr(dbg["fg_mask"]) if debug else None,
+            int(normalise), ptr(items), ptr(partials), tsc, ptr(total), ptr(dbg["fg_mask"]) if debug else None,
             ptr(dbg["target_gt_idx"]) if debug else None, prof_events, ptr(ws), ws.numel(), stream_ptr(dev))
     if xrank is not None:  # two branches, cross-rank exchange fused into the last kernel (dist.PeerLossReducer)
         if n != 2 or debug or not normalise:
@@ -71,14 +73,15 @@ def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_e
         _lib.check(_lib.lib().y3d_v10_loss_fwd_sharded(
             l0.c_ptr, l0.c_sB, l0.c_sC, l1.c_ptr, l1.c_sB, l1.c_sC, l0.c_hw, l0.c_stride, l0.nl, l0.B, nc, REG_MAX,
             ptr(gt) if M > 0 else None, M, int(topk[0]), int(topk[1]), float(gains[0]), float(gains[1]), float(gains[2]),
-            ptr(items), ptr(partials), *xrank.next_call(), prof_events, ptr(ws), ws.numel(), stream_ptr(dev)))
+            ptr(items), ptr(partials), tsc, ptr(total), *xrank.next_call(), prof_events, ptr(ws), ws.numel(),
+            stream_ptr(dev)))
     elif n == 1:
         _lib.check(_lib.lib().y3d_v8_loss_fwd(*l0.args(), l0.B, nc, REG_MAX, *tail))
     else:
         l1 = levels[1]
         _lib.check(_lib.lib().y3d_v10_loss_fwd(l0.c_ptr, l0.c_sB, l0.c_sC, l1.c_ptr, l1.c_sB, l1.c_sC, l0.c_hw,
                                                l0.c_stride, l0.nl, l0.B, nc, REG_MAX, *tail))
-    return dict(items=items, partials=partials, dbg=dbg, ws=ws, gt=gt, M=M)
+    return dict(items=items, partials=partials, dbg=dbg, ws=ws, gt=gt, M=M, total=total)
 
 
 def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, debug=False, prof_events=None):
@@ -90,7 +93,7 @@ def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, 
 
 
 def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(10, 1), normalise=True, debug=False,
-                     prof_events=None, xrank=None):
+                     prof_events=None, xrank=None, total_scale=None, return_total=False):
     """Both branches of ``v10DetectLoss`` through ONE call of ``y3d_v10_loss_fwd`` (same launches for both).
 
     Returns (items float32[8] = (box, cls, dfl, target_scores_sum) x (one2many, one2one) or ``None`` when not
@@ -99,7 +102,9 @@ def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(
     last kernel then sums the partials over the ranks through NVLink peer memory before normalising
     (``y3d_v10_loss_fwd_sharded``), and items / partials are those of the whole batch."""
     r = _branch_forward([Levels(feats_o2m, strides), Levels(feats_o2o, strides)], nc, gt_packed, topk, gains,
-                        normalise, debug, prof_events, xrank)
+                        normalise, debug, prof_events, xrank, total_scale)
+    if return_total:  # ``total_scale`` * (sum of the six loss items), from the last kernel: float32[1]
+        return r["items"], r["partials"], r["dbg"], r["total"]
     return r["items"], r["partials"], r["dbg"]
 
 

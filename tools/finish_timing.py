@@ -22,33 +22,38 @@ dev = torch.device("cuda", 0)
 fm = [torch.from_numpy(f).to(dev) for f in synth.split_levels(xm, lv)]
 fo = [torch.from_numpy(f).to(dev) for f in synth.split_levels(xo, lv)]
 gtd = torch.from_numpy(gt).to(dev)
-for _ in range(5):
+h = _lib.lib()
+h.y3d_debug_read_stamps.argtypes = [ctypes.c_void_p, ctypes.c_int]
+h.y3d_debug_read_topk_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
+for _ in range(8):
     y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
 torch.cuda.synchronize()
-h = _lib.lib()
 n = 2048 * 8
 buf = (ctypes.c_ulonglong * n)()
-h.y3d_debug_read_stamps.argtypes = [ctypes.c_void_p, ctypes.c_int]
+tk = (ctypes.c_ulonglong * 64)()
+h.y3d_debug_read_topk_timeline(tk, 1)
+y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), 80, gtd, (7.5, 0.5, 1.5))
+torch.cuda.synchronize()
 assert h.y3d_debug_read_stamps(buf, n) == 0
-t = np.array(buf, dtype=np.uint64).reshape(2048, 8).astype(np.int64)[:1024]
-# CTA index = (z * B + b) * chunks + chunk, chunks = 8
-t = t.reshape(2, 64, 8, 8)
-t0 = t[..., 0][t[..., 0] > 0].min()
-rel = lambda x: np.where(x > 0, (x - t0) / 1e3, np.nan)
-print("start (us): min/mean/max", np.nanmin(rel(t[..., 0])), np.nanmean(rel(t[..., 0])), np.nanmax(rel(t[..., 0])))
-print("after wait (1): min/mean/max", np.nanmin(rel(t[..., 1])), np.nanmean(rel(t[..., 1])), np.nanmax(rel(t[..., 1])))
+h.y3d_debug_read_topk_timeline(tk, 0)
+T = np.array(tk, dtype=np.uint64).reshape(16, 4)
+row = int(np.argmax(T[:, 1]))
+NOT = (1 << 64) - 1
+tk_first, tk_last_exit, tk_first_exit = NOT - int(T[row, 0]), int(T[row, 1]), NOT - int(T[row, 2])
+t = np.array(buf, dtype=np.uint64).reshape(2048, 8).astype(np.int64)[:1024].reshape(2, 64, 8, 8)
+base = tk_first
+rel = lambda x: (x - base) / 1e3
+print(f"top-k: first warp start 0.0, first exit {rel(tk_first_exit):.1f}, last exit {rel(tk_last_exit):.1f} us")
 valid = (gt[..., 1:5].sum(-1) > 0).sum(1)
-for z in range(2):
-    for b in (0, 1, 2, 5):
-        print(f"z={z} b={b} nGT={valid[b]}")
-        for ch in range(8):
-            r = rel(t[z, b, ch].astype(np.float64))
-            print("   chunk", ch, np.round(r[:7], 1))
-s1 = rel(t[..., 1]); s2 = rel(t[..., 2]); s3 = rel(t[..., 3]); s4 = rel(t[..., 4]); s5 = rel(t[..., 5]); s6 = rel(t[..., 6])
-act = t[..., 2] >= t[..., 1]
-print("phase R duration mean/max:", np.nanmean((s2 - s1)[act]), np.nanmax((s2 - s1)[act]))
-print("fence+count mean/max:", np.nanmean((s3 - s2)[act]), np.nanmax((s3 - s2)[act]))
-last = t[..., 4] >= t[..., 3]
-print("phase S mean/max:", np.nanmean((s4 - s3)[last & act]), np.nanmax((s4 - s3)[last & act]))
-print("ticket mean/max:", np.nanmean((s5 - s4)[last & act]), np.nanmax((s5 - s4)[last & act]))
-print("latest R end", np.nanmax(s2[act]), " latest S end", np.nanmax(s4[last & act]), " final", np.nanmax(np.where(t[..., 6] >= t[..., 5], s6, np.nan)))
+# chunk-0 CTAs ordered by the time they got past the image wait
+c0 = t[:, :, 0, :]
+order = np.dstack(np.unravel_index(np.argsort(c0[..., 1], axis=None), c0[..., 1].shape))[0]
+print("last 8 images to become ready: (z, b, nGT) | past wait | R end | S end | acc | ticket | final   (us after top-k start)")
+for z, b in order[-8:]:
+    r = c0[z, b]
+    vals = [rel(int(v)) if v > 0 and v >= r[0] else float("nan") for v in r[1:7]]
+    print(f"   z={z} b={b:2d} nGT={valid[b]:3d} | " + " | ".join(f"{v:7.1f}" for v in vals))
+d = c0[..., 2] - c0[..., 1]
+print("chunk-0 R duration mean/max (us):", d.mean() / 1e3, d.max() / 1e3)
+d = c0[..., 5] - c0[..., 2]
+print("R end -> ticket mean/max (us):", d.mean() / 1e3, d.max() / 1e3)

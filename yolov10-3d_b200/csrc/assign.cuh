@@ -22,6 +22,7 @@
 namespace y3d {
 
 constexpr int kTopkWarps = 4;  // warps (= GTs) per CTA of tal_topk_kernel
+constexpr int kRecF4 = 3;     // float4 words of a claim record (AssignCtx::rec)
 
 struct AssignCtx {
     // predictions
@@ -58,13 +59,13 @@ struct AssignCtx {
     int *list_count;
     int *list_a;
     int list_cap;
-    // optional (fused loss, anchor-parallel finish): instead of the list, EVERY claim leaves a record of 5 float4 at
-    // rec[b * rec_cap + slot] (slot from list_count[b]) with everything the finishing kernel needs for this
-    // (anchor, GT) pair, gathered here -- spread over this kernel's run time instead of one burst of scattered DRAM
-    // reads at the end of the step:
+    // optional (fused loss, anchor-parallel finish): instead of the list, EVERY claim leaves a record of kRecF4 float4
+    // at rec[(b * rec_cap + slot) * kRecF4] (slot from list_count[b]) with everything the finishing kernel needs for
+    // this (anchor, GT) pair, gathered and evaluated here -- spread over this kernel's run time instead of one burst of
+    // scattered DRAM reads and a latency chain at the very end of the step:
     //   [0] anchor | first-claimer bit << 31, GT index, alignment metric bits, logit of the GT's label
-    //   [1] predicted box xyxy (grid units)   [2] log-sum-exp of the 4 DFL sides
-    //   [3] logit of the lower DFL target bin of every side   [4] logit of the upper one
+    //   [1] clamped exact CIoU (overlap), 1 - CIoU loss term, DFL loss term, 0     (claim_terms below)
+    //   [2] predicted box xyxy (grid units)
     float4 *rec;
     int rec_cap;
     const float *lse;  // [B,A,4] written by the streaming kernel
@@ -299,6 +300,66 @@ __device__ __forceinline__ unsigned long long tk_key(float metric, int a, int in
            (unsigned long long)(in & 1);
 }
 __device__ __forceinline__ int tk_anchor(unsigned long long key) { return 0x7fffffff - (int)((key & 0xffffffffull) >> 1); }
+
+// bbox_iou(box1, box2, xywh=False, CIoU=True) (metrics.py:96-131) with fast division: for VALUES (loss terms, alignment
+// weights), never for anything that decides an index -- those go through the exactly rounded dm::ciou.
+__device__ __forceinline__ float ciou_fast(float4 b1, float4 b2) {
+    const float eps = 1e-7f;
+    const float w1 = b1.z - b1.x, h1 = b1.w - b1.y + eps, w2 = b2.z - b2.x, h2 = b2.w - b2.y + eps;
+    const float iw = fmaxf(fminf(b1.z, b2.z) - fmaxf(b1.x, b2.x), 0.f), ih = fmaxf(fminf(b1.w, b2.w) - fmaxf(b1.y, b2.y), 0.f);
+    const float inter = iw * ih;
+    const float uni = w1 * h1 + w2 * h2 - inter + eps;
+    const float iou = __fdividef(inter, uni);
+    const float cw = fmaxf(b1.z, b2.z) - fminf(b1.x, b2.x), ch = fmaxf(b1.w, b2.w) - fminf(b1.y, b2.y);
+    const float c2 = cw * cw + ch * ch + eps;
+    const float dx = b2.x + b2.z - b1.x - b1.z, dy = b2.y + b2.w - b1.y - b1.w;
+    const float rho2 = (dx * dx + dy * dy) * 0.25f;
+    const float da = atanf(__fdividef(w2, h2)) - atanf(__fdividef(w1, h1));
+    const float v = 0.4052847345693511f * da * da;
+    const float alpha = __fdividef(v, v - iou + (1.0f + eps));
+    return iou - (__fdividef(rho2, c2) + v * alpha);
+}
+
+// What a claim record carries besides the pair's identity (assign.cuh, AssignCtx::rec): the loss inputs of (anchor a of
+// image b, GT g), gathered from the head tensor and the streaming kernel's planes, and the terms that depend on nothing
+// else: the clamped exact CIoU (the pair's `overlaps` entry, tal.py:131), 1 - CIoU(pred, target) in grid units
+// (BboxLoss.forward loss.py:85-86) and the DFL cross-entropy averaged over the four sides (_df_loss loss.py:99-113).
+struct ClaimTerms {
+    float4 terms;  // overlap, 1 - CIoU, DFL, 0
+    float4 box;    // predicted box, grid units
+    float xlab;    // logit of the GT's class
+};
+__device__ __forceinline__ ClaimTerms claim_terms(const AssignCtx &c, int b, int a, const GtRec &g) {
+    ClaimTerms r;
+    const int lv = level_of(c.t, a);
+    const int cell = a - c.t.start[lv];
+    const float st = c.t.stride[lv];
+    const float gx = (float)(cell % c.t.w[lv]) + 0.5f, gy = (float)(cell / c.t.w[lv]) + 0.5f;
+    float4 tb;
+    float tt[4];
+    dfl_target(g.box, st, gx, gy, tb, tt);
+    const float *hp = c.t.ptr[lv] + (long long)b * c.t.sB[lv] + cell;
+    const long long cs = c.t.sC[lv];
+    const int t0 = (int)tt[0], t1 = (int)tt[1], t2 = (int)tt[2], t3 = (int)tt[3];
+    const float xl[4] = {hp[(long long)t0 * cs], hp[(long long)(16 + t1) * cs], hp[(long long)(32 + t2) * cs],
+                         hp[(long long)(48 + t3) * cs]};
+    const float xr[4] = {hp[(long long)(t0 + 1) * cs], hp[(long long)(17 + t1) * cs], hp[(long long)(33 + t2) * cs],
+                         hp[(long long)(49 + t3) * cs]};
+    r.xlab = hp[(long long)(c.cls_ch0 + (g.label < 0 ? 0 : g.label)) * cs];
+    r.box = reinterpret_cast<const float4 *>(c.pd_bboxes)[(long long)b * c.A + a];
+    const float4 l4 = reinterpret_cast<const float4 *>(c.lse)[(long long)b * c.A + a];
+    const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+    float o = dm::ciou(g.box, make_float4(dm::mul(r.box.x, st), dm::mul(r.box.y, st), dm::mul(r.box.z, st), dm::mul(r.box.w, st)), g.at1);
+    o = o < 0.0f ? 0.0f : o;
+    float dfl = 0.f;
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+        const float wl = (float)((int)tt[side] + 1) - tt[side];
+        dfl += (ls[side] - xl[side]) * wl + (ls[side] - xr[side]) * (1.0f - wl);
+    }
+    r.terms = make_float4(o, 1.0f - ciou_fast(r.box, tb), dfl * 0.25f, 0.f);
+    return r;
+}
 
 __device__ __forceinline__ void red_release_add1(unsigned *p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");

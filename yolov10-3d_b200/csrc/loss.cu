@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(kStreamThreads, 4) head_stream_kernel(const __
         if (P.list_count[z]) P.list_count[z][b] = 0;
         if (P.img_cnt[z]) P.img_cnt[z][b] = 0;
         if (P.topk_done[z]) P.topk_done[z][b] = 0u;
-        if (b == 0 && z == 0 && P.counter) { P.counter[0] = 0u; P.counter[1] = 0u; }
+        if (b == 0 && z == 0 && P.counter) {  // tickets, and the fixed-point accumulators of the finishing kernel
+            P.counter[0] = 0u; P.counter[1] = 0u;
+            for (int i = 16; i < 16 + 2 * 2 * 5; ++i) P.counter[i] = 0u;
+        }
     }
     float bce = 0.f;
     if (q * V < A) {
@@ -314,6 +317,9 @@ struct FinishParams {
     float *list_al[2];         // [B,cap] scratch (per-image kernel)
     int *img_cnt[2];           // [B] zeroed by the stream kernel: chunks of the image that have finished
     int *pos[2];               // [B,M,2] zeroed by the stream kernel: per-GT max alignment metric / max overlap (float bits)
+    long long *acc;            // [n_branch][5] zeroed by the stream kernel: fixed-point sums over the images (anchor-parallel
+                               // kernel): iou, dfl, target_scores, x*t, softplus
+    double *img_bce;           // [n_branch][B] scratch: softplus partials of an image, summed ahead of time
     const double *part_bce;    // [n_branch][n_bce]
     double *part_fg;           // [n_branch][B][5]: iou, dfl, target_scores, x*t, softplus
     unsigned *counter;         // zeroed by the stream kernel
@@ -333,25 +339,6 @@ struct FinishParams {
     long long x_timeout;       // clock cycles (xrank_timeout_cycles)
     int *x_status;             // optional: 1 when a peer never arrived
 };
-
-// bbox_iou(box1, box2, xywh=False, CIoU=True) (metrics.py:96-131) with fast division: for VALUES (loss terms, alignment
-// weights), never for anything that decides an index -- those go through the exactly rounded dm::ciou.
-__device__ __forceinline__ float ciou_fast(float4 b1, float4 b2) {
-    const float eps = 1e-7f;
-    const float w1 = b1.z - b1.x, h1 = b1.w - b1.y + eps, w2 = b2.z - b2.x, h2 = b2.w - b2.y + eps;
-    const float iw = fmaxf(fminf(b1.z, b2.z) - fmaxf(b1.x, b2.x), 0.f), ih = fmaxf(fminf(b1.w, b2.w) - fmaxf(b1.y, b2.y), 0.f);
-    const float inter = iw * ih;
-    const float uni = w1 * h1 + w2 * h2 - inter + eps;
-    const float iou = __fdividef(inter, uni);
-    const float cw = fmaxf(b1.z, b2.z) - fminf(b1.x, b2.x), ch = fmaxf(b1.w, b2.w) - fminf(b1.y, b2.y);
-    const float c2 = cw * cw + ch * ch + eps;
-    const float dx = b2.x + b2.z - b1.x - b1.z, dy = b2.y + b2.w - b1.y - b1.w;
-    const float rho2 = (dx * dx + dy * dy) * 0.25f;
-    const float da = atanf(__fdividef(w2, h2)) - atanf(__fdividef(w1, h1));
-    const float v = 0.4052847345693511f * da * da;
-    const float alpha = __fdividef(v, v - iou + (1.0f + eps));
-    return iou - (__fdividef(rho2, c2) + v * alpha);
-}
 
 constexpr double kFix = 4294967296.0;  // 2^32: loss terms are summed as 64-bit fixed point (exact, order-independent)
 __device__ __forceinline__ long long to_fix(float v) { return __double2ll_rn((double)v * kFix); }
@@ -750,8 +737,8 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     __shared__ unsigned long long s_cbest[kFinApThreads];  // (overlap bits << 32) | (0xffffffff - m): atomicMax = first maximum
     __shared__ int2 s_pairs[kFinApPairs];                  // (contested anchor, GT) with the anchor inside the GT
     __shared__ int s_ncf, s_np;
+    __shared__ int s_pos[2 * kFinishApMaxM];               // single-chunk images: per-GT max alignment / max overlap (float bits)
     __shared__ long long s_redl[4][kFinApWarps];
-    __shared__ double s_redd[kFinApWarps];
     __shared__ double s_fin[2][5];
     __shared__ double s_xv[kXMaxVals], s_xs[kXMaxVals];
     __shared__ int s_xfail, s_flag;
@@ -762,6 +749,8 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     Y3D_APSTAMP(0);
     Y3D_TL_MIN(2);
     if (tid == 0) { s_ncf = 0; s_np = 0; }
+    s_pos[tid] = 0;
+    s_pos[tid + kFinApThreads] = 0;
     bool my_valid = false;
     for (int m = tid; m < M; m += kFinApThreads) {
         gts[m] = load_gt(c, b, m);
@@ -769,6 +758,13 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     }
     const int n_valid = __syncthreads_count(my_valid);
     if (chunk > 0 && chunk * kFinApThreads >= n_valid * c.k) return;  // more records than this image can have
+    if (chunk == 0 && wid == 0) {  // off the critical path: this image's softplus partials (written by the stream kernel)
+        double bsum = 0.0;
+        for (int i = lane; i < F.n_bce_x; i += 32)
+            bsum += __ldcg(F.part_bce + ((long long)z * gridDim.y + b) * F.n_bce_x + i);
+        bsum = warp_sum(bsum);
+        if (lane == 0) __stcg(F.img_bce + (long long)z * gridDim.y + b, bsum);
+    }
     // Everything above reads only the caller's inputs.  This grid is launched programmatically dependent on the top-k
     // kernel and becomes resident as that kernel's CTAs retire; it does not wait for the whole grid but for its own
     // image: the top-k kernel counts the GTs it has finished per image (release), all of them = the records are there.
@@ -785,6 +781,12 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     __syncthreads();
     float4 *rec = c.rec + (long long)b * c.rec_cap * kRecF4;
     int *pos = F.pos[z] + (long long)b * M * 2;
+    // An image whose records fit one chunk (every top-k 1 image, the small top-k 10 ones) never leaves this CTA: its per-GT
+    // maxima live in shared memory and phase S runs from registers -- no record rewrite, no fence, no counter.
+    const bool single = n_chunks == 1;
+    bool my_active = false;
+    int my_a = 0, my_gi = 0;
+    float my_alv = 0.f, my_xlab = 0.f, my_tiou = 0.f, my_tdfl = 0.f;
     // ---- phase R: one claim record per thread; only the first claimer of an anchor carries it on
     {
         const int e = chunk * kFinApThreads + tid;
@@ -794,9 +796,11 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
         PairRaw raw;
         raw.box = make_float4(0.f, 0.f, 0.f, 0.f);
         raw.s = 0.f;
-        float4 ls4 = raw.box, xl4 = raw.box, xr4 = raw.box;
+        float4 terms = raw.box;
         if (active) {
             const float4 r0 = __ldcg(rec + (long long)e * kRecF4);
+            terms = __ldcg(rec + (long long)e * kRecF4 + 1);
+            raw.box = __ldcg(rec + (long long)e * kRecF4 + 2);
             const int aw = __float_as_int(r0.x);
             active = aw < 0;  // first-claimer bit
             a = aw & 0x7fffffff;
@@ -805,10 +809,6 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
             xlab = r0.w;
         }
         if (active) {
-            raw.box = __ldcg(rec + (long long)e * kRecF4 + 1);
-            ls4 = __ldcg(rec + (long long)e * kRecF4 + 2);
-            xl4 = __ldcg(rec + (long long)e * kRecF4 + 3);
-            xr4 = __ldcg(rec + (long long)e * kRecF4 + 4);
             const unsigned long long cl = __ldcg(c.claim + (long long)b * A + a);
             cnt = (int)(cl >> 32);
             gi = m0;
@@ -855,125 +855,105 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
             if (contested) gi = (int)(0xffffffffu - (unsigned)(s_cbest[my_ci] & 0xffffffffull));
         }
         if (active) {
-            const GtRec g = gts[gi];
-            const int l = level_of(c.t, a);
-            const int cell = a - c.t.start[l];
-            const float gx = (float)(cell % c.t.w[l]) + 0.5f, gy = (float)(cell / c.t.w[l]) + 0.5f;
-            float4 tb;
-            float tt[4];
-            dfl_target(g.box, st, gx, gy, tb, tt);
-            float ovl = 0.0f;
+            float ovl = terms.x;
             if (gi != m0) {
-                // the anchor went to a GT other than its first claimer (possibly one that never selected it): this
-                // pair's inputs were not gathered by the top-k kernel
-                const float *hp = c.t.ptr[l] + (long long)b * c.t.sB[l] + cell;
-                const long long cs = c.t.sC[l];
-                const int t0 = (int)tt[0], t1 = (int)tt[1], t2 = (int)tt[2], t3 = (int)tt[3];
-                xl4 = make_float4(hp[(long long)t0 * cs], hp[(long long)(kR + t1) * cs], hp[(long long)(2 * kR + t2) * cs],
-                                  hp[(long long)(3 * kR + t3) * cs]);
-                xr4 = make_float4(hp[(long long)(t0 + 1) * cs], hp[(long long)(kR + 1 + t1) * cs],
-                                  hp[(long long)(2 * kR + 1 + t2) * cs], hp[(long long)(3 * kR + 1 + t3) * cs]);
-                xlab = hp[(long long)(4 * kR + (g.label < 0 ? 0 : g.label)) * cs];
+                // the anchor went to a GT other than its first claimer (possibly one that never selected it): the terms of
+                // this pair were not evaluated by the top-k kernel
+                const GtRec g = gts[gi];
+                const ClaimTerms ct = claim_terms(c, b, a, g);
+                terms = ct.terms;
+                xlab = ct.xlab;
                 const float xs = g.label < 0 ? pair_load_score(c, b, a, g.label) : xlab;  // the score the assigner saw
                 metric = 0.0f;
+                ovl = 0.0f;
                 if (g.valid && dm::in_gt(ax, ay, g.box))
                     metric = pair_metric(c, b, gi, g, a, raw, dm::pow_(pair_score(c, xs), c.alpha), ovl);
-            } else {  // metric: the very value the top-k kernel ranked; overlap = clamp(CIoU, 0) as in get_box_metrics
-                ovl = dm::ciou(g.box, pbox, g.at1);
-                ovl = ovl < 0.0f ? 0.0f : ovl;
             }
-            atomicMax(pos + 2 * gi, __float_as_int(metric));  // values >= 0: int order == float order
-            atomicMax(pos + 2 * gi + 1, __float_as_int(ovl));
-            const float iou = ciou_fast(raw.box, tb);  // BboxLoss.forward loss.py:85 (box1 = pred, grid units)
-            const float xl[4] = {xl4.x, xl4.y, xl4.z, xl4.w}, xr[4] = {xr4.x, xr4.y, xr4.z, xr4.w};
-            const float ls[4] = {ls4.x, ls4.y, ls4.z, ls4.w};
-            float dfl = 0.f;
-#pragma unroll
-            for (int side = 0; side < 4; ++side) {  // _df_loss loss.py:99-113
-                const float wl = (float)((int)tt[side] + 1) - tt[side];
-                dfl += (ls[side] - xl[side]) * wl + (ls[side] - xr[side]) * (1.0f - wl);
+            int *pm = single ? s_pos : pos;  // values >= 0: int order == float order
+            atomicMax(pm + 2 * gi, __float_as_int(metric));
+            atomicMax(pm + 2 * gi + 1, __float_as_int(ovl));
+            my_a = a; my_gi = gi; my_alv = metric; my_xlab = xlab; my_tiou = terms.y; my_tdfl = terms.z;
+            if (!single) {  // phase S (whichever chunk runs it) reads words 0 and 1 of the record
+                __stcg(rec + (long long)e * kRecF4, make_float4(__int_as_float(a | (int)0x80000000), __int_as_float(gi), metric, xlab));
+                __stcg(rec + (long long)e * kRecF4 + 1, make_float4(my_tiou, my_tdfl, 0.f, 0.f));
             }
-            // phase S reads words 0 and 1 of the record
-            __stcg(rec + (long long)e * kRecF4, make_float4(__int_as_float(a | (int)0x80000000), __int_as_float(gi), metric, xlab));
-            __stcg(rec + (long long)e * kRecF4 + 1, make_float4(1.0f - iou, dfl * 0.25f, 0.f, 0.f));
         }
+        my_active = active;
     }
-    // ---- which chunk of the image finishes last?
+    long long s_iou = 0, s_dfl = 0, s_ts = 0, s_xt = 0;
+    auto fold = [&](int a, int gi, float alv, float xlab, float tiou, float tdfl, float pa, float po) {
+        const float wgt = dm::div(dm::mul(alv, po), dm::add(pa, c.eps));  // = target_scores.sum(-1), tal.py:89-92
+        // kept for the backward pass: the claim word of a foreground anchor becomes (1 << 63 | GT index << 32 | weight)
+        c.claim[(long long)b * A + a] =
+            0x8000000000000000ull | ((unsigned long long)(unsigned)gi << 32) | (unsigned long long)__float_as_uint(wgt);
+        s_iou += to_fix(tiou * wgt);
+        s_dfl += to_fix(tdfl * wgt);  // .mean(-1) over the 4 sides is in the term
+        s_ts += to_fix(wgt);
+        s_xt += to_fix(xlab * wgt);  // BCE(x,t) - BCE(x,0) = -x*t
+        if (F.dbg_fg[z]) {
+            F.dbg_fg[z][(long long)b * A + a] = 1;
+            F.dbg_gi[z][(long long)b * A + a] = gi;
+        }
+    };
     __syncthreads();
     Y3D_APSTAMP(2);
     Y3D_TL_MAX(4);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_flag = atomicAdd(F.img_cnt[z] + b, 1) == n_chunks - 1;
-    __syncthreads();
-    Y3D_APSTAMP(3);
-    if (!s_flag) return;
-    __threadfence();
-    // ---- phase S: weights and sums of the whole image
-    long long s_iou = 0, s_dfl = 0, s_ts = 0, s_xt = 0;
-    constexpr int SU = 8;  // records in flight per thread: the loop is two dependent round trips per batch
-    for (int e0 = tid; e0 < n; e0 += kFinApThreads * SU) {
-        float4 r0[SU], r1[SU];
-        int2 pp[SU];
+    if (single) {
+        // ---- phase S from registers
+        if (my_active) fold(my_a, my_gi, my_alv, my_xlab, my_tiou, my_tdfl, __int_as_float(s_pos[2 * my_gi]), __int_as_float(s_pos[2 * my_gi + 1]));
+        Y3D_APSTAMP(3);
+    } else {
+        // ---- which chunk of the image finishes last?
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_flag = atomicAdd(F.img_cnt[z] + b, 1) == n_chunks - 1;
+        __syncthreads();
+        Y3D_APSTAMP(3);
+        if (!s_flag) return;
+        __threadfence();
+        // ---- phase S: weights and sums of the whole image
+        constexpr int SU = 8;  // records in flight per thread: the loop is two dependent round trips per batch
+        for (int e0 = tid; e0 < n; e0 += kFinApThreads * SU) {
+            float4 r0[SU], r1[SU];
+            int2 pp[SU];
 #pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            const int e = e0 + u * kFinApThreads;
-            r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            r1[u] = r0[u];
-            if (e < n) {
-                r0[u] = __ldcg(rec + (long long)e * kRecF4);
-                r1[u] = __ldcg(rec + (long long)e * kRecF4 + 1);
+            for (int u = 0; u < SU; ++u) {
+                const int e = e0 + u * kFinApThreads;
+                r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r1[u] = r0[u];
+                if (e < n) {
+                    r0[u] = __ldcg(rec + (long long)e * kRecF4);
+                    r1[u] = __ldcg(rec + (long long)e * kRecF4 + 1);
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            pp[u] = make_int2(0, 0);
-            if (__float_as_int(r0[u].x) < 0) pp[u] = __ldcg(reinterpret_cast<const int2 *>(pos) + __float_as_int(r0[u].y));
-        }
+            for (int u = 0; u < SU; ++u) {
+                pp[u] = make_int2(0, 0);
+                if (__float_as_int(r0[u].x) < 0) pp[u] = __ldcg(reinterpret_cast<const int2 *>(pos) + __float_as_int(r0[u].y));
+            }
 #pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            const int aw = __float_as_int(r0[u].x);
-            if (aw >= 0) continue;  // past the end, or not the anchor's first claimer
-            const int a = aw & 0x7fffffff;
-            const int gi = __float_as_int(r0[u].y);
-            const float alv = r0[u].z, xlab = r0[u].w;
-            const float pa = __int_as_float(pp[u].x), po = __int_as_float(pp[u].y);
-            const float wgt = dm::div(dm::mul(alv, po), dm::add(pa, c.eps));  // = target_scores.sum(-1), tal.py:89-92
-            // kept for the backward pass: the claim word of a foreground anchor becomes (1 << 63 | GT index << 32 | weight)
-            c.claim[(long long)b * A + a] =
-                0x8000000000000000ull | ((unsigned long long)(unsigned)gi << 32) | (unsigned long long)__float_as_uint(wgt);
-            s_iou += to_fix(r1[u].x * wgt);
-            s_dfl += to_fix(r1[u].y * wgt);  // .mean(-1) over the 4 sides is in the record
-            s_ts += to_fix(wgt);
-            s_xt += to_fix(xlab * wgt);  // BCE(x,t) - BCE(x,0) = -x*t
-            if (F.dbg_fg[z]) {
-                F.dbg_fg[z][(long long)b * A + a] = 1;
-                F.dbg_gi[z][(long long)b * A + a] = gi;
+            for (int u = 0; u < SU; ++u) {
+                const int aw = __float_as_int(r0[u].x);
+                if (aw >= 0) continue;  // past the end, or not the anchor's first claimer
+                fold(aw & 0x7fffffff, __float_as_int(r0[u].y), r0[u].z, r0[u].w, r1[u].x, r1[u].y, __int_as_float(pp[u].x),
+                     __int_as_float(pp[u].y));
             }
         }
     }
+    // ---- the image's sums join the batch sums: 64-bit fixed point, so the order of arrival does not matter
     s_iou = warp_sum_ll(s_iou); s_dfl = warp_sum_ll(s_dfl); s_ts = warp_sum_ll(s_ts); s_xt = warp_sum_ll(s_xt);
-    double bce = 0.0;
-    for (int i = tid; i < F.n_bce_x; i += kFinApThreads)
-        bce += __ldcg(F.part_bce + ((long long)z * gridDim.y + b) * F.n_bce_x + i);
-    bce = warp_sum(bce);
-    if (lane == 0) {
-        s_redl[0][wid] = s_iou; s_redl[1][wid] = s_dfl; s_redl[2][wid] = s_ts; s_redl[3][wid] = s_xt;
-        s_redd[wid] = bce;
-    }
+    if (lane == 0) { s_redl[0][wid] = s_iou; s_redl[1][wid] = s_dfl; s_redl[2][wid] = s_ts; s_redl[3][wid] = s_xt; }
     __syncthreads();
     const int B = gridDim.y;
-    double *pimg = F.part_fg + ((long long)z * B + b) * 5;
     if (tid < 4) {
-        long long s = 0;
-        for (int i = 0; i < kFinApWarps; ++i) s += s_redl[tid][i];
-        pimg[tid] = (double)s / kFix;
+        long long sum = 0;
+        for (int i = 0; i < kFinApWarps; ++i) sum += s_redl[tid][i];
+        atomicAdd(reinterpret_cast<unsigned long long *>(F.acc + 5 * z + tid), (unsigned long long)sum);
     } else if (tid == 4) {
-        double s = 0.0;
-        for (int i = 0; i < kFinApWarps; ++i) s += s_redd[i];
-        pimg[4] = s;
+        const double bce = __ldcg(F.img_bce + (long long)z * B + b);  // summed by the image's first chunk before it waited
+        atomicAdd(reinterpret_cast<unsigned long long *>(F.acc + 5 * z + 4), (unsigned long long)__double2ll_rn(bce * kFix));
     }
-    // last image done: fixed-order reduction of the per-image partials (deterministic whichever CTA it is)
+    // last image done?
     Y3D_APSTAMP(4);
     __threadfence();
     __syncthreads();
@@ -981,18 +961,8 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     __syncthreads();
     Y3D_APSTAMP(5);
     if (!s_flag) return;
-    // every image is through, so the top-k kernel has no work left -- but its last warps may still be on their way out,
-    // and the next kernel in the stream (which waits for THIS grid) resets the counters they read: do not complete
-    // before the primary grid has
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     __threadfence();
-    for (int w = wid; w < 5 * F.n_branch; w += kFinApWarps) {  // warp job (zz, k): lane-strided, then a fixed shuffle tree
-        const int zz = w / 5, k = w % 5;
-        double acc = 0.0;
-        for (int i = lane; i < B; i += 32) acc += __ldcg(F.part_fg + ((long long)zz * B + i) * 5 + k);
-        acc = warp_sum(acc);
-        if (lane == 0) s_fin[zz][k] = acc;
-    }
+    if (tid < 5 * F.n_branch) s_fin[tid / 5][tid % 5] = (double)__ldcg(F.acc + tid) / kFix;
     __syncthreads();
     if (tid < 4 * F.n_branch) {  // partials of a branch: iou, bce, dfl, target_scores_sum
         const int zz = tid >> 2, j = tid & 3;
@@ -1199,6 +1169,8 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     F.gt5 = gt;
     F.part_bce = P.part_bce;
     F.part_fg = (double *)(p + w.off_pfg);
+    F.acc = (long long *)(P.counter + 16);
+    F.img_bce = F.part_fg;  // the anchor-parallel kernel does not use the per-image partials: [n_branch][B] doubles fit
     F.counter = P.counter;
     F.partials = partials;
     F.loss_items = loss_items;

@@ -8,7 +8,6 @@ namespace y3d {
 
 constexpr int kR = 16;  // reg_max (head.py:37)
 constexpr int kFinishApMaxM = 128;  // GTs per image up to which the anchor-parallel finishing kernel is used
-constexpr int kRecF4 = 5;           // float4 words of a claim record (assign.cuh)
 
 struct LossWs {  // all offsets 256-byte aligned; per-branch blocks are contiguous
     size_t claim, boxes, lse, list_a, list_gi, list_al, rec, list_count, img_cnt, topk_done, pos, per_branch;

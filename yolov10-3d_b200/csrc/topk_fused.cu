@@ -99,7 +99,8 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
     int *s_info = s_pref + (n_seg + 1);
     if (ORDERED) {
         for (int bb = threadIdx.x; bb < n_img; bb += blockDim.x) {
-            const int4 v = __ldcg(reinterpret_cast<const int4 *>(cc.ord_cnt) + bb);
+            // (plain load: the CTAs of an SM share the line through L1 instead of all 1184 CTAs queueing at one L2 slice)
+            const int4 v = reinterpret_cast<const int4 *>(cc.ord_cnt)[bb];
             const int cnt[4] = {v.x, v.y, v.z, v.w};
             int basec = 0;
 #pragma unroll
@@ -407,38 +408,23 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
             if (cmask) {
                 int a = 0;
                 unsigned long long old = 0ull;
-                float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f), r2 = r1, r3 = r1, r4 = r1;
-                float xlab = 0.f;
+                ClaimTerms ct;
                 if (claiming) {
                     a = tk_anchor(tk);
-                    const int lv = level_of(c.t, a);
-                    const int cell = a - c.t.start[lv];
-                    const float gx = (float)(cell % c.t.w[lv]) + 0.5f, gy = (float)(cell / c.t.w[lv]) + 0.5f;
-                    float4 tb;
-                    float tt[4];
-                    dfl_target(g.box, c.t.stride[lv], gx, gy, tb, tt);
-                    const float *hp = c.t.ptr[lv] + (long long)b * c.t.sB[lv] + cell;
-                    const long long cs = c.t.sC[lv];
-                    const int t_0 = (int)tt[0], t_1 = (int)tt[1], t_2 = (int)tt[2], t_3 = (int)tt[3];
-                    r3 = make_float4(hp[(long long)t_0 * cs], hp[(long long)(16 + t_1) * cs], hp[(long long)(32 + t_2) * cs],
-                                     hp[(long long)(48 + t_3) * cs]);
-                    r4 = make_float4(hp[(long long)(t_0 + 1) * cs], hp[(long long)(17 + t_1) * cs],
-                                     hp[(long long)(33 + t_2) * cs], hp[(long long)(49 + t_3) * cs]);
-                    xlab = hp[(long long)(64 + (g.label < 0 ? 0 : g.label)) * cs];
-                    r1 = reinterpret_cast<const float4 *>(c.pd_bboxes)[(long long)b * A + a];
-                    r2 = reinterpret_cast<const float4 *>(c.lse)[(long long)b * A + a];
                     old = atomicAdd(c.claim + (long long)b * A + a, (1ull << 32) | (unsigned long long)m);
                 }
                 const int leader = __ffs(cmask) - 1;
                 int base = 0;
                 if (lane == leader) base = atomicAdd(c.list_count + b, __popc(cmask));
+                if (claiming) ct = claim_terms(c, b, a, g);
                 base = __shfl_sync(0xffffffffu, base, leader);
                 const int slot = base + __popc(cmask & lt_mask);
                 if (claiming && slot < c.rec_cap) {
-                    float4 *r = c.rec + ((long long)b * c.rec_cap + slot) * 5;
+                    float4 *r = c.rec + ((long long)b * c.rec_cap + slot) * kRecF4;
                     const int first_bit = (old >> 32) == 0 ? (int)0x80000000 : 0;  // the first claimer owns the anchor downstream
-                    r[0] = make_float4(__int_as_float(a | first_bit), __int_as_float(m), __uint_as_float((unsigned)(tk >> 32)), xlab);
-                    r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4;
+                    r[0] = make_float4(__int_as_float(a | first_bit), __int_as_float(m), __uint_as_float((unsigned)(tk >> 32)), ct.xlab);
+                    r[1] = ct.terms;
+                    r[2] = ct.box;
                 }
             }
             // this GT is through: the finishing kernel takes the image when its count is complete

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liby3d_b200.so")
+LIB_PATH = os.environ.get("Y3D_LIB_PATH") or os.path.join(_HERE, "liby3d_b200.so")  # (override: developer A/B builds)
 
 STAGE_POSTPROCESS, STAGE_TAL_ASSIGN, STAGE_V8_LOSS, STAGE_TAL_ASSIGN3D, STAGE_DECODE_TOPK, STAGE_DD_LOSS = 1, 2, 3, 4, 5, 6
 MAX_LEVELS, MAX_TOPK, MAX_DET = 4, 32, 1024

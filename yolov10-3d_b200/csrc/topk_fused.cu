@@ -15,11 +15,15 @@
 //   * the next work ticket is requested before the claims go out, so its round trip overlaps theirs.
 #include "assign.cuh"
 
+#ifndef Y3D_FSORTMERGE
+#define Y3D_FSORTMERGE 6
+#endif
+
 namespace y3d {
 
 constexpr int kFU = 4;                  // units (<= 32 cells each) per round trip
 constexpr int kFQ = 32 * kFU + 32;      // candidate queue slots per warp
-constexpr int kFSortMerge = 6;          // keys above the threshold from which the sorted list is merged, not inserted into
+constexpr int kFSortMerge = Y3D_FSORTMERGE;         // keys above the threshold from which the sorted list is merged, not inserted into
 constexpr int kFCtasPerSM = 8;
 
 __device__ __forceinline__ float f_ex2(float x) {
@@ -114,9 +118,11 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
             }
         }
         __syncthreads();
-        if (wid == 0) {
-            const int chunk = (n_seg + 31) / 32;
-            const int lo = min(lane * chunk, n_seg), hi = min(lo + chunk, n_seg);
+        {   // exclusive scan by the whole CTA: thread-contiguous chunks, warp scans, warp totals through shared memory
+            __shared__ int s_wtot[kTopkWarps];
+            const int nth = kTopkWarps * 32, tid = threadIdx.x;
+            const int chunk = (n_seg + nth - 1) / nth;
+            const int lo = min(tid * chunk, n_seg), hi = min(lo + chunk, n_seg);
             int sum = 0;
             for (int sg = lo; sg < hi; ++sg) sum += s_pref[sg];
             int inc = sum;
@@ -125,13 +131,22 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
                 const int v = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += v;
             }
-            int run = inc - sum;
+            if (lane == 31) s_wtot[wid] = inc;
+            __syncthreads();
+            int wbase = 0, all = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < kTopkWarps; ++w2) {
+                const int v = s_wtot[w2];
+                wbase += w2 < wid ? v : 0;
+                all += v;
+            }
+            int run = wbase + inc - sum;
             for (int sg = lo; sg < hi; ++sg) {
                 const int v = s_pref[sg];
                 s_pref[sg] = run;
                 run += v;
             }
-            if (lane == 31) s_pref[n_seg] = inc;
+            if (tid == 0) s_pref[n_seg] = all;
         }
         __syncthreads();
     }
@@ -282,7 +297,7 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
                 }
                 if (!more) continue;
                 // ---- stage 1: one round trip for the gathers of up to kFU cells per lane, then the bounds
-                const int nu = seed_trip ? 1 : kFU;
+                const int nu = min(seed_trip ? 1 : kFU, n_units - t0);  // units of this trip (warp-uniform)
                 bool h[kFU];
                 int ca[kFU];
                 float x[kFU];
@@ -294,7 +309,7 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
                     x[u] = 0.f;
                     bx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     const int t = t0 + u;
-                    if (u < nu && t < n_units) {
+                    if (u < nu) {
                         int rg = t, sg = 0;
                         if (L_nseg > 1) { rg = t / L_nseg; sg = t - rg * L_nseg; }
                         // centre-out over the row groups: good candidates first raise the k-th metric early
@@ -309,7 +324,7 @@ tal_topk_fused_kernel(const __grid_constant__ AssignCtx2 cc, const int n_branch)
                         }
                     }
                 }
-                const int nlive = min(nu, n_units - t0);  // units of this trip that exist
+                const int nlive = nu;
                 t0 += nu;
                 flush_seed = seed_trip;  // evaluate the seed candidates before walking on
                 seed_trip = false;

@@ -179,6 +179,11 @@ float y3d_expf(float x) {
 /* pow with the exponents the path uses made explicit (torch special-cases 0.5/1/2/3 the same way,
  * aten/src/ATen/native/cpu/PowKernel.cpp); 4 and 6 are fixed multiplication trees; anything else
  * falls back to libm powf (not bit-reproducible on the GPU; tolerance-tested only). */
+/* sigmoid as the fixed sequence 1 / (1 + y3d_expf(-x)): what the GPU's fused decode + top-k ranks by (csrc
+ * y3d_common.cuh dm::sigmoid_).  Weakly monotone over all of binary32 -- oracle/check_sigmoid_monotone.c walks every
+ * float -- so per-anchor maxima can be taken on the logits. */
+float y3d_sigmoidf(float x) { return 1.0f / (1.0f + y3d_expf(-x)); }
+
 float y3d_powf(float x, float e) {
     if (e == 0.5f) return sqrtf(x);
     if (e == 1.0f) return x;
@@ -255,7 +260,7 @@ void y3d_o_decode2d(const float *xcat, int B, int nc, int R, int A, const float 
             yb[3 * (long)A + a] = o3 * st;
             for (int c = 0; c < nc; ++c) {
                 float v = xb[(long)(4 * R + c) * A + a];
-                yb[(long)(4 + c) * A + a] = 1.0f / (1.0f + expf(-v)); /* head.py:78 sigmoid */
+                yb[(long)(4 + c) * A + a] = y3d_sigmoidf(v); /* head.py:78 sigmoid */
             }
         }
     }

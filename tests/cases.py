@@ -116,3 +116,22 @@ def decode3d_inputs(r, z):
     x = synth.head3d(r["B"], r["nc"], lv, seed=r["seed"])
     assert synth.checksum(x) == int(z["in_crc"])
     return lv, x
+
+
+def loss_assign_inputs(r, z):
+    """Same construction as tests/golden/make_golden.py::case_loss_assign."""
+    B, nc, img_hw, M, seed = r["B"], r["nc"], r["img_hw"], r["M"], r["seed"]
+    lv = synth.levels(*img_hw)
+    gt = synth.gt2d(B, M, nc, img_hw, seed=seed + 1, crowd=r["crowd"], full=r["crowd"])
+    xm = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 2, frac=r["frac"])
+    xo = synth.train_like_head2d(B, nc, lv, gt, seed=seed + 3, frac=r["frac"])
+    assert synth.checksum(gt, xm, xo) == int(z["in_crc"]), "regenerated inputs differ"
+    return lv, gt, xm, xo
+
+
+def loss_assign_expected(z, branch, B, A):
+    """(fg_mask bool [B,A], target_gt_idx int64 [B,A] with 0 at background) of one branch of a lossasg_* fixture."""
+    fg = np.unpackbits(z[f"fg{branch}"])[:B * A].reshape(B, A).astype(bool)
+    tgi = np.zeros((B, A), np.int64)
+    tgi[fg] = z[f"tgi{branch}"].astype(np.int64)
+    return fg, tgi

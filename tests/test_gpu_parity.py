@@ -99,23 +99,49 @@ def test_postprocess_full_size_vs_oracle(y3d):
         assert (np.diff(s, axis=1) <= 0).all()
 
 
+def _fused_vs_oracle(y3d, x, lv, nc, D):
+    """Fused decode + top-k == the oracle's decode (same, exactly specified sigmoid) followed by the reference's two-stage
+    top-k: labels, scores and selected anchors bit for bit, boxes (DFL softmax in fast arithmetic) to 1e-5."""
+    out, aidx = y3d.v10detect_export_forward(feats_of(x, lv), synth.STRIDES, nc, D, return_anchor_idx=True)
+    oy = oracle.decode2d(x, lv, synth.STRIDES, nc, xywh=False)
+    ob, osc, ol, oa = oracle.postprocess(oy.transpose(0, 2, 1), D, nc)
+    o = out.cpu().numpy()
+    assert np.array_equal(o[..., 5].astype(np.int64), ol)
+    assert np.array_equal(o[..., 4], osc)
+    assert np.array_equal(aidx.cpu().numpy(), oa)
+    np.testing.assert_allclose(o[..., :4], ob, rtol=RTOL, atol=1e-3)
+    return out
+
+
 @pytest.mark.parametrize("name", cases.names("decode_post_"))
 def test_fused_decode_topk(y3d, name):
     r, z = cases.load(name)
     lv, x = cases.decode_post_inputs(r, z)
-    feats = feats_of(x, lv)
-    out, aidx = y3d.v10detect_export_forward(feats, synth.STRIDES, r["nc"], r["D"], return_anchor_idx=True)
-    # == unfused path of this library, bit for bit (same device arithmetic)
-    y = y3d.detect_inference(feats, synth.STRIDES, r["nc"], export=True)
-    boxes, scores, labels = y3d.v10postprocess(y.permute(0, 2, 1), r["D"], r["nc"])
-    assert torch.equal(out[..., :4], boxes)
-    assert torch.equal(out[..., 4], scores)
-    assert torch.equal(out[..., 5], labels.float())
-    # vs the reference (export path = xyxy boxes): same winners unless two scores differ by < 1 ulp-ish
-    ref_lab = z["labels"]
-    same = (out[..., 5].cpu().numpy() == ref_lab)
-    assert same.mean() > 0.99
+    out = _fused_vs_oracle(y3d, x, lv, r["nc"], r["D"])
+    # vs the REAL reference (fixture): its scores come from torch's sigmoid, ours from the specified one (<= 2 ulp apart),
+    # so a pair of near-equal scores may swap.  Measured on these fixtures: 0 mismatching labels
+    ref_lab, lab = z["labels"], out[..., 5].cpu().numpy()
+    mism = int((lab != ref_lab).sum())
+    print(f"{name}: {mism} of {ref_lab.size} labels differ from the reference fixture")
+    assert mism <= max(1, ref_lab.size // 200)
+    same = lab == ref_lab
     np.testing.assert_allclose(out[..., 4].cpu().numpy()[same], z["scores"][same], rtol=RTOL, atol=1e-7)
+    # the unfused chain of this library (decode2d writes its scores in fast arithmetic: values to 1e-5, so its own
+    # selection can differ from the fused one only where two scores are that close)
+    y = y3d.detect_inference(feats_of(x, lv), synth.STRIDES, r["nc"], export=True)
+    boxes, scores, labels = y3d.v10postprocess(y.permute(0, 2, 1), r["D"], r["nc"])
+    agree = (labels.float() == out[..., 5]).float().mean().item()
+    assert agree > 0.99
+    np.testing.assert_allclose(scores.cpu().numpy(), out[..., 4].cpu().numpy(), rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,hw,seed", [(2, (640, 640), 3), (1, (1280, 1280), 4), (3, (640, 640), 5)])
+def test_fused_decode_topk_full_size_vs_oracle(y3d, B, hw, seed):
+    """cfg1 / cfg4 shapes (A = 8400 / 33600, nc = 80, D = 300): selected anchors, labels and scores bit-exact."""
+    lv = synth.levels(*hw)
+    x = synth.head2d(B, 80, lv, seed=seed)
+    out = _fused_vs_oracle(y3d, x, lv, 80, 300)
+    assert (np.diff(out[..., 4].cpu().numpy(), axis=1) <= 0).all()  # sorted by score
 
 
 # ------------------------------------------------------------------------------------------------ 2D assigner
@@ -369,6 +395,64 @@ def test_fused_loss_assignment_bit_exact(y3d, topk):
     assert float(partials[3]) > 1.0 and o["fg_mask"].sum() > 0
 
 
+@pytest.mark.parametrize("name", cases.names("lossasg_"))
+def test_fused_loss_assignment_vs_reference_at_baseline_shapes(y3d, name):
+    """The assignment the fused loss uses (debug outputs) against the assignment INSIDE the real v10DetectLoss, captured at
+    BASELINE shapes (cfg2 / cfg5: nc 80, 640 x 640, 100 / 500 GT per image) by tests/golden/make_golden.py: fg_mask and
+    target_gt_idx of both branches bit for bit -- the count of mismatches is printed and must be 0 -- loss items to 2e-5."""
+    lossmod = __import__("yolov10_3d_b200").loss
+    r, z = cases.load(name)
+    lv, gt, xm, xo = cases.loss_assign_inputs(r, z)
+    A = synth.num_anchors(lv)
+    items, _, dbg = lossmod.v10_loss_forward(feats_of(xm, lv), feats_of(xo, lv), list(synth.STRIDES), r["nc"], dev(gt),
+                                             tuple(r["gains"]), debug=True)
+    fg, tgi = dbg["fg_mask"].cpu().numpy(), dbg["target_gt_idx"].cpu().numpy().astype(np.int64)
+    for branch in (0, 1):
+        efg, etgi = cases.loss_assign_expected(z, branch, r["B"], A)
+        both = efg & fg[branch]
+        mism = int((fg[branch] != efg).sum() + (tgi[branch][both] != etgi[both]).sum())
+        print(f"{name} branch {branch}: {int(efg.sum())} foreground anchors in the reference, {mism} mismatches")
+        assert mism == 0 and efg.sum() > 0
+    np.testing.assert_allclose(items.view(2, 4)[:, :3].reshape(6).cpu().numpy(), z["items"], rtol=2e-5)
+
+
+SWEEP = ([dict(B=64, M=100, crowd=False, seed=s) for s in range(4)] +      # cfg2, full batch
+         [dict(B=8, M=100, crowd=False, seed=s) for s in range(4, 44)] +   # cfg2 shape, fresh inputs per seed
+         [dict(B=128, M=500, crowd=True, seed=44)] +                       # cfg5, full batch
+         [dict(B=4, M=500, crowd=True, seed=s) for s in range(45, 52)])     # cfg5 shape
+
+
+def test_fused_loss_assignment_seed_sweep_vs_oracle(y3d):
+    """52 seeds at the BASELINE shapes (cfg2 and cfg5, including both full batches): fg_mask / target_gt_idx of the fused
+    loss against the oracle's dense assigner, which tests/test_oracle_vs_golden.py and tests/test_reference_sweep_cpu.py
+    hold to the real reference at these shapes.  The two decode the boxes with different softmax arithmetic (both within
+    1e-5 of the reference), so an assignment can only differ where two alignment metrics of a GT agree to ~1e-6; the
+    sweep prints the count and requires 0."""
+    lossmod = __import__("yolov10_3d_b200").loss
+    nc, hw = 80, (640, 640)
+    lv = synth.levels(*hw)
+    total_fg = total_mism = 0
+    for cfg in SWEEP:
+        B, M, seed = cfg["B"], cfg["M"], 1000 + 10 * cfg["seed"]
+        nb = min(B, 8)  # synthetic inputs are generated for 8 images and tiled with shifted class logits
+        gt = np.concatenate([synth.gt2d(nb, M, nc, hw, seed=seed, crowd=cfg["crowd"], full=cfg["crowd"])] * (B // nb))
+        xm = np.concatenate([synth.train_like_head2d(nb, nc, lv, gt[:nb], seed=seed + 1, frac=0.02)] * (B // nb))
+        xo = np.concatenate([synth.train_like_head2d(nb, nc, lv, gt[:nb], seed=seed + 2, frac=0.02)] * (B // nb))
+        for r_ in range(B // nb):
+            xm[r_ * nb:(r_ + 1) * nb, 64:] += np.float32(0.013 * r_)
+            xo[r_ * nb:(r_ + 1) * nb, :64] += np.float32(0.007 * r_)
+        _, _, dbg = lossmod.v10_loss_forward(feats_of(xm, lv), feats_of(xo, lv), list(synth.STRIDES), nc, dev(gt),
+                                             (7.5, 0.5, 1.5), debug=True)
+        fg, tgi = dbg["fg_mask"].cpu().numpy(), dbg["target_gt_idx"].cpu().numpy().astype(np.int64)
+        for branch, (x, k) in enumerate(((xm, 10), (xo, 1))):
+            _, _, _, ofg, otgi = oracle.v8_loss(x, lv, synth.STRIDES, nc, gt, k, debug=True)
+            both = ofg & fg[branch]
+            total_mism += int((fg[branch] != ofg).sum() + (tgi[branch][both] != otgi[both]).sum())
+            total_fg += int(ofg.sum())
+    print(f"seed sweep: {len(SWEEP)} seeds, {total_fg} foreground anchors, {total_mism} mismatches")
+    assert total_fg > 100000 and total_mism == 0
+
+
 @pytest.mark.parametrize("cfg", [
     dict(name="cfg2", B=64, M=100, crowd=False),   # BASELINE.json configs[1], full size
     dict(name="cfg5", B=128, M=500, crowd=True),   # dense-crowd stress, full size
@@ -489,9 +573,8 @@ def test_odd_shapes_take_the_scalar_paths(y3d):
     boxes, scores, labels = y3d.v10postprocess(ye.permute(0, 2, 1), 100, nc)
     ob, osc, ol, _ = oracle.postprocess(ye.cpu().numpy().transpose(0, 2, 1), 100, nc)
     assert np.array_equal(labels.cpu().numpy(), ol) and np.array_equal(scores.cpu().numpy(), osc)
-    fused = y3d.v10detect_export_forward(fo, synth.STRIDES, nc, 100)
-    assert torch.equal(fused[..., 4], scores) and torch.equal(fused[..., 5], labels.float())
-    assert torch.equal(fused[..., :4], boxes)
+    fused = _fused_vs_oracle(y3d, xo, lv, nc, 100)  # scalar kernel variants against the oracle, bit for bit
+    np.testing.assert_allclose(fused[..., 4].cpu().numpy(), scores.cpu().numpy(), rtol=RTOL, atol=1e-7)
     # training: fused dual loss vs the oracle, and on level tensors that are views with a 4-byte-aligned offset only
     gains = (7.5, 0.5, 1.5)
     items, _, _ = lossmod.v10_loss_forward(fm, fo, list(synth.STRIDES), nc, dev(gt), gains)

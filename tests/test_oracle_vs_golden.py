@@ -53,6 +53,25 @@ def test_v10_loss(name):
     np.testing.assert_allclose(total, float(z["total"]), rtol=2e-5)
 
 
+@pytest.mark.parametrize("name", cases.names("lossasg_"))
+def test_v10_loss_assignment_at_baseline_shapes(name):
+    """BASELINE shapes (cfg2: nc 80, 640 x 640, 100 GT / image; cfg5: 500 GT / image): the assignment INSIDE the real
+    v10DetectLoss (fg_mask / target_gt_idx of both branches, captured from TaskAlignedAssigner.forward at loss.py:231)
+    against the oracle's: zero mismatches, loss items to 2e-5."""
+    r, z = cases.load(name)
+    lv, gt, xm, xo = cases.loss_assign_inputs(r, z)
+    A = synth.num_anchors(lv)
+    items = []
+    for branch, (x, k) in enumerate(((xm, 10), (xo, 1))):
+        it, _, nfg, fg, tgi = oracle.v8_loss(x, lv, synth.STRIDES, r["nc"], gt, k, gains=r["gains"], debug=True)
+        efg, etgi = cases.loss_assign_expected(z, branch, r["B"], A)
+        mism = int((fg != efg).sum() + (tgi[efg & fg] != etgi[efg & fg]).sum())
+        print(f"{name} branch {branch}: {int(efg.sum())} foreground anchors, {mism} mismatches")
+        assert mism == 0 and nfg == int(efg.sum()) > 0
+        items.append(it)
+    np.testing.assert_allclose(np.concatenate(items), z["items"], rtol=2e-5)
+
+
 @pytest.mark.parametrize("name", cases.names("decode3d_"))
 def test_decode3d_and_postprocess(name):
     r, z = cases.load(name)

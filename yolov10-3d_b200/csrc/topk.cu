@@ -41,7 +41,7 @@ __device__ __forceinline__ float src_score(const TopkSrc &s, int b, int a, int c
     if (s.mode == 0) return s.preds[b * s.sB + a * s.sA + (long long)(s.soff + c) * s.sC];
     int l = level_of(s.t, a);
     const float *p = s.t.ptr[l] + (long long)b * s.t.sB[l] + (a - s.t.start[l]);
-    return im::sigmoid(p[(long long)(64 + c) * s.t.sC[l]]);
+    return dm::sigmoid_(p[(long long)(64 + c) * s.t.sC[l]]);  // the exactly specified sigmoid: scores decide indices here
 }
 
 // decode of one axis (0: x1/x2 or cx/w, 1: y1/y2 or cy/h) of one anchor's box from the head -- same arithmetic as
@@ -117,7 +117,12 @@ __global__ void amax_anchor_kernel(const float *__restrict__ preds, long long sB
     for (; c < nc; ++c) top2_push(t, float_key(ldg_stream1(p + c * sC)), c);
     top2_store(t, keys, aux, (long long)b * A + a);
 }
-// head levels -> sigmoid(logit) keys: 4 anchors per thread, 128-bit loads; class channels only are read
+// head levels -> sigmoid(logit) keys: 4 anchors per thread, 128-bit loads; class channels only are read.
+// The two largest LOGITS of an anchor are tracked and only those go through the (exactly specified, weakly monotone)
+// sigmoid: largest score = sigmoid(largest logit), second largest score = sigmoid(second largest logit).  The class of
+// the largest logit is the first class of the largest score unless another class ties with it in score -- and then the
+// second key equals the first, the anchor counts as one that can contribute twice, and the selection kernel ranks its
+// classes from their scores without looking at this argmax.
 template <int VEC>
 __global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total, int nc, int A,
                                                       uint32_t *__restrict__ keys, int2 *__restrict__ aux) {
@@ -135,15 +140,19 @@ __global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total
     for (int c = 0; c < nc; ++c) {
         if constexpr (VEC == 4) {
             float4 v = ldg_stream4(p + c * cs);
-            top2_push(tt[0], float_key(im::sigmoid(v.x)), c); top2_push(tt[1], float_key(im::sigmoid(v.y)), c);
-            top2_push(tt[2], float_key(im::sigmoid(v.z)), c); top2_push(tt[3], float_key(im::sigmoid(v.w)), c);
+            top2_push(tt[0], float_key(v.x), c); top2_push(tt[1], float_key(v.y), c);
+            top2_push(tt[2], float_key(v.z), c); top2_push(tt[3], float_key(v.w), c);
         } else {
-            top2_push(tt[0], float_key(im::sigmoid(ldg_stream1(p + c * cs))), c);
+            top2_push(tt[0], float_key(ldg_stream1(p + c * cs)), c);
         }
     }
     const long long o = (long long)b * A + t.start[l] + cell;
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) top2_store(tt[e], keys, aux, o + e);
+    for (int e = 0; e < VEC; ++e) {
+        tt[e].k1 = float_key(dm::sigmoid_(key_float(tt[e].k1)));
+        if (tt[e].k2) tt[e].k2 = float_key(dm::sigmoid_(key_float(tt[e].k2)));
+        top2_store(tt[e], keys, aux, o + e);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ block select

@@ -290,6 +290,12 @@ __device__ __forceinline__ float exp_(float x) {
     return mul(mul(p, a), b);
 }
 
+// sigmoid as a fixed sequence of rounded operations: 1 / (1 + exp_(-x)).  Exactly the oracle's (oracle/y3d_oracle.c
+// y3d_sigmoidf), and weakly monotone over all of binary32 (checked exhaustively: oracle/check_sigmoid_monotone.c), so the
+// largest score of an anchor is the sigmoid of its largest logit.  Used where a score decides an index (fused decode +
+// top-k); value-only outputs use im::sigmoid.
+__device__ __forceinline__ float sigmoid_(float x) { return div(1.0f, add(1.0f, exp_(-x))); }
+
 static __device__ __noinline__ float pow_generic(float x, float e) { return powf(x, e); }
 
 // pow with the path's exponents explicit (see oracle/y3d_oracle.c::y3d_powf); other exponents -> powf.

@@ -109,19 +109,25 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def config_object(world):
+    """The `config` both arms print (the driver compares them)."""
+    B = CFG["B"]
+    return {"workload": WORKLOAD, "global_batch": B * world, "sharding": f"by image, {B}/GPU",
+            "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed"}
+
+
 def cpu_reference_run(steps, warmup, sample_images):
-    """The reference algorithm (CPU restatement in oracle/, OpenMP over images) on the host cores."""
+    """The reference algorithm (CPU restatement in oracle/, OpenMP over images) on all host cores.  Like the GPU arm's
+    `value`, a step starts from the packed GT and the head tensors in memory."""
     from oracle import oracle
     from tests import synth
 
     cores = os.cpu_count() or 1
     oracle.set_threads(cores)
     lv, gt, xm, xo = make_inputs(seed=0, B=sample_images)
-    bd = synth.batch_dict(gt, CFG["img_hw"])
 
     def step():
-        packed = oracle.preprocess_targets(bd["batch_idx"], bd["cls"], bd["bboxes"], sample_images, CFG["img_hw"])
-        return oracle.v10_loss(xm, xo, lv, synth.STRIDES, CFG["nc"], packed, gains=CFG["gains"])
+        return oracle.v10_loss(xm, xo, lv, synth.STRIDES, CFG["nc"], gt, gains=CFG["gains"])
 
     for _ in range(warmup):
         step()
@@ -132,24 +138,125 @@ def cpu_reference_run(steps, warmup, sample_images):
     return sample_images * steps / dt, dt / steps * 1e3, cores
 
 
+def reference_sample_size(steps, warmup, budget_s=150.0, ips_guess=30.0):
+    """Images per reference step: the full 64-image batch when the run fits the time budget, else a multiple of the core
+    count (the oracle parallelises over images, so fewer images than cores would idle some of them)."""
+    cores = os.cpu_count() or 1
+    per_step = budget_s * ips_guess / max(1, steps + warmup)
+    if per_step >= CFG["B"]:
+        return CFG["B"]
+    return int(max(cores, (int(per_step) // cores) * cores))
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: up to 16 images of the cfg2 workload per step, fewer when many steps are asked for, so that the
-    # whole run stays around two minutes at the ~30 images/s the host cores manage
-    S = max(1, min(16, 3600 // max(1, args.steps + max(args.warmup, 1))))
-    ips, ms, cores = cpu_reference_run(args.steps, max(args.warmup, 1), S)
+    W = max(args.warmup, 1)
+    S = reference_sample_size(args.steps, W)
+    ips, ms, cores = cpu_reference_run(args.steps, W, S)
+    sample = (f"{S} images of cfg2 per step ({'the full batch' if S == CFG['B'] else 'bounded sample, a multiple of the core count'}) "
+              f"x {args.steps} steps, oracle/y3d_oracle.c with OpenMP over images, {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample_images_per_step": S},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{S} images of cfg2 per step x {args.steps} steps, oracle/y3d_oracle.c with OpenMP over images"},
+        "dtype": "f32", "data": "synthetic", "config": config_object(max(1, args.gpus)),
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "cores_used": min(cores, S), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------ other configs
+def _timed_calls(torch, fn, iters, warm, flush=None):
+    """Mean CUDA-event time of fn() in ms.  `flush`: a buffer larger than the L2, rewritten before every timed call (for
+    working sets that would otherwise stay L2-resident between iterations); each call then gets its own event pair."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def measure_other_configs(y3d, torch, dev, peak):
+    """The other BASELINE.json configs on one GPU, each through its public call, timed with CUDA events after the headline
+    region: images/s, ms per call and the fraction of the HBM roof the call's algorithmic bytes amount to."""
+    from tests import synth
+
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def feats(x, lv):
+        return [torch.from_numpy(f).to(dev) for f in synth.split_levels(x, lv)]
+
+    def tile(x, B):
+        return np.concatenate([x] * ((B + x.shape[0] - 1) // x.shape[0]), 0)[:B]
+
+    def put(name, what, ms, alg_bytes, images, l2):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        out[name] = {"workload": what, "ms_per_step": ms, "images_per_s": images / (ms * 1e-3),
+                     "algorithmic_bytes_per_step": alg_bytes, "step_frac": gbs / peak, "l2": l2}
+
+    nc = 80
+    # cfg1: batch 1 at 640 x 640 -- fused decode + top-300 (v10Detect export branch); latency of one image
+    lv = synth.levels(640, 640)
+    A = synth.num_anchors(lv)
+    f = feats(synth.head2d(1, nc, lv, seed=0), lv)
+    ms = _timed_calls(torch, lambda: y3d.v10detect_export_forward(f, synth.STRIDES, nc, 300), 30, 5, flush)
+    put("cfg1", "v10Detect decode + v10postprocess top-300 fused, batch 1, 640x640, nc=80, A=8400", ms,
+        (576.0 * A + 28 * 300) * 1, 1, "flushed before every timed call (4.8 MB input)")
+    # cfg4: 32 images per GPU at 1280 x 1280
+    lv = synth.levels(1280, 1280)
+    A = synth.num_anchors(lv)
+    f = feats(tile(synth.head2d(4, nc, lv, seed=0), 32), lv)
+    ms = _timed_calls(torch, lambda: y3d.v10detect_export_forward(f, synth.STRIDES, nc, 300), 30, 5)
+    put("cfg4", "v10Detect decode + top-300 fused, 32 images/GPU, 1280x1280, nc=80, A=33600 (gather: --config cfg4)", ms,
+        (576.0 * A + 28 * 300) * 32, 32, "inputs (620 MB) exceed the L2")
+    del f
+    # cfg5: dense crowd, 500 GT per image, batch 128 -- fused v10DetectLoss forward
+    lv = synth.levels(640, 640)
+    A = synth.num_anchors(lv)
+    gt = tile(synth.gt2d(8, 500, nc, (640, 640), seed=1, crowd=True, full=True), 128)
+    fm = feats(tile(synth.train_like_head2d(8, nc, lv, gt[:8], seed=2, frac=0.02), 128), lv)
+    fo = feats(tile(synth.train_like_head2d(8, nc, lv, gt[:8], seed=3, frac=0.02), 128), lv)
+    gtd = torch.from_numpy(gt).to(dev)
+    ms = _timed_calls(torch, lambda: y3d.loss.v10_loss_forward(fm, fo, list(synth.STRIDES), nc, gtd, (7.5, 0.5, 1.5)), 20, 4)
+    put("cfg5", "v10DetectLoss fwd fused, batch 128, 640x640, nc=80, 500 GT/img (dense crowd)", ms,
+        (2 * 4.0 * (64 + nc) * A + 20 * 500) * 128, 128, "inputs (1.24 GB) exceed the L2")
+    del fm, fo, gtd
+    # cfg3: the fork's 3D head at KITTI shape 384 x 1280, 3 classes, batch 32 -- DetectLoss3d forward (both branches)
+    nc3, hw3, B3, M3 = 3, (384, 1280), 32, 50
+    lv = synth.levels(*hw3)
+    A = synth.num_anchors(lv)
+    gts = synth.gt3d(B3, M3, nc3, hw3, seed=1)
+    f3m = feats(synth.train_like_head3d(B3, nc3, lv, gts, seed=0, frac=0.03), lv)
+    f3o = feats(synth.train_like_head3d(B3, nc3, lv, gts, seed=5, frac=0.03), lv)
+    gtsd = torch.from_numpy(gts).to(dev)
+    cal = torch.from_numpy(np.tile(np.array(synth.KITTI_CALIB, np.float32), (B3, 1))).to(dev)
+    msz = torch.from_numpy(np.array(synth.KITTI_MEAN_SIZES, np.float32)).to(dev)
+    ms = _timed_calls(torch, lambda: y3d.loss3d.dd_loss_dual_forward(f3m, f3o, list(synth.STRIDES), nc3, gtsd, cal, msz,
+                                                                    (8, 1), (1, 1, 1, 1, 1, 1)), 30, 5, flush)
+    put("cfg3", "DetectLoss3d fwd (3D decode + dual 3D task-aligned assignment + loss), batch 32, 384x1280, nc=3, <=50 GT/img",
+        ms, (2 * 4.0 * (nc3 + 35) * A + 68 * M3) * B3, B3, "flushed before every timed call (98 MB input)")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
@@ -280,6 +387,25 @@ def main_cuda(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(times[0]), float(times[1])
 
+    # correctness of the sharded path, outside the timed region (the driver's scaling run carries the evidence: the GPU
+    # test box has one GPU): the items of the exchange fused into the loss' last kernel == the items of the NCCL route
+    # (partials -> all_reduce -> finalize) on every rank, and bit-identical across the ranks
+    shard_check = None
+    if world > 1:
+        it_fused = items.detach().clone()
+        _, parts, _ = y3d.loss.v10_loss_forward(dev_m, dev_o, strides, nc, gt_dev, gains, normalise=False)
+        it_nccl = y3d.loss.finalize_partials(y3d.dist.reduce_partials(parts), gains).view(2, 4)[:, :3].reshape(6)
+        rel = float(((it_fused - it_nccl).abs() / it_nccl.abs().clamp_min(1e-12)).max())
+        gathered = [torch.empty_like(it_fused) for _ in range(world)]
+        dist.all_gather(gathered, it_fused)
+        same = all(torch.equal(g, gathered[0]) for g in gathered)
+        ok = torch.tensor([1.0 if (rel < 1e-6 and same) else 0.0, rel], device=dev, dtype=torch.float64)
+        dist.all_reduce(ok[:1], op=dist.ReduceOp.MIN)
+        dist.all_reduce(ok[1:], op=dist.ReduceOp.MAX)
+        shard_check = {"ok": bool(ok[0] > 0.5), "max_rel_diff_vs_nccl_route": float(ok[1]),
+                       "identical_on_all_ranks": bool(same), "route": "fused peer-memory exchange" if peer else "nccl",
+                       "what": "loss items of the sharded call vs partials -> NCCL all_reduce -> finalize, every rank"}
+
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = 2 * 4.0 * (64 + nc) * A * B  # 2*4*(4R+nc)*A per image; one launch covers both branches
@@ -291,22 +417,22 @@ def main_cuda(args):
         h2d = sum(f.numel() * 4 for f in host_m + host_o)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            ips, ms, cores = cpu_reference_run(steps=2, warmup=1, sample_images=16)
-            cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "16 images of cfg2 per step x 2 steps, oracle/y3d_oracle.c with OpenMP over images"}
+            ips, ms, cores = cpu_reference_run(steps=3, warmup=1, sample_images=CFG["B"])
+            cpu = {"value": ips, "unit": UNIT, "cores": cores, "cores_used": min(cores, CFG["B"]), "kind": "port",
+                   "sample": f"the full {CFG['B']}-image cfg2 batch per step x 3 steps, oracle/y3d_oracle.c with OpenMP over "
+                             f"images, {cores} threads"}
         line = {
             "metric": METRIC, "value": B * world * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "sharding": f"by image, {B}/GPU",
-                       "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed",
-                       "collective": ("none" if world == 1 else
+            "config": config_object(world),
+            "collective": ("none" if world == 1 else
                                       ("8 float64 loss partials per step, exchanged over NVLink peer memory by the loss' "
                                        "own last kernel (y3d_v10_loss_fwd_sharded, csrc/xrank.cuh): no collective launch"
                                        if not y3d.dist.fused_off() else
                                        "8 float64 loss partials per step: one all-reduce + normalise kernel over NVLink "
                                        "peer memory (csrc/xrank.cu)") if peer else
-                                      "NCCL all_reduce of 8 float64 loss partials per step + finalize kernel")},
+                                      "NCCL all_reduce of 8 float64 loss partials per step + finalize kernel"),
             "roofline": {"bound": "hbm", "kernel": "head_stream_kernel<4>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          # the whole step against the same roof: algorithmic bytes / ms_per_step / peak (north star: >= 0.6)
@@ -328,6 +454,127 @@ def main_cuda(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_other_configs:
+            line["other_configs"] = measure_other_configs(y3d, torch, dev, peak)
+        if shard_check is not None:
+            line["sharded_check"] = shard_check
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_cuda_cfg4(args):
+    """BASELINE.json configs[3]: YOLOv10-x head at 1280 x 1280 (33 600 anchors), 32 images per GPU, image-sharded: every
+    rank decodes + top-300s its images (fused, y3d_decode_topk2d) and the [B/N, 300, 6] detections are gathered on all
+    ranks -- written straight into the peers' buffers by the selection kernel's epilogue (NVLink peer memory) when that
+    is available, else by one NCCL all_gather_into_tensor."""
+    import torch
+    import torch.distributed as dist
+
+    import yolov10_3d_b200 as y3d
+    from tests import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    y3d.lib()
+    Bl, nc, hw, D = 32, 80, (1280, 1280), 300
+    lv = synth.levels(*hw)
+    A = synth.num_anchors(lv)
+    x = synth.head2d(4, nc, lv, seed=100 * rank)
+    x = np.concatenate([x] * (Bl // 4), 0)
+    host = [torch.from_numpy(f).pin_memory() for f in synth.split_levels(x, lv)]
+    feats = [f.to(dev) for f in host]
+    gatherer = y3d.dist.PeerDetectionGather(dev, Bl, D) if (world > 1 and os.environ.get("Y3D_NCCL_GATHER") != "1") else None
+    peer = gatherer is not None and gatherer.available
+    K, W = args.steps, args.warmup
+
+    def step():
+        return y3d.dist.detect_sharded(feats, synth.STRIDES, nc, D, gatherer=gatherer)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 3.0:
+        time.sleep(0.02)
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(K):
+        dets = step()
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = t0.elapsed_time(t1)
+
+    def e2e_step():
+        f = [h.to(dev, non_blocking=True) for h in host]
+        return y3d.dist.detect_sharded(f, synth.STRIDES, nc, D, gatherer=gatherer).cpu()
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    Ke = max(3, min(K, 10))
+    for _ in range(Ke):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    sampler.stop()
+    # gathered detections == every rank's own detections at its slot, and identical on all ranks
+    check = None
+    if world > 1:
+        own = y3d.v10detect_export_forward(feats, synth.STRIDES, nc, D)
+        ref = torch.empty((world * Bl, D, 6), device=dev)
+        dist.all_gather_into_tensor(ref, own.contiguous())
+        okv = torch.tensor([1.0 if torch.equal(ref, dets) else 0.0], device=dev)
+        dist.all_reduce(okv, op=dist.ReduceOp.MIN)
+        check = {"ok": bool(okv[0] > 0.5), "what": "gathered [B, 300, 6] == NCCL all_gather of the ranks' own detections, every rank",
+                 "route": "selection-kernel epilogue over NVLink peer memory" if peer else "nccl all_gather_into_tensor"}
+    times = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(times[0]), float(times[1])
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg = (576.0 * A + 28 * D) * Bl  # SURVEY.md 8(d) S1+S2 fused, per rank
+        line = {
+            "metric": "images/sec, v10 head decode + top-300 at 1280x1280, image-sharded, detections gathered on all ranks",
+            "value": Bl * world * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "cfg4: v10Detect decode + v10postprocess top-300 fused, 1280x1280, A=33600, nc=80, "
+                                   f"{Bl} images/GPU, gather of [B, 300, 6]",
+                       "global_batch": Bl * world, "sharding": f"by image, {Bl}/GPU",
+                       "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed"},
+            "collective": ("none" if world == 1 else ("detections stored into every peer's buffer by the selection kernel's "
+                                                      "epilogue (NVLink peer memory), one flag word per image" if peer else
+                                                      "NCCL all_gather_into_tensor of [B/N, 300, 6]")),
+            "roofline": {"bound": "hbm", "kernel": "whole step (class-max stream + selection)", "achieved": alg / (ms_total / K * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms_total / K * 1e-3) / 1e9 / peak,
+                         "step_frac": alg / (ms_total / K * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg},
+            "e2e": {"value": Bl * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sum(h.numel() * 4 for h in host),
+                    "d2h_bytes_per_step": int(dets.numel() * 4), "steps": Ke},
+            "gpu_launches": 2 * K,
+            "clocks": dict(sampler.summary(), window="timed region + e2e region (nvidia-smi every 100 ms)"),
+        }
+        if check is not None:
+            line["sharded_check"] = check
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -355,8 +602,14 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the cfg1/3/4/5 measurements after the headline")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4"],
+                    help="cfg2 (default, the headline: fused dual-assignment loss) or cfg4 (image-sharded decode + top-300 at "
+                         "1280x1280 with the gather of the detections)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)
+    elif a.config == "cfg4":
+        main_cuda_cfg4(a)
     else:
         main_cuda(a)

@@ -85,6 +85,23 @@ int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const 
                       const float *lvl_stride, int nl, int B, int nc, int reg_max, int xywh, int D, float *out,
                       int32_t *anchor_idx, void *ws, size_t ws_bytes, void *stream);
 
+/* Image-sharded v10Detect export branch (BASELINE.json configs[3]): y3d_decode_topk2d on this
+ * rank's B images, with the gather of the detections fused into the selection kernel -- the CTA that has selected an
+ * image stores its [D,6] rows straight into every peer's gather buffer over NVLink (peer memory) and raises the
+ * image's flag there; a one-CTA kernel then waits until the flags of all world * B images of this call have arrived.
+ *  peer_bufs: HOST array of `world` device pointers, buffer r being rank r's (peer-mapped, e.g. symmetric memory), each
+ *  y3d_gather_buffer_bytes(world, B, D) bytes, zero-filled before the first call: [2][world*B][D][6] floats followed by
+ *  [2][world*B] flag words.  After the call (stream order) rank `rank`'s buffer holds, at parity seq & 1, the
+ *  detections of all ranks in rank order -- equal to all_gather of the ranks' y3d_decode_topk2d outputs.  seq: 1, 2, ...
+ *  the same on every rank, +1 per call (must NOT be replayed from a CUDA graph); every rank must make every call; a
+ *  rank waits up to Y3D_XRANK_TIMEOUT_S seconds (default 600) and then sets *status (optional DEVICE int) to 1.
+ *  Reference consumer: ultralytics/models/yolov10/val.py:10-24 (per-rank postprocess; DDP validation gathers). */
+size_t y3d_gather_buffer_bytes(int world, int n_local, int D);
+int y3d_decode_topk2d_sharded(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                              const float *lvl_stride, int nl, int B, int nc, int reg_max, int xywh, int D, int rank,
+                              int world, void *const *peer_bufs, unsigned long long seq, int *status, void *ws,
+                              size_t ws_bytes, void *stream);
+
 /* TaskAlignedAssigner.forward (ultralytics/utils/tal.py:44-94; get_pos_mask :96, get_box_metrics :108,
  * select_topk_candidates :133, select_highest_overlaps :237, get_targets :169) with CIoU from
  * ultralytics/utils/metrics.py:78-134.  M >= 1 (the M == 0 early-out of tal.py:68-76 is host-side glue).

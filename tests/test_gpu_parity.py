@@ -856,3 +856,22 @@ def test_peer_memory_loss_reduction_multi_gpu():
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "peer reduce == nccl reduce: True" in r.stdout
+
+
+@pytest.mark.gpu
+def test_sharded_detection_gather_multi_gpu():
+    """BASELINE.json configs[3] path: decode + top-k sharded by image, detections gathered by the selection kernel's
+    epilogue over NVLink peer memory (y3d_decode_topk2d_sharded) == the single-process result on the whole batch == the
+    NCCL all_gather route, bit for bit on every rank.  Needs at least two GPUs; skipped otherwise."""
+    import subprocess
+    import sys
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29542", "tools/check_peer_gather.py"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "peer gather == single process == nccl gather: True" in r.stdout

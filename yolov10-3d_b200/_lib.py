@@ -23,6 +23,8 @@ SIGNATURES = {
     "y3d_decode2d": (_i, _LEVELS + [_i, _i, _i, _i, _vp, _vp]),
     "y3d_postprocess": (_i, [_vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "y3d_decode_topk2d": (_i, _LEVELS + [_i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "y3d_gather_buffer_bytes": (_sz, [_i, _i, _i]),
+    "y3d_decode_topk2d_sharded": (_i, _LEVELS + [_i, _i, _i, _i, _i, _i, _i, _vp, C.c_uint64, _vp, _vp, _sz, _vp]),
     "y3d_tal_assign": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp,
                             _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "y3d_v8_loss_fwd": (_i, _LEVELS + [_i, _i, _i, _vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,

@@ -10,6 +10,8 @@
 //                                 select + sort runs over the flattened index i*nc + c (ops.py:861), then
 //                                 labels = idx % nc, anchor = winners[idx // nc], gather of the regression channels.
 // Results are identical to a stable descending sort (lowest index wins ties) -- the order BASELINE.json mandates.
+#include <cstdlib>
+
 #include "y3d_common.cuh"
 
 namespace y3d {
@@ -26,6 +28,36 @@ __device__ __forceinline__ uint32_t float_key(float x) {
 __device__ __forceinline__ float key_float(uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
     return __uint_as_float(u);
+}
+
+constexpr int kGatherMaxWorld = 16;
+// Image-sharded detection path: every rank keeps the detections of ALL ranks in a buffer its peers
+// can address (symmetric memory): [2 parities][world * n_local][D][6] floats, then [2][world * n_local] flag words.  The
+// selection kernel's CTA writes its image's rows into its own buffer and then straight into every peer's (NVLink stores),
+// fences, and raises the image's flag (the call's sequence number) on every rank; gather_wait_kernel returns when all
+// flags of the call have arrived.  Parity = seq & 1: a peer can be at most one call ahead of a rank that is still reading.
+struct GatherOut {
+    float *data[kGatherMaxWorld];      // per rank: its buffer's data of this call's parity
+    unsigned *flags[kGatherMaxWorld];  // per rank: its buffer's flags of this call's parity
+    int rank, world, n_local;
+    unsigned seq;
+};
+
+__global__ void __launch_bounds__(256) gather_wait_kernel(const unsigned *flags, int n, unsigned seq, long long timeout_cycles,
+                                                          int *status) {
+    __shared__ int failed;
+    if (threadIdx.x == 0) failed = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+            if (v != seq && clock64() - t0 > timeout_cycles) { failed = 1; break; }
+        } while (v != seq);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && status && failed) *status = 1;
 }
 
 struct TopkSrc {
@@ -341,7 +373,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
                                                                     int nc, int nreg, int D, int Dpad, int keys2_smem,
                                                                     uint32_t *__restrict__ keys2_ws, float *reg,
                                                                     float *scores, int64_t *labels,
-                                                                    int32_t *anchor_idx, int out_mode) {
+                                                                    int32_t *anchor_idx, int out_mode, GatherOut G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *win1 = (unsigned long long *)smem_raw;
     unsigned long long *win2 = win1 + 2 * Dpad;
@@ -479,6 +511,20 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
         }
     }
     SEL_STAMP(4);
+    if (out_mode != 0 && G.world > 1) {  // this image's [D,6] rows -> every peer's buffer, then the image's flag
+        __syncthreads();  // the rows above were written by this CTA's threads
+        const int slot = G.rank * G.n_local + b;
+        const float2 *src = reinterpret_cast<const float2 *>(reg + (long long)b * D * 6);
+        for (int p = 0; p < G.world; ++p) {
+            if (p == G.rank) continue;
+            float2 *dst = reinterpret_cast<float2 *>(G.data[p] + (long long)slot * D * 6);
+            for (int i = tid; i < D * 3; i += nt) dst[i] = src[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < G.world)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(G.flags[tid] + slot), "r"(G.seq) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------ sparse 3D head glue
@@ -558,7 +604,7 @@ size_t topk_workspace_bytes(int B, int A, int nc, int D) {
 
 static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *aux, int B, int A, int nc, int nreg, int D, float *reg,
                          float *scores, int64_t *labels, int32_t *anchor_idx, int out_mode, uint32_t *keys2_ws,
-                         cudaStream_t s) {
+                         cudaStream_t s, const GatherOut *gather = nullptr) {
     int Dpad = next_pow2(D);
     int n2 = D * nc;
     int k2smem = n2 <= kKeys2SmemCap;
@@ -573,8 +619,10 @@ static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *a
         if (e != cudaSuccess) return (int)e;
         smem_limit = smem;
     }
+    GatherOut G{};
+    if (gather) G = *gather;
     topk_select_kernel<<<B, kTopkThreads, smem, s>>>(src, keys, aux, A, k1smem, nc, nreg, D, Dpad, k2smem, keys2_ws, reg, scores,
-                                                    labels, anchor_idx, out_mode);
+                                                    labels, anchor_idx, out_mode, G);
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }
@@ -614,10 +662,9 @@ extern "C" int y3d_postprocess(const float *preds, int64_t sB, int64_t sA, int64
     return launch_select(src, keys, aux, B, A, nc, nreg, D, reg, scores, labels, anchor_idx, 0, k2, s);
 }
 
-extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
-                                 const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
-                                 int xywh, int D, float *out, int32_t *anchor_idx, void *ws, size_t ws_bytes,
-                                 void *stream) {
+static int decode_topk2d_run(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC, const int *lvl_hw,
+                            const float *lvl_stride, int nl, int B, int nc, int reg_max, int xywh, int D, float *out,
+                            int32_t *anchor_idx, void *ws, size_t ws_bytes, cudaStream_t s, const GatherOut *gather) {
     if (!lvl_ptr || !lvl_sB || !lvl_sC || !out || B < 0 || nc < 1) return Y3D_EINVAL;
     if (reg_max != 16) return Y3D_EUNSUPPORTED;
     TopkSrc src{};
@@ -631,7 +678,6 @@ extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl
     if (!ws || ws_bytes < need) return Y3D_EWORKSPACE;
     if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
     if (B == 0) return Y3D_OK;
-    cudaStream_t s = (cudaStream_t)stream;
     uint32_t *keys = (uint32_t *)ws;
     int2 *aux = (int2 *)((char *)ws + align256(sizeof(uint32_t) * (size_t)B * A));
     uint32_t *k2 = (uint32_t *)((char *)aux + align256(sizeof(int2) * (size_t)B * A));
@@ -650,7 +696,55 @@ extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl
     Y3D_CHECK_LAUNCH();
     src.mode = 1;
     src.xywh = xywh;
-    return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s);
+    return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s, gather);
+}
+
+extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
+                                 const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
+                                 int xywh, int D, float *out, int32_t *anchor_idx, void *ws, size_t ws_bytes,
+                                 void *stream) {
+    return decode_topk2d_run(lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl, B, nc, reg_max, xywh, D, out, anchor_idx, ws,
+                             ws_bytes, (cudaStream_t)stream, nullptr);
+}
+
+static size_t gather_data_floats(int world, int n_local, int D) { return (size_t)world * n_local * D * 6; }
+static size_t gather_flags_off(int world, int n_local, int D) { return align256(sizeof(float) * 2 * gather_data_floats(world, n_local, D)); }
+
+extern "C" size_t y3d_gather_buffer_bytes(int world, int n_local, int D) {
+    if (world < 1 || n_local < 1 || D < 1) return 0;
+    return gather_flags_off(world, n_local, D) + align256(sizeof(unsigned) * 2 * (size_t)world * n_local);
+}
+
+extern "C" int y3d_decode_topk2d_sharded(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
+                                         const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, int reg_max,
+                                         int xywh, int D, int rank, int world, void *const *peer_bufs,
+                                         unsigned long long seq, int *status, void *ws, size_t ws_bytes, void *stream) {
+    if (!peer_bufs || world < 1 || world > kGatherMaxWorld || rank < 0 || rank >= world || seq == 0 || B < 1) return Y3D_EINVAL;
+    GatherOut G{};
+    const int par = (int)(seq & 1ull);
+    const size_t nfl = gather_data_floats(world, B, D), foff = gather_flags_off(world, B, D);
+    for (int r = 0; r < world; ++r) {
+        if (!peer_bufs[r] || ((uintptr_t)peer_bufs[r]) % 256) return Y3D_EALIGN;
+        G.data[r] = (float *)peer_bufs[r] + (size_t)par * nfl;
+        G.flags[r] = (unsigned *)((char *)peer_bufs[r] + foff) + (size_t)par * world * B;
+    }
+    G.rank = rank; G.world = world; G.n_local = B; G.seq = (unsigned)(seq & 0xffffffffull);
+    cudaStream_t s = (cudaStream_t)stream;
+    float *own = G.data[rank] + (size_t)rank * B * D * 6;  // this rank's images inside its own buffer
+    int rc = decode_topk2d_run(lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl, B, nc, reg_max, xywh, D, own, nullptr, ws,
+                               ws_bytes, s, &G);
+    if (rc) return rc;
+    if (world > 1) {
+        static long long timeout = 0;
+        if (timeout == 0) {
+            double sec = 600.0;
+            if (const char *e = getenv("Y3D_XRANK_TIMEOUT_S")) { const double v = atof(e); if (v > 0.0) sec = v; }
+            timeout = (long long)(sec * 2.0e9);
+        }
+        gather_wait_kernel<<<1, 256, 0, s>>>(G.flags[rank], world * B, G.seq, timeout, status);
+        Y3D_CHECK_LAUNCH();
+    }
+    return Y3D_OK;
 }
 
 extern "C" int y3d_select_candidates(const float *cls, int64_t sB, int64_t sC, int B, int nc, int H, int W, int K,

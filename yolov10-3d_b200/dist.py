@@ -54,6 +54,83 @@ def all_gather_detections(dets_local, group=None, equal_shards=None):
     return torch.cat([o[:s] for o, s in zip(out, sizes)])
 
 
+class PeerDetectionGather:
+    """The detection path's one exchange, fused into the selection kernel (csrc/topk.cu, ``y3d_decode_topk2d_sharded``):
+    every rank's CTA that has selected an image stores the image's [D, 6] rows straight into every peer's gather buffer
+    over NVLink peer memory -- no collective launch; a one-CTA kernel waits for the flags of all images.
+
+    The buffers come from ``torch.distributed._symmetric_memory``.  Construction is collective; ``available`` is False when
+    symmetric memory cannot be set up, and :func:`detect_sharded` then uses NCCL.  Every rank must make every call with
+    the same ``n_local`` and ``max_det``."""
+
+    def __init__(self, device, n_local, max_det, group=None):
+        self.available = False
+        self.seq = 0
+        self.n_local, self.max_det = int(n_local), int(max_det)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            pg = group if group is not None else dist.group.WORLD
+            self.world, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+            nbytes = int(_lib.lib().y3d_gather_buffer_bytes(self.world, self.n_local, self.max_det))
+            self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.handle = symm_mem.rendezvous(self.buf, pg.group_name if hasattr(pg, "group_name") else pg)
+            self.ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+            self.status = torch.zeros(1, dtype=torch.int32, device=device)
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._calls, self.check_every, self._pg = 0, 16, pg
+            torch.cuda.synchronize(device)
+            dist.barrier(group=pg)  # every buffer is zeroed before anyone's first store can land
+            self.available = True
+        except Exception as e:  # no peer access / symmetric memory unsupported: NCCL path
+            print(f"[yolov10-3d_b200] peer-memory detection gather unavailable ({type(e).__name__}: {e}); using NCCL",
+                  file=sys.stderr)
+
+    def view(self):
+        """[world * n_local, D, 6] view of this rank's buffer at the parity of the last call: valid until the call after
+        the next one (two parities), for consumers on the same stream."""
+        n = self.world * self.n_local * self.max_det * 6
+        par = self.seq & 1
+        return self.buf[par * n * 4:(par + 1) * n * 4].view(torch.float32).view(self.world * self.n_local, self.max_det, 6)
+
+    def check(self):
+        """As :meth:`PeerLossReducer.check`: raises, a few calls late and without synchronising, when a peer never came."""
+        if int(self._status_host[0]) != 0:
+            raise _lib.Y3DError("peer-memory detection gather timed out: a rank did not make the call within "
+                                "Y3D_XRANK_TIMEOUT_S (default 600 s)")
+        self._calls += 1
+        if self._calls % self.check_every == 0:
+            self._status_host.copy_(self.status, non_blocking=True)
+
+
+def detect_sharded(feats_one2one, strides, nc, max_det=300, group=None, gatherer=None):
+    """``v10Detect.forward`` export branch (head.py:526-531: decode + ``v10postprocess``) on this rank's images of a batch
+    sharded by image, detections gathered on all ranks: returns [world * B_local, max_det, 6] (x1 y1 x2 y2 score label)
+    in rank order, identical on every rank.  With a :class:`PeerDetectionGather` the gather rides in the selection
+    kernel's epilogue (the result is then a view of the gather buffer, see ``PeerDetectionGather.view``); without one,
+    one NCCL ``all_gather_into_tensor`` follows the fused kernel.  One rank: the plain fused call."""
+    from . import head as _head
+    from ._util import Levels, workspace
+
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not (multi and gatherer is not None and gatherer.available):
+        out = _head.v10detect_export_forward(feats_one2one, strides, nc, max_det)
+        return all_gather_detections(out, group, equal_shards=True) if multi else out
+    lv = Levels(feats_one2one, [float(v) for v in strides])
+    if lv.C != 4 * 16 + nc:
+        raise ValueError(f"expected {4 * 16 + nc} channels, got {lv.C}")
+    if lv.B != gatherer.n_local or int(max_det) != gatherer.max_det:
+        raise ValueError("the gatherer was built for another shard size / max_det")
+    ws = workspace(_lib.workspace_bytes(_lib.STAGE_DECODE_TOPK, B=lv.B, A=lv.A, nc=nc, D=int(max_det)), lv.device)
+    gatherer.seq += 1
+    _lib.check(_lib.lib().y3d_decode_topk2d_sharded(*lv.args(), lv.B, nc, 16, 0, int(max_det), gatherer.rank, gatherer.world,
+                                                    gatherer.ptrs, C.c_uint64(gatherer.seq), ptr(gatherer.status), ptr(ws),
+                                                    ws.numel(), stream_ptr(lv.device)))
+    gatherer.check()
+    return gatherer.view()
+
+
 def reduce_partials(partials, group=None):
     """Sum the per-rank loss partials (any shape, float64) over the group, in place."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -43,6 +43,15 @@ def dd_loss_forward(feats, strides, nc, gts_packed, calibs, mean_sizes, topk, ga
     return items, partials, tgi
 
 
+def dd_loss_dual_forward(feats_o2m, feats_o2o, strides, nc, gts_packed, calibs, mean_sizes, topk=(8, 1),
+                         gains=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0), **kw):
+    """Both branches of ``DetectLoss3d`` (loss.py:750-771) forward-only: one2many with ``topk[0]``, one2one with
+    ``topk[1]``.  Returns (items float32[2, 8], partials float64[2, 11])."""
+    im, pm, _ = dd_loss_forward(feats_o2m, strides, nc, gts_packed, calibs, mean_sizes, topk[0], gains, **kw)
+    io, po, _ = dd_loss_forward(feats_o2o, strides, nc, gts_packed, calibs, mean_sizes, topk[1], gains, **kw)
+    return torch.stack((im, io)), torch.stack((pm, po))
+
+
 class _DDLossFn(torch.autograd.Function):
     """autograd node of the fused 3D loss: inputs = the per-level head tensors, output = the six loss items."""
 

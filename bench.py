@@ -264,6 +264,10 @@ def main_cuda(args):
     import torch
     import torch.distributed as dist
 
+    if os.environ.get("Y3D_BENCH_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["Y3D_BENCH_TRACE"]), exit=True, file=sys.stderr)
+
     import yolov10_3d_b200 as y3d
     from tests import synth
 
@@ -319,10 +323,14 @@ def main_cuda(args):
     # ~5 us longer than a plain one).
     EV_EVERY = max(1, int(os.environ.get("Y3D_BENCH_EVENT_EVERY", "8")))
 
+    # several GPUs with peer memory: the loss' last kernel posts the rank's sums to the peers and the collecting kernel
+    # runs on a side stream (dist.v10_loss_sharded(defer=True)): step i's exchange overlaps step i + 1's streaming pass
+    defer = peer and not y3d.dist.fused_off() and os.environ.get("Y3D_NO_DEFER") != "1"
+
     def step(i=None):
         pe = ev_c[i] if (i is not None and i % EV_EVERY == 0) else None
         return y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=pe,
-                                         reducer=reducer)
+                                         reducer=reducer, defer=defer)
 
     sampler = ClockSampler(local)  # clocks / throttle reasons while the GPU is under load: timed region + e2e region
     sampler.start()
@@ -331,18 +339,25 @@ def main_cuda(args):
         time.sleep(0.02)
     # warm-up right before the timed region (the wait above leaves the GPU idle: clocks and caches would be cold)
     for i in range(W):
-        y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=evw_c[i],
-                                  reducer=reducer)
+        r_ = y3d.dist.v10_loss_sharded(dev_m, dev_o, strides, nc, gt_dev, gains, B * world, prof_events=evw_c[i],
+                                       reducer=reducer, defer=defer)
+    if defer and W > 0:
+        r_.wait()
+    if os.environ.get("Y3D_BENCH_TRACE"): print(f"[rank {rank}] warm-up enqueued", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
+    if os.environ.get("Y3D_BENCH_TRACE"): print(f"[rank {rank}] warm-up done", file=sys.stderr, flush=True)
     if world > 1:
         dist.barrier()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
     for i in range(K):
-        total, items = step(i)
+        res = step(i)
+    total, items = res.wait() if defer else res  # (deferred: this stream waits for the last step's collecting kernel)
     t_stop.record()
+    if os.environ.get("Y3D_BENCH_TRACE"): print(f"[rank {rank}] timed enqueued", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
+    if os.environ.get("Y3D_BENCH_TRACE"): print(f"[rank {rank}] timed done", file=sys.stderr, flush=True)
     if world > 1:
         dist.barrier()
     ms_total = t_start.elapsed_time(t_stop)
@@ -427,8 +442,11 @@ def main_cuda(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_object(world),
             "collective": ("none" if world == 1 else
-                                      ("8 float64 loss partials per step, exchanged over NVLink peer memory by the loss' "
-                                       "own last kernel (y3d_v10_loss_fwd_sharded, csrc/xrank.cuh): no collective launch"
+                                      (("8 float64 loss partials per step, posted to the peers over NVLink peer memory by the "
+                                        "loss' own last kernel and collected by a one-CTA kernel on a side stream, overlapping "
+                                        "the next step (y3d_v10_loss_fwd_sharded defer=1 + y3d_loss_exchange_resolve)" if defer else
+                                        "8 float64 loss partials per step, exchanged over NVLink peer memory by the loss' "
+                                        "own last kernel (y3d_v10_loss_fwd_sharded, csrc/xrank.cuh): no collective launch")
                                        if not y3d.dist.fused_off() else
                                        "8 float64 loss partials per step: one all-reduce + normalise kernel over NVLink "
                                        "peer memory (csrc/xrank.cu)") if peer else
@@ -448,7 +466,7 @@ def main_cuda(args):
                     "d2h_bytes_per_step": 24, "steps": Ke},
             # stream, top-k, finish per step (+ the stand-alone exchange kernel when it is not fused; the NCCL route
             # adds NCCL's own kernel on top of our finalize kernel)
-            "gpu_launches": (3 + (1 if world > 1 and (not peer or y3d.dist.fused_off()) else 0)) * K,
+            "gpu_launches": (3 + (1 if world > 1 and (not peer or y3d.dist.fused_off() or defer) else 0)) * K,
             "clocks": dict(sampler.summary(), window="timed region + e2e region (nvidia-smi every 100 ms)"),
             "loss_items": [float(v) for v in items.cpu()],
         }

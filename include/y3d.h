@@ -181,8 +181,20 @@ int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64_t *o2m_sB,
                              const float *gt, int M, int topk_o2m, int topk_o2o, float gain_box, float gain_cls,
                              float gain_dfl, float *loss_items, double *partials, float total_scale,
                              float *loss_total, int rank, int world, void *const *peer_bufs_dev,
-                             unsigned long long seq, int *status, void *const *prof_events, void *ws, size_t ws_bytes,
-                             void *stream);
+                             unsigned long long seq, int defer, int *status, void *const *prof_events, void *ws,
+                             size_t ws_bytes, void *stream);
+
+/* The collecting half of the exchange on its own, for y3d_v10_loss_fwd_sharded(..., defer = 1): that call only POSTS
+ * the rank's partial sums into the peers' buffers (loss_items / loss_total / partials may then be NULL and are not
+ * written); this one waits for the peers' sums of call `seq`, adds them in rank order and writes loss_items [4 n],
+ * loss_total (optional) and global_partials (optional) exactly as the undeferred call would have.  Launched later --
+ * e.g. on a side stream behind an event, or right before the backward call -- the NVLink round trip and the wait for the
+ * slowest rank overlap whatever ran in between.  Flow control is the caller's: a rank may post call j + 2 only after its
+ * own resolve of call j + 1 has completed (two parity slots); dist.v10_loss_sharded(defer=True) does this with events.
+ * peer_bufs: HOST array as in y3d_loss_allreduce_finalize. */
+int y3d_loss_exchange_resolve(int n_branch, int rank, int world, void *const *peer_bufs, unsigned long long seq,
+                              float gain_box, float gain_cls, float gain_dfl, float total_scale, float *loss_items,
+                              float *loss_total, double *global_partials, int *status, void *stream);
 
 /* Backward of y3d_v8_loss_fwd / y3d_v10_loss_fwd: what autograd produces in the reference for loss.py:206-257
  * (BCEWithLogits :240, BboxLoss.forward :82-96, _df_loss :99-113, bbox_decode :197-204; CIoU metrics.py:78-134 with

@@ -41,14 +41,19 @@ def test_argument_errors_come_back_as_codes_not_crashes():
 
 
 def test_sharded_loss_entry_and_peer_exchange_host_side():
-    """The multi-GPU entry validates its arguments before touching the device; the exchange buffer is 2 slots of 32
+    """The multi-GPU entry validates its arguments before touching the device; the exchange buffer is 4 slots of 32
     flag-in-data words per rank; without a process group / peer memory the reducer reports itself unavailable (the
     callers then take the NCCL route) instead of raising."""
     lib = y3d.lib()
-    assert lib.y3d_xrank_buffer_bytes(8) == 2 * 8 * 32 * 8 and lib.y3d_xrank_buffer_bytes(0) == 2 * 32 * 8
+    assert lib.y3d_xrank_buffer_bytes(8) == 4 * 8 * 32 * 8 and lib.y3d_xrank_buffer_bytes(0) == 4 * 32 * 8
     null = [None] * 8
     assert lib.y3d_v10_loss_fwd_sharded(*null, 3, 2, 8, 16, None, 0, 10, 1, 7.5, 0.5, 1.5, None, None, 2.0, None, 0, 2,
-                                        None, ctypes.c_uint64(1), None, None, None, 0, None) == -1
+                                        None, ctypes.c_uint64(1), 0, None, None, None, 0, None) == -1
+    assert lib.y3d_loss_exchange_resolve(2, 0, 2, None, ctypes.c_uint64(1), 7.5, 0.5, 1.5, 2.0, None, None, None, None,
+                                         None) == -1
+    assert lib.y3d_decode_topk2d_sharded(None, None, None, None, None, 3, 2, 8, 16, 0, 50, 0, 2, None, ctypes.c_uint64(1),
+                                         None, None, 0, None) == -1
+    assert lib.y3d_gather_buffer_bytes(2, 4, 300) >= 2 * 2 * 4 * 300 * 6 * 4 + 2 * 2 * 4 * 4
     assert lib.y3d_loss_allreduce_finalize(None, 2, 0, 2, None, ctypes.c_uint64(1), 7.5, 0.5, 1.5, None, None, None,
                                            None) == -1
     red = y3d.dist.PeerLossReducer(torch.device("cpu"))

@@ -64,8 +64,25 @@ for it in range(20):
         print("ranks disagree", rank, it_f, chk)
         break
 assert int(red.status.item()) == 0
+# the deferred variant (post in the loss' last kernel, collect on a side stream, one call of slack): same items, and the
+# two-parity flow control holds over a train of back-to-back calls with a rank that is made slow every few steps
+handles = []
+for it in range(40):
+    if it % 5 == rank % 5:
+        torch.cuda._sleep(3_000_000)  # ~1.5 ms of skew on this rank
+    handles.append(y3d.dist.v10_loss_sharded(fm, fo, list(synth.STRIDES), nc, gtd, gains, Bl * world, reducer=red, defer=True))
+    if it >= 2:
+        tot_d, it_d = handles[it - 2].wait()
+        if not torch.equal(it_d, it_f):
+            ok = False
+            print("deferred sharded loss != fused", rank, it, it_d, it_f)
+            break
+tot_d, it_d = handles[-1].wait()
+torch.cuda.synchronize()
+ok = ok and bool(torch.equal(it_d, it_f)) and abs(float(tot_d) - float(it_f.sum()) * Bl * world) <= 1e-5 * abs(float(tot_d))
+assert int(red.status.item()) == 0
 if rank == 0:
-    print("fused sharded loss == nccl route:", ok, it_f.tolist())
+    print("fused sharded loss == nccl route == deferred:", ok, it_f.tolist())
 # timing: back-to-back calls
 torch.cuda.synchronize()
 dist.barrier()

@@ -33,7 +33,8 @@ SIGNATURES = {
     "y3d_v10_loss_fwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _f, _vp, _vp, _vp,
                               _vp, _vp, _sz, _vp]),
     "y3d_v10_loss_fwd_sharded": (_i, [_vp] * 8 + [_i, _i, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _f, _vp, _i, _i,
-                                      _vp, C.c_uint64, _vp, _vp, _vp, _sz, _vp]),
+                                      _vp, C.c_uint64, _i, _vp, _vp, _vp, _sz, _vp]),
+    "y3d_loss_exchange_resolve": (_i, [_i, _i, _i, _vp, C.c_uint64, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "y3d_v8_loss_finalize": (_i, [_vp, _i, _f, _f, _f, _vp, _vp]),
     "y3d_xrank_buffer_bytes": (_sz, [_i]),
     "y3d_loss_allreduce_finalize": (_i, [_vp, _i, _i, _i, _vp, C.c_uint64, _f, _f, _f, _vp, _vp, _vp, _vp]),

@@ -337,6 +337,7 @@ struct FinishParams {
     int x_rank, x_world;
     unsigned long long x_seq;
     long long x_timeout;       // clock cycles (xrank_timeout_cycles)
+    int x_defer;               // post this rank's partial sums only; y3d_loss_exchange_resolve collects and normalises
     int *x_status;             // optional: 1 when a peer never arrived
 };
 
@@ -672,6 +673,10 @@ __global__ void __launch_bounds__(kFinishThreads) loss_finish_kernel(AssignCtx2 
     }
     __syncthreads();
     const double *tot = S.xv;
+    if (F.x_world > 1 && F.x_defer) {  // post only: the collecting kernel runs later, on the caller's side stream
+        xrank_post(F.x_bufs, F.x_rank, F.x_world, F.x_seq, S.xv, 4 * F.n_branch);
+        return;
+    }
     if (F.x_world > 1) {  // sum over the ranks: stores into every peer's buffer, flag, wait, rank-ordered sum
         xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, S.xv, 4 * F.n_branch, S.xs, &S.xfail, F.x_timeout);
         tot = S.xs;
@@ -970,6 +975,10 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     }
     __syncthreads();
     const double *tot = s_xv;
+    if (F.x_world > 1 && F.x_defer) {  // post only: the collecting kernel runs later, on the caller's side stream
+        xrank_post(F.x_bufs, F.x_rank, F.x_world, F.x_seq, s_xv, 4 * F.n_branch);
+        return;
+    }
     if (F.x_world > 1) {  // sum over the ranks: stores into every peer's buffer, wait, rank-ordered sum
         xrank_allreduce(F.x_bufs, F.x_rank, F.x_world, F.x_seq, s_xv, 4 * F.n_branch, s_xs, &s_xfail, F.x_timeout);
         tot = s_xs;
@@ -1052,6 +1061,7 @@ struct XRankIn {  // cross-rank exchange of the fused loss (world <= 1: none)
     int rank, world;
     unsigned long long seq;
     int *status;
+    int defer;
 };
 
 static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc,
@@ -1063,7 +1073,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     if (xr && xr->world > 1 &&
         (!xr->bufs_dev || xr->world > kXMaxWorld || xr->rank < 0 || xr->rank >= xr->world || xr->seq == 0))
         return Y3D_EINVAL;
-    if (!loss_items && !partials) return Y3D_EINVAL;
+    if (!loss_items && !partials && !(xr && xr->world > 1 && xr->defer)) return Y3D_EINVAL;
     if ((dbg_fg_mask == nullptr) != (dbg_target_gt_idx == nullptr)) return Y3D_EINVAL;
     if (reg_max != kR) return Y3D_EUNSUPPORTED;
     AssignCtx2 cc{};
@@ -1182,6 +1192,7 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
         F.x_bufs = (XSlot *const *)xr->bufs_dev;
         F.x_rank = xr->rank; F.x_world = xr->world; F.x_seq = xr->seq; F.x_status = xr->status;
         F.x_timeout = xrank_timeout_cycles();
+        F.x_defer = xr->defer;
     }
     // programmatic dependent launch: the prologue (GT records) overlaps the top-k kernel's tail
     cudaLaunchConfig_t cfg = {};
@@ -1271,12 +1282,12 @@ extern "C" int y3d_v10_loss_fwd_sharded(const float *const *o2m_ptr, const int64
                                         const float *gt, int M, int topk_o2m, int topk_o2o, float gain_box,
                                         float gain_cls, float gain_dfl, float *loss_items, double *partials,
                                         float total_scale, float *loss_total, int rank, int world,
-                                        void *const *peer_bufs_dev, unsigned long long seq,
+                                        void *const *peer_bufs_dev, unsigned long long seq, int defer,
                                         int *status, void *const *prof_events, void *ws, size_t ws_bytes,
                                         void *stream) {
-    if (!loss_items) return Y3D_EINVAL;
+    if (!loss_items && !defer) return Y3D_EINVAL;
     BranchIn br[2] = {{o2m_ptr, o2m_sB, o2m_sC, topk_o2m}, {o2o_ptr, o2o_sB, o2o_sC, topk_o2o}};
-    XRankIn xr = {peer_bufs_dev, rank, world, seq, status};
+    XRankIn xr = {peer_bufs_dev, rank, world, seq, status, defer};
     return loss_run(2, br, lvl_hw, lvl_stride, nl, B, nc, reg_max, gt, M, gain_box, gain_cls, gain_dfl, 1, loss_items,
                     partials, nullptr, nullptr, prof_events, ws, ws_bytes, stream, &xr, total_scale, loss_total);
 }

@@ -138,6 +138,18 @@ def reduce_partials(partials, group=None):
     return partials
 
 
+class DeferredLoss:
+    """Result of ``v10_loss_sharded(..., defer=True)``: the loss items are being collected on a side stream.  ``wait()``
+    makes the current stream wait for them (no host synchronisation) and returns ``(total, items[6])``."""
+
+    def __init__(self, items8, total, event):
+        self._items8, self._total, self.event = items8, total, event
+
+    def wait(self):
+        torch.cuda.current_stream(self._items8.device).wait_event(self.event)
+        return self._total[0], self._items8.view(2, 4)[:, :3].reshape(6)
+
+
 class PeerLossReducer:
     """The loss path's one exchange as ONE kernel over NVLink peer memory (csrc/xrank.cu): every rank stores its 8
     partial sums straight into every peer's exchange buffer, waits for the peers' sequence flags, sums in rank order
@@ -170,6 +182,7 @@ class PeerLossReducer:
             self.status = torch.zeros(1, dtype=torch.int32, device=device)
             self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._calls, self.check_every, self._pg = 0, 16, pg
+            self._side, self._ring, self._resolved = None, None, []
             torch.cuda.synchronize(device)
             dist.barrier(group=pg)  # every buffer is zeroed before anyone's first store can land
             self.available = True
@@ -204,11 +217,41 @@ class PeerLossReducer:
         torch.cuda.synchronize(self.buf.device)
         dist.barrier(group=self._pg)
 
-    def next_call(self):
-        """Arguments (rank, world, peer_bufs_dev, seq, status) of ``y3d_v10_loss_fwd_sharded`` for the next collective
-        call; every rank must make that call."""
+    def next_call(self, defer=False):
+        """Arguments (rank, world, peer_bufs_dev, seq, defer, status) of ``y3d_v10_loss_fwd_sharded`` for the next
+        collective call; every rank must make that call."""
         self.seq += 1
-        return self.rank, self.world, ptr(self.ptrs_dev), C.c_uint64(self.seq), ptr(self.status)
+        return self.rank, self.world, ptr(self.ptrs_dev), C.c_uint64(self.seq), int(bool(defer)), ptr(self.status)
+
+    def resolve_deferred(self, gains, total_scale):
+        """The collecting half of the call just posted with ``defer=True``: ``y3d_loss_exchange_resolve`` on this reducer's
+        side stream, behind an event on the current stream.  Returns a :class:`DeferredLoss`.
+
+        Flow control (two parity slots in the exchange buffers): before the NEXT post, the caller's stream is made to wait
+        for the resolve before this one (``pre_post``), so a rank is never more than one call ahead of its own collects --
+        and therefore never overwrites a slot a peer has not read."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.buf.device)
+            self._ring = [(torch.empty(8, dtype=torch.float32, device=self.buf.device),
+                           torch.empty(1, dtype=torch.float32, device=self.buf.device)) for _ in range(4)]
+        main = torch.cuda.current_stream(self.buf.device)
+        posted = torch.cuda.Event()
+        posted.record(main)
+        items, total = self._ring[self.seq % len(self._ring)]
+        self._side.wait_event(posted)
+        _lib.check(_lib.lib().y3d_loss_exchange_resolve(
+            2, self.rank, self.world, self.ptrs, C.c_uint64(self.seq), float(gains[0]), float(gains[1]), float(gains[2]),
+            float(total_scale), ptr(items), ptr(total), None, ptr(self.status), C.c_void_p(self._side.cuda_stream)))
+        done = torch.cuda.Event()
+        done.record(self._side)
+        self._resolved = (self._resolved + [done])[-2:]
+        self.check()
+        return DeferredLoss(items, total, done)
+
+    def pre_post(self):
+        """Before a deferred post: the current stream waits for the resolve two calls back (see ``resolve_deferred``)."""
+        if len(self._resolved) == 2:
+            torch.cuda.current_stream(self.buf.device).wait_event(self._resolved[0])
 
     def __call__(self, partials, gains):
         """partials float64[4n] of this rank -> items float32[4n] of the global batch (same on every rank)."""
@@ -229,14 +272,24 @@ def fused_off():
 
 
 def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_batch, group=None, prof_events=None,
-                     reducer=None):
+                     reducer=None, defer=False):
     """``v10DetectLoss`` (loss.py:727-737) on this rank's image shard, normalised over the GLOBAL batch.
 
-    Returns ``(total, items[6])`` identical on every rank and equal to the single-process result on the full batch.
+    Returns ``(total, items[6])`` identical on every rank and equal to the single-process result on the full batch -- or,
+    with ``defer=True`` and a peer-memory ``reducer``, a :class:`DeferredLoss` whose ``wait()`` returns them: the cross-rank
+    exchange is then collected on a side stream while this stream goes on (the next step's kernels, or the host's way to
+    the backward call), so neither the NVLink round trip nor the slowest rank is waited for inside the step.
     One rank: the kernels normalise directly.  Several ranks with a ``reducer`` (:class:`PeerLossReducer`): the
     loss' last kernel exchanges the partial sums over NVLink peer memory itself (``y3d_v10_loss_fwd_sharded``);
     without one: un-normalised partials -> NCCL all_reduce of 8 doubles -> ``y3d_v8_loss_finalize``."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if defer and multi and reducer is not None and reducer.available and not fused_off():
+        # the loss' last kernel only POSTS this rank's sums to the peers; the collecting kernel runs on a side stream, so
+        # the NVLink round trip and the wait for the slowest rank overlap whatever this stream does next
+        reducer.pre_post()
+        _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains, prof_events=prof_events, xrank=reducer,
+                               total_scale=global_batch, return_total=True, defer=True)
+        return reducer.resolve_deferred(gains, global_batch)
     if (multi and reducer is not None and reducer.available and not fused_off()) or not multi:
         # one rank, or the exchange rides in the loss' last kernel: no collective launch at all, and the same kernel
         # writes the total (global_batch * sum of the items)

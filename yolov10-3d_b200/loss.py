@@ -39,7 +39,8 @@ def pack_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device, extra=Non
     return out
 
 
-def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_events, xrank=None, total_scale=None):
+def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_events, xrank=None, total_scale=None,
+                    defer=False):
     """Shared body of the one- and two-branch forward calls.  ``levels``: list of 1 or 2 ``Levels``.  Returns a dict with
     ``items`` (float32[4n] or None), ``partials`` (float64[4n]), ``dbg``, ``total`` (float32[1] = ``total_scale`` * sum
     of the loss items, written by the last kernel, or None) and what the backward pass needs (``ws``, ``gt``, ``M``)."""
@@ -73,7 +74,7 @@ def _branch_forward(levels, nc, gt_packed, topk, gains, normalise, debug, prof_e
         _lib.check(_lib.lib().y3d_v10_loss_fwd_sharded(
             l0.c_ptr, l0.c_sB, l0.c_sC, l1.c_ptr, l1.c_sB, l1.c_sC, l0.c_hw, l0.c_stride, l0.nl, l0.B, nc, REG_MAX,
             ptr(gt) if M > 0 else None, M, int(topk[0]), int(topk[1]), float(gains[0]), float(gains[1]), float(gains[2]),
-            ptr(items), ptr(partials), tsc, ptr(total), *xrank.next_call(), prof_events, ptr(ws), ws.numel(),
+            ptr(items), ptr(partials), tsc, ptr(total), *xrank.next_call(defer), prof_events, ptr(ws), ws.numel(),
             stream_ptr(dev)))
     elif n == 1:
         _lib.check(_lib.lib().y3d_v8_loss_fwd(*l0.args(), l0.B, nc, REG_MAX, *tail))
@@ -93,7 +94,7 @@ def v8_loss_forward(feats, strides, nc, gt_packed, topk, gains, normalise=True, 
 
 
 def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(10, 1), normalise=True, debug=False,
-                     prof_events=None, xrank=None, total_scale=None, return_total=False):
+                     prof_events=None, xrank=None, total_scale=None, return_total=False, defer=False):
     """Both branches of ``v10DetectLoss`` through ONE call of ``y3d_v10_loss_fwd`` (same launches for both).
 
     Returns (items float32[8] = (box, cls, dfl, target_scores_sum) x (one2many, one2one) or ``None`` when not
@@ -102,7 +103,7 @@ def v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_packed, gains, topk=(
     last kernel then sums the partials over the ranks through NVLink peer memory before normalising
     (``y3d_v10_loss_fwd_sharded``), and items / partials are those of the whole batch."""
     r = _branch_forward([Levels(feats_o2m, strides), Levels(feats_o2o, strides)], nc, gt_packed, topk, gains,
-                        normalise, debug, prof_events, xrank, total_scale)
+                        normalise, debug, prof_events, xrank, total_scale, defer)
     if return_total:  # ``total_scale`` * (sum of the six loss items), from the last kernel: float32[1]
         return r["items"], r["partials"], r["dbg"], r["total"]
     return r["items"], r["partials"], r["dbg"]

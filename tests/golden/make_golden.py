@@ -222,6 +222,27 @@ def case_loss_assign(name, B, nc, img_hw, M, seed, crowd=False, frac=0.02):
     save(name, recipe, in_crc=np.int64(synth.checksum(gt, xm, xo)), total=np.float64(total.item()),
          items=items.detach().numpy().astype(np.float64), **arrays)
 
+
+from tests.golden.sparse_feat import sparse_feat_modules  # noqa: E402
+
+
+def case_forward_feat(name, B, C, mid, img_hw, K, seed):
+    """The real v10Detect3d.inference_forward_feat (head.py:694-716) on seeded feature maps and plain torch heads."""
+    out_ch = {"cls": 3, "o2d": 2, "s2d": 2, "o3d": 2, "s3d": 3, "hd": 24, "dep": 1, "dep_un": 1}
+    lv = synth.levels(*img_hw)
+    g = synth.rng(seed)
+    x = [t(g.standard_normal((B, C, h, w), dtype=np.float32)) for h, w in lv]
+    heads = sparse_feat_modules(C, mid, out_ch, len(lv), seed)
+    ns = types.SimpleNamespace(nl=len(lv), output_channels=out_ch, max_det=K, patch_size=5)
+    ns.unravel_index = partial(v10Detect3d.unravel_index, ns)
+    ns.select_candidates = partial(v10Detect3d.select_candidates, ns)
+    ns.extract_patches = partial(v10Detect3d.extract_patches, ns)
+    with patched_topk(), torch.no_grad():
+        y = v10Detect3d.inference_forward_feat(ns, x, heads)
+    recipe = dict(kind="forward_feat", B=B, C=C, mid=mid, img_hw=img_hw, K=K, seed=seed, out_ch=out_ch)
+    save(name, recipe, in_crc=np.int64(synth.checksum(*[v.numpy() for v in x])),
+         **{f"y{i}": v.numpy() for i, v in enumerate(y)})
+
 # ---------------------------------------------------------------------------------------------- 3D
 def head3d_ns(nc, strides):
     ns = types.SimpleNamespace(nc=nc, no=nc + 35, dynamic=False, shape=None, export=False, format=None,
@@ -454,6 +475,8 @@ if __name__ == "__main__":
     if want("sparse_head"):
         case_sparse_head("sparse_head_kitti", B=3, nc=3, C=16, H=12, W=40, K=50, Cout=24, seed=70)
         case_sparse_head("sparse_head_ties", B=2, nc=3, C=8, H=24, W=80, K=50, Cout=3, seed=71, quantise=2)
+    if want("forward_feat"):
+        case_forward_feat("forward_feat_kitti", B=2, C=16, mid=8, img_hw=(96, 320), K=20, seed=75)
     if want("loss3d"):
         case_loss3d("loss3d_k8", B=2, nc=3, img_hw=(96, 320), M=8, topk=8, seed=60)
         case_loss3d("loss3d_k1", B=2, nc=3, img_hw=(96, 320), M=8, topk=1, seed=61)

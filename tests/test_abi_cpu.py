@@ -97,3 +97,33 @@ def test_make_anchors_matches_oracle():
     anc, st = y3d.make_anchors(feats, synth.STRIDES)
     oanc, ost = oracle.make_anchors(lv, synth.STRIDES)
     assert np.array_equal(anc.numpy(), oanc) and np.array_equal(st.numpy()[:, 0], ost)
+
+
+def test_mirror_signatures_against_the_committed_reference_signatures():
+    """tests/golden/api_signatures.json holds the reference's signatures (written where /root/reference exists, by
+    tests/test_reference_api_cpu.py); the mirrors must keep them wherever this runs: same names, order and defaults, extra
+    mirror parameters optional."""
+    import inspect
+    import json
+
+    fixture = json.load(open(os.path.join(ROOT, "tests", "golden", "api_signatures.json")))
+    mirrors = {
+        "ops.v10postprocess": y3d.v10postprocess, "ops.v10_3Dpostprocess": y3d.v10_3Dpostprocess,
+        "ops.xywh2xyxy": y3d.xywh2xyxy, "tal.make_anchors": y3d.make_anchors,
+        "tal.TaskAlignedAssigner.__init__": y3d.TaskAlignedAssigner.__init__,
+        "tal.TaskAlignedAssigner.forward": y3d.TaskAlignedAssigner.forward,
+        "tal.TaskAlignedAssigner3d.__init__": y3d.TaskAlignedAssigner3d.__init__,
+        "tal.TaskAlignedAssigner3d.forward": y3d.TaskAlignedAssigner3d.forward,
+        "loss.v8DetectionLoss.__init__": y3d.v8DetectionLoss.__init__, "loss.v8DetectionLoss.__call__": y3d.v8DetectionLoss.__call__,
+        "loss.v10DetectLoss.__init__": y3d.v10DetectLoss.__init__, "loss.v10DetectLoss.__call__": y3d.v10DetectLoss.__call__,
+        "loss.DDDetectionLoss.__init__": y3d.DDDetectionLoss.__init__, "loss.DDDetectionLoss.__call__": y3d.DDDetectionLoss.__call__,
+        "loss.DetectLoss3d.__init__": y3d.DetectLoss3d.__init__, "loss.DetectLoss3d.__call__": y3d.DetectLoss3d.__call__,
+    }
+    for name, fn in mirrors.items():
+        got = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+               for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+        want = fixture[name]
+        assert got[:len(want)] == want, f"{name}: mirror {got} vs reference {want}"
+        assert all(d is not None for _, d in got[len(want):]), f"{name}: extra mirror parameters must be optional"
+    got = [p.name for p in inspect.signature(y3d.head.inference_forward_feat).parameters.values()]
+    assert got[1:] == [n for n, _ in fixture["head.v10Detect3d.inference_forward_feat"]]

@@ -680,7 +680,7 @@ def test_dd_loss_backward_vs_reference_autograd(y3d, name):
     B, C = r["B"], r["nc"] + 35
     batch = {k: torch.from_numpy(v) for k, v in synth.batch_dict3d(gts, r["img_hw"], calibs, ms).items()}
     f = [t.requires_grad_(True) for t in feats_of(x, lv)]
-    total, items = y3d.DDDetectionLoss(FakeModel3d(r["nc"], r, r["topk"]), tal_topk=r["topk"])(f, batch)
+    total, items = y3d.DDDetectionLoss(FakeModel3d(r["nc"], r, r["topk"]), tal_topk=r["topk"])(f, batch, None)
     total.backward()
     g = torch.cat([t.grad.view(B, C, -1) for t in f], 2).cpu().numpy()
     ref = z["grad"]
@@ -695,7 +695,7 @@ def test_dd_loss_backward_vs_reference_autograd(y3d, name):
     # no targets: the reference's loss is a constant zero -> zero gradient
     f0 = [t.requires_grad_(True) for t in feats_of(x, lv)]
     empty = {k: (v[:0] if k not in ("calib", "mean_sizes") else v) for k, v in batch.items()}
-    t0, _ = y3d.DDDetectionLoss(FakeModel3d(r["nc"], r, r["topk"]), tal_topk=r["topk"])(f0, empty)
+    t0, _ = y3d.DDDetectionLoss(FakeModel3d(r["nc"], r, r["topk"]), tal_topk=r["topk"])(f0, empty, None)
     t0.backward()
     assert float(t0.detach()) == 0.0 and all(not t.grad.any() for t in f0)
 
@@ -712,8 +712,8 @@ def test_dd_loss_no_targets_and_dual(y3d):
     dual = y3d.DetectLoss3d(model)
     tot, items = dual({"one2many": f, "one2one": f, "o2m_embs": None, "o2o_embs": None}, batch)
     assert items.shape == (12,)
-    t8, i8 = y3d.DDDetectionLoss(model, tal_topk=8)(f, batch)
-    t1, i1 = y3d.DDDetectionLoss(model, tal_topk=1)(f, batch)
+    t8, i8 = y3d.DDDetectionLoss(model, tal_topk=8)(f, batch, None)
+    t1, i1 = y3d.DDDetectionLoss(model, tal_topk=1)(f, batch, None)
     np.testing.assert_allclose(items.cpu().numpy(), torch.cat((i8, i1)).cpu().numpy(), rtol=1e-6)
     np.testing.assert_allclose(float(tot), float(t8 + t1), rtol=1e-6)
     tot1, items1 = dual({"one2one": f, "o2o_embs": None}, batch)  # eval: only the one2one branch (loss.py:771)
@@ -746,6 +746,49 @@ def test_sparse_head_glue(y3d, name):
         y3d.select_candidates(dev(s2[:, :, :2, :3]), 50)  # K > cells: torch.topk raises too
 
 
+def test_inference_forward_feat_vs_reference(y3d):
+    """``head.inference_forward_feat`` (select -> extract -> the heads' convolutions on the patches -> scatter, per level)
+    against the real ``v10Detect3d.inference_forward_feat`` (fixture): same maps -- zero outside the candidate cells,
+    values to 1e-5 (cuDNN vs CPU convolutions)."""
+    import types
+
+    from tests.golden.sparse_feat import sparse_feat_modules
+
+    r, z = cases.load("forward_feat_kitti")
+    lv = synth.levels(*r["img_hw"])
+    g = synth.rng(r["seed"])
+    xs = [g.standard_normal((r["B"], r["C"], h, w), dtype=np.float32) for h, w in lv]
+    assert synth.checksum(*xs) == int(z["in_crc"])
+    heads = [m.cuda() for m in sparse_feat_modules(r["C"], r["mid"], r["out_ch"], len(lv), r["seed"])]
+    det = types.SimpleNamespace(nl=len(lv), output_channels=r["out_ch"], max_det=r["K"], patch_size=5)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # the fixture's convolutions ran in fp32 on the CPU
+    try:
+        with torch.no_grad():
+            y = y3d.head.inference_forward_feat(det, [dev(x) for x in xs], heads)
+            cls_maps = [heads[0][i](dev(xs[i])) for i in range(len(lv))]
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    nc = r["out_ch"]["cls"]
+    for i, yi in enumerate(y):
+        want, got = z[f"y{i}"], yi.cpu().numpy()
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got[:, :nc], want[:, :nc], rtol=1e-4, atol=2e-5)  # the class map (dense)
+        # the cells filled are exactly the oracle's top-K of the class map this run produced ...
+        oidx = oracle.select_candidates(cls_maps[i].cpu().numpy(), r["K"])
+        filled = np.zeros(got.shape[:1] + got.shape[2:], bool)
+        for b in range(got.shape[0]):
+            filled[b, oidx[b, :, 0], oidx[b, :, 1]] = True
+        assert np.array_equal(np.abs(got[:, nc:]).sum(1) != 0, filled)
+        # ... which are the reference's up to candidates whose scores differ by convolution rounding only
+        ref_filled = np.abs(want[:, nc:]).sum(1) != 0
+        both = filled & ref_filled
+        assert both.sum() >= 0.9 * ref_filled.sum()
+        sel = np.broadcast_to(both[:, None], got[:, nc:].shape)
+        np.testing.assert_allclose(got[:, nc:][sel], want[:, nc:][sel], rtol=1e-4, atol=2e-5)
+        assert not got[:, nc:][~np.broadcast_to(filled[:, None], got[:, nc:].shape)].any()  # zero elsewhere
+
+
 def test_rotate_iou_eval(y3d):
     """y3d_rotate_iou_eval against the reference fixture (numba kernel under the CUDA simulator) and the oracle; numpy
     in -> numpy out like the reference, CUDA tensor in -> CUDA tensor out."""
@@ -776,6 +819,10 @@ def test_decode_preds(y3d):
         got = np.array(res[files[b]], dtype=np.float64).reshape(-1, 14)
         assert got.shape[0] == n
         np.testing.assert_allclose(got, z["rows"][b, :n], rtol=1e-6, atol=1e-6)
+    for kw in (dict(undo_augment=False), dict(use_camera_dis=True)):  # branches outside the hot path raise, loudly
+        with pytest.raises(y3d.Y3DError):
+            y3d.kitti.decode_preds(dev(z["dets"]), cal, files, [(z["ratio"][b], (0.0, 0.0)) for b in range(B)],
+                                   list(z["inv_affine"]), z["cls_mean_size"], **kw)
 
 
 @pytest.mark.parametrize("grid", [False, True])

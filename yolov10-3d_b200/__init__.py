@@ -9,7 +9,7 @@ from . import _lib  # noqa: F401
 from . import dist, head, kitti, loss, loss3d, ops, tal  # noqa: F401
 from ._lib import Y3DError, lib  # noqa: F401
 from .head import (V10DetectDecoder, detect3d_decode, detect3d_postprocess, detect_inference, extract_patches,  # noqa: F401
-                   scatter_candidates, select_candidates, v10detect_export_forward)
+                   inference_forward_feat, scatter_candidates, select_candidates, v10detect_export_forward)
 from .loss import v8DetectionLoss, v10DetectLoss  # noqa: F401
 from .loss3d import DDDetectionLoss, DetectLoss3d  # noqa: F401
 from .ops import v10_3Dpostprocess, v10postprocess, xywh2xyxy  # noqa: F401

@@ -142,3 +142,29 @@ def scatter_candidates(values, indices, output_shape):
     out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=v.device)
     _lib.check(_lib.lib().y3d_scatter_candidates(ptr(v), ptr(idx), B, Cout, H, W, K, ptr(out), stream_ptr(v.device)))
     return out
+
+
+def inference_forward_feat(det, x, heads):
+    """``v10Detect3d.inference_forward_feat(x, heads)`` (head.py:694-716) with the head module passed as ``det``: per level,
+    the class head runs on the whole feature map, the ``det.max_det`` best cells are selected, and the regression heads
+    run on the 5 x 5 patches around them only; their outputs are scattered back into zero maps and concatenated behind
+    the class map.  The convolutions stay ``torch`` modules (``heads[j][i]``); candidate selection, patch extraction and
+    the scatter -- a ``for b in range(batch)`` loop with CPU index tensors in the reference -- are one kernel each and
+    never leave the device.  Returns the list of per-level tensors [B, sum(output_channels), H_l, W_l]."""
+    y = []
+    head_names = list(det.output_channels.keys())
+    out_ch = list(det.output_channels.values())
+    patch = getattr(det, "patch_size", 5)
+    for i in range(det.nl):
+        outputs = {head_names[0]: heads[0][i](x[i])}
+        cand = select_candidates(outputs[head_names[0]], det.max_det)
+        inputs = extract_patches(x[i], cand, patch)
+        for j, module in enumerate(heads[1:]):
+            for layer in module[i]:  # head.py:704-706: the patch already carries the receptive field of the first conv
+                if hasattr(layer, "conv") and hasattr(layer.conv, "padding") and type(layer).__name__ == "Conv":
+                    layer.conv.padding = 0
+            shape = (x[i].shape[0], out_ch[j + 1], x[i].shape[2], x[i].shape[3])
+            vals = module[i](inputs)[:, :, 0, 0]  # [B * K, Cout]
+            outputs[head_names[j + 1]] = scatter_candidates(vals, cand, shape)
+        y.append(torch.cat(list(outputs.values()), dim=1))
+    return y

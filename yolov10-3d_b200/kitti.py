@@ -30,9 +30,19 @@ def decode_preds_tensor(preds, calib, inv_affine, ratio, cls_mean_size, threshol
     return rows, valid
 
 
-def decode_preds(preds, calibs, im_files, ratio_pad, inv_trans, cls_mean_size, threshold=0.001):
+def decode_preds(preds, calibs, im_files, ratio_pad, inv_trans, cls_mean_size, undo_augment=True, threshold=0.001,
+                 use_camera_dis=False):
     """Reference-shaped result: ``{im_file: [[cls, alpha, x1, y1, x2, y2, h, w, l, x, y, z, ry, score], ...]}``.
-    ``calibs``: objects with cu, cv, fu, fv, tx, ty (kitti_utils.Calibration) or [B,6] array."""
+    ``calibs``: objects with cu, cv, fu, fv, tx, ty (kitti_utils.Calibration) or [B,6] array.  ``cls_mean_size`` is the
+    dataset attribute the reference method reads from ``self`` (kitti.py:38-41).
+
+    Only the branch the validator takes is compiled -- ``undo_augment=True`` with ``use_camera_dis`` off (kitti.py:551-557);
+    the fixed 1242/1280 rescale (``undo_augment=False``) and ``camera_dis_to_rect`` raise instead of silently computing
+    something else."""
+    if not undo_augment:
+        raise _lib.Y3DError("decode_preds: undo_augment=False (kitti.py:558-564) is outside the B200 hot path")
+    if use_camera_dis:
+        raise _lib.Y3DError("decode_preds: use_camera_dis (Calibration.camera_dis_to_rect) is outside the B200 hot path")
     if hasattr(calibs[0], "cu"):
         calib = np.array([[c.cu, c.cv, c.fu, c.fv, c.tx, c.ty] for c in calibs], dtype=np.float64)
     else:

@@ -130,8 +130,12 @@ def _branch_backward(levels, nc, fwd, topk, gains, items, grad_items):
 
 
 class _FusedLossFn(torch.autograd.Function):
-    """autograd node of the fused loss: forward = the three forward kernels, backward = the two backward kernels.
-    Inputs: the per-level head tensors of every branch; output: the 3 loss items of every branch."""
+    """autograd node of the fused loss: forward = the three forward kernels, backward = the backward kernel.
+    Inputs: the per-level head tensors of every branch; output: the 3 loss items of every branch.
+
+    Everything the backward pass reads -- the head tensors, the workspace the forward kernels left behind, the packed GT
+    and the items -- goes through ``ctx.save_for_backward``, so autograd's version counters catch an in-place change of
+    a feature map between forward and backward instead of the backward silently using changed logits."""
 
     @staticmethod
     def forward(ctx, cfg, *feats):
@@ -140,14 +144,19 @@ class _FusedLossFn(torch.autograd.Function):
         nl = len(feats) // n
         levels = [Levels(feats[i * nl:(i + 1) * nl], strides) for i in range(n)]
         fwd = _branch_forward(levels, nc, gt, topk, gains, True, False, None)
-        ctx.levels, ctx.fwd, ctx.cfg = levels, fwd, cfg
+        used = [f for lv in levels for f in lv.feats]  # fp32, dense rows: the tensors the kernels actually read
+        ctx.save_for_backward(*used, fwd["ws"], fwd["gt"], fwd["items"])
+        ctx.cfg = (strides, nc, topk, gains, n, nl, fwd["M"])
         ctx.in_dtypes = [f.dtype for f in feats]
         return fwd["items"].view(n, 4)[:, :3].reshape(3 * n)
 
     @staticmethod
     def backward(ctx, grad_items):
-        strides, nc, gt, topk, gains = ctx.cfg
-        grads = _branch_backward(ctx.levels, nc, ctx.fwd, topk, gains, ctx.fwd["items"], grad_items)
+        strides, nc, topk, gains, n, nl, M = ctx.cfg
+        saved = ctx.saved_tensors
+        used, (ws, gt, items) = saved[:n * nl], saved[n * nl:]
+        levels = [Levels(used[i * nl:(i + 1) * nl], strides) for i in range(n)]
+        grads = _branch_backward(levels, nc, dict(ws=ws, gt=gt, M=M), topk, gains, items, grad_items)
         flat = [g for br in grads for g in br]
         return (None, *[g.to(dt) for g, dt in zip(flat, ctx.in_dtypes)])
 

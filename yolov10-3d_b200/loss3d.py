@@ -72,14 +72,17 @@ class _DDLossFn(torch.autograd.Function):
                                               int(topk), float(kw["alpha"]), float(kw["beta"]), float(kw["gamma"]),
                                               flags, g, 1, ptr(items), ptr(partials), None, ptr(ws), ws.numel(),
                                               stream_ptr(dev)))
-        ctx.lv, ctx.saved = lv, (gts, M, ws, items, g, nc)
+        ctx.save_for_backward(*lv.feats, gts, ws, items)  # version-checked by autograd (see loss._FusedLossFn)
+        ctx.cfg = (lv.strides, M, g, nc, len(lv.feats))
         ctx.in_dtypes = [f.dtype for f in feats]
         return items[:6].clone()
 
     @staticmethod
     def backward(ctx, grad_items):
-        lv = ctx.lv
-        gts, M, ws, items, g, nc = ctx.saved
+        strides, M, g, nc, nl = ctx.cfg
+        saved = ctx.saved_tensors
+        lv = Levels(saved[:nl], strides)
+        gts, ws, items = saved[nl:]
         grads = [torch.empty_like(f) for f in lv.feats]
         gl = Levels(grads, lv.strides)
         gi = grad_items.to(lv.device, torch.float32).contiguous()
@@ -105,7 +108,7 @@ class DDDetectionLoss:
         if getattr(h, "distillation", False):
             raise _lib.Y3DError("distillation (SupervisionLoss, loss.py:792) is outside the B200 hot path")
 
-    def __call__(self, preds, batch, embeddings=None):
+    def __call__(self, preds, batch, embeddings):
         feats = preds[1] if isinstance(preds, tuple) else preds  # loss.py:824
         B = feats[0].shape[0]
         dev = feats[0].device

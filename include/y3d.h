@@ -312,6 +312,17 @@ int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const in
                     const float *mean_sizes, int topk, float alpha, float beta, float gamma, int flags,
                     const float *gains, int normalise, float *loss_items, double *partials,
                     int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes, void *stream);
+/* Both branches of DetectLoss3d (loss.py:750-771) in the SAME four launches (streaming pass, top-k, conflict resolution,
+ * foreground terms; the branch is a grid dimension): one2many with topk_o2m, one2one with topk_o2o.  Arguments as in
+ * y3d_dd_loss_fwd; loss_items: DEVICE float[2][8], partials: DEVICE double[2][11], dbg_target_gt_idx [2,B,A] (optional);
+ * ws: 2 x y3d_workspace_bytes(Y3D_STAGE_DD_LOSS, ...) bytes -- branch z owns the z-th half, which is what
+ * y3d_dd_loss_bwd takes for that branch. */
+int y3d_dd_loss_dual_fwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC,
+                         const float *const *o2o_ptr, const int64_t *o2o_sB, const int64_t *o2o_sC, const int *lvl_hw,
+                         const float *lvl_stride, int nl, int B, int nc, const float *gts, int M, const float *calibs,
+                         const float *mean_sizes, int topk_o2m, int topk_o2o, float alpha, float beta, float gamma,
+                         int flags, const float *gains, int normalise, float *loss_items, double *partials,
+                         int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes, void *stream);
 int y3d_dd_loss_finalize(const double *partials, int M, const float *gains, float *loss_items, void *stream);
 /* Backward of y3d_dd_loss_fwd (autograd of loss.py:879-888 through compute_box2d_loss, compute_box3d_loss, the
  * Laplacian depth term and compute_heading_loss): call with the same geometry / gts / M and the untouched workspace of

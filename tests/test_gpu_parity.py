@@ -515,6 +515,38 @@ def test_v10_loss_full_size_properties(y3d, cfg):
     np.testing.assert_allclose(it2.view(2, 4)[:, :3].reshape(6).cpu().numpy(), o, rtol=2e-5)
 
 
+@pytest.mark.parametrize("M,nbig", [(100, 100), (200, 200), (300, 40)])
+def test_fused_loss_overflow_branches_vs_oracle(y3d, M, nbig):
+    """Many GTs sharing one region, so that (almost) every claimed anchor is contested by dozens of GTs:
+    * M = 100: the anchor-parallel finishing kernel's (contested anchor, GT) pair buffer overflows (kFinApPairs = 1024) and
+      pairs are evaluated in place;
+    * M = 200 / 300 (per-image finishing kernel): the coarse GT index exceeds its capacity (kBucketCap) and the kernel falls
+      back to the cooperative all-GT scan, whose buffers (kConfMax = 1024 contested anchors) overflow into the serial scan.
+    Assignment and loss must still equal the oracle's, bit for bit / to 2e-5."""
+    lossmod = __import__("yolov10_3d_b200").loss
+    B, nc, hw = 2, 8, (320, 320)
+    lv = synth.levels(*hw)
+    g = synth.rng(900 + M)
+    gt = np.zeros((B, M, 5), np.float32)
+    for b in range(B):
+        gt[b, :, 0] = g.integers(0, nc, M)
+        # nbig boxes over nearly the same large region (jittered by a few pixels), the rest small and scattered
+        j = g.uniform(-6, 6, (nbig, 4)).astype(np.float32)
+        gt[b, :nbig, 1:5] = np.array([40, 30, 290, 300], np.float32) + j
+        n_s = M - nbig
+        if n_s:
+            c = g.uniform(30, 290, (n_s, 2)).astype(np.float32)
+            wh = g.uniform(10, 60, (n_s, 2)).astype(np.float32)
+            gt[b, nbig:, 1:5] = np.concatenate([c - wh / 2, c + wh / 2], 1)
+    x = synth.train_like_head2d(B, nc, lv, gt, seed=901 + M, frac=0.05)
+    for k in (10, 1):
+        items, _, dbg = lossmod.v8_loss_forward(feats_of(x, lv), list(synth.STRIDES), nc, dev(gt), k, (7.5, 0.5, 1.5), debug=True)
+        oit, _, nfg, ofg, otgi = oracle.v8_loss(x, lv, synth.STRIDES, nc, gt, k, debug=True)
+        fg, tgi = dbg["fg_mask"].cpu().numpy(), dbg["target_gt_idx"].cpu().numpy().astype(np.int64)
+        assert np.array_equal(fg, ofg) and np.array_equal(tgi[ofg], otgi[ofg]) and nfg > 0
+        np.testing.assert_allclose(items[:3].cpu().numpy(), oit, rtol=2e-5)
+
+
 def test_ordered_queue_many_images_bit_exact(y3d):
     """Many small images: the top-k kernel's longest-first queue has more (class, branch, image) segments than one
     32 x 32 lookup covers (second lookup step over up to 64 entries), GT sizes span all four size classes, some images
@@ -718,6 +750,27 @@ def test_dd_loss_no_targets_and_dual(y3d):
     np.testing.assert_allclose(float(tot), float(t8 + t1), rtol=1e-6)
     tot1, items1 = dual({"one2one": f, "o2o_embs": None}, batch)  # eval: only the one2one branch (loss.py:771)
     assert float(tot1) == 0.0 and items1.shape == (6,)
+    # both branches in the same launches (y3d_dd_loss_dual_fwd) == one call per branch: assignment bit for bit, items,
+    # and the gradients of the dual autograd node == the two single-branch nodes'
+    x2 = synth.train_like_head3d(r["B"], r["nc"], lv, gts, seed=r["seed"] + 77, frac=0.05)
+    f2 = feats_of(x2, lv)
+    itd, pd_, tgd = y3d.loss3d.dd_loss_dual_forward(f, f2, list(synth.STRIDES), r["nc"], dev(z["packed"]), dev(calibs), dev(ms),
+                                                    (8, 1), r["gains"], debug=True, **cases.loss3d_kwargs(r))
+    for zz, (ff, k) in enumerate(((f, 8), (f2, 1))):
+        its, ps, tgs = y3d.loss3d.dd_loss_forward(ff, list(synth.STRIDES), r["nc"], dev(z["packed"]), dev(calibs), dev(ms), k,
+                                                  r["gains"], debug=True, **cases.loss3d_kwargs(r))
+        assert torch.equal(tgd[zz], tgs)
+        np.testing.assert_allclose(itd[zz].cpu().numpy(), its.cpu().numpy(), rtol=1e-6)
+        np.testing.assert_allclose(pd_[zz].cpu().numpy(), ps.cpu().numpy(), rtol=1e-12)
+    fa = [t.clone().requires_grad_(True) for t in f]
+    fb = [t.clone().requires_grad_(True) for t in f2]
+    tot, _ = dual({"one2many": fa, "one2one": fb, "o2m_embs": None, "o2o_embs": None}, batch)
+    tot.backward()
+    fc = [t.clone().requires_grad_(True) for t in f]
+    fd = [t.clone().requires_grad_(True) for t in f2]
+    (y3d.DDDetectionLoss(model, tal_topk=8)(fc, batch, None)[0] + y3d.DDDetectionLoss(model, tal_topk=1)(fd, batch, None)[0]).backward()
+    for a_, b_ in zip(fa + fb, fc + fd):
+        assert a_.grad is not None and torch.allclose(a_.grad, b_.grad, rtol=1e-6, atol=1e-9)
 
 
 @pytest.mark.parametrize("name", cases.names("sparse_head_"))

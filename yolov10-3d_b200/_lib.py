@@ -41,6 +41,8 @@ SIGNATURES = {
     "y3d_v8_loss_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "y3d_v10_loss_bwd": (_i, [_vp] * 14 + [_i, _i, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "y3d_dd_loss_fwd": (_i, _LEVELS + [_i, _i, _vp, _i, _vp, _vp, _i, _f, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "y3d_dd_loss_dual_fwd": (_i, [_vp] * 8 + [_i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _f, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp,
+                                  _sz, _vp]),
     "y3d_dd_loss_finalize": (_i, [_vp, _i, _vp, _vp, _vp]),
     "y3d_dd_loss_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "y3d_select_candidates": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp]),

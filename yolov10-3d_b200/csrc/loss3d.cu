@@ -40,14 +40,47 @@ struct DDParams {
     int B, nc, A, M;
 };
 
-// grid (ceil(A/128), B), one thread per anchor
-__global__ void __launch_bounds__(128) dd_stream_kernel(DDParams P, int *work_counter) {
+struct DDParams2 {
+    DDParams p[2];  // one2many / one2one of DetectLoss3d in the same launches (blockIdx.z)
+};
+
+// GT keypoints of image b (add_cls_mean_size tal.py:605-609 + get_3d_keypoints): out of line, run by one CTA per image
+static __device__ __noinline__ void dd_gt_keypoints(const float *gts, const float *calibs, const float *mean_sizes, int b,
+                                                    int M, int nc, float *gt_kps) {
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const float *g = gts + ((long long)b * M + m) * 17;
+        int lab = (int)g[0];
+        lab = lab < 0 ? 0 : (lab >= nc ? nc - 1 : lab);
+        const float sh_ = dm::add(mean_sizes[3 * lab], g[11]), sw_ = dm::add(mean_sizes[3 * lab + 1], g[12]),
+                    sl_ = dm::add(mean_sizes[3 * lab + 2], g[13]);
+        float out[24];
+        keypoints24(g[9], g[10], g[14], sh_, sw_, sl_, (int)g[15], g[16], calibs + 6 * b, out);
+        for (int j = 0; j < 24; ++j) gt_kps[((long long)b * M + m) * 24 + j] = out[j];
+    }
+}
+
+// grid (ceil(A/128), B, n_branch), one thread per anchor.  Besides the pass over the head: zeroes what the assigner core
+// expects zeroed (claim words, per-GT maxima, work counter) and, in branch 0, computes the GT keypoints -- no memset and
+// no separate small kernel in front of the top-k kernel.
+__global__ void __launch_bounds__(128) dd_stream_kernel(const __grid_constant__ DDParams2 PP, int *work_counter,
+                                                        int *pos_align0, int *pos_ov0, int *pos_align1, int *pos_ov1,
+                                                        float *gt_kps) {
     __shared__ double red[4];
+    const DDParams &P = PP.p[blockIdx.z];
     const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0 && work_counter) *work_counter = 0;
+    if (blockIdx.x == 0 && b == 0 && blockIdx.z == 0 && threadIdx.x == 0 && work_counter) *work_counter = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.tickets[b] = 0u;
         if (b == 0) P.tickets[P.B] = 0u;
+    }
+    if (blockIdx.x == 0) {
+        int *pa = blockIdx.z ? pos_align1 : pos_align0, *po = blockIdx.z ? pos_ov1 : pos_ov0;
+        if (pa)
+            for (int m = threadIdx.x; m < P.M; m += blockDim.x) {
+                pa[(long long)b * P.M + m] = 0;
+                po[(long long)b * P.M + m] = 0;
+            }
+        if (gt_kps && blockIdx.z == 0) dd_gt_keypoints(P.gts, P.calibs, P.mean_sizes, b, P.M, P.nc, gt_kps);
     }
     double soft = 0.0;
     if (a < P.A) {
@@ -127,8 +160,11 @@ __device__ __forceinline__ void dd_items(const double *p, int M, const float *g,
 // grid (ceil(ceil(A/128) / kFgRows), B): a CTA covers the anchors of kFgRows CTAs of the streaming kernel and puts
 // their foreground sums into slots 1..kNSum of the first of those partial rows (n_rows = the streaming kernel's grid.x)
 constexpr int kFgRows = 1;  // (4 measured slower: the few foreground anchors of a thread then run back to back, and the kernel is one latency chain)
-__global__ void __launch_bounds__(128) dd_fg_kernel(AssignCtx c, DDParams P, int n_rows) {
+__global__ void __launch_bounds__(128) dd_fg_kernel(const __grid_constant__ AssignCtx2 cc, const __grid_constant__ DDParams2 PP,
+                                                    int n_rows) {
     __shared__ double red[kNSum][4];
+    const AssignCtx &c = cc.c[blockIdx.z];
+    const DDParams &P = PP.p[blockIdx.z];
     const int b = blockIdx.y;
     double s[kNSum];
 #pragma unroll
@@ -377,76 +413,113 @@ size_t dd_loss_workspace_bytes(int B, int A, int M) { return dd_ws_layout(B, A, 
 
 using namespace y3d;
 
+struct DDBranchIn {
+    const float *const *lvl_ptr;
+    const int64_t *sB, *sC;
+    int topk;
+};
+
+// nb = 1: one branch (DDDetectionLoss); nb = 2: both branches of DetectLoss3d in the same four launches.  Branch z uses
+// the workspace block [z * dd_ws_layout().total, ...); loss_items [nb][8], partials [nb][kNSum + 1], dbg [nb][B][A].
+static int dd_loss_run(int nb, const DDBranchIn *br, const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc,
+                       const float *gts, int M, const float *calibs, const float *mean_sizes, float alpha, float beta,
+                       float gamma, int flags, const float *gains, int normalise, float *loss_items, double *partials,
+                       int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes, void *stream) {
+    if (!lvl_hw || !lvl_stride || !calibs || !mean_sizes || !gains) return Y3D_EINVAL;
+    if (B < 1 || nc < 1 || M < 0 || (M > 0 && !gts) || !partials || (normalise && !loss_items)) return Y3D_EINVAL;
+    const int use_2d = flags & 1, use_3d = (flags >> 1) & 1, kps_l2 = (flags >> 2) & 1, constrain = (flags >> 3) & 1;
+    if (!use_2d && !use_3d) return Y3D_EINVAL;  // tal.py:486
+    DDParams2 PP{};
+    AssignCtx2 cc{};
+    int A = 0;
+    for (int z = 0; z < nb; ++z) {
+        if (!br[z].lvl_ptr || !br[z].sB || !br[z].sC) return Y3D_EINVAL;
+        A = make_level_table(PP.p[z].t, br[z].lvl_ptr, br[z].sB, br[z].sC, lvl_hw, lvl_stride, nl);
+        if (A < 0) return A;
+        for (int l = 0; l < nl; ++l)
+            if (!br[z].lvl_ptr[l]) return Y3D_EINVAL;
+        if (br[z].topk < 1 || br[z].topk > A) return Y3D_EINVAL;
+        if (br[z].topk > Y3D_MAX_TOPK) return Y3D_EUNSUPPORTED;
+    }
+    const DDWs w = dd_ws_layout(B, A, M);
+    if (!ws || ws_bytes < (size_t)nb * w.total) return Y3D_EWORKSPACE;
+    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    const AssignWs aw = assign_ws_layout(B, A, M);
+    float *gt_kps = (float *)((char *)ws + w.gt_kps);  // shared by the branches (same GT)
+    for (int z = 0; z < nb; ++z) {
+        char *p = (char *)ws + (size_t)z * w.total;
+        DDParams &P = PP.p[z];
+        AssignCtx &c = cc.c[z];
+        c.t = P.t;
+        assign_bind_ws(c, p + w.assign, aw);
+        P.gts = gts; P.calibs = calibs; P.mean_sizes = mean_sizes;
+        P.boxes = (float *)(p + w.boxes);
+        P.pd_kps = (float *)(p + w.pd_kps);
+        P.claim = M > 0 ? c.claim : nullptr;  // zeroed by the streaming kernel, like the per-GT maxima and the work counter
+        P.part = (double *)(p + w.part);
+        P.part_img = (double *)(p + w.part_img);
+        P.tickets = (unsigned *)(p + w.tickets);
+        P.partials = partials + (size_t)z * (kNSum + 1);
+        P.items = normalise ? loss_items + 8 * z : nullptr;
+        for (int i = 0; i < 6; ++i) P.gain[i] = gains[i];
+        P.B = B; P.nc = nc; P.A = A; P.M = M;
+        c.score_mode = 1; c.cls_ch0 = 0;  // class logits are the first nc channels of the head
+        c.pd_bboxes = P.boxes; c.box_grid_units = 0; c.box_soa = 0;
+        c.use_grid = 1;
+        c.gt_labels = gts; c.gl_stride = 17;
+        c.gt_bboxes = gts ? gts + 1 : nullptr; c.gb_stride = 17;
+        c.mask_gt = nullptr;  // valid iff the box sums to > 0 (loss.py:857)
+        c.B = B; c.A = A; c.nc = nc; c.M = M; c.k = br[z].topk;
+        c.alpha = alpha; c.beta = beta; c.gamma = gamma; c.eps = 1e-9f;
+        c.use_2d = use_2d; c.use_3d = use_3d; c.kps_l2 = kps_l2; c.constrain = constrain;
+        c.pd_kps = P.pd_kps; c.gt_kps = gt_kps;
+    }
+    cc.work_counter = (int *)((char *)ws + w.assign + aw.off_work);
+    dim3 grid((A + 127) / 128, B, nb);
+    dd_stream_kernel<<<grid, 128, 0, s>>>(PP, M > 0 ? cc.work_counter : nullptr, M > 0 ? cc.c[0].pos_align : nullptr,
+                                          cc.c[0].pos_ov, nb > 1 ? cc.c[1].pos_align : nullptr, cc.c[1].pos_ov,
+                                          M > 0 ? gt_kps : nullptr);
+    Y3D_CHECK_LAUNCH();
+    if (M > 0) {
+        const int rc = assign_run_core(cc, nb, s);
+        if (rc) return rc;
+    }
+    dd_fg_kernel<<<dim3((grid.x + kFgRows - 1) / kFgRows, B, nb), 128, 0, s>>>(cc, PP, (int)grid.x);
+    Y3D_CHECK_LAUNCH();
+    if (dbg_target_gt_idx) {  // assigned GT per anchor, -1 = background
+        for (int z = 0; z < nb; ++z) {
+            cudaError_t e;
+            int32_t *dst = dbg_target_gt_idx + (size_t)z * B * A;
+            if (M == 0) e = cudaMemsetAsync(dst, 0xff, sizeof(int32_t) * (size_t)B * A, s);
+            else e = cudaMemcpyAsync(dst, cc.c[z].tgi, sizeof(int32_t) * (size_t)B * A, cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    return Y3D_OK;
+}
+
 extern "C" int y3d_dd_loss_fwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
                                const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, const float *gts, int M,
                                const float *calibs, const float *mean_sizes, int topk, float alpha, float beta,
                                float gamma, int flags, const float *gains, int normalise, float *loss_items,
                                double *partials, int32_t *dbg_target_gt_idx, void *ws, size_t ws_bytes,
                                void *stream) {
-    if (!lvl_ptr || !lvl_sB || !lvl_sC || !lvl_hw || !lvl_stride || !calibs || !mean_sizes || !gains) return Y3D_EINVAL;
-    if (B < 1 || nc < 1 || M < 0 || (M > 0 && !gts) || !partials || (normalise && !loss_items)) return Y3D_EINVAL;
-    const int use_2d = flags & 1, use_3d = (flags >> 1) & 1, kps_l2 = (flags >> 2) & 1, constrain = (flags >> 3) & 1;
-    if (!use_2d && !use_3d) return Y3D_EINVAL;  // tal.py:486
-    DDParams P{};
-    const int A = make_level_table(P.t, lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl);
-    if (A < 0) return A;
-    for (int l = 0; l < nl; ++l)
-        if (!lvl_ptr[l]) return Y3D_EINVAL;
-    if (topk < 1 || topk > A) return Y3D_EINVAL;
-    if (topk > Y3D_MAX_TOPK) return Y3D_EUNSUPPORTED;
-    const DDWs w = dd_ws_layout(B, A, M);
-    if (!ws || ws_bytes < w.total) return Y3D_EWORKSPACE;
-    if (((uintptr_t)ws) % 256) return Y3D_EALIGN;
-    cudaStream_t s = (cudaStream_t)stream;
-    char *p = (char *)ws;
-    const AssignWs aw = assign_ws_layout(B, A, M);
-    AssignCtx c{};
-    c.t = P.t;
-    assign_bind_ws(c, p + w.assign, aw);
-    P.gts = gts; P.calibs = calibs; P.mean_sizes = mean_sizes;
-    P.boxes = (float *)(p + w.boxes);
-    P.pd_kps = (float *)(p + w.pd_kps);
-    P.claim = nullptr;  // zeroed by the memset below together with the per-GT maxima
-    P.part = (double *)(p + w.part);
-    P.part_img = (double *)(p + w.part_img);
-    P.tickets = (unsigned *)(p + w.tickets);
-    P.partials = partials;
-    P.items = normalise ? loss_items : nullptr;
-    for (int i = 0; i < 6; ++i) P.gain[i] = gains[i];
-    P.B = B; P.nc = nc; P.A = A; P.M = M;
-    dim3 grid((A + 127) / 128, B);
-    cudaError_t e = cudaMemsetAsync(p + w.assign + aw.off_cnt, 0, aw.zero_bytes, s);
-    if (e != cudaSuccess) return (int)e;
-    dd_stream_kernel<<<grid, 128, 0, s>>>(P, nullptr);
-    Y3D_CHECK_LAUNCH();
-    if (M > 0) {
-        float *gt_kps = (float *)(p + w.gt_kps);
-        int rc = launch_kps_gt(gts, calibs, mean_sizes, B, M, nc, gt_kps, s);
-        if (rc) return rc;
-        c.score_mode = 1; c.cls_ch0 = 0;  // class logits are the first nc channels of the head
-        c.pd_bboxes = P.boxes; c.box_grid_units = 0; c.box_soa = 0;
-        c.use_grid = 1;
-        c.gt_labels = gts; c.gl_stride = 17;
-        c.gt_bboxes = gts + 1; c.gb_stride = 17;
-        c.mask_gt = nullptr;  // valid iff the box sums to > 0 (loss.py:857)
-        c.B = B; c.A = A; c.nc = nc; c.M = M; c.k = topk;
-        c.alpha = alpha; c.beta = beta; c.gamma = gamma; c.eps = 1e-9f;
-        c.use_2d = use_2d; c.use_3d = use_3d; c.kps_l2 = kps_l2; c.constrain = constrain;
-        c.pd_kps = P.pd_kps; c.gt_kps = gt_kps;
-        AssignCtx2 cc{};
-        cc.c[0] = c;
-        cc.work_counter = (int *)(p + w.assign + aw.off_work);
-        rc = assign_run_core(cc, 1, s);
-        if (rc) return rc;
-    }
-    dd_fg_kernel<<<dim3((grid.x + kFgRows - 1) / kFgRows, B), 128, 0, s>>>(c, P, (int)grid.x);
-    Y3D_CHECK_LAUNCH();
-    if (dbg_target_gt_idx) {  // assigned GT per anchor, -1 = background
-        if (M == 0) e = cudaMemsetAsync(dbg_target_gt_idx, 0xff, sizeof(int32_t) * (size_t)B * A, s);
-        else e = cudaMemcpyAsync(dbg_target_gt_idx, c.tgi, sizeof(int32_t) * (size_t)B * A, cudaMemcpyDeviceToDevice, s);
-        if (e != cudaSuccess) return (int)e;
-    }
-    return Y3D_OK;
+    DDBranchIn br[1] = {{lvl_ptr, lvl_sB, lvl_sC, topk}};
+    return dd_loss_run(1, br, lvl_hw, lvl_stride, nl, B, nc, gts, M, calibs, mean_sizes, alpha, beta, gamma, flags, gains,
+                       normalise, loss_items, partials, dbg_target_gt_idx, ws, ws_bytes, stream);
+}
+
+extern "C" int y3d_dd_loss_dual_fwd(const float *const *o2m_ptr, const int64_t *o2m_sB, const int64_t *o2m_sC,
+                                    const float *const *o2o_ptr, const int64_t *o2o_sB, const int64_t *o2o_sC,
+                                    const int *lvl_hw, const float *lvl_stride, int nl, int B, int nc, const float *gts,
+                                    int M, const float *calibs, const float *mean_sizes, int topk_o2m, int topk_o2o,
+                                    float alpha, float beta, float gamma, int flags, const float *gains, int normalise,
+                                    float *loss_items, double *partials, int32_t *dbg_target_gt_idx, void *ws,
+                                    size_t ws_bytes, void *stream) {
+    DDBranchIn br[2] = {{o2m_ptr, o2m_sB, o2m_sC, topk_o2m}, {o2o_ptr, o2o_sB, o2o_sC, topk_o2o}};
+    return dd_loss_run(2, br, lvl_hw, lvl_stride, nl, B, nc, gts, M, calibs, mean_sizes, alpha, beta, gamma, flags, gains,
+                       normalise, loss_items, partials, dbg_target_gt_idx, ws, ws_bytes, stream);
 }
 
 extern "C" int y3d_dd_loss_bwd(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,

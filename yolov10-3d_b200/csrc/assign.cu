@@ -585,6 +585,9 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(AssignCtx2 cc) {
     const int b = blockIdx.y;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const long long o = (long long)b * c.A + a;
+    // (a no-op after an ordinary launch; the fused 3D loss launches this grid programmatically dependent on the top-k grid)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     const unsigned long long cl = a < c.A ? c.claim[o] : 0ull;
     const int cnt = (int)(cl >> 32);
     const int any_multi = __syncthreads_or(cnt > 1);  // does any anchor of this block need the all-GT scan?
@@ -657,7 +660,8 @@ int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl) {
     // one persistent warp per GT fills the machine only when there are many GTs; with few (e.g. KITTI: 32 x 50) the
     // kernel's duration is one GT's latency, so each GT is split over kTopkWarps warps instead
     const int sms = device_sm_count();
-    const bool few = items < 16LL * sms;
+    // (3D similarity: every candidate costs a 96-byte gather and 24 coordinate terms, so the split pays for longer)
+    const bool few = items < (c.use_3d ? 32LL : 16LL) * sms;
     const int wpg = (c.use_grid && c.constrain && cc.work_counter && !few) ? 1 : kTopkWarps;
     if (items >= 0x7fffffffLL) return Y3D_EUNSUPPORTED;
     long long blocks = wpg == 1 ? (items + kTopkWarps - 1) / kTopkWarps : items;
@@ -681,9 +685,9 @@ int assign_run_topk(const AssignCtx2 &cc, int n, cudaStream_t s, bool pdl) {
     return Y3D_OK;
 }
 
-int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk) {
+int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk, bool pdl) {
     const AssignCtx &c = cc.c[0];
-    int rc0 = assign_run_topk(cc, n, s);
+    int rc0 = assign_run_topk(cc, n, s, pdl);
     if (rc0) return rc0;
     if (after_topk) cudaEventRecord(after_topk, s);
     size_t smem = sizeof(GtRec) * (size_t)c.M;
@@ -694,7 +698,22 @@ int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t aft
         smem_limit = smem;
     }
     dim3 grid((c.A + 255) / 256, c.B, n);
-    tal_resolve_kernel<<<grid, 256, smem, s>>>(cc);
+    if (pdl) {  // scheduled as the top-k grid drains; waits for it before it reads
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, tal_resolve_kernel, cc);
+        if (le != cudaSuccess) return (int)le;
+    } else {
+        tal_resolve_kernel<<<grid, 256, smem, s>>>(cc);
+    }
     Y3D_CHECK_LAUNCH();
     return Y3D_OK;
 }

@@ -401,7 +401,7 @@ inline void assign_bind_ws(AssignCtx &c, void *ws, const AssignWs &w) {
 // enqueue top-k + resolve for n (1 or 2) branches of identical B, A, M (defined in assign.cu).  The caller has
 // zero-filled [off_cnt, off_cnt + zero_bytes) of every branch's workspace.  After this c.tgi / c.alignv / c.pos_*
 // are final.
-int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk = nullptr);
+int assign_run_core(const AssignCtx2 &cc, int n, cudaStream_t s, cudaEvent_t after_topk = nullptr, bool pdl = false);
 // GT keypoints [B,M,24] from packed [B,M,17] rows (add_cls_mean_size tal.py:605-609 + get_3d_keypoints)
 int launch_kps_gt(const float *gts, const float *calibs, const float *mean_sizes, int B, int M, int nc, float *gt_kps,
                   cudaStream_t s);

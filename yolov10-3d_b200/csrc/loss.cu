@@ -26,6 +26,8 @@
 //        writes the loss items -- after summing them over the ranks through NVLink peer memory when the batch is
 //        sharded over several GPUs (y3d_v10_loss_fwd_sharded).  The claim word of a foreground anchor ends up as
 //        (GT index, alignment weight): what the backward pass reads.
+#include <cstdlib>
+
 #include "loss.cuh"
 #include "xrank.cuh"
 
@@ -756,6 +758,9 @@ __global__ void __launch_bounds__(kFinApThreads) loss_finish_ap_kernel(AssignCtx
     if (tid == 0) { s_ncf = 0; s_np = 0; }
     s_pos[tid] = 0;
     s_pos[tid + kFinApThreads] = 0;
+    // Without GTs there is no top-k grid in between (whose own wait orders this grid behind the streaming kernel): the
+    // streaming grid itself is then the programmatic primary, and its softplus partials and zeroed counters are read below.
+    if (M == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
     bool my_valid = false;
     for (int m = tid; m < M; m += kFinApThreads) {
         gts[m] = load_gt(c, b, m);
@@ -1203,6 +1208,15 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (use_ap) {  // claimed anchors spread over the machine, kFinApThreads per CTA
+        static int carve = -1;  // Y3D_CARVEOUT=1 (measurement): one shared-memory split for the three kernels of the step
+        if (carve < 0) {
+            const char *v = getenv("Y3D_CARVEOUT");
+            carve = v && *v == '1';
+            if (carve) {
+                cudaFuncSetAttribute(loss_finish_ap_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(head_stream_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            }
+        }
         cfg.gridDim = dim3((unsigned)((w.rcap + kFinApThreads - 1) / kFinApThreads), B, nb);
         cfg.blockDim = dim3(kFinApThreads);
         cfg.dynamicSmemBytes = sizeof(GtRec) * (size_t)M;

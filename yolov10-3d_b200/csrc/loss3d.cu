@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(128) dd_stream_kernel(const __grid_constant__ 
     __shared__ double red[4];
     const DDParams &P = PP.p[blockIdx.z];
     const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    // the next kernel of the call is launched programmatically dependent on this one: scheduled as this grid drains
+    asm volatile("griddepcontrol.launch_dependents;");
     if (blockIdx.x == 0 && b == 0 && blockIdx.z == 0 && threadIdx.x == 0 && work_counter) *work_counter = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.tickets[b] = 0u;
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(const __grid_constant__ Assi
     const AssignCtx &c = cc.c[blockIdx.z];
     const DDParams &P = PP.p[blockIdx.z];
     const int b = blockIdx.y;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent of the resolve (or the streaming) kernel
     double s[kNSum];
 #pragma unroll
     for (int i = 0; i < kNSum; ++i) s[i] = 0.0;
@@ -482,10 +485,22 @@ static int dd_loss_run(int nb, const DDBranchIn *br, const int *lvl_hw, const fl
                                           M > 0 ? gt_kps : nullptr);
     Y3D_CHECK_LAUNCH();
     if (M > 0) {
-        const int rc = assign_run_core(cc, nb, s);
+        const int rc = assign_run_core(cc, nb, s, nullptr, /*pdl=*/true);
         if (rc) return rc;
     }
-    dd_fg_kernel<<<dim3((grid.x + kFgRows - 1) / kFgRows, B, nb), 128, 0, s>>>(cc, PP, (int)grid.x);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((grid.x + kFgRows - 1) / kFgRows, B, nb);
+        cfg.blockDim = dim3(128);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, dd_fg_kernel, cc, PP, (int)grid.x);
+        if (le != cudaSuccess) return (int)le;
+    }
     Y3D_CHECK_LAUNCH();
     if (dbg_target_gt_idx) {  // assigned GT per anchor, -1 = background
         for (int z = 0; z < nb; ++z) {

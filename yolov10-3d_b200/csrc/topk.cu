@@ -17,7 +17,7 @@
 namespace y3d {
 
 constexpr int kTopkThreads = 1024;
-constexpr int kKeys2SmemCap = 40960;  // uint32 keys of stage 2 kept in shared memory (160 KB)
+constexpr int kKeys2SmemCap = 40960;  // uint32 keys kept in shared memory (160 KB; + 64 KB of lists / histograms at D = 1024)
 
 __device__ __forceinline__ uint32_t float_key(float x) {
     if (x != x) return 0xFFFFFFFFu;  // NaN sorts first, like torch.topk
@@ -74,24 +74,6 @@ __device__ __forceinline__ float src_score(const TopkSrc &s, int b, int a, int c
     int l = level_of(s.t, a);
     const float *p = s.t.ptr[l] + (long long)b * s.t.sB[l] + (a - s.t.start[l]);
     return dm::sigmoid_(p[(long long)(64 + c) * s.t.sC[l]]);  // the exactly specified sigmoid: scores decide indices here
-}
-
-// decode of one axis (0: x1/x2 or cx/w, 1: y1/y2 or cy/h) of one anchor's box from the head -- same arithmetic as
-// decode2d_kernel; the 32 bin gathers of the two sides are issued together
-__device__ __forceinline__ void src_box_axis(const TopkSrc &s, int b, int a, int axis, float &o0, float &o1) {
-    const int l = level_of(s.t, a);
-    const int cell = a - s.t.start[l];
-    const float *p = s.t.ptr[l] + (long long)b * s.t.sB[l] + cell;
-    const long long cs = s.t.sC[l];
-    float xl[16], xh[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        xl[j] = p[(long long)(axis * 16 + j) * cs];
-        xh[j] = p[(long long)((axis + 2) * 16 + j) * cs];
-    }
-    const int w = s.t.w[l];
-    const float anc = (float)(axis == 0 ? cell % w : cell / w) + 0.5f;
-    im::box_axis(anc, im::dfl16(xl), im::dfl16(xh), s.t.stride[l], s.xywh, o0, o1);
 }
 
 // ------------------------------------------------------------------------------------------ stage 0 kernels
@@ -155,32 +137,79 @@ __global__ void amax_anchor_kernel(const float *__restrict__ preds, long long sB
 // the largest logit is the first class of the largest score unless another class ties with it in score -- and then the
 // second key equals the first, the anchor counts as one that can contribute twice, and the selection kernel ranks its
 // classes from their scores without looking at this argmax.
+// grid (ceil(quads / 32), B), block 128 = 32 units of VEC anchors x 4 class parts (warp = part: classes [p*nc/4, ...)),
+// up to ten channel rows in flight per thread; the parts' top-2 meet in shared memory, part 0 merges them in class order
+// (strict comparisons keep the first maximum) and writes the keys.
 template <int VEC>
-__global__ void __launch_bounds__(128) cls_max_kernel(LevelTable t, int nq_total, int nc, int A,
-                                                      uint32_t *__restrict__ keys, int2 *__restrict__ aux) {
-    // quads are enumerated level by level
-    int q = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (q >= nq_total) return;
+__global__ void __launch_bounds__(128) cls_max_kernel(const __grid_constant__ LevelTable t, int nq_total, int nc, int A,
+                                                      uint32_t *__restrict__ keys, int2 *__restrict__ aux,
+                                                      unsigned *__restrict__ img_done) {
+    __shared__ uint32_t s_k1[3][32 * VEC], s_k2[3][32 * VEC];
+    if (blockIdx.x == 0 && threadIdx.x == 0) img_done[blockIdx.y] = 0u;  // counter of box_decode_kernel (sharded path)
+    __shared__ int s_arg[3][32 * VEC];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int q = blockIdx.x * 32 + lane, b = blockIdx.y;
+    const bool on = q < nq_total;
     int l = 0, qs = 0;
-    for (int i = 0; i + 1 < t.nl; ++i) {  // levels are enumerated in order; start[] is in anchors = VEC * quads
+    for (int i = 0; i + 1 < t.nl; ++i) {  // quads are enumerated level by level; start[] is in anchors = VEC * quads
         if (q >= t.start[i + 1] / VEC) { l = i + 1; qs = t.start[i + 1] / VEC; }
     }
-    int cell = (q - qs) * VEC;
-    const float *p = t.ptr[l] + (long long)b * t.sB[l] + cell + 64LL * t.sC[l];
+    const int cell = (q - qs) * VEC;
     const long long cs = t.sC[l];
+    const int cpp = (nc + 3) >> 2;
+    const int c_lo = part * cpp, c_hi = min(nc, c_lo + cpp);
     Top2 tt[VEC];
-    for (int c = 0; c < nc; ++c) {
-        if constexpr (VEC == 4) {
-            float4 v = ldg_stream4(p + c * cs);
-            top2_push(tt[0], float_key(v.x), c); top2_push(tt[1], float_key(v.y), c);
-            top2_push(tt[2], float_key(v.z), c); top2_push(tt[3], float_key(v.w), c);
-        } else {
-            top2_push(tt[0], float_key(ldg_stream1(p + c * cs)), c);
+    if (on) {
+        const float *p = t.ptr[l] + (long long)b * t.sB[l] + cell + (64LL + c_lo) * cs;
+        constexpr int CB = 10;
+        int c = c_lo;
+        for (; c + CB <= c_hi; c += CB, p += CB * cs) {
+            float v[CB][VEC];
+#pragma unroll
+            for (int jj = 0; jj < CB; ++jj) {
+                if constexpr (VEC == 4) {
+                    const float4 r = ldg_stream4(p + jj * cs);
+                    v[jj][0] = r.x; v[jj][1] = r.y; v[jj][2] = r.z; v[jj][3] = r.w;
+                } else {
+                    v[jj][0] = ldg_stream1(p + jj * cs);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < CB; ++jj)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) top2_push(tt[e], float_key(v[jj][e]), c + jj);
+        }
+        for (; c < c_hi; ++c, p += cs) {
+            if constexpr (VEC == 4) {
+                const float4 r = ldg_stream4(p);
+                top2_push(tt[0], float_key(r.x), c); top2_push(tt[1], float_key(r.y), c);
+                top2_push(tt[2], float_key(r.z), c); top2_push(tt[3], float_key(r.w), c);
+            } else {
+                top2_push(tt[0], float_key(ldg_stream1(p)), c);
+            }
         }
     }
+    if (part > 0) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            s_k1[part - 1][lane * VEC + e] = tt[e].k1;
+            s_k2[part - 1][lane * VEC + e] = tt[e].k2;
+            s_arg[part - 1][lane * VEC + e] = tt[e].arg;
+        }
+    }
+    __syncthreads();
+    if (part != 0 || !on) return;
     const long long o = (long long)b * A + t.start[l] + cell;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp) {  // later parts hold higher classes: they win only when strictly larger
+            const uint32_t ok1 = s_k1[pp][lane * VEC + e], ok2 = s_k2[pp][lane * VEC + e];
+            const bool theirs = ok1 > tt[e].k1;
+            const uint32_t loser = theirs ? tt[e].k1 : ok1;
+            tt[e].k2 = max(max(tt[e].k2, ok2), loser);
+            if (theirs) { tt[e].k1 = ok1; tt[e].arg = s_arg[pp][lane * VEC + e]; }
+        }
         tt[e].k1 = float_key(dm::sigmoid_(key_float(tt[e].k1)));
         if (tt[e].k2) tt[e].k2 = float_key(dm::sigmoid_(key_float(tt[e].k2)));
         top2_store(tt[e], keys, aux, o + e);
@@ -259,8 +288,11 @@ __device__ void block_sort_desc(unsigned long long *buf, int L) {
 // MSD radix select, 8 bits per pass, that stops as soon as the boundary bucket is small: everything above the bucket
 // plus the whole bucket (at most 2 * Dpad composites) is sorted directly, which also resolves ties in index order.
 // Only when even the full 32-bit key leaves too many equal keys does the ordered tie pass run.
+// whist (optional): 32 x 256 counters, one private histogram per warp -- plain shared-memory atomics without the
+// cross-warp contention on a few hot digits (score keys cluster in a handful of exponents) and without match_any.
 template <class KeyAt>
-__device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long long *out, SelShared &sh) {
+__device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long long *out, SelShared &sh,
+                           unsigned *whist = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const int cap = 2 * Dpad;
     if (tid == 0) { sh.prefix = 0; sh.need = D; sh.n_eq = (unsigned)n; }
@@ -273,17 +305,33 @@ __device__ void block_topk(KeyAt key_at, int n, int D, int Dpad, unsigned long l
         for (int i = tid; i < 256; i += nt) sh.hist[i] = 0;
         __syncthreads();
         const unsigned prefix = sh.prefix;
-        for (int i0 = 0; i0 < n; i0 += nt) {
-            int i = i0 + tid;
-            bool on = i < n;
-            unsigned k = on ? key_at(i) : 0u;
-            on = on && ((k & mask) == prefix);
-            unsigned digit = (k >> shift) & 255u;
-            // warp-aggregated shared atomics: one add per distinct digit per warp
-            unsigned act = __ballot_sync(0xffffffffu, on);
-            if (on) {
-                unsigned peers = __match_any_sync(act, digit);
-                if (lane == __ffs(peers) - 1) atomicAdd(&sh.hist[digit], (unsigned)__popc(peers));
+        if (whist) {
+            for (int i = tid; i < 32 * 256; i += nt) whist[i] = 0;
+            __syncthreads();
+            unsigned *mine = whist + wid * 256;
+            for (int i = tid; i < n; i += nt) {
+                const unsigned k = key_at(i);
+                if ((k & mask) == prefix) atomicAdd(&mine[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            for (int d = tid; d < 256; d += nt) {
+                unsigned sum = 0;
+                for (int w = 0; w < (nt >> 5); ++w) sum += whist[w * 256 + d];
+                sh.hist[d] = sum;
+            }
+        } else {
+            for (int i0 = 0; i0 < n; i0 += nt) {
+                int i = i0 + tid;
+                bool on = i < n;
+                unsigned k = on ? key_at(i) : 0u;
+                on = on && ((k & mask) == prefix);
+                unsigned digit = (k >> shift) & 255u;
+                // warp-aggregated shared atomics: one add per distinct digit per warp
+                unsigned act = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    unsigned peers = __match_any_sync(act, digit);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&sh.hist[digit], (unsigned)__popc(peers));
+                }
             }
         }
         __syncthreads();
@@ -373,21 +421,23 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
                                                                     int nc, int nreg, int D, int Dpad, int keys2_smem,
                                                                     uint32_t *__restrict__ keys2_ws, float *reg,
                                                                     float *scores, int64_t *labels,
-                                                                    int32_t *anchor_idx, int out_mode, GatherOut G) {
+                                                                    int32_t *anchor_idx, int out_mode, int32_t *win_anchor) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *win1 = (unsigned long long *)smem_raw;
     unsigned long long *win2 = win1 + 2 * Dpad;
-    uint32_t *k2s = (uint32_t *)(win2 + 2 * Dpad);
+    unsigned *whist = (unsigned *)(win2 + 2 * Dpad);         // 32 per-warp histograms of the radix passes
+    uint32_t *k2s = (uint32_t *)(whist + 32 * 256);
     __shared__ SelShared sh;
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const uint32_t *kb = keys + (long long)b * A;
+    asm volatile("griddepcontrol.launch_dependents;");  // (fused mode: box_decode_kernel is scheduled as this grid drains)
     SEL_STAMP(0);
     if (keys1_smem) {  // the radix passes re-read the keys: stage them in shared memory once (aliases the stage-2 buffer)
         for (int i = tid; i < A; i += nt) k2s[i] = kb[i];
         __syncthreads();
-        block_topk([&](int i) { return k2s[i]; }, A, D, Dpad, win1, sh);
+        block_topk([&](int i) { return k2s[i]; }, A, D, Dpad, win1, sh, whist);
     } else {
-        block_topk([&](int i) { return kb[i]; }, A, D, Dpad, win1, sh);
+        block_topk([&](int i) { return kb[i]; }, A, D, Dpad, win1, sh, whist);
     }
     SEL_STAMP(1);
     // stage 2: D x nc candidate scores, flattened index j = i*nc + c   (ops.py:858-861).
@@ -471,7 +521,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
             k2[j] = float_key(src_score(src, b, a, c));
         }
         __syncthreads();
-        block_topk([&](int j) { return k2[j]; }, n2, D, Dpad, win2, sh);
+        block_topk([&](int j) { return k2[j]; }, n2, D, Dpad, win2, sh, whist);
     }
     SEL_STAMP(3);
     for (int r = tid; r < D; r += nt) {
@@ -482,22 +532,13 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
         float sc = key_float((uint32_t)(w >> 32));
         long long o = (long long)b * D + r;
         if (anchor_idx) anchor_idx[o] = a;
+        if (win_anchor) win_anchor[o] = a;
         if (out_mode == 0) {
             scores[o] = sc;
             labels[o] = c;
         } else {  // fused export layout [B,D,6] = box, score, label (head.py:531)
             float *q = reg + o * 6;
             q[4] = sc; q[5] = (float)c;
-        }
-    }
-    if (out_mode != 0) {  // boxes of the winners: one thread per (detection, axis)
-        for (int e = tid; e < 2 * D; e += nt) {
-            const int r = e >> 1, axis = e & 1;
-            const unsigned long long w = win2[r];
-            const int j = (int)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull));
-            const int a = (int)(0xFFFFFFFFu - (unsigned)(win1[j / nc] & 0xFFFFFFFFull));
-            float *q = reg + ((long long)b * D + r) * 6;
-            src_box_axis(src, b, a, axis, q[axis], q[axis + 2]);
         }
     }
     if (out_mode == 0) {
@@ -511,19 +552,65 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
         }
     }
     SEL_STAMP(4);
-    if (out_mode != 0 && G.world > 1) {  // this image's [D,6] rows -> every peer's buffer, then the image's flag
-        __syncthreads();  // the rows above were written by this CTA's threads
-        const int slot = G.rank * G.n_local + b;
-        const float2 *src = reinterpret_cast<const float2 *>(reg + (long long)b * D * 6);
-        for (int p = 0; p < G.world; ++p) {
-            if (p == G.rank) continue;
-            float2 *dst = reinterpret_cast<float2 *>(G.data[p] + (long long)slot * D * 6);
-            for (int i = tid; i < D * 3; i += nt) dst[i] = src[i];
+}
+
+// Boxes of the winners of the fused decode + top-k, spread over the whole machine (the selection kernel is one CTA per
+// image: the 64 bin gathers per detection -- random 32-byte sectors of the head tensor -- would all queue behind that one
+// SM's load pipe; 25 us at 32 images x 1280^2, against ~5 us here).  grid (ceil(4 D / 256), B), thread = (detection,
+// side): 16 gathers in flight, softmax expectation, the four lanes of a detection meet through shuffles; arithmetic of
+// decode2d_kernel.  Launched programmatically dependent on the selection kernel, which left (score, label) in the
+// row and the anchor in win_anchor.  Image-sharded detection path (G.world > 1): each finished row also goes straight
+// into every peer's buffer (NVLink stores); the CTA that completes an image (counter) raises the image's flag there.
+__global__ void __launch_bounds__(256) box_decode_kernel(const __grid_constant__ TopkSrc src, const int32_t *__restrict__ win_anchor,
+                                                         int D, float *reg, unsigned *img_done, const __grid_constant__ GatherOut G) {
+    __shared__ int s_last;
+    const int b = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = e >> 2, side = e & 3;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    float d = 0.f;
+    int a = 0, l = 0;
+    if (r < D) {
+        a = __ldcg(win_anchor + (long long)b * D + r);
+        l = level_of(src.t, a);
+        const float *p = src.t.ptr[l] + (long long)b * src.t.sB[l] + (a - src.t.start[l]) + (long long)(side * 16) * src.t.sC[l];
+        const long long cs = src.t.sC[l];
+        float x[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) x[jj] = p[jj * cs];
+        d = im::dfl16(x);
+    }
+    const int base = (threadIdx.x & 31) & ~3;
+    const float d0 = __shfl_sync(0xffffffffu, d, base), d1 = __shfl_sync(0xffffffffu, d, base + 1),
+                d2 = __shfl_sync(0xffffffffu, d, base + 2), d3 = __shfl_sync(0xffffffffu, d, base + 3);
+    if (r < D && side == 0) {
+        const int cell = a - src.t.start[l], wd = src.t.w[l];
+        float *q = reg + ((long long)b * D + r) * 6;
+        float bx[4];
+        im::box_axis((float)(cell % wd) + 0.5f, d0, d2, src.t.stride[l], src.xywh, bx[0], bx[2]);
+        im::box_axis((float)(cell / wd) + 0.5f, d1, d3, src.t.stride[l], src.xywh, bx[1], bx[3]);
+        const float2 r0 = make_float2(bx[0], bx[1]), r1 = make_float2(bx[2], bx[3]);
+        reinterpret_cast<float2 *>(q)[0] = r0;
+        reinterpret_cast<float2 *>(q)[1] = r1;
+        if (G.world > 1) {
+            const float2 r2 = __ldcg(reinterpret_cast<const float2 *>(q) + 2);  // score, label: the selection kernel's
+            const long long row = ((long long)(G.rank * G.n_local + b) * D + r) * 3;
+            for (int pr = 0; pr < G.world; ++pr) {
+                if (pr == G.rank) continue;
+                float2 *dst = reinterpret_cast<float2 *>(G.data[pr]) + row;
+                dst[0] = r0; dst[1] = r1; dst[2] = r2;
+            }
         }
+    }
+    if (G.world > 1) {  // rows out -> fence -> count; the CTA that completes the image raises its flag on every rank
         __threadfence_system();
         __syncthreads();
-        if (tid < G.world)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(G.flags[tid] + slot), "r"(G.seq) : "memory");
+        if (threadIdx.x == 0) s_last = atomicAdd(img_done + b, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence_system();
+            if (threadIdx.x < G.world)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(G.flags[threadIdx.x] + G.rank * G.n_local + b), "r"(G.seq) : "memory");
+        }
     }
 }
 
@@ -599,12 +686,14 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t topk_workspace_bytes(int B, int A, int nc, int D) {
     size_t keys = align256(sizeof(uint32_t) * (size_t)B * A) + align256(sizeof(int2) * (size_t)B * A);
     size_t k2 = (D * nc > kKeys2SmemCap) ? align256(sizeof(uint32_t) * (size_t)B * D * nc) : 0;
-    return keys + k2;
+    // fused decode + top-k: anchors of the winners [B, D] and the per-image counters of box_decode_kernel [B]
+    return keys + k2 + align256(sizeof(int32_t) * (size_t)B * D) + align256(sizeof(unsigned) * (size_t)B);
 }
 
 static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *aux, int B, int A, int nc, int nreg, int D, float *reg,
                          float *scores, int64_t *labels, int32_t *anchor_idx, int out_mode, uint32_t *keys2_ws,
-                         cudaStream_t s, const GatherOut *gather = nullptr) {
+                         cudaStream_t s, const GatherOut *gather = nullptr, int32_t *win_anchor = nullptr,
+                         unsigned *img_done = nullptr) {
     int Dpad = next_pow2(D);
     int n2 = D * nc;
     int k2smem = n2 <= kKeys2SmemCap;
@@ -612,18 +701,32 @@ static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *a
     size_t nkeys = 0;
     if (k2smem) nkeys = (size_t)n2;
     if (k1smem && (size_t)A > nkeys) nkeys = (size_t)A;
-    size_t smem = sizeof(unsigned long long) * 4 * (size_t)Dpad + sizeof(uint32_t) * nkeys;
+    size_t smem = sizeof(unsigned long long) * 4 * (size_t)Dpad + sizeof(unsigned) * 32 * 256 + sizeof(uint32_t) * nkeys;
     static size_t smem_limit = 48 * 1024;  // raised once per process to the largest size asked for
     if (smem > smem_limit) {
         cudaError_t e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         smem_limit = smem;
     }
-    GatherOut G{};
-    if (gather) G = *gather;
     topk_select_kernel<<<B, kTopkThreads, smem, s>>>(src, keys, aux, A, k1smem, nc, nreg, D, Dpad, k2smem, keys2_ws, reg, scores,
-                                                    labels, anchor_idx, out_mode, G);
+                                                    labels, anchor_idx, out_mode, win_anchor);
     Y3D_CHECK_LAUNCH();
+    if (out_mode != 0) {  // boxes of the winners (+ the peer copies of the image-sharded path), over all SMs
+        GatherOut G{};
+        if (gather) G = *gather;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((4 * D + 255) / 256), (unsigned)B);
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, box_decode_kernel, src, (const int32_t *)win_anchor, D, reg, img_done, G);
+        if (le != cudaSuccess) return (int)le;
+        Y3D_CHECK_LAUNCH();
+    }
     return Y3D_OK;
 }
 
@@ -681,22 +784,24 @@ static int decode_topk2d_run(const float *const *lvl_ptr, const int64_t *lvl_sB,
     uint32_t *keys = (uint32_t *)ws;
     int2 *aux = (int2 *)((char *)ws + align256(sizeof(uint32_t) * (size_t)B * A));
     uint32_t *k2 = (uint32_t *)((char *)aux + align256(sizeof(int2) * (size_t)B * A));
+    int32_t *win_anchor = (int32_t *)((char *)k2 + ((D * nc > kKeys2SmemCap) ? align256(sizeof(uint32_t) * (size_t)B * D * nc) : 0));
+    unsigned *img_done = (unsigned *)((char *)win_anchor + align256(sizeof(int32_t) * (size_t)B * D));
     bool v4 = true;
     for (int l = 0; l < nl; ++l)
         v4 = v4 && (src.t.h[l] * src.t.w[l]) % 4 == 0 && ((uintptr_t)lvl_ptr[l]) % 16 == 0 && lvl_sB[l] % 4 == 0 &&
              lvl_sC[l] % 4 == 0;
     if (v4) {
         int nq = A / 4;
-        dim3 grid((nq + 127) / 128, B);
-        cls_max_kernel<4><<<grid, 128, 0, s>>>(src.t, nq, nc, A, keys, aux);
+        dim3 grid((nq + 31) / 32, B);
+        cls_max_kernel<4><<<grid, 128, 0, s>>>(src.t, nq, nc, A, keys, aux, img_done);
     } else {
-        dim3 grid((A + 127) / 128, B);
-        cls_max_kernel<1><<<grid, 128, 0, s>>>(src.t, A, nc, A, keys, aux);
+        dim3 grid((A + 31) / 32, B);
+        cls_max_kernel<1><<<grid, 128, 0, s>>>(src.t, A, nc, A, keys, aux, img_done);
     }
     Y3D_CHECK_LAUNCH();
     src.mode = 1;
     src.xywh = xywh;
-    return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s, gather);
+    return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s, gather, win_anchor, img_done);
 }
 
 extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,

@@ -256,6 +256,22 @@ def measure_other_configs(y3d, torch, dev, peak):
                                                                     (8, 1), (1, 1, 1, 1, 1, 1)), 30, 5, flush)
     put("cfg3", "DetectLoss3d fwd (3D decode + dual 3D task-aligned assignment + loss), batch 32, 384x1280, nc=3, <=50 GT/img",
         ms, (2 * 4.0 * (nc3 + 35) * A + 68 * M3) * B3, B3, "flushed before every timed call (98 MB input)")
+    # f4: rotated-box overlap of the KITTI evaluator (the reference's one GPU kernel, numba-CUDA: kitti_eval.py:263-344).
+    # ALU-bound, not HBM-bound: ~1.5 k fp32 operations per (box, query) pair against 4 output bytes; reported as pairs/s
+    # and as a fraction of the fp32 FMA peak (SMs x 128 lanes x 2 x max SM clock).  The numba kernel itself cannot be timed
+    # beside it on the GPU box: it is reference source (which does not travel), and numba JIT-compiles it at import.
+    rng = np.random.default_rng(0)
+    Nb = 4096
+    bx = np.concatenate([rng.uniform(0, 70, (Nb, 2)), rng.uniform(1.5, 5, (Nb, 2)), rng.uniform(-3.14, 3.14, (Nb, 1))], 1)
+    bt = torch.from_numpy(bx.astype(np.float32)).to(dev)
+    qt = torch.from_numpy(np.roll(bx, 7, 0).astype(np.float32) + np.float32(0.3)).to(dev)
+    ms = _timed_calls(torch, lambda: y3d.kitti.rotate_iou_gpu_eval(bt, qt, -1), 20, 3)
+    props = torch.cuda.get_device_properties(dev)
+    fp32_peak = props.multi_processor_count * 128 * 2 * 1.965e9
+    out["f4_rotate_iou"] = {"workload": "rotate_iou_gpu_eval, 4096 x 4096 boxes (16.8 M pairs), criterion -1", "ms_per_step": ms,
+                            "pairs_per_s": Nb * Nb / (ms * 1e-3), "bound": "fp32 ALU",
+                            "flop_per_pair_estimate": 1500, "frac_of_fp32_peak": 1500.0 * Nb * Nb / (ms * 1e-3) / fp32_peak,
+                            "output_bytes": 4 * Nb * Nb}
     return out
 
 
@@ -562,7 +578,7 @@ def main_cuda_cfg4(args):
         okv = torch.tensor([1.0 if torch.equal(ref, dets) else 0.0], device=dev)
         dist.all_reduce(okv, op=dist.ReduceOp.MIN)
         check = {"ok": bool(okv[0] > 0.5), "what": "gathered [B, 300, 6] == NCCL all_gather of the ranks' own detections, every rank",
-                 "route": "selection-kernel epilogue over NVLink peer memory" if peer else "nccl all_gather_into_tensor"}
+                 "route": "box-decode kernel epilogue over NVLink peer memory" if peer else "nccl all_gather_into_tensor"}
     times = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -579,16 +595,18 @@ def main_cuda_cfg4(args):
                                    f"{Bl} images/GPU, gather of [B, 300, 6]",
                        "global_batch": Bl * world, "sharding": f"by image, {Bl}/GPU",
                        "l2": "inputs (620 MB head tensors per step) exceed the 126 MB L2; no flush needed"},
-            "collective": ("none" if world == 1 else ("detections stored into every peer's buffer by the selection kernel's "
-                                                      "epilogue (NVLink peer memory), one flag word per image" if peer else
+            "collective": ("none" if world == 1 else ("detection rows stored into every peer's buffer by the box-decode kernel's "
+                                                      "epilogue (NVLink peer memory, flag-in-data 64-bit words: no fence, no flag), unpacked by a "
+                                                      "small collect kernel" if peer else
                                                       "NCCL all_gather_into_tensor of [B/N, 300, 6]")),
-            "roofline": {"bound": "hbm", "kernel": "whole step (class-max stream + selection)", "achieved": alg / (ms_total / K * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "whole step (class-max stream + selection + box decode)", "achieved": alg / (ms_total / K * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg / (ms_total / K * 1e-3) / 1e9 / peak,
                          "step_frac": alg / (ms_total / K * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg},
             "e2e": {"value": Bl * world * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sum(h.numel() * 4 for h in host),
                     "d2h_bytes_per_step": int(dets.numel() * 4), "steps": Ke},
-            "gpu_launches": 2 * K,
+            # class maxima, selection, box decode (+ the collect kernel of the sharded path)
+            "gpu_launches": (3 + (1 if world > 1 and peer else 0)) * K,
             "clocks": dict(sampler.summary(), window="timed region + e2e region (nvidia-smi every 100 ms)"),
         }
         if check is not None:

@@ -86,14 +86,16 @@ int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const 
                       int32_t *anchor_idx, void *ws, size_t ws_bytes, void *stream);
 
 /* Image-sharded v10Detect export branch (BASELINE.json configs[3]): y3d_decode_topk2d on this
- * rank's B images, with the gather of the detections fused into the selection kernel -- the CTA that has selected an
- * image stores its [D,6] rows straight into every peer's gather buffer over NVLink (peer memory) and raises the
- * image's flag there; a one-CTA kernel then waits until the flags of all world * B images of this call have arrived.
+ * rank's B images, with the gather of the detections fused into its last kernels -- the box-decode kernel stores every
+ * finished [D,6] row straight into every peer's gather buffer over NVLink (peer memory), value and call number in one
+ * 64-bit word, so neither a fence nor a flag follows the data; a small kernel (one CTA per remote image) unpacks the
+ * peers' words of this call into the result as they arrive.
  *  peer_bufs: HOST array of `world` device pointers, buffer r being rank r's (peer-mapped, e.g. symmetric memory), each
- *  y3d_gather_buffer_bytes(world, B, D) bytes, zero-filled before the first call: [2][world*B][D][6] floats followed by
- *  [2][world*B] flag words.  After the call (stream order) rank `rank`'s buffer holds, at parity seq & 1, the
- *  detections of all ranks in rank order -- equal to all_gather of the ranks' y3d_decode_topk2d outputs.  seq: 1, 2, ...
- *  the same on every rank, +1 per call (must NOT be replayed from a CUDA graph); every rank must make every call; a
+ *  y3d_gather_buffer_bytes(world, B, D) bytes, zero-filled before the first call: [2][world*B][D][6] floats (the result)
+ *  followed by [2][world*B][6 D] 64-bit staging words.  After the call (stream order) rank `rank`'s buffer holds, at parity
+ *  seq & 1, the detections of all ranks in rank order -- equal to all_gather of the ranks' y3d_decode_topk2d outputs;
+ *  valid for consumers enqueued before this rank's next call.  seq: 1, 2, ... the same on every rank, +1 per call
+ *  (must NOT be replayed from a CUDA graph; the low 32 bits must not be 0); every rank must make every call; a
  *  rank waits up to Y3D_XRANK_TIMEOUT_S seconds (default 600) and then sets *status (optional DEVICE int) to 1.
  *  Reference consumer: ultralytics/models/yolov10/val.py:10-24 (per-rank postprocess; DDP validation gathers). */
 size_t y3d_gather_buffer_bytes(int world, int n_local, int D);

@@ -960,7 +960,7 @@ def test_peer_memory_loss_reduction_multi_gpu():
 
 @pytest.mark.gpu
 def test_sharded_detection_gather_multi_gpu():
-    """BASELINE.json configs[3] path: decode + top-k sharded by image, detections gathered by the selection kernel's
+    """BASELINE.json configs[3] path: decode + top-k sharded by image, detections gathered by the box-decode kernel's
     epilogue over NVLink peer memory (y3d_decode_topk2d_sharded) == the single-process result on the whole batch == the
     NCCL all_gather route, bit for bit on every rank.  Needs at least two GPUs; skipped otherwise."""
     import subprocess

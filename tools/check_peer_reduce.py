@@ -64,6 +64,32 @@ for it in range(20):
         print("ranks disagree", rank, it_f, chk)
         break
 assert int(red.status.item()) == 0
+# training through the sharded call: gradients of the global-batch loss w.r.t. this rank's head tensors == the rows of
+# this rank in the gradients one process computes on the whole batch (every rank builds the whole batch for the check)
+gts_all = [synth.gt2d(Bl, M, nc, hw, seed=100 + r) for r in range(world)]
+gts_all[world - 1][1:] = 0
+xm_all = np.concatenate([synth.train_like_head2d(Bl, nc, lv, gts_all[r], seed=200 + r, frac=0.05) for r in range(world)])
+xo_all = np.concatenate([synth.train_like_head2d(Bl, nc, lv, gts_all[r], seed=300 + r, frac=0.05) for r in range(world)])
+gt_all = torch.from_numpy(np.concatenate(gts_all)).to(dev)
+fm_all = [torch.from_numpy(f).to(dev).requires_grad_() for f in synth.split_levels(xm_all, lv)]
+fo_all = [torch.from_numpy(f).to(dev).requires_grad_() for f in synth.split_levels(xo_all, lv)]
+loss_1 = y3d.loss._FusedLossFn.apply((list(map(float, synth.STRIDES)), nc, gt_all, (10, 1), gains), *fm_all, *fo_all)
+(loss_1.sum() * (Bl * world)).backward()
+fm_g = [f.clone().requires_grad_() for f in fm]
+fo_g = [f.clone().requires_grad_() for f in fo]
+tot_s, it_s = y3d.dist.v10_loss_sharded(fm_g, fo_g, list(synth.STRIDES), nc, gtd, gains, Bl * world, reducer=red)
+tot_s.backward()
+lo = rank * Bl
+for name, loc, full in (("one2many", fm_g, fm_all), ("one2one", fo_g, fo_all)):
+    for a, b_ in zip(loc, full):
+        want = b_.grad[lo:lo + Bl]
+        if not torch.allclose(a.grad, want, rtol=1e-5, atol=1e-7):
+            ok = False
+            print("sharded gradient != single-process gradient", rank, name, (a.grad - want).abs().max().item())
+if not torch.allclose(it_s, loss_1.detach(), rtol=1e-6, atol=0):
+    ok = False
+    print("sharded items (autograd route) != single-process items", rank, it_s, loss_1)
+assert int(red.status.item()) == 0
 # the deferred variant (post in the loss' last kernel, collect on a side stream, one call of slack): same items, and the
 # two-parity flow control holds over a train of back-to-back calls with a rank that is made slow every few steps
 handles = []

@@ -2,7 +2,8 @@
 //   y3d_rotate_iou_eval   rotate_iou_gpu_eval / rotate_iou_kernel_eval
 //                         reference ultralytics/data/datasets/kitti_eval.py:60-345 (the reference's only GPU code: a
 //                         numba-CUDA kernel JIT-compiled at import, with a host round trip per call)
-// One thread per (box, query) pair, boxes of a 64 x 64 tile staged in shared memory.  The overlap polygon of two
+// A CTA of 256 threads owns a 64 x 64 tile of the overlap matrix (four threads per box row, 16 queries each), the tile's
+// boxes staged in shared memory.  The overlap polygon of two
 // rotated rectangles = corners of one inside the other + edge intersections, ordered around the centroid, measured
 // as a triangle fan -- the reference's sequence of float32 operations, so degenerate pairs (identical boxes give
 // 1/3, not 1) come out exactly as they do there.

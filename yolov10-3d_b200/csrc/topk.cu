@@ -32,32 +32,43 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 
 constexpr int kGatherMaxWorld = 16;
 // Image-sharded detection path: every rank keeps the detections of ALL ranks in a buffer its peers
-// can address (symmetric memory): [2 parities][world * n_local][D][6] floats, then [2][world * n_local] flag words.  The
-// selection kernel's CTA writes its image's rows into its own buffer and then straight into every peer's (NVLink stores),
-// fences, and raises the image's flag (the call's sequence number) on every rank; gather_wait_kernel returns when all
-// flags of the call have arrived.  Parity = seq & 1: a peer can be at most one call ahead of a rank that is still reading.
+// can address (symmetric memory): [2 parities][world * n_local][D][6] floats (the result), then a staging area
+// [2][world * n_local][6 D] 64-bit words the peers write into.  Flag-in-data, as in xrank.cuh: a finished row travels as
+// six aligned 64-bit stores (float bits << 32 | sequence number of the call) -- single-copy atomic, so a word is either
+// old or complete and neither a system-scope fence nor a flag store follows the data (both were measured: the fences
+// cost 15 us per step, the release stores of the flags 11 us).  gather_collect_kernel, one CTA per remote image, polls
+// the staged words of the call and unpacks them into the result.  Parity = seq & 1: a peer can be at most one call ahead
+// of a rank that is still reading.
 struct GatherOut {
-    float *data[kGatherMaxWorld];      // per rank: its buffer's data of this call's parity
-    unsigned *flags[kGatherMaxWorld];  // per rank: its buffer's flags of this call's parity
+    float *data[kGatherMaxWorld];                // per rank: its buffer's result rows of this call's parity
+    unsigned long long *stage[kGatherMaxWorld];  // per rank: its buffer's staging words of this call's parity
     int rank, world, n_local;
     unsigned seq;
 };
 
-__global__ void __launch_bounds__(256) gather_wait_kernel(const unsigned *flags, int n, unsigned seq, long long timeout_cycles,
-                                                          int *status) {
-    __shared__ int failed;
-    if (threadIdx.x == 0) failed = 0;
-    __syncthreads();
+// grid ((world - 1) * n_local), block 256: CTA = one image of one peer.  Launched as a programmatic dependent of
+// box_decode_kernel (it reads nothing of this rank's own kernels: it can poll while they still run); it waits for that
+// grid at its very end, so that "this kernel has completed" keeps meaning "all rows, own and remote, are in place".
+__global__ void __launch_bounds__(256) gather_collect_kernel(const __grid_constant__ GatherOut G, int D,
+                                                             long long timeout_cycles, int *status) {
+    const int pi = blockIdx.x / G.n_local, b = blockIdx.x - pi * G.n_local;
+    const int pr = pi + (pi >= G.rank ? 1 : 0);  // the peers in rank order, this rank left out
+    const long long slot = (long long)pr * G.n_local + b;
+    const unsigned long long *src = G.stage[G.rank] + slot * 6 * D;
+    float *dst = G.data[G.rank] + slot * 6 * D;
     const long long t0 = clock64();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
-            if (v != seq && clock64() - t0 > timeout_cycles) { failed = 1; break; }
-        } while (v != seq);
+    bool dead = false;
+    for (int i = threadIdx.x; i < 6 * D && !dead; i += blockDim.x) {
+        unsigned long long w;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src + i) : "memory");
+            if ((unsigned)(w & 0xffffffffull) == G.seq) break;
+            if (clock64() - t0 > timeout_cycles) { dead = true; break; }
+        }
+        if (!dead) dst[i] = __uint_as_float((unsigned)(w >> 32));
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && status && failed) *status = 1;
+    if (dead && status) *status = 1;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 struct TopkSrc {
@@ -137,16 +148,30 @@ __global__ void amax_anchor_kernel(const float *__restrict__ preds, long long sB
 // the largest logit is the first class of the largest score unless another class ties with it in score -- and then the
 // second key equals the first, the anchor counts as one that can contribute twice, and the selection kernel ranks its
 // classes from their scores without looking at this argmax.
+// The two largest LOGITS of an anchor in the float domain (first maximum, like the keys: -0 == +0; NaN never wins here --
+// the caller notes it and falls back to the key path, where NaN sorts first like torch.topk).
+struct Top2f {
+    float k1 = -INFINITY, k2 = -INFINITY;
+    int arg = 0;
+};
+__device__ __forceinline__ void top2f_push(Top2f &t, float v, int c) {
+    const bool first = v > t.k1;
+    const float lo = first ? t.k1 : v;  // the smaller of (old maximum, v) when v takes over, v itself otherwise
+    t.k2 = fmaxf(t.k2, lo);
+    t.k1 = first ? v : t.k1;
+    t.arg = first ? c : t.arg;
+}
+
 // grid (ceil(quads / 32), B), block 128 = 32 units of VEC anchors x 4 class parts (warp = part: classes [p*nc/4, ...)),
 // up to ten channel rows in flight per thread; the parts' top-2 meet in shared memory, part 0 merges them in class order
 // (strict comparisons keep the first maximum) and writes the keys.
 template <int VEC>
 __global__ void __launch_bounds__(128) cls_max_kernel(const __grid_constant__ LevelTable t, int nq_total, int nc, int A,
-                                                      uint32_t *__restrict__ keys, int2 *__restrict__ aux,
-                                                      unsigned *__restrict__ img_done) {
-    __shared__ uint32_t s_k1[3][32 * VEC], s_k2[3][32 * VEC];
-    if (blockIdx.x == 0 && threadIdx.x == 0) img_done[blockIdx.y] = 0u;  // counter of box_decode_kernel (sharded path)
+                                                      uint32_t *__restrict__ keys, int2 *__restrict__ aux) {
+    __shared__ float s_k1[3][32 * VEC], s_k2[3][32 * VEC];
     __shared__ int s_arg[3][32 * VEC];
+    __shared__ int s_nan;
+    if (threadIdx.x == 0) s_nan = 0;
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
     const int q = blockIdx.x * 32 + lane, b = blockIdx.y;
     const bool on = q < nq_total;
@@ -158,7 +183,9 @@ __global__ void __launch_bounds__(128) cls_max_kernel(const __grid_constant__ Le
     const long long cs = t.sC[l];
     const int cpp = (nc + 3) >> 2;
     const int c_lo = part * cpp, c_hi = min(nc, c_lo + cpp);
-    Top2 tt[VEC];
+    Top2f tt[VEC];
+    bool nan_seen = false;
+    __syncthreads();
     if (on) {
         const float *p = t.ptr[l] + (long long)b * t.sB[l] + cell + (64LL + c_lo) * cs;
         constexpr int CB = 10;
@@ -177,18 +204,27 @@ __global__ void __launch_bounds__(128) cls_max_kernel(const __grid_constant__ Le
 #pragma unroll
             for (int jj = 0; jj < CB; ++jj)
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) top2_push(tt[e], float_key(v[jj][e]), c + jj);
+                for (int e = 0; e < VEC; ++e) {
+                    top2f_push(tt[e], v[jj][e], c + jj);
+                    nan_seen |= v[jj][e] != v[jj][e];
+                }
         }
         for (; c < c_hi; ++c, p += cs) {
+            float v[VEC];
             if constexpr (VEC == 4) {
                 const float4 r = ldg_stream4(p);
-                top2_push(tt[0], float_key(r.x), c); top2_push(tt[1], float_key(r.y), c);
-                top2_push(tt[2], float_key(r.z), c); top2_push(tt[3], float_key(r.w), c);
+                v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
             } else {
-                top2_push(tt[0], float_key(ldg_stream1(p)), c);
+                v[0] = ldg_stream1(p);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                top2f_push(tt[e], v[e], c);
+                nan_seen |= v[e] != v[e];
             }
         }
     }
+    if (nan_seen) s_nan = 1;
     if (part > 0) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
@@ -200,19 +236,33 @@ __global__ void __launch_bounds__(128) cls_max_kernel(const __grid_constant__ Le
     __syncthreads();
     if (part != 0 || !on) return;
     const long long o = (long long)b * A + t.start[l] + cell;
+    if (s_nan) {  // some logit of this CTA's anchors is NaN: the order-preserving keys decide (NaN first, like torch.topk)
+        const float *p0 = t.ptr[l] + (long long)b * t.sB[l] + cell + 64LL * cs;
+#pragma unroll 1
+        for (int e = 0; e < VEC; ++e) {
+            Top2 tk;
+            for (int c = 0; c < nc; ++c) top2_push(tk, float_key(p0[(long long)c * cs + e]), c);
+            tk.k1 = float_key(dm::sigmoid_(key_float(tk.k1)));
+            if (tk.k2) tk.k2 = float_key(dm::sigmoid_(key_float(tk.k2)));
+            top2_store(tk, keys, aux, o + e);
+        }
+        return;
+    }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
 #pragma unroll
         for (int pp = 0; pp < 3; ++pp) {  // later parts hold higher classes: they win only when strictly larger
-            const uint32_t ok1 = s_k1[pp][lane * VEC + e], ok2 = s_k2[pp][lane * VEC + e];
+            const float ok1 = s_k1[pp][lane * VEC + e], ok2 = s_k2[pp][lane * VEC + e];
             const bool theirs = ok1 > tt[e].k1;
-            const uint32_t loser = theirs ? tt[e].k1 : ok1;
-            tt[e].k2 = max(max(tt[e].k2, ok2), loser);
+            const float loser = theirs ? tt[e].k1 : ok1;
+            tt[e].k2 = fmaxf(fmaxf(tt[e].k2, ok2), loser);
             if (theirs) { tt[e].k1 = ok1; tt[e].arg = s_arg[pp][lane * VEC + e]; }
         }
-        tt[e].k1 = float_key(dm::sigmoid_(key_float(tt[e].k1)));
-        if (tt[e].k2) tt[e].k2 = float_key(dm::sigmoid_(key_float(tt[e].k2)));
-        top2_store(tt[e], keys, aux, o + e);
+        Top2 tk;  // only the two survivors go through the (exactly specified, weakly monotone) sigmoid
+        tk.k1 = float_key(dm::sigmoid_(tt[e].k1));
+        tk.k2 = nc > 1 ? float_key(dm::sigmoid_(tt[e].k2)) : 0u;
+        tk.arg = tt[e].arg;
+        top2_store(tk, keys, aux, o + e);
     }
 }
 
@@ -559,11 +609,11 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
 // SM's load pipe; 25 us at 32 images x 1280^2, against ~5 us here).  grid (ceil(4 D / 256), B), thread = (detection,
 // side): 16 gathers in flight, softmax expectation, the four lanes of a detection meet through shuffles; arithmetic of
 // decode2d_kernel.  Launched programmatically dependent on the selection kernel, which left (score, label) in the
-// row and the anchor in win_anchor.  Image-sharded detection path (G.world > 1): each finished row also goes straight
-// into every peer's buffer (NVLink stores); the CTA that completes an image (counter) raises the image's flag there.
+// row and the anchor in win_anchor.  Image-sharded detection path (G.world > 1): the CTA's 64 finished rows also go straight
+// into every peer's staging area (coalesced NVLink stores, sequence number inside every word: see GatherOut).
 __global__ void __launch_bounds__(256) box_decode_kernel(const __grid_constant__ TopkSrc src, const int32_t *__restrict__ win_anchor,
-                                                         int D, float *reg, unsigned *img_done, const __grid_constant__ GatherOut G) {
-    __shared__ int s_last;
+                                                         int D, float *reg, const __grid_constant__ GatherOut G) {
+    __shared__ float2 s_rows[3 * 64];
     const int b = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = e >> 2, side = e & 3;
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -591,25 +641,25 @@ __global__ void __launch_bounds__(256) box_decode_kernel(const __grid_constant__
         const float2 r0 = make_float2(bx[0], bx[1]), r1 = make_float2(bx[2], bx[3]);
         reinterpret_cast<float2 *>(q)[0] = r0;
         reinterpret_cast<float2 *>(q)[1] = r1;
-        if (G.world > 1) {
-            const float2 r2 = __ldcg(reinterpret_cast<const float2 *>(q) + 2);  // score, label: the selection kernel's
-            const long long row = ((long long)(G.rank * G.n_local + b) * D + r) * 3;
-            for (int pr = 0; pr < G.world; ++pr) {
-                if (pr == G.rank) continue;
-                float2 *dst = reinterpret_cast<float2 *>(G.data[pr]) + row;
-                dst[0] = r0; dst[1] = r1; dst[2] = r2;
-            }
+        if (G.world > 1) {  // the CTA's 64 rows are contiguous in the output: staged, then stored to the peers coalesced
+            const int lr = threadIdx.x >> 2;
+            s_rows[3 * lr] = r0;
+            s_rows[3 * lr + 1] = r1;
+            s_rows[3 * lr + 2] = __ldcg(reinterpret_cast<const float2 *>(q) + 2);  // score, label: the selection kernel's
         }
     }
-    if (G.world > 1) {  // rows out -> fence -> count; the CTA that completes the image raises its flag on every rank
-        __threadfence_system();
+    if (G.world > 1) {  // the staged rows -> every peer's staging area, value and sequence number in one 64-bit word
         __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(img_done + b, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (s_last) {
-            __threadfence_system();
-            if (threadIdx.x < G.world)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(G.flags[threadIdx.x] + G.rank * G.n_local + b), "r"(G.seq) : "memory");
+        const int r_first = (blockIdx.x * blockDim.x) >> 2;
+        const int nw = 6 * max(0, min(D - r_first, (int)blockDim.x >> 2));  // floats of this CTA's rows
+        const long long w0 = ((long long)(G.rank * G.n_local + b) * D + r_first) * 6;
+        const float *sf = reinterpret_cast<const float *>(s_rows);
+        for (int pr = 0; pr < G.world; ++pr) {
+            if (pr == G.rank) continue;
+            unsigned long long *dst = G.stage[pr] + w0;
+            for (int i = threadIdx.x; i < nw; i += blockDim.x)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + i),
+                             "l"(((unsigned long long)__float_as_uint(sf[i]) << 32) | (unsigned long long)G.seq) : "memory");
         }
     }
 }
@@ -686,14 +736,13 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t topk_workspace_bytes(int B, int A, int nc, int D) {
     size_t keys = align256(sizeof(uint32_t) * (size_t)B * A) + align256(sizeof(int2) * (size_t)B * A);
     size_t k2 = (D * nc > kKeys2SmemCap) ? align256(sizeof(uint32_t) * (size_t)B * D * nc) : 0;
-    // fused decode + top-k: anchors of the winners [B, D] and the per-image counters of box_decode_kernel [B]
-    return keys + k2 + align256(sizeof(int32_t) * (size_t)B * D) + align256(sizeof(unsigned) * (size_t)B);
+    // fused decode + top-k: anchors of the winners [B, D] (read by box_decode_kernel)
+    return keys + k2 + align256(sizeof(int32_t) * (size_t)B * D);
 }
 
 static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *aux, int B, int A, int nc, int nreg, int D, float *reg,
                          float *scores, int64_t *labels, int32_t *anchor_idx, int out_mode, uint32_t *keys2_ws,
-                         cudaStream_t s, const GatherOut *gather = nullptr, int32_t *win_anchor = nullptr,
-                         unsigned *img_done = nullptr) {
+                         cudaStream_t s, const GatherOut *gather = nullptr, int32_t *win_anchor = nullptr) {
     int Dpad = next_pow2(D);
     int n2 = D * nc;
     int k2smem = n2 <= kKeys2SmemCap;
@@ -723,7 +772,7 @@ static int launch_select(const TopkSrc &src, const uint32_t *keys, const int2 *a
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, box_decode_kernel, src, (const int32_t *)win_anchor, D, reg, img_done, G);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, box_decode_kernel, src, (const int32_t *)win_anchor, D, reg, G);
         if (le != cudaSuccess) return (int)le;
         Y3D_CHECK_LAUNCH();
     }
@@ -785,7 +834,6 @@ static int decode_topk2d_run(const float *const *lvl_ptr, const int64_t *lvl_sB,
     int2 *aux = (int2 *)((char *)ws + align256(sizeof(uint32_t) * (size_t)B * A));
     uint32_t *k2 = (uint32_t *)((char *)aux + align256(sizeof(int2) * (size_t)B * A));
     int32_t *win_anchor = (int32_t *)((char *)k2 + ((D * nc > kKeys2SmemCap) ? align256(sizeof(uint32_t) * (size_t)B * D * nc) : 0));
-    unsigned *img_done = (unsigned *)((char *)win_anchor + align256(sizeof(int32_t) * (size_t)B * D));
     bool v4 = true;
     for (int l = 0; l < nl; ++l)
         v4 = v4 && (src.t.h[l] * src.t.w[l]) % 4 == 0 && ((uintptr_t)lvl_ptr[l]) % 16 == 0 && lvl_sB[l] % 4 == 0 &&
@@ -793,15 +841,15 @@ static int decode_topk2d_run(const float *const *lvl_ptr, const int64_t *lvl_sB,
     if (v4) {
         int nq = A / 4;
         dim3 grid((nq + 31) / 32, B);
-        cls_max_kernel<4><<<grid, 128, 0, s>>>(src.t, nq, nc, A, keys, aux, img_done);
+        cls_max_kernel<4><<<grid, 128, 0, s>>>(src.t, nq, nc, A, keys, aux);
     } else {
         dim3 grid((A + 31) / 32, B);
-        cls_max_kernel<1><<<grid, 128, 0, s>>>(src.t, A, nc, A, keys, aux, img_done);
+        cls_max_kernel<1><<<grid, 128, 0, s>>>(src.t, A, nc, A, keys, aux);
     }
     Y3D_CHECK_LAUNCH();
     src.mode = 1;
     src.xywh = xywh;
-    return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s, gather, win_anchor, img_done);
+    return launch_select(src, keys, aux, B, A, nc, 4, D, out, nullptr, nullptr, anchor_idx, 1, k2, s, gather, win_anchor);
 }
 
 extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
@@ -813,11 +861,11 @@ extern "C" int y3d_decode_topk2d(const float *const *lvl_ptr, const int64_t *lvl
 }
 
 static size_t gather_data_floats(int world, int n_local, int D) { return (size_t)world * n_local * D * 6; }
-static size_t gather_flags_off(int world, int n_local, int D) { return align256(sizeof(float) * 2 * gather_data_floats(world, n_local, D)); }
+static size_t gather_stage_off(int world, int n_local, int D) { return align256(sizeof(float) * 2 * gather_data_floats(world, n_local, D)); }
 
 extern "C" size_t y3d_gather_buffer_bytes(int world, int n_local, int D) {
     if (world < 1 || n_local < 1 || D < 1) return 0;
-    return gather_flags_off(world, n_local, D) + align256(sizeof(unsigned) * 2 * (size_t)world * n_local);
+    return gather_stage_off(world, n_local, D) + align256(sizeof(unsigned long long) * 2 * gather_data_floats(world, n_local, D));
 }
 
 extern "C" int y3d_decode_topk2d_sharded(const float *const *lvl_ptr, const int64_t *lvl_sB, const int64_t *lvl_sC,
@@ -827,13 +875,15 @@ extern "C" int y3d_decode_topk2d_sharded(const float *const *lvl_ptr, const int6
     if (!peer_bufs || world < 1 || world > kGatherMaxWorld || rank < 0 || rank >= world || seq == 0 || B < 1) return Y3D_EINVAL;
     GatherOut G{};
     const int par = (int)(seq & 1ull);
-    const size_t nfl = gather_data_floats(world, B, D), foff = gather_flags_off(world, B, D);
+    const size_t nfl = gather_data_floats(world, B, D), soff = gather_stage_off(world, B, D);
     for (int r = 0; r < world; ++r) {
         if (!peer_bufs[r] || ((uintptr_t)peer_bufs[r]) % 256) return Y3D_EALIGN;
         G.data[r] = (float *)peer_bufs[r] + (size_t)par * nfl;
-        G.flags[r] = (unsigned *)((char *)peer_bufs[r] + foff) + (size_t)par * world * B;
+        G.stage[r] = (unsigned long long *)((char *)peer_bufs[r] + soff) + (size_t)par * nfl;
     }
-    G.rank = rank; G.world = world; G.n_local = B; G.seq = (unsigned)(seq & 0xffffffffull);
+    G.rank = rank; G.world = world; G.n_local = B;
+    G.seq = (unsigned)(seq & 0xffffffffull);
+    if (G.seq == 0) return Y3D_EINVAL;  // (the zero-filled staging area reads as sequence number 0)
     cudaStream_t s = (cudaStream_t)stream;
     float *own = G.data[rank] + (size_t)rank * B * D * 6;  // this rank's images inside its own buffer
     int rc = decode_topk2d_run(lvl_ptr, lvl_sB, lvl_sC, lvl_hw, lvl_stride, nl, B, nc, reg_max, xywh, D, own, nullptr, ws,
@@ -846,7 +896,17 @@ extern "C" int y3d_decode_topk2d_sharded(const float *const *lvl_ptr, const int6
             if (const char *e = getenv("Y3D_XRANK_TIMEOUT_S")) { const double v = atof(e); if (v > 0.0) sec = v; }
             timeout = (long long)(sec * 2.0e9);
         }
-        gather_wait_kernel<<<1, 256, 0, s>>>(G.flags[rank], world * B, G.seq, timeout, status);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((world - 1) * B));
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, gather_collect_kernel, G, D, timeout, status);
+        if (le != cudaSuccess) return (int)le;
         Y3D_CHECK_LAUNCH();
     }
     return Y3D_OK;

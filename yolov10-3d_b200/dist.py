@@ -55,9 +55,10 @@ def all_gather_detections(dets_local, group=None, equal_shards=None):
 
 
 class PeerDetectionGather:
-    """The detection path's one exchange, fused into the selection kernel (csrc/topk.cu, ``y3d_decode_topk2d_sharded``):
-    every rank's CTA that has selected an image stores the image's [D, 6] rows straight into every peer's gather buffer
-    over NVLink peer memory -- no collective launch; a one-CTA kernel waits for the flags of all images.
+    """The detection path's one exchange, fused into the last kernels of the fused decode + top-k (csrc/topk.cu,
+    ``y3d_decode_topk2d_sharded``): the box-decode kernel stores every finished [D, 6] row straight into every peer's
+    gather buffer over NVLink peer memory -- value and call number in one 64-bit word, so no fence and no flag follow the
+    data, and no collective is launched; a small kernel (one CTA per remote image) unpacks the peers' words as they arrive.
 
     The buffers come from ``torch.distributed._symmetric_memory``.  Construction is collective; ``available`` is False when
     symmetric memory cannot be set up, and :func:`detect_sharded` then uses NCCL.  Every rank must make every call with
@@ -88,8 +89,10 @@ class PeerDetectionGather:
                   file=sys.stderr)
 
     def view(self):
-        """[world * n_local, D, 6] view of this rank's buffer at the parity of the last call: valid until the call after
-        the next one (two parities), for consumers on the same stream."""
+        """[world * n_local, D, 6] view of this rank's buffer at the parity of the last call.  Valid for consumers
+        enqueued on the same stream BEFORE this rank's next call: a peer may run one call ahead of this rank's next post,
+        and its rows for that call land in this parity's twin -- but the call after that reuses this parity, and the
+        only thing that holds a peer back is this rank's next post."""
         n = self.world * self.n_local * self.max_det * 6
         par = self.seq & 1
         return self.buf[par * n * 4:(par + 1) * n * 4].view(torch.float32).view(self.world * self.n_local, self.max_det, 6)
@@ -107,7 +110,7 @@ class PeerDetectionGather:
 def detect_sharded(feats_one2one, strides, nc, max_det=300, group=None, gatherer=None):
     """``v10Detect.forward`` export branch (head.py:526-531: decode + ``v10postprocess``) on this rank's images of a batch
     sharded by image, detections gathered on all ranks: returns [world * B_local, max_det, 6] (x1 y1 x2 y2 score label)
-    in rank order, identical on every rank.  With a :class:`PeerDetectionGather` the gather rides in the selection
+    in rank order, identical on every rank.  With a :class:`PeerDetectionGather` the gather rides in the box-decode
     kernel's epilogue (the result is then a view of the gather buffer, see ``PeerDetectionGather.view``); without one,
     one NCCL ``all_gather_into_tensor`` follows the fused kernel.  One rank: the plain fused call."""
     from . import head as _head
@@ -279,6 +282,9 @@ def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_
     with ``defer=True`` and a peer-memory ``reducer``, a :class:`DeferredLoss` whose ``wait()`` returns them: the cross-rank
     exchange is then collected on a side stream while this stream goes on (the next step's kernels, or the host's way to
     the backward call), so neither the NVLink round trip nor the slowest rank is waited for inside the step.
+    When a head tensor requires grad (and no ``defer``), ``total`` carries the autograd node of ``loss.v10DetectLoss``:
+    ``total.backward()`` gives this rank's share of the gradient of the global-batch loss (one rank, or the fused
+    peer-memory route; the NCCL-fallback and deferred routes are forward-only).
     One rank: the kernels normalise directly.  Several ranks with a ``reducer`` (:class:`PeerLossReducer`): the
     loss' last kernel exchanges the partial sums over NVLink peer memory itself (``y3d_v10_loss_fwd_sharded``);
     without one: un-normalised partials -> NCCL all_reduce of 8 doubles -> ``y3d_v8_loss_finalize``."""
@@ -291,6 +297,15 @@ def v10_loss_sharded(feats_o2m, feats_o2o, strides, nc, gt_local, gains, global_
                                total_scale=global_batch, return_total=True, defer=True)
         return reducer.resolve_deferred(gains, global_batch)
     if (multi and reducer is not None and reducer.available and not fused_off()) or not multi:
+        if torch.is_grad_enabled() and any(f.requires_grad for f in (*feats_o2m, *feats_o2o)):
+            # training: the same autograd node as loss.v10DetectLoss; its backward kernel reads the globally normalised
+            # target_scores_sum from the items of the sharded forward, so total.backward() yields this rank's share of
+            # the global-batch gradient (the NCCL-fallback and deferred routes below are forward / evaluation only)
+            loss = _loss._FusedLossFn.apply(([float(v) for v in strides], nc, gt_local, (10, 1), gains,
+                                             reducer if multi else None, float(global_batch)), *feats_o2m, *feats_o2o)
+            if multi:
+                reducer.check()
+            return loss.sum() * global_batch, loss.detach()
         # one rank, or the exchange rides in the loss' last kernel: no collective launch at all, and the same kernel
         # writes the total (global_batch * sum of the items)
         items, _, _, total = _loss.v10_loss_forward(feats_o2m, feats_o2o, strides, nc, gt_local, gains,

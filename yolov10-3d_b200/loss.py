@@ -139,11 +139,15 @@ class _FusedLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, *feats):
-        strides, nc, gt, topk, gains = cfg
+        strides, nc, gt, topk, gains = cfg[:5]
+        # image-sharded batch (dist.v10_loss_sharded): cfg[5] = dist.PeerLossReducer or None, cfg[6] = global batch size.
+        # The items then are those of the GLOBAL batch (sums exchanged by the last forward kernel), and the backward
+        # kernel normalises this rank's gradients by the global target_scores_sum it finds in them.
+        xrank, total_scale = (cfg[5], cfg[6]) if len(cfg) > 5 else (None, None)
         n = len(topk)
         nl = len(feats) // n
         levels = [Levels(feats[i * nl:(i + 1) * nl], strides) for i in range(n)]
-        fwd = _branch_forward(levels, nc, gt, topk, gains, True, False, None)
+        fwd = _branch_forward(levels, nc, gt, topk, gains, True, False, None, xrank, total_scale)
         used = [f for lv in levels for f in lv.feats]  # fp32, dense rows: the tensors the kernels actually read
         ctx.save_for_backward(*used, fwd["ws"], fwd["gt"], fwd["items"])
         ctx.cfg = (strides, nc, topk, gains, n, nl, fwd["M"])

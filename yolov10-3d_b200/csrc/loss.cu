@@ -1208,15 +1208,6 @@ static int loss_run(int nb, const BranchIn *br, const int *lvl_hw, const float *
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (use_ap) {  // claimed anchors spread over the machine, kFinApThreads per CTA
-        static int carve = -1;  // Y3D_CARVEOUT=1 (measurement): one shared-memory split for the three kernels of the step
-        if (carve < 0) {
-            const char *v = getenv("Y3D_CARVEOUT");
-            carve = v && *v == '1';
-            if (carve) {
-                cudaFuncSetAttribute(loss_finish_ap_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-                cudaFuncSetAttribute(head_stream_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-            }
-        }
         cfg.gridDim = dim3((unsigned)((w.rcap + kFinApThreads - 1) / kFinApThreads), B, nb);
         cfg.blockDim = dim3(kFinApThreads);
         cfg.dynamicSmemBytes = sizeof(GtRec) * (size_t)M;

@@ -13,8 +13,6 @@
 //   * one 16-byte load fetches a candidate's box, the fast IoU bound works in grid units against the GT box divided
 //     by the level's stride (no per-candidate scaling);
 //   * the next work ticket is requested before the claims go out, so its round trip overlaps theirs.
-#include <cstdlib>
-
 #include "assign.cuh"
 
 #ifndef Y3D_FSORTMERGE
@@ -493,10 +491,6 @@ static int launch_fused(const AssignCtx2 &cc, int n, long long items, size_t sme
     static size_t ctas_smem = ~(size_t)0;
     if (ctas_per_sm == 0 || ctas_smem != smem) {
         int v = 0;
-        const char *cv = getenv("Y3D_CARVEOUT");
-        if (cv && *cv == '1')
-            cudaFuncSetAttribute(tal_topk_fused_kernel<ORDERED, REC>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 (int)cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, tal_topk_fused_kernel<ORDERED, REC>, kTopkWarps * 32, smem) !=
                 cudaSuccess || v <= 0)
             v = 4;

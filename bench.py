@@ -500,7 +500,7 @@ def main_cuda(args):
 def main_cuda_cfg4(args):
     """BASELINE.json configs[3]: YOLOv10-x head at 1280 x 1280 (33 600 anchors), 32 images per GPU, image-sharded: every
     rank decodes + top-300s its images (fused, y3d_decode_topk2d) and the [B/N, 300, 6] detections are gathered on all
-    ranks -- written straight into the peers' buffers by the selection kernel's epilogue (NVLink peer memory) when that
+    ranks -- written straight into the peers' buffers by the box-decode kernel's epilogue (NVLink peer memory) when that
     is available, else by one NCCL all_gather_into_tensor."""
     import torch
     import torch.distributed as dist

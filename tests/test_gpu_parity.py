@@ -144,6 +144,40 @@ def test_fused_decode_topk_full_size_vs_oracle(y3d, B, hw, seed):
     assert (np.diff(out[..., 4].cpu().numpy(), axis=1) <= 0).all()  # sorted by score
 
 
+def test_fused_decode_topk_nan_logits(y3d):
+    """NaN class logits: the class-maximum kernel tracks maxima in the float domain and falls back to the order-preserving
+    keys for a CTA that saw a NaN -- there NaN sorts first, like torch.topk (ops.py:855-861).  Checked against this
+    library's other route to the same selection (per-anchor keys over the decoded tensor, amax_anchor_kernel), on an input
+    whose NaNs sit in different class parts, anchor quads and levels; elsewhere the result must not change at all."""
+    nc, D, hw = 80, 300, (640, 640)
+    lv = synth.levels(*hw)
+    x = synth.head2d(2, nc, lv, seed=11)
+    clean = y3d.v10detect_export_forward(feats_of(x, lv), synth.STRIDES, nc, D).cpu().numpy()
+    A = x.shape[2]
+    spots = [(0, 64 + 3, 5), (0, 64 + 79, 5), (0, 64 + 41, 4099), (1, 64 + 20, 6400 + 17), (1, 64 + 60, A - 1)]
+    for b, c, a in spots:
+        x[b, c, a] = np.nan
+    fused, aidx = y3d.v10detect_export_forward(feats_of(x, lv), synth.STRIDES, nc, D, return_anchor_idx=True)
+    fused, aidx = fused.cpu().numpy(), aidx.cpu().numpy()
+    y = y3d.detect_inference(feats_of(x, lv), synth.STRIDES, nc, export=True)
+    _, scores, labels = y3d.v10postprocess(y.permute(0, 2, 1), D, nc)
+    scores, labels = scores.cpu().numpy(), labels.cpu().numpy()
+    for b in range(2):
+        n_nan = sum(1 for bb, _, _ in spots if bb == b)
+        # the NaN candidates lead both lists, in the same (anchor, class) order
+        assert np.isnan(fused[b, :n_nan, 4]).all() and np.isnan(scores[b, :n_nan]).all()
+        assert not np.isnan(fused[b, n_nan:, 4]).any()
+        assert np.array_equal(fused[b, :n_nan, 5].astype(np.int64), labels[b, :n_nan])
+        want = sorted((a, c - 64) for bb, c, a in spots if bb == b)
+        assert [(int(aidx[b, i]), int(fused[b, i, 5])) for i in range(n_nan)] == want
+        # behind them: the finite candidates, as the unfused route ranks them (its scores come from decode2d's fast
+        # sigmoid: values to 1e-5, labels may swap only where two scores are that close) ...
+        np.testing.assert_allclose(fused[b, n_nan:, 4], scores[b, n_nan:], rtol=RTOL, atol=1e-7)
+        assert (fused[b, n_nan:, 5].astype(np.int64) == labels[b, n_nan:]).mean() > 0.99
+        # ... and almost all of the clean run's selection (the NaN anchors displace the weakest stage-1 anchors)
+        assert len(set(map(tuple, fused[b, n_nan:, 4:])) & set(map(tuple, clean[b, :, 4:]))) >= D - 3 * n_nan - 3
+
+
 # ------------------------------------------------------------------------------------------------ 2D assigner
 def run_assign(y3d, inp, topk, alpha, beta, grid):
     asg = y3d.TaskAlignedAssigner(topk=topk, num_classes=inp["pd_scores"].shape[-1], alpha=alpha, beta=beta,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU check of the image-sharded detection path (y3d_decode_topk2d_sharded: the gather of the [B/N, 300, 6]
-detections fused into the selection kernel's epilogue over NVLink peer memory) against the single-process result and the
+detections fused into the box-decode kernel's epilogue over NVLink peer memory) against the single-process result and the
 NCCL route, plus timings.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29534 \

@@ -482,6 +482,8 @@ if __name__ == "__main__":
         case_loss3d("loss3d_k1", B=2, nc=3, img_hw=(96, 320), M=8, topk=1, seed=61)
         case_loss3d("loss3d_free_l2", B=2, nc=3, img_hw=(96, 320), M=6, topk=8, seed=62, beta=3.0, gamma=3.0,
                     kps_dist_metric="l2", constrain_anchors=False)
+    if want("loss3d_cfg3"):  # BASELINE cfg3 shape: KITTI 384 x 1280, 3 classes, up to 50 GT per image, top-k 8
+        case_loss3d("loss3d_cfg3", B=2, nc=3, img_hw=(384, 1280), M=50, topk=8, seed=63)
     if want("assign3d"):
         case_assign3d("assign3d_k8", B=2, nc=3, img_hw=(96, 320), M=8, topk=8, seed=50, alpha=0.5, beta=1.0, gamma=1.0)
         case_assign3d("assign3d_k1", B=2, nc=3, img_hw=(96, 320), M=8, topk=1, seed=51, alpha=0.5, beta=1.0, gamma=1.0)

@@ -61,3 +61,62 @@ def test_reference_vs_oracle_assignment_seed_sweep():
         worst = max(worst, float(np.max(np.abs(np.concatenate(items) / ref_items - 1.0))))
     print(f"reference vs oracle: {SEEDS} seeds, {n_fg} foreground anchors, {n_mism} mismatches, worst item deviation {worst:.2e}")
     assert n_fg > 20000 and n_mism == 0 and worst < 2e-5
+
+
+SEEDS_3D = 16
+
+
+def test_reference_vs_oracle_3d_assignment_seed_sweep():
+    """The same at BASELINE cfg3 shape (KITTI 384 x 1280, 3 classes, up to 50 GT per image, top-k 8 and 1): the assignment of
+    the REAL TaskAlignedAssigner3d inside the REAL DDDetectionLoss (loss.py:821-900, tal.py:391-700) against the oracle's."""
+    import torch
+
+    from tests.golden import make_golden as mg
+
+    nc, hw, M = 3, (384, 1280), 50
+    lv = synth.levels(*hw)
+    ms = np.array(synth.KITTI_MEAN_SIZES, np.float32)
+    calibs = np.array(synth.KITTI_CALIB, np.float32)[None]
+    gains = dict(loss2d=1.3, cls=0.7, depth=1.1, offset3d=0.9, size3d=1.2, heading=0.8)
+    n_fg = n_mism = 0
+    worst = 0.0
+    for s in range(SEEDS_3D):
+        topk = 8 if s % 2 == 0 else 1
+        gts = synth.gt3d(1, M, nc, hw, seed=6000 + s)
+        x = synth.train_like_head3d(1, nc, lv, gts, seed=7000 + s, frac=0.03)
+        args = types.SimpleNamespace(distillation=False, tal_topk=topk, tal_alpha=0.5, tal_beta=1.0, tal_gamma=1.0,
+                                     tal_2d=True, tal_3d=True, kps_dist_metric="l1", constrain_anchors=True, **gains)
+        model = mg.FakeModel(nc, synth.STRIDES, args)
+        model.model[0].no = nc + 35
+        crit = mg.ref_loss.DDDetectionLoss(model, tal_topk=topk)
+        captured = {}
+        inner = crit.assigner.forward
+
+        def fwd(*a, _inner=inner, **k):
+            out = _inner(*a, **k)
+            captured["fg"], captured["tgi"] = out[1].numpy().copy(), out[2].numpy().copy()
+            return out
+
+        crit.assigner.forward = fwd
+        feats = [mg.t(f) for f in synth.split_levels(x, lv)]
+        batch = {k: mg.t(v) for k, v in synth.batch_dict3d(gts, hw, calibs, ms).items()}
+        orig_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self  # loss.py:1132 calls .cuda() on a fresh one-hot
+        try:
+            with mg.patched_topk(), torch.no_grad():
+                _, ref_items = crit(feats, batch, embeddings=None)
+        finally:
+            torch.Tensor.cuda = orig_cuda
+        bd = synth.batch_dict3d(gts, hw, calibs, ms)
+        extra = np.concatenate([bd["center_2d"], bd["size_2d"], bd["center_3d"], bd["size_3d"], bd["depth"][:, None],
+                                bd["heading_bin"][:, None], bd["heading_res"][:, None]], 1)
+        packed = oracle.preprocess_targets(bd["batch_idx"], bd["cls"], bd["bboxes"], 1, hw, extra=extra)
+        items, _, _, asg = oracle.dd_loss(x, lv, synth.STRIDES, nc, packed, calibs, ms, topk, gains=list(gains.values()))
+        rfg, rtgi = captured["fg"].astype(bool), captured["tgi"]
+        both = rfg & asg["fg_mask"]
+        n_mism += int((asg["fg_mask"] != rfg).sum() + (asg["target_gt_idx"][both] != rtgi[both]).sum())
+        n_fg += int(rfg.sum())
+        worst = max(worst, float(np.max(np.abs(items / ref_items.numpy().astype(np.float64) - 1.0))))
+    print(f"reference vs oracle (3D): {SEEDS_3D} seeds, {n_fg} foreground anchors, {n_mism} mismatches, "
+          f"worst item deviation {worst:.2e}")
+    assert n_fg > 500 and n_mism == 0 and worst < 3e-5

@@ -26,3 +26,14 @@ for _ in range(4):  # both branches in the same launches (y3d_dd_loss_dual_fwd),
     flush.zero_()
     y3d.loss3d.dd_loss_dual_forward(f3, f3o, list(synth.STRIDES), nc, g, cal, ms, (8, 1), (1, 1, 1, 1, 1, 1))
 torch.cuda.synchronize()
+# timing (CUDA events, L2 flushed before every call), as bench.py's other_configs.cfg3
+tot = 0.0
+for _ in range(30):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    y3d.loss3d.dd_loss_dual_forward(f3, f3o, list(synth.STRIDES), nc, g, cal, ms, (8, 1), (1, 1, 1, 1, 1, 1))
+    e1.record()
+    torch.cuda.synchronize()
+    tot += e0.elapsed_time(e1)
+print(f"cfg3 dual 3D loss forward: {tot / 30 * 1e3:.1f} us per call")

@@ -159,31 +159,67 @@ __device__ __forceinline__ void dd_items(const double *p, int M, const float *g,
     items[7] = (float)nfg;
 }
 
-// grid (ceil(ceil(A/128) / kFgRows), B): a CTA covers the anchors of kFgRows CTAs of the streaming kernel and puts
-// their foreground sums into slots 1..kNSum of the first of those partial rows (n_rows = the streaming kernel's grid.x)
-constexpr int kFgRows = 1;  // (4 measured slower: the few foreground anchors of a thread then run back to back, and the kernel is one latency chain)
+// grid (ceil(ceil(A/128) / kFgRows), B, n_branch): a CTA covers the anchors of kFgRows CTAs of the streaming kernel and puts
+// their foreground sums into slots 1..kNSum of the first of those partial rows (n_rows = the streaming kernel's grid.x).
+// Only a few per cent of the anchors are foreground: the CTA first compacts its foreground anchors (in anchor order, so
+// the sums do not depend on timing) and then gives every one of them its own thread -- a quarter of the CTAs, fences and
+// tickets of a one-anchor-per-thread grid, and no thread runs two latency chains back to back.
+constexpr int kFgRows = 4;
 __global__ void __launch_bounds__(128) dd_fg_kernel(const __grid_constant__ AssignCtx2 cc, const __grid_constant__ DDParams2 PP,
                                                     int n_rows) {
     __shared__ double red[kNSum][4];
+    __shared__ int s_cnt[kFgRows][4];
+    __shared__ int s_fa[kFgRows * 128], s_fgi[kFgRows * 128];
     const AssignCtx &c = cc.c[blockIdx.z];
     const DDParams &P = PP.p[blockIdx.z];
     const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent of the resolve (or the streaming) kernel
     double s[kNSum];
 #pragma unroll
     for (int i = 0; i < kNSum; ++i) s[i] = 0.0;
     int gis[kFgRows];
+    unsigned bal[kFgRows];
 #pragma unroll
     for (int i = 0; i < kFgRows; ++i) {
         const int a = (blockIdx.x * kFgRows + i) * 128 + threadIdx.x;
         gis[i] = (a < P.A && P.M > 0) ? c.tgi[(long long)b * P.A + a] : -1;
     }
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < kFgRows; ++i) {
-        const int a = (blockIdx.x * kFgRows + i) * 128 + threadIdx.x;
+        bal[i] = __ballot_sync(0xffffffffu, gis[i] >= 0);
+        if (lane == 0) s_cnt[i][wid] = __popc(bal[i]);
+    }
+    __syncthreads();
+    int n_fg = 0;
+    {   // position of (row i, warp w) in anchor order = everything before it
+        int before[kFgRows];
+        int run = 0;
+#pragma unroll
+        for (int i = 0; i < kFgRows; ++i) {
+            before[i] = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (w == wid) before[i] = run;
+                run += s_cnt[i][w];
+            }
+        }
+        n_fg = run;
+#pragma unroll
+        for (int i = 0; i < kFgRows; ++i)
+            if (gis[i] >= 0) {
+                const int pos = before[i] + __popc(bal[i] & ((1u << lane) - 1u));
+                s_fa[pos] = (blockIdx.x * kFgRows + i) * 128 + threadIdx.x;
+                s_fgi[pos] = gis[i];
+            }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int e = threadIdx.x; e < n_fg; e += 128) {
+        const int a = s_fa[e];
         const long long o = (long long)b * P.A + a;
-        const int gi = gis[i];
-        if (gi >= 0) {
+        const int gi = s_fgi[e];
+        {
             const LevelTable &t = P.t;
             const int l = level_of(t, a);
             const int cell = a - t.start[l];
@@ -245,7 +281,6 @@ __global__ void __launch_bounds__(128) dd_fg_kernel(const __grid_constant__ Assi
     __shared__ unsigned s_ticket;
     __shared__ double s_fin[kNSum + 1];
     constexpr int W = kNSum + 1;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(P.tickets + b, 1u);

@@ -12,22 +12,23 @@
 //   1. head_stream_kernel : the ONE pass over the two head tensors (4*(4R+nc)*A bytes per image and branch).
 //        A thread owns 4 consecutive anchors (128-bit loads along the anchor axis, 512 contiguous bytes per warp and
 //        channel row) and one quarter of the channels: DFL side `part` (16 bins) and nc/4 classes.  Out: boxes
-//        (xyxy, grid units) and the per-side log-sum-exp as [B,4,A] planes (coalesced 128-bit stores; 32 B/anchor,
+//        (xyxy, grid units) and the per-side log-sum-exp as [B,A,4] records (coalesced 128-bit stores; 32 B/anchor,
 //        the only dense writes), zeroed claim words, and sum softplus(logit) = sum BCE(logit, 0) per CTA.
 //        pd_scores and the dense target_scores of the reference are never materialised:
 //        sum BCE(x,t) = sum BCE(x,0) - sum_fg x[label]*t.  One warp per image also sorts the image's valid GTs into
 //        size classes: the work order of the next kernel.
-//   2. tal_topk_kernel (assign.cu) : per-GT candidate walk + top-k + claims, biggest GTs first; first claimers append
-//        the anchor to the image's list.  Scores are read as logits straight from the head.  Launched
+//   2. tal_topk_fused_kernel (topk_fused.cu; the generic tal_topk_kernel of assign.cu when there are few GTs): per-GT
+//        candidate walk + top-k + claims, biggest GTs first.  Scores are read as logits straight from the head.  With up
+//        to kFinishApMaxM GTs per image the claiming lane also evaluates the pair's loss terms and appends a claim
+//        record to the image's list; a per-image counter tells kernel 3 when an image is complete.  Launched
 //        programmatically dependent on 1, as 3 is on 2.
-//   3. loss_finish_kernel : one CTA per (image, branch) over the claimed anchors only: conflict resolution
-//        (select_highest_overlaps), per-GT maxima in shared memory, CIoU / DFL-CE / BCE-correction terms, exact
-//        (fixed-point, order-independent) block sums; the last CTA reduces all partials in a fixed order and
-//        writes the loss items -- after summing them over the ranks through NVLink peer memory when the batch is
-//        sharded over several GPUs (y3d_v10_loss_fwd_sharded).  The claim word of a foreground anchor ends up as
-//        (GT index, alignment weight): what the backward pass reads.
-#include <cstdlib>
-
+//   3. loss_finish_ap_kernel (M <= kFinishApMaxM): the claim records of an image spread over the machine, 128 per CTA:
+//        conflict resolution (select_highest_overlaps), per-GT maxima, weights, exact (fixed-point, order-independent)
+//        sums; the CTA that finishes last for the batch normalises and writes the loss items -- after summing them over
+//        the ranks through NVLink peer memory when the batch is sharded over several GPUs (y3d_v10_loss_fwd_sharded).
+//      loss_finish_kernel (more GTs per image): one CTA per (image, branch) over the image's list of claimed anchors.
+//      Either way the claim word of a foreground anchor ends up as (GT index, alignment weight): what the backward
+//      pass reads.
 #include "loss.cuh"
 #include "xrank.cuh"
 

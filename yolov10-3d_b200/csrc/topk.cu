@@ -9,6 +9,9 @@
 // Stage 2 (same CTA)            : the D x nc scores of the winners are gathered into shared memory, the same
 //                                 select + sort runs over the flattened index i*nc + c (ops.py:861), then
 //                                 labels = idx % nc, anchor = winners[idx // nc], gather of the regression channels.
+// Fused export branch (y3d_decode_topk2d): stage 0 reads the class logits of the head levels (cls_max_kernel), stages 1-2
+// rank by the exactly specified sigmoid, and the boxes of the D winners are decoded by box_decode_kernel, a machine-wide
+// grid behind the selection kernel -- which also carries the peer-memory epilogue of the image-sharded path.
 // Results are identical to a stable descending sort (lowest index wins ties) -- the order BASELINE.json mandates.
 #include <cstdlib>
 

@@ -60,6 +60,25 @@ def test_sharded_loss_entry_and_peer_exchange_host_side():
     assert red.available is False
 
 
+def test_sharded_detection_entry_host_side():
+    """y3d_gather_buffer_bytes / y3d_decode_topk2d_sharded without a GPU: the buffer holds the two result parities the
+    mirror's view() addresses plus as many 64-bit staging words, and argument errors come back as codes."""
+    lib = y3d.lib()
+    world, n_local, D = 4, 8, 300
+    n = world * n_local * D * 6
+    need = int(lib.y3d_gather_buffer_bytes(world, n_local, D))
+    assert need >= 2 * n * 4 + 2 * n * 8 and need % 256 == 0  # [2][world*B][D][6] floats, then [2][world*B][6 D] u64
+    assert int(lib.y3d_gather_buffer_bytes(0, n_local, D)) == 0 and int(lib.y3d_gather_buffer_bytes(world, 0, D)) == 0
+    bufs = (ctypes.c_void_p * world)(*[0x10000 * (r + 1) for r in range(world)])
+    args = [None] * 5 + [3, 2, 8, 16, 0, 50]
+    assert lib.y3d_decode_topk2d_sharded(*args, 0, world, None, ctypes.c_uint64(1), None, None, 0, None) == -1  # no buffers
+    assert lib.y3d_decode_topk2d_sharded(*args, world, world, bufs, ctypes.c_uint64(1), None, None, 0, None) == -1  # rank
+    assert lib.y3d_decode_topk2d_sharded(*args, 0, world, bufs, ctypes.c_uint64(0), None, None, 0, None) == -1  # seq 0
+    assert lib.y3d_decode_topk2d_sharded(*args, 0, 17, bufs, ctypes.c_uint64(1), None, None, 0, None) == -1  # world > 16
+    # the sequence number travels in the low 32 bits of every word: a call whose low half is 0 would read fresh memory
+    assert lib.y3d_decode_topk2d_sharded(*args, 0, world, bufs, ctypes.c_uint64(1 << 32), None, None, 0, None) == -1
+
+
 def test_no_cpu_fallback():
     with pytest.raises(y3d.Y3DError):
         y3d.v10postprocess(torch.zeros(1, 10, 6), 5, 2)

@@ -13,83 +13,89 @@ namespace y3d {
 
 constexpr int kTile = 64;
 
-__device__ __forceinline__ void riou_corners(const float *rb, float *c) {  // rbbox_to_corners :149-172
-    const float a_cos = cosf(rb[4]), a_sin = sinf(rb[4]);
-    const float xd = rb[2], yd = rb[3];
-    const float cx[4] = {-xd / 2, -xd / 2, xd / 2, xd / 2};
-    const float cy[4] = {-yd / 2, yd / 2, yd / 2, -yd / 2};
+// Individually rounded helpers: the reference computes every product and sum in float32, one operation at a time.
+__device__ __forceinline__ float det2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+__device__ __forceinline__ float dot2(float2 u, float2 v) { return __fadd_rn(__fmul_rn(u.x, v.x), __fmul_rn(u.y, v.y)); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// the four corners of a rotated rectangle (cx, cy, dx, dy, angle), in the reference's order (rbbox_to_corners :149-172)
+__device__ __forceinline__ void rect_corners(const float *rb, float2 (&q)[4]) {
+    const float ca = cosf(rb[4]), sa = sinf(rb[4]);
+    const float hx = rb[2] / 2, hy = rb[3] / 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        c[2 * i] = __fadd_rn(__fadd_rn(__fmul_rn(a_cos, cx[i]), __fmul_rn(a_sin, cy[i])), rb[0]);
-        c[2 * i + 1] = __fadd_rn(__fadd_rn(__fmul_rn(-a_sin, cx[i]), __fmul_rn(a_cos, cy[i])), rb[1]);
+        const float lx = i < 2 ? -hx : hx, ly = (i == 1 || i == 2) ? hy : -hy;  // (-,-) (-,+) (+,+) (+,-)
+        q[i].x = __fadd_rn(__fadd_rn(__fmul_rn(ca, lx), __fmul_rn(sa, ly)), rb[0]);
+        q[i].y = __fadd_rn(__fadd_rn(__fmul_rn(-sa, lx), __fmul_rn(ca, ly)), rb[1]);
     }
 }
-__device__ __forceinline__ bool riou_point_in_quad(float px, float py, const float *c) {  // :105-122
-    const float ab0 = c[2] - c[0], ab1 = c[3] - c[1], ad0 = c[6] - c[0], ad1 = c[7] - c[1];
-    const float ap0 = px - c[0], ap1 = py - c[1];
-    const float abab = __fadd_rn(__fmul_rn(ab0, ab0), __fmul_rn(ab1, ab1)), abap = __fadd_rn(__fmul_rn(ab0, ap0), __fmul_rn(ab1, ap1));
-    const float adad = __fadd_rn(__fmul_rn(ad0, ad0), __fmul_rn(ad1, ad1)), adap = __fadd_rn(__fmul_rn(ad0, ap0), __fmul_rn(ad1, ap1));
-    const float eps = -1e-6f;
-    return abab - abap >= eps && abap >= eps && adad - adap >= eps && adap >= eps;
+// is p inside the rectangle q?  Projections of (p - q0) on the two edges leaving q0 lie within the edges' squared
+// lengths, with the reference's tolerance (point_in_quadrilateral :105-122)
+__device__ __forceinline__ bool inside_rect(float2 p, const float2 (&q)[4]) {
+    const float2 e1 = q[1] - q[0], e3 = q[3] - q[0], w = p - q[0];
+    const float l1 = dot2(e1, e1), p1 = dot2(e1, w), l3 = dot2(e3, e3), p3 = dot2(e3, w);
+    const float tol = -1e-6f;
+    return l1 - p1 >= tol && p1 >= tol && l3 - p3 >= tol && p3 >= tol;
 }
-__device__ __forceinline__ bool riou_seg_intersect(const float *p1, const float *p2, int i, int j, float *t) {  // :60-102
-    const int i1 = (i + 1) & 3, j1 = (j + 1) & 3;
-    const float A0 = p1[2 * i], A1 = p1[2 * i + 1], B0 = p1[2 * i1], B1 = p1[2 * i1 + 1];
-    const float C0 = p2[2 * j], C1 = p2[2 * j + 1], D0 = p2[2 * j1], D1 = p2[2 * j1 + 1];
-    const float BA0 = B0 - A0, BA1 = B1 - A1, DA0 = D0 - A0, CA0 = C0 - A0, DA1 = D1 - A1, CA1 = C1 - A1;
-    const bool acd = __fmul_rn(DA1, CA0) > __fmul_rn(CA1, DA0);
-    const bool bcd = __fmul_rn(D1 - B1, C0 - B0) > __fmul_rn(C1 - B1, D0 - B0);
-    if (acd == bcd) return false;
-    const bool abc = __fmul_rn(CA1, BA0) > __fmul_rn(BA1, CA0), abd = __fmul_rn(DA1, BA0) > __fmul_rn(BA1, DA0);
-    if (abc == abd) return false;
-    const float DC0 = D0 - C0, DC1 = D1 - C1;
-    const float ABBA = __fsub_rn(__fmul_rn(A0, B1), __fmul_rn(B0, A1)), CDDC = __fsub_rn(__fmul_rn(C0, D1), __fmul_rn(D0, C1));
-    const float DH = __fsub_rn(__fmul_rn(BA1, DC0), __fmul_rn(BA0, DC1));
-    t[0] = __fdiv_rn(__fsub_rn(__fmul_rn(ABBA, DC0), __fmul_rn(BA0, CDDC)), DH);
-    t[1] = __fdiv_rn(__fsub_rn(__fmul_rn(ABBA, DC1), __fmul_rn(BA1, CDDC)), DH);
+// orientation predicate of the reference's segment test: (r - p) x (q - p) compared as two rounded products
+__device__ __forceinline__ bool turns(float2 p, float2 q, float2 r) {
+    return __fmul_rn(r.y - p.y, q.x - p.x) > __fmul_rn(q.y - p.y, r.x - p.x);
+}
+// edge i of rectangle u against edge j of rectangle v: the crossing point, if the two segments straddle each other
+// (line_segment_intersection :60-102; Cramer's rule on the two line equations)
+__device__ __forceinline__ bool edges_cross(const float2 (&u)[4], const float2 (&v)[4], int i, int j, float2 &x) {
+    const float2 a = u[i], b = u[(i + 1) & 3], c = v[j], d = v[(j + 1) & 3];
+    if (turns(a, c, d) == turns(b, c, d)) return false;
+    if (turns(a, b, c) == turns(a, b, d)) return false;
+    const float2 ab = b - a, cd = d - c;
+    const float ka = det2(a.x, b.y, b.x, a.y), kc = det2(c.x, d.y, d.x, c.y);
+    const float den = det2(ab.y, cd.x, ab.x, cd.y);
+    x.x = __fdiv_rn(det2(ka, cd.x, ab.x, kc), den);
+    x.y = __fdiv_rn(det2(ka, cd.y, ab.y, kc), den);
     return true;
 }
-__device__ float riou_inter(const float *r1, const float *r2) {  // inter :231-245
-    float c1[8], c2[8], ip[48], t[2];
-    riou_corners(r1, c1);
-    riou_corners(r2, c2);
+// area of the overlap polygon of two rotated rectangles (inter :231-245): its vertices are the corners of one rectangle
+// inside the other plus the edge crossings (quadrilateral_intersection :125-146), ordered around their centroid by a
+// monotone function of the angle (sort_vertex_in_convex_polygon :175-212), measured as a triangle fan (area :215-228)
+__device__ float riou_inter(const float *r1, const float *r2) {
+    float2 u[4], v[4], pts[24];
+    rect_corners(r1, u);
+    rect_corners(r2, v);
     int n = 0;
-    for (int i = 0; i < 4; ++i) {  // quadrilateral_intersection :125-146
-        if (riou_point_in_quad(c1[2 * i], c1[2 * i + 1], c2)) { ip[2 * n] = c1[2 * i]; ip[2 * n + 1] = c1[2 * i + 1]; ++n; }
-        if (riou_point_in_quad(c2[2 * i], c2[2 * i + 1], c1)) { ip[2 * n] = c2[2 * i]; ip[2 * n + 1] = c2[2 * i + 1]; ++n; }
+    for (int i = 0; i < 4; ++i) {
+        if (inside_rect(u[i], v)) pts[n++] = u[i];
+        if (inside_rect(v[i], u)) pts[n++] = v[i];
     }
+    float2 x;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j)
-            if (riou_seg_intersect(c1, c2, i, j, t)) { ip[2 * n] = t[0]; ip[2 * n + 1] = t[1]; ++n; }
-    if (n > 0) {  // sort_vertex_in_convex_polygon :175-212
-        float cx = 0.0f, cy = 0.0f, vs[24];
-        for (int i = 0; i < n; ++i) { cx = __fadd_rn(cx, ip[2 * i]); cy = __fadd_rn(cy, ip[2 * i + 1]); }
-        cx = __fdiv_rn(cx, (float)n);
-        cy = __fdiv_rn(cy, (float)n);
-        for (int i = 0; i < n; ++i) {
-            float v0 = ip[2 * i] - cx, v1 = ip[2 * i + 1] - cy;
-            const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)));
-            v0 = __fdiv_rn(v0, d);
-            v1 = __fdiv_rn(v1, d);
-            if (v1 < 0) v0 = -2 - v0;
-            vs[i] = v0;
+            if (edges_cross(u, v, i, j, x)) pts[n++] = x;
+    if (n > 0) {
+        float2 ctr = make_float2(0.0f, 0.0f);
+        float key[24];
+        for (int i = 0; i < n; ++i) { ctr.x = __fadd_rn(ctr.x, pts[i].x); ctr.y = __fadd_rn(ctr.y, pts[i].y); }
+        ctr.x = __fdiv_rn(ctr.x, (float)n);
+        ctr.y = __fdiv_rn(ctr.y, (float)n);
+        for (int i = 0; i < n; ++i) {  // unit direction from the centroid: x in [-1, 1] above it, -2 - x below
+            const float2 dir = pts[i] - ctr;
+            const float len = __fsqrt_rn(dot2(dir, dir));
+            const float ux = __fdiv_rn(dir.x, len), uy = __fdiv_rn(dir.y, len);
+            key[i] = uy < 0 ? -2 - ux : ux;
         }
-        for (int i = 1; i < n; ++i)
-            if (vs[i - 1] > vs[i]) {
-                const float temp = vs[i], tx = ip[2 * i], ty = ip[2 * i + 1];
-                int j = i;
-                while (j > 0 && vs[j - 1] > temp) {
-                    vs[j] = vs[j - 1]; ip[2 * j] = ip[2 * j - 2]; ip[2 * j + 1] = ip[2 * j - 1];
-                    --j;
-                }
-                vs[j] = temp; ip[2 * j] = tx; ip[2 * j + 1] = ty;
-            }
+        for (int i = 1; i < n; ++i) {  // stable insertion sort, ascending keys
+            if (!(key[i - 1] > key[i])) continue;
+            const float k = key[i];
+            const float2 p = pts[i];
+            int j = i;
+            for (; j > 0 && key[j - 1] > k; --j) { key[j] = key[j - 1]; pts[j] = pts[j - 1]; }
+            key[j] = k;
+            pts[j] = p;
+        }
     }
-    float area = 0.0f;  // area :221-228, trangle_area :215-218
-    for (int i = 0; i < n - 2; ++i) {
-        const float *a = ip, *b = ip + 2 * i + 2, *c = ip + 2 * i + 4;
-        const float tr = __fdiv_rn(__fsub_rn(__fmul_rn(a[0] - c[0], b[1] - c[1]), __fmul_rn(a[1] - c[1], b[0] - c[0])), 2.0f);
-        area = __fadd_rn(area, fabsf(tr));
+    float area = 0.0f;
+    for (int i = 1; i + 1 < n; ++i) {  // fan around pts[0]: triangles (pts[0], pts[i], pts[i + 1])
+        const float2 e = pts[0] - pts[i + 1], f = pts[i] - pts[i + 1];
+        area = __fadd_rn(area, fabsf(__fdiv_rn(det2(e.x, f.y, e.y, f.x), 2.0f)));
     }
     return area;
 }

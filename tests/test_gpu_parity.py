@@ -876,6 +876,31 @@ def test_inference_forward_feat_vs_reference(y3d):
         assert not got[:, nc:][~np.broadcast_to(filled[:, None], got[:, nc:].shape)].any()  # zero elsewhere
 
 
+def test_dd_loss_shards_add_up(y3d):
+    """The 3D loss over an image-sharded batch (dist.dd_loss_sharded: partials -> all_reduce -> y3d_dd_loss_finalize): the
+    un-normalised sums of two shards, added, finalise to the items of the whole batch -- foreground-count and L1-mean terms
+    included (loss.py:879-888, 923-924, 939).  One GPU: the addition stands in for the all_reduce (gloo-tested on CPU)."""
+    r, z = cases.load("loss3d_k8")
+    lv, gts, x, calibs, ms = cases.loss3d_inputs(r, z)
+    x2 = np.ascontiguousarray(x[::-1])  # a second, different head for the one2one branch
+    packed, cal, msz = dev(z["packed"]), dev(calibs), dev(ms)
+    kw = cases.loss3d_kwargs(r)
+    full, _, _ = y3d.loss3d.dd_loss_dual_forward(feats_of(x, lv), feats_of(x2, lv), list(synth.STRIDES), r["nc"], packed, cal,
+                                                 msz, (8, 1), r["gains"], **kw)
+    parts = []
+    for lo, hi in ((0, 1), (1, r["B"])):
+        _, p, _ = y3d.loss3d.dd_loss_dual_forward(feats_of(x[lo:hi], lv), feats_of(x2[lo:hi], lv), list(synth.STRIDES), r["nc"],
+                                                  packed[lo:hi], cal[lo:hi], msz, (8, 1), r["gains"], normalise=False, **kw)
+        parts.append(p)
+    items = y3d.loss3d.finalize_partials3d(parts[0] + parts[1], True, r["gains"])
+    np.testing.assert_allclose(items.cpu().numpy(), full.cpu().numpy(), rtol=1e-6)
+    # one rank (no process group): the sharded entry is the plain dual call
+    tot, it12 = y3d.dist.dd_loss_sharded(feats_of(x, lv), feats_of(x2, lv), list(synth.STRIDES), r["nc"], packed, cal, msz,
+                                         r["gains"], r["B"], **kw)
+    np.testing.assert_allclose(it12.cpu().numpy(), full[:, :6].reshape(12).cpu().numpy(), rtol=1e-6)
+    assert abs(float(tot) - float(full[:, :6].sum()) * r["B"]) <= 1e-5 * abs(float(tot))
+
+
 def test_rotate_iou_eval(y3d):
     """y3d_rotate_iou_eval against the reference fixture (numba kernel under the CUDA simulator) and the oracle; numpy
     in -> numpy out like the reference, CUDA tensor in -> CUDA tensor out."""

@@ -141,6 +141,23 @@ def reduce_partials(partials, group=None):
     return partials
 
 
+def dd_loss_sharded(feats_o2m, feats_o2o, strides, nc, gts_local, calibs_local, mean_sizes, gains, global_batch,
+                    topk=(8, 1), group=None, **kw):
+    """``DetectLoss3d`` (loss.py:741-771), forward / evaluation only, on this rank's image shard, normalised over the GLOBAL
+    batch: the un-normalised sums of both branches (2 x 11 doubles -- foreground counts and L1 sums included, SURVEY.md
+    section 8e) -> ONE all_reduce -> ``y3d_dd_loss_finalize``.  Returns ``(total, items[12])`` identical on every rank and equal
+    to the single-process result on the whole batch.  (NCCL route only: the 3D path has no peer-memory exchange.)"""
+    from . import loss3d as _loss3d
+
+    items, parts, _ = _loss3d.dd_loss_dual_forward(feats_o2m, feats_o2o, strides, nc, gts_local, calibs_local, mean_sizes,
+                                                   topk, gains, normalise=False, **kw)
+    # one more word rides along: does ANY rank hold targets?  (without any the reference returns zeros, loss.py:873-876)
+    buf = torch.cat([parts.reshape(-1), parts.new_tensor([1.0 if gts_local.shape[1] > 0 else 0.0])])
+    reduce_partials(buf, group)
+    items = _loss3d.finalize_partials3d(buf[:-1], bool(buf[-1] > 0), gains)[:, :6].reshape(12)
+    return items.sum() * global_batch, items
+
+
 class DeferredLoss:
     """Result of ``v10_loss_sharded(..., defer=True)``: the loss items are being collected on a side stream.  ``wait()``
     makes the current stream wait for them (no host synchronisation) and returns ``(total, items[6])``."""

@@ -90,6 +90,18 @@ def dd_loss_dual_forward(feats_o2m, feats_o2o, strides, nc, gts_packed, calibs, 
     return items, partials, tgi
 
 
+def finalize_partials3d(partials, has_targets, gains):
+    """Un-normalised sums of the 3D loss, float64 [n, 11] (summed over the ranks of an image-sharded batch) -> items
+    float32 [n, 8] = six loss items, target_scores_sum, n_fg (``y3d_dd_loss_finalize``, loss.py:879-888).
+    ``has_targets`` False: the reference's early return (loss.py:873-876), all items zero."""
+    p = partials.reshape(-1, 11).contiguous()
+    items = torch.empty((p.shape[0], 8), dtype=torch.float32, device=p.device)
+    g = (C.c_float * 6)(*[float(v) for v in gains])
+    for z in range(p.shape[0]):
+        _lib.check(_lib.lib().y3d_dd_loss_finalize(ptr(p[z]), 1 if has_targets else 0, g, ptr(items[z]), stream_ptr(p.device)))
+    return items
+
+
 class _DDLossDualFn(torch.autograd.Function):
     """autograd node of the dual 3D loss: inputs = the per-level head tensors of both branches, output = the twelve loss
     items (one2many, one2one).  Forward: one ``y3d_dd_loss_dual_fwd``; backward: ``y3d_dd_loss_bwd`` per branch on that

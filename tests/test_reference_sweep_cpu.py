@@ -120,3 +120,40 @@ def test_reference_vs_oracle_3d_assignment_seed_sweep():
     print(f"reference vs oracle (3D): {SEEDS_3D} seeds, {n_fg} foreground anchors, {n_mism} mismatches, "
           f"worst item deviation {worst:.2e}")
     assert n_fg > 500 and n_mism == 0 and worst < 3e-5
+
+
+SEEDS_DET = 12
+
+
+def test_reference_vs_oracle_decode_topk_seed_sweep():
+    """Inference path at BASELINE cfg1 / cfg4 shapes (nc = 80, 640 x 640 / 1280 x 1280, top-300): the REAL Detect.inference
+    (head.py:53-79) + ops.v10postprocess (ops.py:852-865) against the oracle's decode + two-stage top-k.  The selection
+    runs on the reference's own decoded tensor (so only the selection is compared, bit for bit: labels and scores), and
+    the decoded tensor itself is held to 1e-5."""
+    import torch
+
+    from tests.golden import make_golden as mg
+
+    nc, D = 80, 300
+    n_det = n_mism = 0
+    worst = 0.0
+    for s in range(SEEDS_DET):
+        hw = (1280, 1280) if s % 4 == 3 else (640, 640)
+        lv = synth.levels(*hw)
+        x = synth.head2d(1, nc, lv, seed=8000 + s)
+        feats = [mg.t(f) for f in synth.split_levels(x, lv)]
+        ns = mg.head_ns(nc, synth.STRIDES)
+        with torch.no_grad():
+            y, _ = mg.Detect.inference(ns, feats)
+            with mg.patched_topk():
+                boxes, scores, labels = mg.ref_ops.v10postprocess(y.permute(0, 2, 1), D, nc)
+        y = y.numpy()
+        oy = oracle.decode2d(x, lv, synth.STRIDES, nc)
+        worst = max(worst, float(np.max(np.abs(oy[:, 4:] - y[:, 4:]) / np.maximum(np.abs(y[:, 4:]), 1e-6))))
+        np.testing.assert_allclose(oy[:, :4], y[:, :4], rtol=1e-5, atol=1e-3)
+        ob, osc, ol, _ = oracle.postprocess(y.transpose(0, 2, 1), D, nc)
+        n_mism += int((ol != labels.numpy()).sum() + (osc != scores.numpy()).sum() + (ob != boxes.numpy()).sum())
+        n_det += ol.size
+    print(f"reference vs oracle (decode + top-k): {SEEDS_DET} seeds, {n_det} detections, {n_mism} mismatches, "
+          f"worst relative score deviation of the decode {worst:.2e}")
+    assert n_det == SEEDS_DET * D and n_mism == 0 and worst < 1e-5
